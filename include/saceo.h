@@ -1,0 +1,221 @@
+/*
+ * saceo.h - C ABI of the B200-native SAC-EO gradient-update hot path.
+ *
+ * The reference (noc-lab/sac-expert) is pure Python on TensorFlow-2 eager and has no FFI or
+ * plugin layer; its de-facto operator API for this path is a set of Python methods.  Each
+ * entry point below names the reference call site(s) it replaces (paths relative to the
+ * reference checkout, file:line).  The Python mirror classes in sac_expert_b200/sac_eo/ bind
+ * these through ctypes (sac_expert_b200/lib.py); INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SACEO_E_* code, never throws;
+ *     saceo_last_error() returns a thread-local human-readable message for the last failure.
+ *   - all pointers inside saceo_tables are DEVICE pointers owned by the caller (PyTorch only
+ *     supplies tensor.data_ptr()); the library owns its context and workspace and never frees
+ *     caller memory.
+ *   - calls are stream-ordered on the cudaStream_t passed as `stream` (void* to keep this
+ *     header free of CUDA includes) and non-blocking, except the *_host variants, which are
+ *     documented to synchronise.
+ *   - one context per (process, device); contexts are not re-entrant.
+ *   - there is NO CPU fallback: create() fails if no sm_100 device is present.
+ *
+ * Population model: `n_agents` independent agents (seeds x hyper-parameters) share one set of
+ * static dimensions; every table is [n_agents, ...] with the strides saceo_query_layout()
+ * reports.  n_agents = 1 reproduces the reference's single-agent behaviour.
+ *
+ * Flat parameter layout per network (Keras get_weights() order, each tensor row-major,
+ * sac_eo/common/nn_utils.py:86-138,162-182; actor: sac_eo/actors/continuous_actors.py:201-209):
+ *     [ W0 (in x h1) | b0 (h1) | W1 (h1 x h2) | b1 (h2) | W2 (h2 x out) | b2 (out) | logstd (A)* ]
+ *     (*) only for a state-independent-std actor.  W is [in, out], y = x @ W + b.
+ */
+#ifndef SACEO_H_
+#define SACEO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SACEO_ABI_VERSION 1
+
+enum {
+  SACEO_OK = 0,
+  SACEO_E_INVALID = -1,   /* bad argument / unsupported configuration */
+  SACEO_E_CUDA = -2,      /* CUDA runtime error (message in saceo_last_error) */
+  SACEO_E_NODEVICE = -3,  /* no sm_100-class GPU: the library refuses to run */
+  SACEO_E_UNBOUND = -4,   /* tables not bound yet */
+  SACEO_E_NOMEM = -5
+};
+
+enum { SACEO_ACT_RELU = 0, SACEO_ACT_TANH = 1, SACEO_ACT_ELU = 2 };
+
+/* GEMM engine for the hidden x hidden per-agent contractions. */
+enum {
+  SACEO_GEMM_FP32_SIMT = 0,   /* CUDA-core fp32 FMA (exact fp32 products) */
+  SACEO_GEMM_TCGEN05_BF16X3 = 1 /* tcgen05.mma kind::f16, bf16 hi/lo split, 3 MMAs, fp32 accum in TMEM */
+};
+
+/* Static dimensions - what the reference passes through its kwargs dicts
+ * (sac_eo/common/train_parser.py: --actor_layers/--critic_layers/--model_layers,
+ *  --*_activations, --actor_per_state_std, --separate_reward_nn, --delta_clip_pred,
+ *  --num_models, --sac_batch_size, --expert_buffer_size/--expert_batch_size,
+ *  --target_update_int, --actor_std_mult). */
+typedef struct saceo_config {
+  int32_t abi_version;        /* = SACEO_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t n_agents;
+  int32_t S, A;               /* observation / action dims */
+  int32_t actor_hidden[2], critic_hidden[2], model_hidden[2];
+  int32_t actor_act[2], critic_act[2], model_act[2];   /* SACEO_ACT_* per hidden layer */
+  int32_t per_state_std;      /* actor outputs 2A (mean, logstd) instead of A */
+  int32_t separate_reward_nn; /* model outputs S instead of S+1 */
+  int32_t num_models;         /* 0 = plain SAC (SAC.py), 1 / 2 = SAC-EO branches (SAC_expert.py:271,299) */
+  float   delta_clip_pred;    /* 0 = off (base_world_model.py:80-82) */
+  int32_t B;                  /* sac_batch_size */
+  int32_t E;                  /* expert rows per update; must be even when num_models == 2 */
+  int32_t target_update_int;  /* Polyak gate: num_timesteps % target_update_int == 0 (SAC_expert.py:475) */
+  int32_t replay_capacity;    /* rows per agent in the device replay table */
+  int32_t fvp_rows;           /* N states for the Fisher-vector product (0 = CG unused) */
+  float   std_mult;           /* --actor_std_mult, only used by the GaussianActor._forward (CG) path */
+  int32_t gemm_mode;          /* SACEO_GEMM_* */
+  int32_t use_graph;          /* capture one update into a CUDA graph and replay it */
+  int32_t reserved[8];
+} saceo_config;
+
+/* Strides/offsets (in 4-byte words unless stated) derived from a config. */
+typedef struct saceo_layout {
+  int64_t na, nc, nm;                 /* parameter counts actor / one critic / one model */
+  int64_t na_stride, nc_stride, nm_stride;   /* padded per-agent (per-net) strides */
+  int32_t Ao, model_out;
+  /* device replay row (AoS, 16-byte aligned): [ s(S) | a(A) | sp(S) | r | pad | d (f64, 2 words) | pad ] */
+  int32_t row_words, off_s, off_a, off_sp, off_r, off_d;
+  /* per-agent normaliser record */
+  int32_t norm_stride, off_s_mean, off_s_std, off_a_mean, off_a_std, off_ret_std,
+          off_m_s_mean, off_m_s_std, off_m_a_mean, off_m_a_std, off_m_d_mean, off_m_d_std,
+          off_act_limit;
+  int32_t hyper_stride;               /* = 8: gamma,tau,lr_q,lr_pi,lr_alpha,eps,target_entropy,damp */
+  int32_t n_losses;                   /* = 8: L_q1,L_q2,L_pi,mse,p_loss,alpha_loss,alpha,eps */
+  int64_t workspace_bytes;            /* what create() will cudaMalloc */
+} saceo_layout;
+
+/* Device tables, all caller-owned.  Shapes use the strides of saceo_layout.
+ * They replace the reference's tf.Variable / optimizer-slot / NumPy state:
+ *   actor*       SquashedGaussianActor._nn (+logstd)        continuous_actors.py:46-57
+ *   q*, qt       QCritic._nn x2 live, x2 targets            critics/init_critic.py:27-35
+ *   model        MSEModel/GaussianModel._nn x2 (frozen)     models/init_world_models.py:5-29
+ *   alpha*       self.alpha (raw, log-initialised)          SAC_expert.py:106
+ *   *_m,*_v,adam_t   tf.keras.optimizers.Adam slots x4      SAC_expert.py:108-115
+ *   norm         RunningNormalizers stats                   common/normalizer.py:126-190
+ *   replay*      TrajectoryBuffer arrays                    common/buffers.py:28-39
+ *   expert_*     expert_reg[0], expert_reg[2]               SAC_expert.py:423 */
+typedef struct saceo_tables {
+  float *actor, *actor_m, *actor_v;          /* [n_agents, na_stride] */
+  float *q, *q_m, *q_v;                      /* [n_agents, 2, nc_stride] */
+  float *qt;                                 /* [n_agents, 2, nc_stride] */
+  const float *model;                        /* [n_agents, 2, nm_stride] (unused if num_models == 0) */
+  float *alpha, *alpha_m, *alpha_v;          /* [n_agents] */
+  int32_t *adam_t;                           /* [n_agents, 4]: q1, q2, actor, alpha step counts */
+  const float *norm;                         /* [n_agents, norm_stride] */
+  const float *hyper;                        /* [n_agents, hyper_stride] */
+  const float *replay;                       /* [n_agents, replay_capacity, row_words] */
+  const int32_t *replay_size;                /* [n_agents] rows currently valid */
+  const int32_t *replay_start;               /* [n_agents] physical row of logical index 0 (ring), may be NULL */
+  const float *expert_s, *expert_sp;         /* [n_agents, E, S] */
+  const float *fvp_states;                   /* [n_agents, fvp_rows, S] or NULL */
+} saceo_tables;
+
+typedef struct saceo_ctx saceo_ctx;
+
+/* Layout helper (pure host arithmetic; callable without a GPU). */
+int saceo_query_layout(const saceo_config *cfg, saceo_layout *out);
+
+/* Lifetime.  create() allocates the workspace on cfg->device and fails with
+ * SACEO_E_NODEVICE when there is no compute-capability-10.x GPU. */
+int saceo_create(const saceo_config *cfg, saceo_ctx **out);
+int saceo_destroy(saceo_ctx *ctx);
+int saceo_bind(saceo_ctx *ctx, const saceo_tables *tables);
+
+/* TrajectoryBuffer.get_offmodel_info / get_model_info (common/buffers.py:107-144): for the SAME
+ * int64 indices (device, [n_agents, B], logical row numbers) writes exact copies of the rows:
+ * out_s [n,B,S] f32, out_a [n,B,A] f32, out_sp [n,B,S] f32, out_r [n,B] f32, out_d [n,B] f64.
+ * Any out_* may be NULL.  Bit-exact. */
+int saceo_gather(saceo_ctx *ctx, const int64_t *idx, float *out_s, float *out_a, float *out_sp,
+                 float *out_r, double *out_d, void *stream);
+
+/* Inject the random draws of the next update(s) (parity mode), device pointers, any may be NULL:
+ * idx [n,B] int64 (np.random.randint, buffers.py:135); noise [n, 3B+E, A] f32 in reference draw
+ * order u1 | u2 | u3,u4 (expert rows, permuted order) | u5 (np.random.normal,
+ * continuous_actors.py:297,350); expert_perm [n,E] int32 = concatenated array_split sections of
+ * the shuffled arange (SAC_expert.py:301-303). */
+int saceo_set_draws(saceo_ctx *ctx, const int64_t *idx, const float *noise,
+                    const int32_t *expert_perm, void *stream);
+
+/* SAC_exp._update / SAC._update (SAC_expert.py:463-477, SAC.py:236-250) for every agent,
+ * n_steps times.  use_device_rng != 0: idx/noise/permutation are drawn in-kernel (Philox4x32-10
+ * keyed by seed, agent, step) before each step; otherwise the draws last injected with
+ * saceo_set_draws() are consumed (n_steps should then be 1).  num_timesteps gates the Polyak
+ * update of step i on (num_timesteps + i) % target_update_int == 0.  losses_out (device,
+ * [n_agents, n_losses], may be NULL) receives the values of the LAST step. */
+int saceo_update(saceo_ctx *ctx, int32_t n_steps, int64_t num_timesteps, int32_t use_device_rng,
+                 uint64_t seed, float *losses_out, void *stream);
+
+/* Same, through HOST buffers (the call the Python `_update` makes per step): copies idx_host
+ * [n,B] int64 (may be NULL => device RNG) and expert_host [n, 2, E, S] f32 (sE then s'E; may be
+ * NULL => keep bound tables) host->device, runs one update, copies losses [n, n_losses] back into
+ * losses_host and synchronises the stream. */
+int saceo_update_host(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,
+                      const float *expert_host, float *losses_host, void *stream);
+
+/* Phase-split form of one update for the optional single-agent data-parallel mode (gradients are
+ * all-reduced by the caller between *_grads and *_apply; torch.distributed/NCCL does the
+ * collective).  phase: 0 = TD target + critic grads, 1 = critic Adam(+Polyak), 2 = actor grads,
+ * 3 = actor Adam, 4 = alpha grad, 5 = alpha Adam + clamp.  grad buffers: saceo_debug_ptr(). */
+int saceo_update_phase(saceo_ctx *ctx, int32_t phase, int64_t num_timesteps, void *stream);
+
+/* actor.sample(s, deterministic) for the population (SAC_expert.py:779; samplers.py:31):
+ * obs [n_agents, rows, S] -> act_out [n_agents, rows, A] (device).  noise [n_agents, rows, A] or
+ * NULL (=> deterministic mean action).  Also returns neglogp [n_agents, rows] if non-NULL
+ * (= actor.evaluate, continuous_actors.py:327-379). */
+int saceo_actor_forward(saceo_ctx *ctx, const float *obs, int32_t rows, const float *noise,
+                        float *act_out, float *neglogp_out, void *stream);
+
+/* critic._forward / critic.value (critics.py:84-103): which = 0 live, 1 target.
+ * q_out [n_agents, 2, rows] = normalised-space output; scale_ret != 0 multiplies by max(ret_std,1e-8). */
+int saceo_critic_forward(saceo_ctx *ctx, int32_t which, const float *obs, const float *act,
+                         int32_t rows, int32_t scale_ret, float *q_out, void *stream);
+
+/* model.sample(s, a, deterministic=True) (continuous_models.py:244-254): sp_out [n_agents, 2, rows, S]. */
+int saceo_model_eval(saceo_ctx *ctx, const float *obs, const float *act, int32_t rows,
+                     float *sp_out, void *stream);
+
+/* TRPO._make_F closure (model_free/trpo.py:200-227): Fx = d/dtheta((d/dtheta mean KL) . x) + damp x
+ * on the bound fvp_states, x and Fx [n_agents, na_stride] device. */
+int saceo_fvp(saceo_ctx *ctx, const float *x, float damp, float *Fx, void *stream);
+
+/* cg(F, b, cg_iters, residual_tol) (common/update_utils.py:4-24) followed by vFv = x.F(x)
+ * (trpo.py:185): b, x_out [n_agents, na_stride], vFv_out [n_agents] device. */
+int saceo_cg_solve(saceo_ctx *ctx, const float *b, int32_t iters, float tol, float damp,
+                   float *x_out, float *vFv_out, void *stream);
+
+/* Test / inspection surface: device pointer of a named workspace buffer (e.g. "g_q", "g_actor",
+ * "y", "losses", "idx", "noise") and its size in bytes; NULL if unknown. */
+void *saceo_debug_ptr(saceo_ctx *ctx, const char *name, int64_t *bytes_out);
+
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+int64_t saceo_launch_count(const saceo_ctx *ctx);
+
+/* Standalone batched GEMM self-test surface used by tests/: C[z] = op(A[z]) . op(B[z]) with the
+ * engine selected by gemm_mode; all device pointers, row-major. */
+int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int32_t N, int32_t K,
+                    int32_t transA, int32_t transB, const float *A, const float *Bm, float *C,
+                    void *stream);
+
+const char *saceo_last_error(void);
+int saceo_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SACEO_H_ */

@@ -1,0 +1,839 @@
+// libsaceo: C ABI + launch orchestration of the SAC-EO gradient-update hot path on B200 (sm_100a).
+// See include/saceo.h for the contract and the reference call sites each entry point replaces.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/saceo.h"
+#include "gemm_simt.cuh"
+#include "elem.cuh"
+#include "fvp.cuh"
+#include "tc_gemm.cuh"
+
+using namespace saceo;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+  return fail(SACEO_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
+
+static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct NetD {            // one (population of) MLP(s) in the flat Keras layout
+  const float* theta; long long sa, sn; int nnet;
+  int in, h1, h2, out, act0, act1;
+  long long oW0() const { return 0; }
+  long long ob0() const { return (long long)in * h1; }
+  long long oW1() const { return ob0() + h1; }
+  long long ob1() const { return oW1() + (long long)h1 * h2; }
+  long long oW2() const { return ob1() + h2; }
+  long long ob2() const { return oW2() + (long long)h2 * out; }
+};
+
+struct saceo_ctx {
+  saceo_config cfg;
+  saceo_layout L;
+  KCtx k;                 // device-visible view (tables + workspace)
+  FvpWs f;
+  bool bound = false;
+  void* ws = nullptr;
+  long long ws_bytes = 0;
+  std::map<std::string, std::pair<void*, long long>> names;
+  float *exp_stage = nullptr;          // [n, 2, E, S] host-staged expert rows
+  long long* idx_stage = nullptr;
+  long long launches = 0;
+  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [rng][polyak]
+  long long graph_nodes[2][2] = {{0, 0}, {0, 0}};
+};
+
+#define LAUNCH(ctx, kern, grid, block, smem, st, ...) do { \
+  kern<<<grid, block, smem, st>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+static int validate(const saceo_config* c) {
+  if (!c) return fail(SACEO_E_INVALID, "null config");
+  if (c->abi_version != SACEO_ABI_VERSION) return fail(SACEO_E_INVALID, "abi_version %d != %d", c->abi_version, SACEO_ABI_VERSION);
+  if (c->n_agents < 1 || c->n_agents > 32000) return fail(SACEO_E_INVALID, "n_agents out of range");
+  if (c->S < 1 || c->A < 1 || c->B < 1) return fail(SACEO_E_INVALID, "S, A, B must be positive");
+  for (int i = 0; i < 2; ++i) {
+    if (c->actor_hidden[i] < 1 || c->critic_hidden[i] < 1) return fail(SACEO_E_INVALID, "hidden sizes must be positive");
+    if (c->actor_act[i] < 0 || c->actor_act[i] > 2 || c->critic_act[i] < 0 || c->critic_act[i] > 2 ||
+        c->model_act[i] < 0 || c->model_act[i] > 2)
+      return fail(SACEO_E_INVALID, "activations must be tanh, relu or elu");   // nn_utils.py:18
+  }
+  if (c->num_models < 0 || c->num_models > 2) return fail(SACEO_E_INVALID, "num_models must be 0, 1 or 2 (only models[0..1] are used, SAC_expert.py:325-326)");
+  if (c->num_models > 0) {
+    if (c->E < 1) return fail(SACEO_E_INVALID, "E must be positive for SAC-EO");
+    if (c->num_models == 2 && (c->E & 1)) return fail(SACEO_E_INVALID, "E must be even with two models (unequal array_split halves cannot be added, SAC_expert.py:329-332)");
+    if (c->model_hidden[0] < 1 || c->model_hidden[1] < 1) return fail(SACEO_E_INVALID, "model hidden sizes must be positive");
+  }
+  if (c->target_update_int < 1) return fail(SACEO_E_INVALID, "target_update_int must be >= 1");
+  if (c->replay_capacity < 1) return fail(SACEO_E_INVALID, "replay_capacity must be >= 1");
+  if (c->gemm_mode != SACEO_GEMM_FP32_SIMT && c->gemm_mode != SACEO_GEMM_TCGEN05_BF16X3)
+    return fail(SACEO_E_INVALID, "unknown gemm_mode");
+  return 0;
+}
+
+struct Bump {   // workspace carver (also used dry to size it)
+  char* base; long long off = 0;
+  std::map<std::string, std::pair<void*, long long>>* names;
+  template <typename T> T* get(const char* name, long long count) {
+    off = rup(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    long long bytes = count * (long long)sizeof(T);
+    if (names && base) (*names)[name] = {p, bytes};
+    off += bytes;
+    return p;
+  }
+};
+
+static void fill_layout(const saceo_config* c, saceo_layout* L) {
+  memset(L, 0, sizeof(*L));
+  const int S = c->S, A = c->A;
+  L->Ao = c->per_state_std ? 2 * A : A;
+  L->model_out = c->separate_reward_nn ? S : S + 1;
+  auto cnt = [](long long in, long long h1, long long h2, long long out) {
+    return in * h1 + h1 + h1 * h2 + h2 + h2 * out + out; };
+  L->na = cnt(S, c->actor_hidden[0], c->actor_hidden[1], L->Ao) + (c->per_state_std ? 0 : A);
+  L->nc = cnt(S + A, c->critic_hidden[0], c->critic_hidden[1], 1);
+  L->nm = c->num_models > 0 ? cnt(S + A, c->model_hidden[0], c->model_hidden[1], L->model_out) : 0;
+  L->na_stride = rup(L->na + 1, 32);   // last padded word carries g_alpha in the grad buffer
+  L->nc_stride = rup(L->nc, 32);
+  L->nm_stride = rup(L->nm > 0 ? L->nm : 1, 32);
+  L->off_s = 0; L->off_a = S; L->off_sp = S + A; L->off_r = 2 * S + A;
+  L->off_d = (int)rup(2 * S + A + 1, 2);
+  L->row_words = (int)rup(L->off_d + 2, 4);
+  int o = 0;
+  L->off_s_mean = o; o += S; L->off_s_std = o; o += S;
+  L->off_a_mean = o; o += A; L->off_a_std = o; o += A;
+  L->off_ret_std = o; o += 1;
+  L->off_m_s_mean = o; o += S; L->off_m_s_std = o; o += S;
+  L->off_m_a_mean = o; o += A; L->off_m_a_std = o; o += A;
+  L->off_m_d_mean = o; o += S; L->off_m_d_std = o; o += S;
+  L->off_act_limit = o; o += A;
+  L->norm_stride = (int)rup(o, 4);
+  L->hyper_stride = 8;
+  L->n_losses = 8;
+}
+
+static void carve(saceo_ctx* x, char* base) {
+  const saceo_config& c = x->cfg; const saceo_layout& L = x->L;
+  KCtx& k = x->k;
+  Bump b{base, 0, base ? &x->names : nullptr};
+  const long long n = c.n_agents;
+  const int S = c.S, A = c.A, B = c.B, E = c.num_models > 0 ? c.E : 0, R = B + E;
+  const int SA = S + A;
+  k.idx = b.get<long long>("idx", n * B);
+  k.noise = b.get<float>("noise", n * (3LL * B + E) * A);
+  k.perm = b.get<int>("perm", n * (E > 0 ? E : 1));
+  k.mb_s = b.get<float>("mb_s", n * B * S);   k.mb_a = b.get<float>("mb_a", n * B * A);
+  k.mb_sp = b.get<float>("mb_sp", n * B * S); k.mb_r = b.get<float>("mb_r", n * B);
+  k.mb_omd = b.get<float>("mb_omd", n * B);
+  k.Xpi = b.get<float>("Xpi", n * R * S);
+  k.aH1 = b.get<float>("aH1", n * R * c.actor_hidden[0]);  k.aH2 = b.get<float>("aH2", n * R * c.actor_hidden[1]);
+  k.aOut = b.get<float>("aOut", n * R * L.Ao);             k.daOut = b.get<float>("daOut", n * R * L.Ao);
+  k.daH2 = b.get<float>("daH2", n * R * c.actor_hidden[1]); k.daH1 = b.get<float>("daH1", n * R * c.actor_hidden[0]);
+  k.dls = b.get<float>("dls", n * R * A);
+  k.Xc = b.get<float>("Xc", n * B * SA);
+  k.cH1 = b.get<float>("cH1", n * 2 * B * c.critic_hidden[0]);  k.cH2 = b.get<float>("cH2", n * 2 * B * c.critic_hidden[1]);
+  k.cQ = b.get<float>("cQ", n * 2 * B);                          k.cdQ = b.get<float>("cdQ", n * 2 * B);
+  k.cdH2 = b.get<float>("cdH2", n * 2 * B * c.critic_hidden[1]); k.cdH1 = b.get<float>("cdH1", n * 2 * B * c.critic_hidden[0]);
+  k.cdXa = b.get<float>("cdXa", n * 2 * B * A);
+  const long long e1 = E > 0 ? E : 1;
+  const int mh1 = c.num_models > 0 ? c.model_hidden[0] : 1, mh2 = c.num_models > 0 ? c.model_hidden[1] : 1;
+  k.Xm = b.get<float>("Xm", n * 2 * e1 * SA);
+  k.mH1 = b.get<float>("mH1", n * 2 * e1 * mh1);   k.mH2 = b.get<float>("mH2", n * 2 * e1 * mh2);
+  k.mOut = b.get<float>("mOut", n * 2 * e1 * L.model_out); k.mdOut = b.get<float>("mdOut", n * 2 * e1 * S);
+  k.mdH2 = b.get<float>("mdH2", n * 2 * e1 * mh2); k.mdH1 = b.get<float>("mdH1", n * 2 * e1 * mh1);
+  k.mdXa = b.get<float>("mdXa", n * 2 * e1 * A);
+  k.y = b.get<float>("y", n * B);  k.nlp = b.get<float>("nlp", n * R);
+  k.g_q = b.get<float>("g_q", n * 2 * L.nc_stride);
+  k.g_actor = b.get<float>("g_actor", n * L.na_stride);
+  k.lrt = b.get<float>("lrt", n * 4);
+  k.losses = b.get<float>("losses", n * L.n_losses);
+  k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
+  x->exp_stage = b.get<float>("exp_stage", n * 2 * e1 * S);
+  x->idx_stage = b.get<long long>("idx_stage", n * B);
+  // Fisher-vector / CG workspace
+  FvpWs& f = x->f;
+  const long long N = c.fvp_rows;
+  f.N = (int)N;
+  if (N > 0) {
+    f.X = b.get<float>("fX", n * N * S);
+    f.H1 = b.get<float>("fH1", n * N * c.actor_hidden[0]); f.H2 = b.get<float>("fH2", n * N * c.actor_hidden[1]);
+    f.Out = b.get<float>("fOut", n * N * L.Ao);
+    f.T1 = b.get<float>("fT1", n * N * c.actor_hidden[0]); f.T2 = b.get<float>("fT2", n * N * c.actor_hidden[1]);
+    f.Tmp = b.get<float>("fTmp", n * N * (long long)(c.actor_hidden[1] > L.Ao ? c.actor_hidden[1] : L.Ao));
+    f.TOut = b.get<float>("fTOut", n * N * L.Ao);
+    f.G = b.get<float>("fG", n * N * L.Ao);
+    f.dH2 = b.get<float>("fdH2", n * N * c.actor_hidden[1]); f.dH1 = b.get<float>("fdH1", n * N * c.actor_hidden[0]);
+    f.gls = b.get<float>("fgls", n * N * A);
+    f.p = b.get<float>("cg_p", n * L.na_stride); f.r = b.get<float>("cg_r", n * L.na_stride);
+    f.z = b.get<float>("cg_z", n * L.na_stride); f.x = b.get<float>("cg_x", n * L.na_stride);
+    f.sc = b.get<float>("cg_sc", n * 8);
+  }
+  x->ws_bytes = rup(b.off, 256);
+}
+
+extern "C" int saceo_query_layout(const saceo_config* cfg, saceo_layout* out) {
+  int rc = validate(cfg); if (rc) return rc;
+  if (!out) return fail(SACEO_E_INVALID, "null out");
+  fill_layout(cfg, out);
+  saceo_ctx tmp; tmp.cfg = *cfg; tmp.L = *out;
+  carve(&tmp, nullptr);
+  out->workspace_bytes = tmp.ws_bytes;
+  return 0;
+}
+
+extern "C" int saceo_abi_version(void) { return SACEO_ABI_VERSION; }
+extern "C" const char* saceo_last_error(void) { return g_err; }
+
+extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
+  int rc = validate(cfg); if (rc) return rc;
+  if (!out) return fail(SACEO_E_INVALID, "null out");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SACEO_E_NODEVICE, "no CUDA device: libsaceo has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SACEO_E_INVALID, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(SACEO_E_NODEVICE, "device %d is sm_%d%d; libsaceo is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  CU(cudaSetDevice(cfg->device));
+  saceo_ctx* x = new saceo_ctx();
+  x->cfg = *cfg;
+  fill_layout(cfg, &x->L);
+  memset(&x->k, 0, sizeof(KCtx)); memset(&x->f, 0, sizeof(FvpWs));
+  carve(x, nullptr);
+  x->L.workspace_bytes = x->ws_bytes;
+  if (cudaMalloc(&x->ws, (size_t)x->ws_bytes) != cudaSuccess) {
+    cudaGetLastError(); long long wb = x->ws_bytes; delete x;
+    return fail(SACEO_E_NOMEM, "cudaMalloc of %lld workspace bytes failed", wb);
+  }
+  CU(cudaMemset(x->ws, 0, (size_t)x->ws_bytes));
+  carve(x, (char*)x->ws);
+  KCtx& k = x->k;
+  k.n_agents = cfg->n_agents; k.S = cfg->S; k.A = cfg->A; k.Ao = x->L.Ao; k.mo = x->L.model_out;
+  k.B = cfg->B; k.E = cfg->num_models > 0 ? cfg->E : 0; k.R = k.B + k.E; k.nmod = cfg->num_models;
+  k.per_state_std = cfg->per_state_std; k.sep_reward = cfg->separate_reward_nn;
+  k.ah1 = cfg->actor_hidden[0]; k.ah2 = cfg->actor_hidden[1];
+  k.ch1 = cfg->critic_hidden[0]; k.ch2 = cfg->critic_hidden[1];
+  k.mh1 = cfg->model_hidden[0]; k.mh2 = cfg->model_hidden[1];
+  k.aact0 = cfg->actor_act[0]; k.aact1 = cfg->actor_act[1];
+  k.cact0 = cfg->critic_act[0]; k.cact1 = cfg->critic_act[1];
+  k.mact0 = cfg->model_act[0]; k.mact1 = cfg->model_act[1];
+  k.delta_clip = cfg->delta_clip_pred; k.cap = cfg->replay_capacity; k.L = x->L;
+  // identity expert permutation until draws are injected / generated
+  if (k.E > 0) {
+    std::vector<int> pm((size_t)cfg->n_agents * k.E);
+    for (int a = 0; a < cfg->n_agents; ++a) for (int i = 0; i < k.E; ++i) pm[(size_t)a * k.E + i] = i;
+    CU(cudaMemcpy(k.perm, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CU(tc_gemm_init());
+  *out = x;
+  return 0;
+}
+
+extern "C" int saceo_destroy(saceo_ctx* x) {
+  if (!x) return 0;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
+  if (x->ws) cudaFree(x->ws);
+  delete x;
+  return 0;
+}
+
+extern "C" int saceo_bind(saceo_ctx* x, const saceo_tables* t) {
+  if (!x || !t) return fail(SACEO_E_INVALID, "null argument");
+  if (!t->actor || !t->actor_m || !t->actor_v || !t->q || !t->q_m || !t->q_v || !t->qt || !t->alpha ||
+      !t->alpha_m || !t->alpha_v || !t->adam_t || !t->norm || !t->hyper)
+    return fail(SACEO_E_INVALID, "a required table pointer is NULL");
+  if (x->cfg.num_models > 0 && (!t->model || !t->expert_s || !t->expert_sp))
+    return fail(SACEO_E_INVALID, "SAC-EO needs model, expert_s and expert_sp tables");
+  x->k.T = *t;
+  x->k.expert_s = t->expert_s; x->k.expert_sp = t->expert_sp;
+  x->bound = true;
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+    if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
+  return 0;
+}
+
+extern "C" void* saceo_debug_ptr(saceo_ctx* x, const char* name, int64_t* bytes_out) {
+  if (!x || !name) return nullptr;
+  auto it = x->names.find(name);
+  if (it == x->names.end()) return nullptr;
+  if (bytes_out) *bytes_out = it->second.second;
+  return it->second.first;
+}
+extern "C" int64_t saceo_launch_count(const saceo_ctx* x) { return x ? x->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------
+static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+  if (x && x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && tc_gemm_eligible(TA, TB, ONES, p)) {
+    int rc = tc_gemm_launch(TA, TB, ONES, p, nagents, st);
+    if (rc == 0) { if (x) x->launches += tc_gemm_launches_per_call(); return 0; }
+    if (rc < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
+  }
+  dim3 grid(cdiv(p.N, SG_BN), cdiv(p.M, SG_BM), nagents * p.nnet), block(SG_THREADS);
+  if (!TA && !TB) k_gemm_simt<false, false, false><<<grid, block, 0, st>>>(p);
+  else if (!TA && TB) k_gemm_simt<false, true, false><<<grid, block, 0, st>>>(p);
+  else if (TA && !TB && ONES) k_gemm_simt<true, false, true><<<grid, block, 0, st>>>(p);
+  else if (TA && !TB) k_gemm_simt<true, false, false><<<grid, block, 0, st>>>(p);
+  else k_gemm_simt<true, true, false><<<grid, block, 0, st>>>(p);
+  if (x) x->launches++;
+  return 0;
+}
+
+// forward through one population of 3-layer MLPs (nn_utils.py:101-136)
+static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
+                       int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
+                       long long sOa, long long sOn, cudaStream_t st) {
+  const int na = x->cfg.n_agents;
+  GemmP p{}; p.nnet = n.nnet;
+  // layer 0
+  p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
+  p.B = n.theta + n.oW0(); p.ldb = n.h1; p.sBa = n.sa; p.sBn = n.sn;
+  p.bias = n.theta + n.ob0(); p.sba = n.sa; p.sbn = n.sn;
+  p.C = H1; p.ldc = n.h1; p.sCa = (long long)n.nnet * rowsAllocH * n.h1; p.sCn = rowsAllocH * n.h1;
+  p.M = rows; p.N = n.h1; p.K = n.in; p.epi = EPI_ACT; p.act = n.act0;
+  int rc = gemm(x, false, false, false, p, na, st); if (rc) return rc;
+  // layer 1
+  p.A = H1; p.lda = n.h1; p.sAa = p.sCa; p.sAn = p.sCn;
+  p.B = n.theta + n.oW1(); p.ldb = n.h2; p.bias = n.theta + n.ob1();
+  p.C = H2; p.ldc = n.h2; p.sCa = (long long)n.nnet * rowsAllocH * n.h2; p.sCn = rowsAllocH * n.h2;
+  p.M = rows; p.N = n.h2; p.K = n.h1; p.act = n.act1;
+  rc = gemm(x, false, false, false, p, na, st); if (rc) return rc;
+  // layer 2 (linear)
+  p.A = H2; p.lda = n.h2; p.sAa = p.sCa; p.sAn = p.sCn;
+  p.B = n.theta + n.oW2(); p.ldb = n.out; p.bias = n.theta + n.ob2();
+  p.C = Out; p.ldc = ldo; p.sCa = sOa; p.sCn = sOn;
+  p.M = rows; p.N = n.out; p.K = n.h2; p.epi = EPI_NONE; p.act = ACT_LINEAR;
+  return gemm(x, false, false, false, p, na, st);
+}
+
+// backward through the same MLPs.  grads (nullable): flat [W|b] blocks via the ones-row trick.
+// dXa (nullable): gradient w.r.t. the ACTION columns of the input only (rows S.. of W0).
+static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
+                        int rows, const float* H1, const float* H2, long long rowsAllocH,
+                        const float* dOut, int ldd, long long sDa, long long sDn, int out_cols,
+                        float* dH2, float* dH1, float* grads, long long sGa, long long sGn,
+                        float* dXa, int S_cols, int A_cols, long long sXaA, long long sXaN, cudaStream_t st) {
+  const int na = x->cfg.n_agents;
+  const long long sH1a = (long long)n.nnet * rowsAllocH * n.h1, sH1n = rowsAllocH * n.h1;
+  const long long sH2a = (long long)n.nnet * rowsAllocH * n.h2, sH2n = rowsAllocH * n.h2;
+  int rc;
+  GemmP p{};
+  if (grads) {   // [dW2; db2] = [H2,1]^T . dOut
+    p = GemmP{}; p.nnet = n.nnet;
+    p.A = H2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
+    p.B = dOut; p.ldb = ldd; p.sBa = sDa; p.sBn = sDn;
+    p.C = grads + n.oW2(); p.ldc = n.out; p.sCa = sGa; p.sCn = sGn;
+    p.M = n.h2 + 1; p.N = n.out; p.K = rows; p.epi = EPI_NONE;
+    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+  }
+  // dH2 = (dOut . W2[:, :out_cols]^T) * act1'(H2)
+  p = GemmP{}; p.nnet = n.nnet;
+  p.A = dOut; p.lda = ldd; p.sAa = sDa; p.sAn = sDn;
+  p.B = n.theta + n.oW2(); p.ldb = n.out; p.sBa = n.sa; p.sBn = n.sn;
+  p.C = dH2; p.ldc = n.h2; p.sCa = sH2a; p.sCn = sH2n; p.aux = H2;
+  p.M = rows; p.N = n.h2; p.K = out_cols; p.epi = EPI_MUL_DACT; p.act = n.act1;
+  rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
+  if (grads) {   // [dW1; db1] = [H1,1]^T . dH2
+    p = GemmP{}; p.nnet = n.nnet;
+    p.A = H1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
+    p.B = dH2; p.ldb = n.h2; p.sBa = sH2a; p.sBn = sH2n;
+    p.C = grads + n.oW1(); p.ldc = n.h2; p.sCa = sGa; p.sCn = sGn;
+    p.M = n.h1 + 1; p.N = n.h2; p.K = rows; p.epi = EPI_NONE;
+    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+  }
+  // dH1 = (dH2 . W1^T) * act0'(H1)
+  p = GemmP{}; p.nnet = n.nnet;
+  p.A = dH2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
+  p.B = n.theta + n.oW1(); p.ldb = n.h2; p.sBa = n.sa; p.sBn = n.sn;
+  p.C = dH1; p.ldc = n.h1; p.sCa = sH1a; p.sCn = sH1n; p.aux = H1;
+  p.M = rows; p.N = n.h1; p.K = n.h2; p.epi = EPI_MUL_DACT; p.act = n.act0;
+  rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
+  if (grads) {   // [dW0; db0] = [X,1]^T . dH1
+    p = GemmP{}; p.nnet = n.nnet;
+    p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
+    p.B = dH1; p.ldb = n.h1; p.sBa = sH1a; p.sBn = sH1n;
+    p.C = grads + n.oW0(); p.ldc = n.h1; p.sCa = sGa; p.sCn = sGn;
+    p.M = n.in + 1; p.N = n.h1; p.K = rows; p.epi = EPI_NONE;
+    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+  }
+  if (dXa) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
+    p = GemmP{}; p.nnet = n.nnet;
+    p.A = dH1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
+    p.B = n.theta + n.oW0() + (long long)S_cols * n.h1; p.ldb = n.h1; p.sBa = n.sa; p.sBn = n.sn;
+    p.C = dXa; p.ldc = A_cols; p.sCa = sXaA; p.sCn = sXaN;
+    p.M = rows; p.N = A_cols; p.K = n.h1; p.epi = EPI_NONE;
+    rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
+  }
+  return 0;
+}
+
+static NetD actor_net(const saceo_ctx* x) {
+  const saceo_config& c = x->cfg;
+  return NetD{x->k.T.actor, x->L.na_stride, 0, 1, c.S, c.actor_hidden[0], c.actor_hidden[1], x->L.Ao,
+              c.actor_act[0], c.actor_act[1]};
+}
+static NetD critic_net(const saceo_ctx* x, bool target) {
+  const saceo_config& c = x->cfg;
+  return NetD{target ? x->k.T.qt : x->k.T.q, 2 * x->L.nc_stride, x->L.nc_stride, 2, c.S + c.A,
+              c.critic_hidden[0], c.critic_hidden[1], 1, c.critic_act[0], c.critic_act[1]};
+}
+static NetD model_net(const saceo_ctx* x, int nnet) {
+  const saceo_config& c = x->cfg;
+  return NetD{x->k.T.model, 2 * x->L.nm_stride, x->L.nm_stride, nnet, c.S + c.A, c.model_hidden[0],
+              c.model_hidden[1], x->L.model_out, c.model_act[0], c.model_act[1]};
+}
+
+// ------------------------------------------------------------------------------------------
+// update phases
+// ------------------------------------------------------------------------------------------
+static int check_launch() {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(SACEO_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int phase_gather(saceo_ctx* x, cudaStream_t st) {
+  const KCtx& k = x->k;
+  LAUNCH(x, k_gather, dim3(cdiv(k.B, 8), k.n_agents), 256, 0, st, k, k.idx, k.mb_s, k.mb_a, k.mb_sp, k.mb_r,
+         (double*)nullptr, k.mb_omd);
+  return check_launch();
+}
+
+// phase 0: TD target + critic gradients
+static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A;
+  int rc;
+  NetD an = actor_net(x), tn = critic_net(x, true), qn = critic_net(x, false);
+  LAUNCH(x, k_stage, dim3(cdiv((long long)B * S, 256), n), 256, 0, st, k, 0);
+  rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
+                   (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+  LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 0, 1,
+         (float*)nullptr, (float*)nullptr, 0LL, 0);
+  rc = mlp_forward(x, tn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
+  LAUNCH(x, k_stage, dim3(cdiv((long long)B * SA, 256), n), 256, 0, st, k, 1);
+  rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
+  rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+                    k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st);
+  if (rc) return rc;
+  return check_launch();
+}
+
+static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
+  const KCtx& k = x->k;
+  LAUNCH(x, k_adam, dim3(cdiv(x->L.nc, 256), 2, k.n_agents), 256, 0, st, k.T.q, k.T.q_m, k.T.q_v, k.g_q, k.T.qt,
+         k.lrt, k.T.hyper, x->L.hyper_stride, 0, x->L.nc, x->L.nc_stride, 2, do_polyak);
+  return check_launch();
+}
+
+// phase 2: actor gradients (policy loss through the UPDATED critics + expert-observation term)
+static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E;
+  int rc;
+  NetD an = actor_net(x), qn = critic_net(x, false);
+  LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
+  rc = mlp_forward(x, an, k.Xpi, S, (long long)R * S, 0, R, k.aH1, k.aH2, R, k.aOut, k.Ao, (long long)R * k.Ao, 0, st);
+  if (rc) return rc;
+  LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 1,
+         (float*)nullptr, (float*)nullptr, 0LL, 0);
+  rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
+  rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+                    k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
+  if (rc) return rc;
+  if (k.nmod > 0) {
+    const int half = k.nmod == 2 ? E / 2 : E;
+    NetD mn = model_net(x, k.nmod);
+    // model buffers are laid out [agent][2][E rows]; net strides are fixed at E rows regardless of nmod
+    // forward
+    {
+      GemmP p{}; p.nnet = mn.nnet;
+      p.A = k.Xm; p.lda = SA; p.sAa = 2LL * E * SA; p.sAn = (long long)E * SA;
+      p.B = mn.theta + mn.oW0(); p.ldb = mn.h1; p.sBa = mn.sa; p.sBn = mn.sn;
+      p.bias = mn.theta + mn.ob0(); p.sba = mn.sa; p.sbn = mn.sn;
+      p.C = k.mH1; p.ldc = mn.h1; p.sCa = 2LL * E * mn.h1; p.sCn = (long long)E * mn.h1;
+      p.M = half; p.N = mn.h1; p.K = SA; p.epi = EPI_ACT; p.act = mn.act0;
+      rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+      p.A = k.mH1; p.lda = mn.h1; p.sAa = p.sCa; p.sAn = p.sCn;
+      p.B = mn.theta + mn.oW1(); p.ldb = mn.h2; p.bias = mn.theta + mn.ob1();
+      p.C = k.mH2; p.ldc = mn.h2; p.sCa = 2LL * E * mn.h2; p.sCn = (long long)E * mn.h2;
+      p.N = mn.h2; p.K = mn.h1; p.act = mn.act1;
+      rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+      p.A = k.mH2; p.lda = mn.h2; p.sAa = p.sCa; p.sAn = p.sCn;
+      p.B = mn.theta + mn.oW2(); p.ldb = mn.out; p.bias = mn.theta + mn.ob2();
+      p.C = k.mOut; p.ldc = mn.out; p.sCa = 2LL * E * mn.out; p.sCn = (long long)E * mn.out;
+      p.N = mn.out; p.K = mn.h2; p.epi = EPI_NONE; p.act = ACT_LINEAR;
+      rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+    }
+    LAUNCH(x, k_model_loss, dim3(n), 256, 0, st, k);
+    // backward to the action columns (weights frozen)
+    {
+      GemmP p{}; p.nnet = mn.nnet;
+      p.A = k.mdOut; p.lda = S; p.sAa = 2LL * E * S; p.sAn = (long long)E * S;
+      p.B = mn.theta + mn.oW2(); p.ldb = mn.out; p.sBa = mn.sa; p.sBn = mn.sn;
+      p.C = k.mdH2; p.ldc = mn.h2; p.sCa = 2LL * E * mn.h2; p.sCn = (long long)E * mn.h2; p.aux = k.mH2;
+      p.M = half; p.N = mn.h2; p.K = S; p.epi = EPI_MUL_DACT; p.act = mn.act1;
+      rc = gemm(x, false, true, false, p, n, st); if (rc) return rc;
+      p = GemmP{}; p.nnet = mn.nnet;
+      p.A = k.mdH2; p.lda = mn.h2; p.sAa = 2LL * E * mn.h2; p.sAn = (long long)E * mn.h2;
+      p.B = mn.theta + mn.oW1(); p.ldb = mn.h2; p.sBa = mn.sa; p.sBn = mn.sn;
+      p.C = k.mdH1; p.ldc = mn.h1; p.sCa = 2LL * E * mn.h1; p.sCn = (long long)E * mn.h1; p.aux = k.mH1;
+      p.M = half; p.N = mn.h1; p.K = mn.h2; p.epi = EPI_MUL_DACT; p.act = mn.act0;
+      rc = gemm(x, false, true, false, p, n, st); if (rc) return rc;
+      p = GemmP{}; p.nnet = mn.nnet;
+      p.A = k.mdH1; p.lda = mn.h1; p.sAa = 2LL * E * mn.h1; p.sAn = (long long)E * mn.h1;
+      p.B = mn.theta + mn.oW0() + (long long)S * mn.h1; p.ldb = mn.h1; p.sBa = mn.sa; p.sBn = mn.sn;
+      p.C = k.mdXa; p.ldc = A; p.sCa = 2LL * E * A; p.sCn = (long long)E * A;
+      p.M = half; p.N = A; p.K = mn.h1; p.epi = EPI_NONE;
+      rc = gemm(x, false, true, false, p, n, st); if (rc) return rc;
+    }
+  }
+  LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
+  rc = mlp_backward(x, an, k.Xpi, S, (long long)R * S, 0, R, k.aH1, k.aH2, R, k.daOut, k.Ao, (long long)R * k.Ao, 0,
+                    k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st);
+  if (rc) return rc;
+  if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
+  return check_launch();
+}
+
+static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
+  const KCtx& k = x->k;
+  LAUNCH(x, k_adam, dim3(cdiv(x->L.na, 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
+         k.g_actor, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0);
+  return check_launch();
+}
+
+// phase 4/5: temperature (forward of the UPDATED actor on s with fresh noise u5)
+static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A;
+  NetD an = actor_net(x);
+  int rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
+                       (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+  LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 2 * B + k.E, 0,
+         (float*)nullptr, (float*)nullptr, 0LL, 0);
+  LAUNCH(x, k_alpha_step, dim3(n), 256, 0, st, k, apply);
+  return check_launch();
+}
+
+static int step_once(saceo_ctx* x, int use_rng, int do_polyak, cudaStream_t st) {
+  const KCtx& k = x->k;
+  int rc;
+  LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, use_rng);
+  if (use_rng) {
+    const int items = ((3 * k.B + k.E) * k.A + 3) / 4;
+    LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k);
+  }
+  if ((rc = phase_gather(x, st))) return rc;
+  if ((rc = phase_critic_grads(x, st))) return rc;
+  if ((rc = phase_critic_apply(x, do_polyak, st))) return rc;
+  if ((rc = phase_actor_grads(x, st))) return rc;
+  if ((rc = phase_actor_apply(x, st))) return rc;
+  if ((rc = phase_alpha(x, 1, st))) return rc;
+  return 0;
+}
+
+extern "C" int saceo_set_draws(saceo_ctx* x, const int64_t* idx, const float* noise, const int32_t* perm, void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  if (idx) CU(cudaMemcpyAsync(k.idx, idx, sizeof(long long) * k.n_agents * k.B, cudaMemcpyDeviceToDevice, st));
+  if (noise) CU(cudaMemcpyAsync(k.noise, noise, sizeof(float) * k.n_agents * (3LL * k.B + k.E) * k.A, cudaMemcpyDeviceToDevice, st));
+  if (perm && k.E > 0) CU(cudaMemcpyAsync(k.perm, perm, sizeof(int) * k.n_agents * k.E, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int saceo_update(saceo_ctx* x, int32_t n_steps, int64_t num_timesteps, int32_t use_device_rng,
+                            uint64_t seed, float* losses_out, void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  if (!x->k.T.replay || !x->k.T.replay_size) return fail(SACEO_E_UNBOUND, "replay tables are not bound");
+  if (n_steps < 1) return fail(SACEO_E_INVALID, "n_steps must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rng = use_device_rng ? 1 : 0;
+  if (rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, x->k, (unsigned long long)seed);
+  for (int i = 0; i < n_steps; ++i) {
+    const int pol = ((num_timesteps + i) % x->cfg.target_update_int) == 0 ? 1 : 0;
+    if (x->cfg.use_graph) {
+      if (!x->graph[rng][pol]) {
+        cudaGraph_t g;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const long long before = x->launches;
+        int rc = step_once(x, rng, pol, st);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        x->graph_nodes[rng][pol] = x->launches - before;
+        x->launches = before;
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(SACEO_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        CU(cudaGraphInstantiate(&x->graph[rng][pol], g, 0));
+        cudaGraphDestroy(g);
+      }
+      CU(cudaGraphLaunch(x->graph[rng][pol], st));
+      x->launches += x->graph_nodes[rng][pol];
+    } else {
+      int rc = step_once(x, rng, pol, st); if (rc) return rc;
+    }
+  }
+  if (losses_out)
+    CU(cudaMemcpyAsync(losses_out, x->k.losses, sizeof(float) * x->k.n_agents * x->L.n_losses, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,
+                                 const float* expert_host, float* losses_host, void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream; KCtx& k = x->k;
+  if (expert_host && k.E > 0) {
+    const long long ne = (long long)k.n_agents * k.E * k.S;
+    // host layout [n, 2, E, S] -> two device planes
+    for (int a = 0; a < k.n_agents; ++a) {
+      CU(cudaMemcpyAsync(x->exp_stage + (long long)a * k.E * k.S, expert_host + (long long)a * 2 * k.E * k.S,
+                         sizeof(float) * k.E * k.S, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(x->exp_stage + ne + (long long)a * k.E * k.S, expert_host + ((long long)a * 2 + 1) * k.E * k.S,
+                         sizeof(float) * k.E * k.S, cudaMemcpyHostToDevice, st));
+    }
+    if (k.expert_s != x->exp_stage) {
+      k.expert_s = x->exp_stage; k.expert_sp = x->exp_stage + ne;
+      for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+        if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
+    }
+  }
+  int rng = 1;
+  if (idx_host) {
+    CU(cudaMemcpyAsync(k.idx, idx_host, sizeof(long long) * k.n_agents * k.B, cudaMemcpyHostToDevice, st));
+    rng = 2;   // host indices, device noise/permutation
+  }
+  int rc;
+  if (rng == 2) {
+    // noise + permutation from the device generator, indices from the host: run the generator first,
+    // then overwrite idx (stream order keeps the host copy last)
+    LAUNCH(x, k_set_seed, 1, 1, 0, st, k, (unsigned long long)seed);
+    const int pol = (num_timesteps % x->cfg.target_update_int) == 0 ? 1 : 0;
+    LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, 1);
+    const int items = ((3 * k.B + k.E) * k.A + 3) / 4;
+    LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k);
+    CU(cudaMemcpyAsync(k.idx, idx_host, sizeof(long long) * k.n_agents * k.B, cudaMemcpyHostToDevice, st));
+    if ((rc = phase_gather(x, st))) return rc;
+    if ((rc = phase_critic_grads(x, st))) return rc;
+    if ((rc = phase_critic_apply(x, pol, st))) return rc;
+    if ((rc = phase_actor_grads(x, st))) return rc;
+    if ((rc = phase_actor_apply(x, st))) return rc;
+    if ((rc = phase_alpha(x, 1, st))) return rc;
+  } else {
+    rc = saceo_update(x, 1, num_timesteps, 1, seed, nullptr, stream); if (rc) return rc;
+  }
+  if (losses_host)
+    CU(cudaMemcpyAsync(losses_host, k.losses, sizeof(float) * k.n_agents * x->L.n_losses, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int saceo_update_phase(saceo_ctx* x, int32_t phase, int64_t num_timesteps, void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  int rc;
+  switch (phase) {
+    case 0:
+      LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, 0);
+      if ((rc = phase_gather(x, st))) return rc;
+      return phase_critic_grads(x, st);
+    case 1: return phase_critic_apply(x, (num_timesteps % x->cfg.target_update_int) == 0 ? 1 : 0, st);
+    case 2: return phase_actor_grads(x, st);
+    case 3: return phase_actor_apply(x, st);
+    case 4: return phase_alpha(x, 0, st);
+    case 5: LAUNCH(x, k_alpha_apply, dim3(cdiv(k.n_agents, 128)), 128, 0, st, k); return check_launch();
+    default: return fail(SACEO_E_INVALID, "phase must be 0..5");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather / inference entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int saceo_gather(saceo_ctx* x, const int64_t* idx, float* out_s, float* out_a, float* out_sp,
+                            float* out_r, double* out_d, void* stream) {
+  if (!x || !idx) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound || !x->k.T.replay) return fail(SACEO_E_UNBOUND, "replay table is not bound");
+  const KCtx& k = x->k;
+  LAUNCH(x, k_gather, dim3(cdiv(k.B, 8), k.n_agents), 256, 0, (cudaStream_t)stream, k, (const long long*)idx,
+         out_s, out_a, out_sp, out_r, out_d, (float*)nullptr);
+  return check_launch();
+}
+
+extern "C" int saceo_actor_forward(saceo_ctx* x, const float* obs, int32_t rows, const float* noise,
+                                   float* act_out, float* neglogp_out, void* stream) {
+  if (!x || !obs || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents;
+  NetD an = actor_net(x);
+  // expert rows would be routed to the model input: use only the first B ("main") rows per chunk
+  for (int r0 = 0; r0 < rows; r0 += k.B) {
+    const int nr = rows - r0 < k.B ? rows - r0 : k.B;
+    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xpi, k.S,
+           (long long)k.R * k.S, 0);
+    int rc = mlp_forward(x, an, k.Xpi, k.S, (long long)k.R * k.S, 0, nr, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
+                         (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+    LAUNCH(x, k_head_fwd, dim3(cdiv(nr, 128), n), 128, 0, st, k, nr, nr, noise, (long long)rows * k.A, r0, 0,
+           act_out, neglogp_out, (long long)rows, r0);
+  }
+  return check_launch();
+}
+
+extern "C" int saceo_critic_forward(saceo_ctx* x, int32_t which, const float* obs, const float* act, int32_t rows,
+                                    int32_t scale_ret, float* q_out, void* stream) {
+  if (!x || !obs || !act || !q_out || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents, SA = k.S + k.A;
+  NetD qn = critic_net(x, which != 0);
+  for (int r0 = 0; r0 < rows; r0 += k.B) {
+    const int nr = rows - r0 < k.B ? rows - r0 : k.B;
+    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xc, SA,
+           (long long)k.B * SA, 0);
+    LAUNCH(x, k_stage_act, dim3(cdiv((long long)nr * k.A, 256), n), 256, 0, st, k, act, rows, r0, nr, k.Xc, SA,
+           (long long)k.B * SA, 0);
+    int rc = mlp_forward(x, qn, k.Xc, SA, (long long)k.B * SA, 0, nr, k.cH1, k.cH2, k.B, q_out + r0, 1,
+                         2LL * rows, rows, st); if (rc) return rc;
+  }
+  if (scale_ret) LAUNCH(x, k_scale_ret, dim3(cdiv(2LL * rows, 256), n), 256, 0, st, k, q_out, rows);
+  return check_launch();
+}
+
+extern "C" int saceo_model_eval(saceo_ctx* x, const float* obs, const float* act, int32_t rows, float* sp_out,
+                                void* stream) {
+  if (!x || !obs || !act || !sp_out || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  if (x->cfg.num_models < 1) return fail(SACEO_E_INVALID, "no models configured");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents, SA = k.S + k.A, E = k.E;
+  NetD mn = model_net(x, k.nmod);
+  for (int r0 = 0; r0 < rows; r0 += E) {
+    const int nr = rows - r0 < E ? rows - r0 : E;
+    // every model sees the same rows: stage them into net 0's block and read it with a zero net stride
+    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xm, SA,
+           2LL * E * SA, 1);
+    LAUNCH(x, k_stage_act, dim3(cdiv((long long)nr * k.A, 256), n), 256, 0, st, k, act, rows, r0, nr, k.Xm, SA,
+           2LL * E * SA, 1);
+    int rc = mlp_forward(x, mn, k.Xm, SA, 2LL * E * SA, 0, nr, k.mH1, k.mH2, E, k.mOut, mn.out,
+                         2LL * E * mn.out, (long long)E * mn.out, st); if (rc) return rc;
+    LAUNCH(x, k_model_out, dim3(cdiv((long long)nr * k.S, 256), n, k.nmod), 256, 0, st, k, obs, rows, r0, nr, sp_out);
+  }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fisher-vector product and conjugate gradient (trpo.py:200-227, update_utils.py:4-24)
+// ------------------------------------------------------------------------------------------
+static int fvp_prepare(saceo_ctx* x, cudaStream_t st) {
+  const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
+  NetD an = actor_net(x);
+  LAUNCH(x, k_stage_obs, dim3(cdiv((long long)N * k.S, 256), n), 256, 0, st, k, k.T.fvp_states, N, 0, N, f.X, k.S,
+         (long long)N * k.S, 0);
+  return mlp_forward(x, an, f.X, k.S, (long long)N * k.S, 0, N, f.H1, f.H2, N, f.Out, k.Ao, (long long)N * k.Ao, 0, st);
+}
+
+// Fx = J^T M J x / N + damp x, with the activations of fvp_prepare() resident
+static int fvp_apply(saceo_ctx* x, const float* xin, float damp, float* Fx, cudaStream_t st) {
+  const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
+  NetD an = actor_net(x);
+  NetD tn = an; tn.theta = xin;                       // tangent "network": same flat layout
+  const long long sH1 = (long long)N * an.h1, sH2 = (long long)N * an.h2, sO = (long long)N * k.Ao;
+  int rc; GemmP p{};
+  // T1 = (X.P0 + c0) * act0'(H1)
+  p = GemmP{}; p.nnet = 1; p.A = f.X; p.lda = k.S; p.sAa = (long long)N * k.S;
+  p.B = tn.theta + tn.oW0(); p.ldb = an.h1; p.sBa = an.sa; p.bias = tn.theta + tn.ob0(); p.sba = an.sa;
+  p.C = f.T1; p.ldc = an.h1; p.sCa = sH1; p.aux = f.H1; p.M = N; p.N = an.h1; p.K = k.S; p.epi = EPI_MUL_DACT; p.act = an.act0;
+  rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+  // Tmp = T1.W1 ;  T2 = (H1.P1 + c1 + Tmp) * act1'(H2)
+  p = GemmP{}; p.nnet = 1; p.A = f.T1; p.lda = an.h1; p.sAa = sH1; p.B = an.theta + an.oW1(); p.ldb = an.h2; p.sBa = an.sa;
+  p.C = f.Tmp; p.ldc = an.h2; p.sCa = sH2; p.M = N; p.N = an.h2; p.K = an.h1; p.epi = EPI_NONE;
+  rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+  p = GemmP{}; p.nnet = 1; p.A = f.H1; p.lda = an.h1; p.sAa = sH1; p.B = tn.theta + tn.oW1(); p.ldb = an.h2; p.sBa = an.sa;
+  p.bias = tn.theta + tn.ob1(); p.sba = an.sa; p.addend = f.Tmp; p.aux = f.H2;
+  p.C = f.T2; p.ldc = an.h2; p.sCa = sH2; p.M = N; p.N = an.h2; p.K = an.h1; p.epi = EPI_MUL_DACT; p.act = an.act1;
+  rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+  // Tmp = T2.W2 ; TOut = H2.P2 + c2 + Tmp
+  p = GemmP{}; p.nnet = 1; p.A = f.T2; p.lda = an.h2; p.sAa = sH2; p.B = an.theta + an.oW2(); p.ldb = k.Ao; p.sBa = an.sa;
+  p.C = f.Tmp; p.ldc = k.Ao; p.sCa = sO; p.M = N; p.N = k.Ao; p.K = an.h2; p.epi = EPI_NONE;
+  rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+  p = GemmP{}; p.nnet = 1; p.A = f.H2; p.lda = an.h2; p.sAa = sH2; p.B = tn.theta + tn.oW2(); p.ldb = k.Ao; p.sBa = an.sa;
+  p.bias = tn.theta + tn.ob2(); p.sba = an.sa; p.addend = f.Tmp;
+  p.C = f.TOut; p.ldc = k.Ao; p.sCa = sO; p.M = N; p.N = k.Ao; p.K = an.h2; p.epi = EPI_NONE;
+  rc = gemm(x, false, false, false, p, n, st); if (rc) return rc;
+  // metric: G = M . J x / N   (per row), plus per-row logstd_var contribution
+  LAUNCH(x, k_fvp_metric, dim3(cdiv(N, 128), n), 128, 0, st, k, f, xin, x->cfg.std_mult);
+  // J^T G  -> Fx (flat layout), then + damp x
+  rc = mlp_backward(x, an, f.X, k.S, (long long)N * k.S, 0, N, f.H1, f.H2, N, f.G, k.Ao, sO, 0, k.Ao, f.dH2, f.dH1,
+                    Fx, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st); if (rc) return rc;
+  LAUNCH(x, k_fvp_finish, dim3(cdiv(x->L.na, 256), n), 256, 0, st, k, f, xin, damp, Fx);
+  return check_launch();
+}
+
+extern "C" int saceo_fvp(saceo_ctx* x, const float* xin, float damp, float* Fx, void* stream) {
+  if (!x || !xin || !Fx) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound || !x->k.T.fvp_states || x->f.N < 1) return fail(SACEO_E_UNBOUND, "fvp_states not bound / fvp_rows == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = fvp_prepare(x, st); if (rc) return rc;
+  return fvp_apply(x, xin, damp, Fx, st);
+}
+
+extern "C" int saceo_cg_solve(saceo_ctx* x, const float* b, int32_t iters, float tol, float damp, float* x_out,
+                              float* vFv_out, void* stream) {
+  if (!x || !b || !x_out) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound || !x->k.T.fvp_states || x->f.N < 1) return fail(SACEO_E_UNBOUND, "fvp_states not bound / fvp_rows == 0");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents;
+  int rc = fvp_prepare(x, st); if (rc) return rc;
+  LAUNCH(x, k_cg_init, dim3(n), 256, 0, st, k, f, b);                 // p = r = b, x = 0, rr = r.r, active = 1
+  for (int it = 0; it < iters; ++it) {
+    rc = fvp_apply(x, f.p, damp, f.z, st); if (rc) return rc;         // z = F(p)
+    LAUNCH(x, k_cg_step, dim3(n), 256, 0, st, k, f, tol);             // v, x, r, rr', mu, p, early-exit latch
+  }
+  CU(cudaMemcpyAsync(x_out, f.x, sizeof(float) * n * x->L.na_stride, cudaMemcpyDeviceToDevice, st));
+  if (vFv_out) {
+    rc = fvp_apply(x, f.x, damp, f.z, st); if (rc) return rc;         // vFv = x . F(x)   (trpo.py:185)
+    LAUNCH(x, k_cg_vfv, dim3(n), 256, 0, st, k, f, vFv_out);
+  }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone GEMM self-test surface
+// ------------------------------------------------------------------------------------------
+extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int32_t N, int32_t K, int32_t transA,
+                               int32_t transB, const float* A, const float* Bm, float* C, void* stream) {
+  if (!A || !Bm || !C || batch < 1) return fail(SACEO_E_INVALID, "bad argument");
+  GemmP p{}; p.nnet = 1; p.A = A; p.B = Bm; p.C = C; p.M = M; p.N = N; p.K = K;
+  p.lda = transA ? M : K; p.ldb = transB ? K : N; p.ldc = N;
+  p.sAa = (long long)M * K; p.sBa = (long long)K * N; p.sCa = (long long)M * N; p.epi = EPI_NONE;
+  saceo_ctx tmp; tmp.cfg.gemm_mode = gemm_mode; tmp.cfg.n_agents = batch;
+  if (gemm_mode == SACEO_GEMM_TCGEN05_BF16X3) {
+    CU(tc_gemm_init());
+    if (!tc_gemm_eligible(transA != 0, transB != 0, false, p))
+      return fail(SACEO_E_INVALID, "shape not eligible for the tcgen05 engine");
+  }
+  int rc = gemm(&tmp, transA != 0, transB != 0, false, p, batch, (cudaStream_t)stream); if (rc) return rc;
+  return check_launch();
+}

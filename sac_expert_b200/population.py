@@ -1,0 +1,412 @@
+"""Population of independent SAC / SAC-EO agents resident on one B200.
+
+This is the device-side state the reference keeps in ``tf.Variable`` s, Keras optimizer slots and
+NumPy buffers (``/root/reference/sac_eo/algs/SAC_expert.py:28-116``), batched over ``n_agents``
+(seeds x hyper-parameters) and laid out as flat per-agent tables (include/saceo.h).  PyTorch only
+supplies the device allocations (``tensor.data_ptr()``) and the stream; every computation goes
+through the C ABI in ``lib.py``.  ``n_agents == 1`` is the reference's single-agent behaviour and is
+what the class mirrors in ``sac_expert_b200/sac_eo`` use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as _l
+
+LOSS_NAMES = ("q1_loss", "q2_loss", "pi_loss", "mse_loss", "p_loss", "alpha_loss", "alpha", "epsilon")
+HYPER_NAMES = ("gamma", "tau", "lr_q", "lr_pi", "lr_alpha", "eps", "target_entropy", "damp")
+
+
+@dataclass
+class PopulationSpec:
+    n_agents: int
+    S: int
+    A: int
+    actor_hidden: Tuple[int, int] = (256, 256)
+    critic_hidden: Tuple[int, int] = (256, 256)
+    model_hidden: Tuple[int, int] = (512, 512)
+    actor_acts: Tuple[str, str] = ("relu", "relu")
+    critic_acts: Tuple[str, str] = ("relu", "relu")
+    model_acts: Tuple[str, str] = ("relu", "relu")
+    per_state_std: bool = True
+    separate_reward_nn: bool = False
+    num_models: int = 2            # 0 = plain SAC
+    delta_clip_pred: float = 0.0
+    B: int = 256
+    E: int = 20
+    target_update_int: int = 1
+    replay_capacity: int = 100_000
+    fvp_rows: int = 0
+    std_mult: float = 1.0
+    gemm_mode: int = _l.GEMM_FP32_SIMT
+    use_graph: bool = False
+    device: int = 0
+
+    def to_config(self) -> _l.Config:
+        c = _l.Config()
+        c.abi_version = _l.ABI_VERSION
+        c.device = self.device
+        c.n_agents = self.n_agents
+        c.S, c.A = self.S, self.A
+        for i in range(2):
+            c.actor_hidden[i] = self.actor_hidden[i]
+            c.critic_hidden[i] = self.critic_hidden[i]
+            c.model_hidden[i] = self.model_hidden[i]
+            for dst, src in ((c.actor_act, self.actor_acts), (c.critic_act, self.critic_acts),
+                             (c.model_act, self.model_acts)):
+                if src[i] not in _l.ACT_IDS:
+                    raise ValueError("activations must be tanh, relu or elu")   # nn_utils.py:18
+                dst[i] = _l.ACT_IDS[src[i]]
+        c.per_state_std = int(self.per_state_std)
+        c.separate_reward_nn = int(self.separate_reward_nn)
+        c.num_models = self.num_models
+        c.delta_clip_pred = float(self.delta_clip_pred or 0.0)
+        c.B, c.E = self.B, self.E
+        c.target_update_int = self.target_update_int
+        c.replay_capacity = self.replay_capacity
+        c.fvp_rows = self.fvp_rows
+        c.std_mult = self.std_mult
+        c.gemm_mode = self.gemm_mode
+        c.use_graph = int(self.use_graph)
+        return c
+
+
+def net_shapes(n_in: int, hidden: Sequence[int], n_out: int) -> List[Tuple[int, ...]]:
+    """Keras ``get_weights()`` shapes ``[W0,b0,W1,b1,W2,b2]`` (nn_utils.py:86-138)."""
+    return [(n_in, hidden[0]), (hidden[0],), (hidden[0], hidden[1]), (hidden[1],), (hidden[1], n_out), (n_out,)]
+
+
+def pack_flat(ws: Sequence[np.ndarray]) -> np.ndarray:
+    """``list_to_flat`` (nn_utils.py:177-182)."""
+    return np.concatenate([np.asarray(w, np.float32).reshape(-1) for w in ws])
+
+
+def unpack_flat(vec: np.ndarray, shapes: Sequence[Tuple[int, ...]]) -> List[np.ndarray]:
+    """``flat_to_list`` (nn_utils.py:162-175)."""
+    out, o = [], 0
+    for sh in shapes:
+        n = int(np.prod(sh))
+        out.append(np.array(vec[o:o + n], np.float32).reshape(sh))
+        o += n
+    return out
+
+
+class _DevBuf:
+    """Zero-copy view of a library-owned device buffer through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class Population:
+    def __init__(self, spec: PopulationSpec):
+        if not torch.cuda.is_available():
+            raise _l.SaceoError("sac_expert_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.spec = spec
+        self.lib = _l.load()
+        self.cfg = spec.to_config()
+        self.L = _l.query_layout(self.cfg)
+        self.dev = torch.device("cuda", spec.device)
+        self.stream = torch.cuda.Stream(self.dev)
+        n, L = spec.n_agents, self.L
+        z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)
+        self.t: Dict[str, torch.Tensor] = dict(
+            actor=z(n, L.na_stride), actor_m=z(n, L.na_stride), actor_v=z(n, L.na_stride),
+            q=z(n, 2, L.nc_stride), q_m=z(n, 2, L.nc_stride), q_v=z(n, 2, L.nc_stride), qt=z(n, 2, L.nc_stride),
+            model=z(n, 2, L.nm_stride),
+            alpha=z(n), alpha_m=z(n), alpha_v=z(n), adam_t=z(n, 4, dt=torch.int32),
+            norm=z(n, L.norm_stride), hyper=z(n, L.hyper_stride),
+            replay=z(n, spec.replay_capacity, L.row_words),
+            replay_size=z(n, dt=torch.int32), replay_start=z(n, dt=torch.int32),
+            expert_s=z(n, max(spec.E, 1), spec.S), expert_sp=z(n, max(spec.E, 1), spec.S),
+        )
+        if spec.fvp_rows > 0:
+            self.t["fvp_states"] = z(n, spec.fvp_rows, spec.S)
+        # identity normalisers by default (RunningNormalizer.__init__, normalizer.py:17-24)
+        nm = self.t["norm"]
+        for off, cnt in ((L.off_s_std, spec.S), (L.off_a_std, spec.A), (L.off_ret_std, 1), (L.off_m_s_std, spec.S),
+                         (L.off_m_a_std, spec.A), (L.off_m_d_std, spec.S), (L.off_act_limit, spec.A)):
+            nm[:, off:off + cnt] = 1.0
+        self.shapes = dict(
+            actor=net_shapes(spec.S, spec.actor_hidden, L.Ao) + ([] if spec.per_state_std else [(1, spec.A)]),
+            q=net_shapes(spec.S + spec.A, spec.critic_hidden, 1),
+            model=net_shapes(spec.S + spec.A, spec.model_hidden, L.model_out),
+        )
+        self._host_size = np.zeros(n, np.int64)
+        self._host_start = np.zeros(n, np.int64)
+        self.ctx = C.c_void_p()
+        torch.cuda.synchronize(self.dev)
+        _l.check(self.lib.saceo_create(C.byref(self.cfg), C.byref(self.ctx)))
+        self._bind()
+        self.losses = z(n, L.n_losses)
+        self._pin_idx = None
+        self._pin_exp = None
+        self._pin_loss = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _bind(self):
+        tb = _l.Tables()
+        for name, _ in _l.Tables._fields_:
+            tens = self.t.get(name)
+            setattr(tb, name, tens.data_ptr() if tens is not None else None)
+        _l.check(self.lib.saceo_bind(self.ctx, C.byref(tb)))
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            torch.cuda.synchronize(self.dev)
+            self.lib.saceo_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _enter(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        return self.stream.cuda_stream
+
+    def _exit(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+
+    def debug(self, name: str, dtype=torch.float32) -> torch.Tensor:
+        """View of a named library workspace buffer (tests / inspection)."""
+        nb = C.c_int64()
+        ptr = self.lib.saceo_debug_ptr(self.ctx, name.encode(), C.byref(nb))
+        if not ptr:
+            raise KeyError(name)
+        item = torch.empty((), dtype=dtype).element_size()
+        ts = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.float64: "<f8"}[dtype]
+        return torch.as_tensor(_DevBuf(ptr, (nb.value // item,), ts), device=self.dev)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.saceo_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ state in / out
+    def _net_table(self, name: str) -> Tuple[torch.Tensor, str, Optional[int]]:
+        if name == "actor":
+            return self.t["actor"], "actor", None
+        if name in ("q1", "q2"):
+            return self.t["q"], "q", int(name[1]) - 1
+        if name in ("t1", "t2"):
+            return self.t["qt"], "q", int(name[1]) - 1
+        if name in ("m1", "m2"):
+            return self.t["model"], "model", int(name[1]) - 1
+        raise KeyError(name)
+
+    def set_net(self, agent: int, name: str, weights: Sequence[np.ndarray], table: Optional[str] = None):
+        tab, kind, net = self._net_table(name)
+        if table is not None:   # Adam slot tables share the layout of their network
+            tab = self.t[table]
+        flat = pack_flat(weights)
+        shapes = self.shapes[kind]
+        if flat.size != sum(int(np.prod(s)) for s in shapes):
+            raise ValueError(f"{name}: expected shapes {shapes}")
+        dst = tab[agent] if net is None else tab[agent, net]
+        dst[:flat.size].copy_(torch.from_numpy(flat))
+
+    def get_net(self, agent: int, name: str, table: Optional[str] = None) -> List[np.ndarray]:
+        tab, kind, net = self._net_table(name)
+        if table is not None:
+            tab = self.t[table]
+        src = tab[agent] if net is None else tab[agent, net]
+        return unpack_flat(src.detach().cpu().numpy(), self.shapes[kind])
+
+    def set_norm(self, agent: int, **stats):
+        """Normaliser record: s_mean,s_std,a_mean,a_std,ret_std and the model set m_* (normalizer.py)."""
+        L, row = self.L, self.t["norm"][agent]
+        for key, val in stats.items():
+            off = getattr(L, "off_" + key)
+            v = torch.as_tensor(np.atleast_1d(np.asarray(val, np.float32)))
+            row[off:off + v.numel()].copy_(v)
+
+    def set_hyper(self, agent: int, **hy):
+        row = self.t["hyper"][agent]
+        for key, val in hy.items():
+            row[HYPER_NAMES.index(key)] = float(val)
+
+    def load_agent(self, agent: int, st: Dict, hyper: Dict):
+        """Loads one agent from the NumPy problem dict the oracle builders produce."""
+        for name in ("actor", "q1", "q2", "t1", "t2"):
+            self.set_net(agent, name, st[name])
+        if self.spec.num_models > 0:
+            for name in ("m1", "m2")[: max(self.spec.num_models, 1)]:
+                self.set_net(agent, name, st[name])
+        self.t["alpha"][agent] = float(st["alpha"])
+        for k, (tm, tv) in (("actor", ("actor_m", "actor_v")), ("q1", ("q_m", "q_v")), ("q2", ("q_m", "q_v"))):
+            ad = st.get("adam_" + k)
+            if ad is not None:
+                self.set_net(agent, k, ad["m"], table=tm)
+                self.set_net(agent, k, ad["v"], table=tv)
+                self.t["adam_t"][agent, {"q1": 0, "q2": 1, "actor": 2}[k]] = int(ad["t"])
+        ad = st.get("adam_alpha")
+        if ad is not None:
+            self.t["alpha_m"][agent] = float(ad["m"])
+            self.t["alpha_v"][agent] = float(ad["v"])
+            self.t["adam_t"][agent, 3] = int(ad["t"])
+        self.set_norm(agent, **{k: st[k] for k in ("s_mean", "s_std", "a_mean", "a_std", "ret_std", "m_s_mean",
+                                                    "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std",
+                                                    "act_limit") if k in st})
+        self.set_hyper(agent, **{k: hyper[k] for k in HYPER_NAMES if k in hyper})
+
+    # ------------------------------------------------------------------ replay / expert rows
+    def pack_rows(self, s, a, r, sp, d) -> np.ndarray:
+        """Host-side AoS packing of replay rows: [s | a | sp | r | pad | d(f64) | pad]."""
+        L = self.L
+        n = len(r)
+        rows = np.zeros((n, L.row_words), np.float32)
+        rows[:, L.off_s:L.off_s + self.spec.S] = np.asarray(s, np.float32).reshape(n, -1)
+        rows[:, L.off_a:L.off_a + self.spec.A] = np.asarray(a, np.float32).reshape(n, -1)
+        rows[:, L.off_sp:L.off_sp + self.spec.S] = np.asarray(sp, np.float32).reshape(n, -1)
+        rows[:, L.off_r] = np.asarray(r, np.float32)
+        rows[:, L.off_d:L.off_d + 2] = np.asarray(d, np.float64).reshape(n, 1).view(np.float32)
+        return rows
+
+    def append_rows(self, agent: int, s, a, r, sp, d):
+        """``TrajectoryBuffer.add`` (buffers.py:41-71) on the device table: append, and when the
+        capacity is exceeded keep the LAST ``capacity`` rows (ring; logical index 0 = oldest)."""
+        rows = self.pack_rows(s, a, r, sp, d)
+        cap = self.spec.replay_capacity
+        if len(rows) > cap:
+            rows = rows[-cap:]
+        size, start = int(self._host_size[agent]), int(self._host_start[agent])
+        pos = (start + size) % cap
+        first = min(len(rows), cap - pos)
+        tab = self.t["replay"][agent]
+        tab[pos:pos + first].copy_(torch.from_numpy(rows[:first]))
+        if first < len(rows):
+            tab[:len(rows) - first].copy_(torch.from_numpy(rows[first:]))
+        over = max(0, size + len(rows) - cap)
+        self._host_size[agent] = min(cap, size + len(rows))
+        self._host_start[agent] = (start + over) % cap
+        self.t["replay_size"][agent] = int(self._host_size[agent])
+        self.t["replay_start"][agent] = int(self._host_start[agent])
+
+    def set_expert(self, agent: int, sE, spE):
+        self.t["expert_s"][agent].copy_(torch.from_numpy(np.asarray(sE, np.float32)))
+        self.t["expert_sp"][agent].copy_(torch.from_numpy(np.asarray(spE, np.float32)))
+
+    # ------------------------------------------------------------------ hot path
+    def gather(self, idx: torch.Tensor):
+        """``get_offmodel_info`` for the given int64 indices [n_agents, B] -> (s, a, sp, r, d)."""
+        sp_ = self.spec
+        n, B = sp_.n_agents, sp_.B
+        idx = idx.to(self.dev, torch.int64).contiguous()
+        s = torch.empty(n, B, sp_.S, device=self.dev)
+        a = torch.empty(n, B, sp_.A, device=self.dev)
+        spn = torch.empty(n, B, sp_.S, device=self.dev)
+        r = torch.empty(n, B, device=self.dev)
+        d = torch.empty(n, B, device=self.dev, dtype=torch.float64)
+        st = self._enter()
+        _l.check(self.lib.saceo_gather(self.ctx, idx.data_ptr(), s.data_ptr(), a.data_ptr(), spn.data_ptr(),
+                                       r.data_ptr(), d.data_ptr(), st))
+        self._exit()
+        return s, a, spn, r, d
+
+    def set_draws(self, idx=None, noise=None, perm=None):
+        ten = []
+        for v, dt in ((idx, torch.int64), (noise, torch.float32), (perm, torch.int32)):
+            ten.append(None if v is None else torch.as_tensor(v).to(self.dev, dt).contiguous())
+        st = self._enter()
+        _l.check(self.lib.saceo_set_draws(self.ctx, *[t.data_ptr() if t is not None else None for t in ten], st))
+        self._exit()
+        self._keep = ten
+
+    def update(self, n_steps: int = 1, num_timesteps: int = 0, use_device_rng: bool = True, seed: int = 0):
+        st = self._enter()
+        _l.check(self.lib.saceo_update(self.ctx, n_steps, num_timesteps, int(use_device_rng), seed,
+                                       self.losses.data_ptr(), st))
+        self._exit()
+        return self.losses
+
+    def update_host(self, num_timesteps: int, seed: int, idx_host: Optional[np.ndarray] = None,
+                    expert_host: Optional[np.ndarray] = None) -> np.ndarray:
+        """One update through HOST buffers (pinned staging), synchronous - the per-step call of the
+        reference-style ``alg._update``."""
+        n, sp_ = self.spec.n_agents, self.spec
+        if self._pin_loss is None:
+            self._pin_loss = torch.empty(n, self.L.n_losses, pin_memory=True)
+        ip = ep = None
+        if idx_host is not None:
+            if self._pin_idx is None:
+                self._pin_idx = torch.empty(n, sp_.B, dtype=torch.int64, pin_memory=True)
+            self._pin_idx.numpy()[...] = idx_host
+            ip = self._pin_idx.data_ptr()
+        if expert_host is not None:
+            if self._pin_exp is None:
+                self._pin_exp = torch.empty(n, 2, sp_.E, sp_.S, pin_memory=True)
+            self._pin_exp.numpy()[...] = expert_host
+            ep = self._pin_exp.data_ptr()
+        st = self._enter()
+        _l.check(self.lib.saceo_update_host(self.ctx, num_timesteps, seed, ip, ep, self._pin_loss.data_ptr(), st))
+        self._exit()
+        return self._pin_loss.numpy()
+
+    def update_phase(self, phase: int, num_timesteps: int = 0):
+        st = self._enter()
+        _l.check(self.lib.saceo_update_phase(self.ctx, phase, num_timesteps, st))
+        self._exit()
+
+    # ------------------------------------------------------------------ inference entry points
+    def actor_forward(self, obs: torch.Tensor, noise: Optional[torch.Tensor] = None, want_neglogp: bool = False):
+        n, sp_ = self.spec.n_agents, self.spec
+        obs = obs.to(self.dev, torch.float32).contiguous().view(n, -1, sp_.S)
+        rows = obs.shape[1]
+        if noise is not None:
+            noise = noise.to(self.dev, torch.float32).contiguous()
+        act = torch.empty(n, rows, sp_.A, device=self.dev)
+        nlp = torch.empty(n, rows, device=self.dev) if want_neglogp else None
+        st = self._enter()
+        _l.check(self.lib.saceo_actor_forward(self.ctx, obs.data_ptr(), rows,
+                                              noise.data_ptr() if noise is not None else None, act.data_ptr(),
+                                              nlp.data_ptr() if nlp is not None else None, st))
+        self._exit()
+        return (act, nlp) if want_neglogp else act
+
+    def critic_forward(self, obs, act, target: bool = False, scale_ret: bool = False):
+        n, sp_ = self.spec.n_agents, self.spec
+        obs = torch.as_tensor(obs).to(self.dev, torch.float32).contiguous().view(n, -1, sp_.S)
+        act = torch.as_tensor(act).to(self.dev, torch.float32).contiguous().view(n, -1, sp_.A)
+        rows = obs.shape[1]
+        q = torch.empty(n, 2, rows, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_critic_forward(self.ctx, int(target), obs.data_ptr(), act.data_ptr(), rows,
+                                               int(scale_ret), q.data_ptr(), st))
+        self._exit()
+        return q
+
+    def model_eval(self, obs, act):
+        n, sp_ = self.spec.n_agents, self.spec
+        obs = torch.as_tensor(obs).to(self.dev, torch.float32).contiguous().view(n, -1, sp_.S)
+        act = torch.as_tensor(act).to(self.dev, torch.float32).contiguous().view(n, -1, sp_.A)
+        rows = obs.shape[1]
+        out = torch.zeros(n, 2, rows, sp_.S, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_model_eval(self.ctx, obs.data_ptr(), act.data_ptr(), rows, out.data_ptr(), st))
+        self._exit()
+        return out
+
+    # ------------------------------------------------------------------ CG / Fisher-vector
+    def fvp(self, x: torch.Tensor, damp: float) -> torch.Tensor:
+        x = x.to(self.dev, torch.float32).contiguous()
+        out = torch.zeros_like(x)
+        st = self._enter()
+        _l.check(self.lib.saceo_fvp(self.ctx, x.data_ptr(), damp, out.data_ptr(), st))
+        self._exit()
+        return out
+
+    def cg_solve(self, b: torch.Tensor, iters: int = 20, tol: float = 1e-10, damp: float = 0.01):
+        b = b.to(self.dev, torch.float32).contiguous()
+        x = torch.zeros_like(b)
+        vfv = torch.zeros(self.spec.n_agents, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_cg_solve(self.ctx, b.data_ptr(), iters, tol, damp, x.data_ptr(), vfv.data_ptr(), st))
+        self._exit()
+        return x, vfv

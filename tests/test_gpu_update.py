@@ -1,0 +1,39 @@
+"""GPU parity: one injected-draw SAC / SAC-EO update vs the CPU oracle (1e-3 relative, north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac_eo_oracle import NetCfg
+from tests.helpers import build, compare_update
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3   # BASELINE.json north_star: losses, gradients and parameters within 1e-3 relative
+
+CASES = {
+    "hopper_saceo": (NetCfg(S=11, A=3, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(96, 96)), 64, 20),
+    "state_indep_std_one_model": (NetCfg(S=7, A=2, actor_hidden=(32, 48), critic_hidden=(40, 32), model_hidden=(64, 32),
+                                         per_state_std=False, num_models=1, actor_acts=("tanh", "tanh"),
+                                         critic_acts=("elu", "tanh"), model_acts=("relu", "elu"),
+                                         delta_clip_pred=0.05), 48, 10),
+    "plain_sac_halfcheetah": (NetCfg(S=17, A=6, actor_hidden=(64, 64), critic_hidden=(64, 64), num_models=0), 64, 0),
+    "sep_reward": (NetCfg(S=5, A=2, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(32, 32),
+                          separate_reward_nn=True), 32, 6),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_update_matches_oracle(name):
+    cfg, B, E = CASES[name]
+    pop, probs = build(cfg, n_agents=3, B=B, E=max(E, 2), N=500, seed=3)
+    worst = compare_update(pop, cfg, probs, verbose=True)
+    bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
+    assert not bad, bad
+
+
+def test_full_size_hopper():
+    cfg = NetCfg(S=11, A=3)   # 2x256 actor/critics, 2x512 models, B=256, E=20 (configs[0])
+    pop, probs = build(cfg, n_agents=2, B=256, E=20, N=2000, seed=5)
+    worst = compare_update(pop, cfg, probs, verbose=True)
+    bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
+    assert not bad, bad
