@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py - agent-updates/sec of the SAC-EO population update on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU update step (oracle port)
+
+A "step" is ONE `SAC_exp._update` for EVERY agent of the population resident on a GPU (gather ->
+critics -> actor (+expert term) -> temperature -> Polyak).  Weak scaling: every rank holds
+`--agents` agents (default 256), no data-path collective (agents are independent).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--shape", default="ant", choices=["hopper", "halfcheetah", "ant", "humanoid"])
+    p.add_argument("--agents", type=int, default=256, help="agents per GPU")
+    p.add_argument("--replay-rows", type=int, default=100_000)
+    p.add_argument("--plain-sac", action="store_true", help="no expert term (BASELINE configs[1])")
+    p.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 bf16x3 (default: best available)")
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def workload_name(a):
+    from sac_expert_b200.synth import SHAPES
+    S, A, B = SHAPES[a.shape]
+    alg = "plain SAC" if a.plain_sac else "SAC-EO (2 MSEModels 2x512, E=20, eps=1e-3)"
+    return (f"{alg} {a.shape}-shaped (obs {S}, act {A}), actor/critics 2x256 relu, batch {B}, "
+            f"{a.agents}-agent population per GPU, replay {a.replay_rows} rows/agent")
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the reference's update step, restated (oracle port), on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_update_rate(a, seconds, threads=None):
+    """Times oracle.sac_eo_update (torch-CPU eager, autograd = tf.GradientTape, per-tensor Keras Adam,
+    Polyak) for ONE agent at the benchmark's dimensions.  TensorFlow is not installable offline, so this is
+    kind="port" (see DESIGN.md)."""
+    import numpy as np
+    import torch
+    from oracle.sac_eo_oracle import NetCfg, draw_batch, make_problem, sac_eo_update, to_torch_state
+    from sac_expert_b200.synth import SHAPES
+    S, A, B = SHAPES[a.shape]
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = NetCfg(S=S, A=A, num_models=0 if a.plain_sac else 2)
+    st, replay, expert, hyper = make_problem(cfg, B, 20, 20000, seed=0)
+    state = to_torch_state(st)
+    n, t0 = 0, None
+    deadline = None
+    while True:
+        batch = draw_batch(cfg, replay, expert, B, seed=n)      # includes the gather, like _update does
+        out = sac_eo_update(cfg, state, batch, hyper)
+        new = out["new"]
+        for k in ("actor", "q1", "q2", "t1", "t2", "alpha", "adam_actor", "adam_q1", "adam_q2", "adam_alpha"):
+            state[k] = new[k]
+        n += 1
+        if n == 3:                       # warm-up
+            t0 = time.perf_counter(); deadline = t0 + seconds; n0 = n
+        if deadline is not None and time.perf_counter() >= deadline:
+            break
+    dt = time.perf_counter() - t0
+    return (n - n0) / dt, cores, n - n0
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # K "steps", each a bounded sample (a fixed number of single-agent updates) of the population step
+    per_step_budget = max(0.5, min(6.0, 120.0 / max(1, a.steps + a.warmup)))
+    rate, cores, n = cpu_update_rate(a, per_step_budget * (a.steps + a.warmup))
+    line = {
+        "impl": "reference", "metric": "agent-updates/sec", "value": rate, "unit": "agent-updates/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 / rate,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} consecutive single-agent updates of the same shape (oracle/sac_eo_oracle.py, "
+                                   f"torch-CPU eager restatement of SAC_exp._update; TensorFlow not installable)"},
+        "e2e": {"value": rate, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sac_expert_b200 import lib
+    from sac_expert_b200.population import Population, PopulationSpec
+    from sac_expert_b200.synth import SHAPES, algorithmic_bytes, algorithmic_flops, fill_synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    S, A, B = SHAPES[a.shape]
+    gemm_mode = a.gemm_mode if a.gemm_mode is not None else lib.GEMM_TCGEN05_BF16X3
+    spec = PopulationSpec(n_agents=a.agents, S=S, A=A, B=B, E=20, num_models=0 if a.plain_sac else 2,
+                          replay_capacity=a.replay_rows, gemm_mode=gemm_mode, use_graph=not a.no_graph, device=local)
+    pop = Population(spec)
+    fill_synthetic(pop, seed=1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ------------------------------------------------
+    for w in range(a.warmup):
+        pop.update(1, num_timesteps=w, use_device_rng=True, seed=99)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = pop.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(pop.stream):
+        e0.record(pop.stream)
+    pop.update(a.steps, num_timesteps=a.warmup, use_device_rng=True, seed=99)
+    with torch.cuda.stream(pop.stream):
+        e1.record(pop.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pop.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    losses = pop.losses.cpu().numpy()
+    if not np.isfinite(losses).all():
+        raise RuntimeError("non-finite losses after the timed region")
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * a.agents * a.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer API ("e2e") -------------------------------------
+    rng = np.random.default_rng(7 + rank)
+    sizes = pop._host_size
+    expert = np.concatenate([pop.t["expert_s"].cpu().numpy()[:, None], pop.t["expert_sp"].cpu().numpy()[:, None]], 1) \
+        if spec.num_models > 0 else None
+    e2e_steps = max(3, min(a.steps, 20))
+    for w in range(2):
+        idx = rng.integers(0, sizes[:, None], size=(a.agents, B)).astype(np.int64)
+        pop.update_host(w, 5, idx, expert)
+    barrier()
+    t0 = time.perf_counter()
+    for sidx in range(e2e_steps):
+        idx = rng.integers(0, sizes[:, None], size=(a.agents, B)).astype(np.int64)   # np.random.randint, buffers.py:135
+        out = pop.update_host(sidx, 5, idx, expert)                                 # H2D idx+expert rows, D2H losses
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * a.agents * e2e_steps / float(dt.item())
+    h2d = a.agents * (B * 8 + (2 * spec.E * S * 4 if spec.num_models > 0 else 0))
+    d2h = a.agents * pop.L.n_losses * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bytes_step = algorithmic_bytes(spec, pop.L) * a.agents
+    achieved = bytes_step / (ms / a.steps * 1e-3) / 1e9
+    flops_step = algorithmic_flops(spec) * a.agents
+    line = {
+        "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "agents_per_gpu": a.agents, "batch": B,
+                   "gemm_engine": "tcgen05 bf16x3 (fp32 accum in TMEM)" if gemm_mode == 1 else "fp32 SIMT",
+                   "cuda_graph": not a.no_graph, "rng": "in-kernel Philox4x32-10",
+                   "l2_note": f"population state {bytes_step / 1e9:.2f} GB/step >> 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "note": "Population.update_host: host np.random.randint indices + host expert rows "
+                                            "copied H2D from pinned memory every step, losses copied D2H, stream sync"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "scope": "whole update step (sequence of kernels, per-kernel shares in profiles/); algorithmic bytes "
+                              f"{algorithmic_bytes(spec, pop.L) / 1e6:.2f} MB/agent-update",
+                     "algorithmic_tflops": flops_step / (ms / a.steps * 1e-3) / 1e12},
+    }
+    if not a.no_cpu_baseline:
+        rate, cores, nupd = cpu_update_rate(a, a.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port",
+                                "sample": f"{nupd} consecutive single-agent updates of the same shape in {a.cpu_seconds:.0f} s "
+                                          "(oracle/sac_eo_oracle.py, torch-CPU eager restatement of SAC_exp._update)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

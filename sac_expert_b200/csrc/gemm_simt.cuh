@@ -32,6 +32,7 @@ struct GemmP {
   long long sba, sbn;   // bias
   int nnet;
   int epi, act;
+  int m_off;            // first output row handled by this launch (tail launches after a tensor-core main part)
 };
 
 __device__ __forceinline__ float apply_act(int act, float v) {
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_gemm_simt(GemmP p) {
   const float* __restrict__ B = p.B + agent * p.sBa + net * p.sBn;
   const long long offC = agent * p.sCa + net * p.sCn;
   float* __restrict__ C = p.C + offC;
-  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int m0 = p.m_off + blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
   float acc[4][4];

@@ -294,7 +294,7 @@ static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int n
     if (rc == 0) { if (x) x->launches += tc_gemm_launches_per_call(); return 0; }
     if (rc < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
   }
-  dim3 grid(cdiv(p.N, SG_BN), cdiv(p.M, SG_BM), nagents * p.nnet), block(SG_THREADS);
+  dim3 grid(cdiv(p.N, SG_BN), cdiv(p.M - p.m_off, SG_BM), nagents * p.nnet), block(SG_THREADS);
   if (!TA && !TB) k_gemm_simt<false, false, false><<<grid, block, 0, st>>>(p);
   else if (!TA && TB) k_gemm_simt<false, true, false><<<grid, block, 0, st>>>(p);
   else if (TA && !TB && ONES) k_gemm_simt<true, false, true><<<grid, block, 0, st>>>(p);

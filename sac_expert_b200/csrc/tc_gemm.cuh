@@ -1,10 +1,313 @@
-// tcgen05 (5th-gen tensor core) batched GEMM engine - placeholder until the UMMA path lands.
+// tcgen05 (5th-generation tensor core) batched GEMM engine for the hidden x hidden per-agent
+// contractions of the SAC-EO update (gemm_mode SACEO_GEMM_TCGEN05_BF16X3).
+//
+// fp32 parity on tensor cores: every fp32 operand x is split into bf16 hi = rn(x) and
+// lo = rn(x - hi); the product is accumulated as hi.hi + hi.lo + lo.hi with fp32 accumulation in
+// TMEM (three tcgen05.mma kind::f16 per K slab).  The dropped lo.lo term and the second-order
+// residuals are O(2^-16) relative, far inside the 1e-3 parity budget that single-pass TF32 (2^-11
+// per operand, truncated by the MMA) would consume after six chained GEMMs.
+//
+// Layout: one CTA owns a 128 x BN tile of C for one (agent, net).  All threads load a 64-wide K
+// slab of both fp32 operands from global/L2, split it, and write the bf16 planes into shared memory
+// in the canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte atoms, 16-byte chunk index
+// XOR row-in-atom) - whatever the storage order of the operand, so a single shared-memory
+// descriptor format serves forward (X.W), input-gradient (dY.W^T) and weight-gradient (X^T.dY)
+// GEMMs.  One thread issues the MMAs; tcgen05.commit on an mbarrier releases the stage to the
+// loaders; the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 columns per warp) and
+// applies the same fused epilogue as the SIMT engine (bias, addend, activation / activation
+// derivative).  Rows that do not fill a 128-row tile (the E expert rows, the ones-row of the
+// [dW; db] trick) are finished by the SIMT engine (GemmP::m_off).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
 #include "gemm_simt.cuh"
+
 namespace saceo {
-static inline cudaError_t tc_gemm_init() { return cudaSuccess; }
-static inline bool tc_gemm_eligible(bool, bool, bool, const GemmP&) { return false; }
-static inline int tc_gemm_launch(bool, bool, bool, const GemmP&, int, cudaStream_t) { return 1; }
-static inline int tc_gemm_launches_per_call() { return 1; }
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+
+struct TcP {
+  GemmP g;
+  int m_rows;          // valid rows of op(A) handled by the tensor-core launch
+  long long a_sr, a_sk, b_sr, b_sk;   // element strides of op(A)(m,k) and op(B)(k,n): (row=m|n, k)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    // a lost arrival must fail loudly instead of hanging the GPU (each try_wait already sleeps in hardware)
+    if (!ok && ++spins > (1u << 24)) __trap();
+  } while (!ok);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, ignored for swizzled K-major) | SBO>>4 [32,46) (8 rows * 128 B)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, A/B K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Loads a ROWS x 64 slab of a fp32 operand (element (r,k) at src[r*sr + k*sk], zero outside
+// [0,rlim) x [0,klim)), splits it and stores the two bf16 planes in K-major SW128 layout.
+template <int ROWS>
+__device__ __forceinline__ void load_slab(const float* __restrict__ src, long long sr, long long sk, int r0, int rlim,
+                                          int k0, int klim, uint8_t* hi, uint8_t* lo) {
+  const int t = threadIdx.x;
+  constexpr int ITEMS = ROWS * 8;           // (row, 8-wide k chunk)
+  if (sk == 1) {
+    const bool vec = ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+#pragma unroll 4
+    for (int it = t; it < ITEMS; it += TC_THREADS) {
+      const int kc = it & 7, r = it >> 3;
+      const int gr = r0 + r, gk = k0 + kc * 8;
+      float x[8];
+      if (gr < rlim && vec && gk + 8 <= klim) {
+        const float4* p4 = reinterpret_cast<const float4*>(src + (long long)gr * sr + gk);
+        const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          x[j] = (gr < rlim && gk + j < klim) ? __ldg(src + (long long)gr * sr + gk + j) : 0.f;
+      }
+      uint4 h, l;
+      split8(x, h, l);
+      const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  } else {
+    // storage contiguous along the row (M/N) index: lanes walk rows so each load is coalesced
+#pragma unroll 2
+    for (int it = t; it < ITEMS; it += TC_THREADS) {
+      const int r = it % ROWS, kc = it / ROWS;
+      const int gr = r0 + r, gk = k0 + kc * 8;
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        x[j] = (gr < rlim && gk + j < klim) ? __ldg(src + (long long)gr * sr + (long long)(gk + j) * sk) : 0.f;
+      uint4 h, l;
+      split8(x, h, l);
+      const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  }
+}
+
+template <int BN, int NSTAGE>
+struct TcSmem {
+  static constexpr int A_PLANE = TC_BM * 128;       // bytes of one bf16 plane of the A slab
+  static constexpr int B_PLANE = BN * 128;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int BYTES = NSTAGE * STAGE + 1024 /*align slack*/ + 64 /*barriers + tmem ptr*/;
+};
+
+template <int BN, int NSTAGE>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(TcP q) {
+  using SM = TcSmem<BN, NSTAGE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * SM::STAGE);   // [NSTAGE] free + [1] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + 1);
+
+  const GemmP& p = q.g;
+  const int z = blockIdx.z;
+  const int agent = z / p.nnet, net = z - agent * p.nnet;
+  const float* __restrict__ A = p.A + agent * p.sAa + net * p.sAn;
+  const float* __restrict__ B = p.B + agent * p.sBa + net * p.sBn;
+  const long long offC = agent * p.sCa + net * p.sCn;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s <= NSTAGE; ++s) mbar_init(smem_u32(bars + s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
+  for (int kc = 0; kc < nk; ++kc) {
+    const int s = kc % NSTAGE;
+    uint8_t* st = smem + s * SM::STAGE;
+    if (kc >= NSTAGE) mbar_wait(smem_u32(bars + s), (uint32_t)((kc / NSTAGE - 1) & 1));   // MMAs of slab kc-NSTAGE retired
+    load_slab<TC_BM>(A, q.a_sr, q.a_sk, m0, q.m_rows, kc * TC_BK, p.K, st, st + SM::A_PLANE);
+    load_slab<BN>(B, q.b_sr, q.b_sk, n0, p.N, kc * TC_BK, p.K, st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + SM::A_PLANE;
+      const uint32_t b_hi = a_hi + 2 * SM::A_PLANE, b_lo = b_hi + SM::B_PLANE;
+#pragma unroll
+      for (int kk = 0; kk < TC_BK / 16; ++kk) {
+        const uint32_t ko = kk * 32;               // 16 bf16 = 32 bytes along K inside the 128-byte swizzled row
+        umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_hi + ko), IDESC, (kc | kk) ? 1u : 0u);
+        umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_lo + ko), IDESC, 1u);
+        umma_f16(tmem, umma_desc(a_lo + ko), umma_desc(b_hi + ko), IDESC, 1u);
+      }
+      umma_commit(smem_u32(bars + s));
+      if (kc == nk - 1) umma_commit(smem_u32(bars + NSTAGE));
+    }
+  }
+  mbar_wait(smem_u32(bars + NSTAGE), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns of half (w/4) ----------------------
+  const int row = m0 + (warp & 3) * 32 + lane;
+  const int chalf = (warp >> 2) * (BN / 2);
+  const float* bias = p.bias ? p.bias + agent * p.sba + net * p.sbn : nullptr;
+  const float* addend = p.addend ? p.addend + offC : nullptr;
+  const float* aux = p.aux ? p.aux + offC : nullptr;
+  float* __restrict__ C = p.C + offC;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf + c0);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < q.m_rows) {
+      const int gn0 = n0 + chalf + c0;
+      const long long o0 = (long long)row * p.ldc + gn0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gn = gn0 + j;
+        if (gn < p.N) {
+          float x = __uint_as_float(v[j]);
+          if (bias) x += __ldg(bias + gn);
+          if (addend) x += addend[o0 + j];
+          if (p.epi == EPI_ACT) x = apply_act(p.act, x);
+          else if (p.epi == EPI_MUL_DACT) x *= dact_from_out(p.act, aux[o0 + j]);
+          C[o0 + j] = x;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline cudaError_t tc_gemm_init() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_gemm_tc<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256, 2>::BYTES); if (e) return e;
+  e = cudaFuncSetAttribute(k_gemm_tc<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, 3>::BYTES); if (e) return e;
+  e = cudaFuncSetAttribute(k_gemm_tc<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, 4>::BYTES); if (e) return e;
+  done = true;
+  return cudaSuccess;
+}
+
+// rows of op(A) that go to the tensor-core launch (multiple of 128, or everything when the tail is >= 96 rows)
+static inline int tc_rows(bool ONES, const GemmP& p) {
+  const int mmain = ONES ? p.M - 1 : p.M;
+  int tiles = mmain / TC_BM;
+  if (mmain % TC_BM >= 96) tiles += 1;
+  const int r = tiles * TC_BM;
+  return r < mmain ? r : mmain;
+}
+static inline bool tc_gemm_eligible(bool TA, bool TB, bool ONES, const GemmP& p) {
+  (void)TA; (void)TB;
+  return p.m_off == 0 && tc_rows(ONES, p) >= TC_BM - 32 && p.N >= 64 && p.K >= 8;
+}
+static thread_local int g_tc_launches = 1;
+static inline int tc_gemm_launches_per_call() { return g_tc_launches; }
+
+// returns 0 on success (whole GEMM done, SIMT tail included), <0 on a launch error
+static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
+  TcP q; q.g = p;
+  q.m_rows = tc_rows(ONES, p);
+  q.a_sr = TA ? 1 : p.lda; q.a_sk = TA ? p.lda : 1;
+  q.b_sr = TB ? p.ldb : 1; q.b_sk = TB ? 1 : p.ldb;
+  const int mt = (q.m_rows + TC_BM - 1) / TC_BM;
+  g_tc_launches = 1;
+  if (p.N > 128) {
+    dim3 grid((p.N + 255) / 256, mt, nagents * p.nnet);
+    k_gemm_tc<256, 2><<<grid, TC_THREADS, TcSmem<256, 2>::BYTES, st>>>(q);
+  } else if (p.N > 64) {
+    dim3 grid(1, mt, nagents * p.nnet);
+    k_gemm_tc<128, 3><<<grid, TC_THREADS, TcSmem<128, 3>::BYTES, st>>>(q);
+  } else {
+    dim3 grid(1, mt, nagents * p.nnet);
+    k_gemm_tc<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::BYTES, st>>>(q);
+  }
+  if (cudaPeekAtLastError() != cudaSuccess) return -1;
+  if (q.m_rows < p.M) {     // tail rows (expert rows / ones-row) on the SIMT engine
+    GemmP t = p; t.m_off = q.m_rows;
+    dim3 grid((p.N + SG_BN - 1) / SG_BN, (p.M - t.m_off + SG_BM - 1) / SG_BM, nagents * p.nnet), block(SG_THREADS);
+    if (!TA && !TB) k_gemm_simt<false, false, false><<<grid, block, 0, st>>>(t);
+    else if (!TA && TB) k_gemm_simt<false, true, false><<<grid, block, 0, st>>>(t);
+    else if (TA && !TB && ONES) k_gemm_simt<true, false, true><<<grid, block, 0, st>>>(t);
+    else if (TA && !TB) k_gemm_simt<true, false, false><<<grid, block, 0, st>>>(t);
+    else k_gemm_simt<true, true, false><<<grid, block, 0, st>>>(t);
+    g_tc_launches = 2;
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+  }
+  return 0;
+}
+
+}  // namespace saceo

@@ -37,3 +37,15 @@ def test_full_size_hopper():
     worst = compare_update(pop, cfg, probs, verbose=True)
     bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("shape", ["hopper", "ant"])
+def test_full_size_tcgen05(shape):
+    """Same parity bar with the tcgen05 bf16x3 engine on the 2x256 nets (B=256, E=20)."""
+    from sac_expert_b200 import lib as L
+    S, A = {"hopper": (11, 3), "ant": (27, 8)}[shape]
+    cfg = NetCfg(S=S, A=A)
+    pop, probs = build(cfg, n_agents=2, B=256, E=20, N=2000, seed=9, gemm_mode=L.GEMM_TCGEN05_BF16X3)
+    worst = compare_update(pop, cfg, probs, verbose=True)
+    bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
+    assert not bad, bad
