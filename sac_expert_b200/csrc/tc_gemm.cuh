@@ -25,7 +25,7 @@
 
 namespace saceo {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 512;
 
 struct TcP {
   GemmP g;
@@ -90,53 +90,57 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Loads a ROWS x 64 slab of a fp32 operand (element (r,k) at src[r*sr + k*sk], zero outside
-// [0,rlim) x [0,klim)), splits it and stores the two bf16 planes in K-major SW128 layout.
+// Register-staged slab loader.  A ROWS x 64 slab of a fp32 operand (element (r,k) at src[r*sr + k*sk],
+// zero outside [0,rlim) x [0,klim)) is cut into ROWS*8 items of 8 consecutive k; thread t owns items
+// t, t+TC_THREADS, ...  ld() only ISSUES the global loads (so the next slab is in flight while the
+// tensor core works on the current one); st() splits fp32 -> bf16 hi/lo and stores both planes in the
+// K-major SWIZZLE_128B layout (conflict-free 16-byte stores for either storage order).
 template <int ROWS>
-__device__ __forceinline__ void load_slab(const float* __restrict__ src, long long sr, long long sk, int r0, int rlim,
-                                          int k0, int klim, uint8_t* hi, uint8_t* lo) {
-  const int t = threadIdx.x;
-  constexpr int ITEMS = ROWS * 8;           // (row, 8-wide k chunk)
-  if (sk == 1) {
-    const bool vec = ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-#pragma unroll 4
-    for (int it = t; it < ITEMS; it += TC_THREADS) {
-      const int kc = it & 7, r = it >> 3;
+struct Slab {
+  static constexpr int ITEMS = ROWS * 8;
+  static constexpr int PER = (ITEMS + TC_THREADS - 1) / TC_THREADS;
+  float x[PER][8];
+
+  __device__ __forceinline__ static void coords(int it, bool kcontig, int& r, int& kc) {
+    if (kcontig) { kc = it & 7; r = it >> 3; }          // 8 lanes cover one row's 256 contiguous bytes
+    else { r = it % ROWS; kc = it / ROWS; }               // lanes walk rows: each scalar load is coalesced
+  }
+  __device__ __forceinline__ void ld(const float* __restrict__ src, long long sr, long long sk, int r0, int rlim,
+                                     int k0, int klim) {
+    const bool kcontig = (sk == 1);
+    const bool vec = kcontig && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int it = threadIdx.x + i * TC_THREADS;
+      int r, kc; coords(it, kcontig, r, kc);
       const int gr = r0 + r, gk = k0 + kc * 8;
-      float x[8];
-      if (gr < rlim && vec && gk + 8 <= klim) {
+      const bool rin = (it < ITEMS) && (gr < rlim);
+      if (vec && rin && gk + 8 <= klim) {
         const float4* p4 = reinterpret_cast<const float4*>(src + (long long)gr * sr + gk);
         const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w;
+        x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          x[j] = (gr < rlim && gk + j < klim) ? __ldg(src + (long long)gr * sr + gk + j) : 0.f;
+          x[i][j] = (rin && gk + j < klim) ? __ldg(src + (long long)gr * sr + (long long)(gk + j) * sk) : 0.f;
       }
-      uint4 h, l;
-      split8(x, h, l);
-      const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(lo + off) = l;
     }
-  } else {
-    // storage contiguous along the row (M/N) index: lanes walk rows so each load is coalesced
-#pragma unroll 2
-    for (int it = t; it < ITEMS; it += TC_THREADS) {
-      const int r = it % ROWS, kc = it / ROWS;
-      const int gr = r0 + r, gk = k0 + kc * 8;
-      float x[8];
+  }
+  __device__ __forceinline__ void st(bool kcontig, uint8_t* hi, uint8_t* lo) const {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        x[j] = (gr < rlim && gk + j < klim) ? __ldg(src + (long long)gr * sr + (long long)(gk + j) * sk) : 0.f;
+    for (int i = 0; i < PER; ++i) {
+      const int it = threadIdx.x + i * TC_THREADS;
+      if (it >= ITEMS) break;
+      int r, kc; coords(it, kcontig, r, kc);
       uint4 h, l;
-      split8(x, h, l);
+      split8(x[i], h, l);
       const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(hi + off) = h;
       *reinterpret_cast<uint4*>(lo + off) = l;
     }
   }
-}
+};
 
 template <int BN, int NSTAGE>
 struct TcSmem {
@@ -178,12 +182,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(TcP q) {
 
   const int nk = (p.K + TC_BK - 1) / TC_BK;
   constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
+  Slab<TC_BM> ra;
+  Slab<BN> rb;
+  const bool a_kc = (q.a_sk == 1), b_kc = (q.b_sk == 1);
+  ra.ld(A, q.a_sr, q.a_sk, m0, q.m_rows, 0, p.K);
+  rb.ld(B, q.b_sr, q.b_sk, n0, p.N, 0, p.K);
   for (int kc = 0; kc < nk; ++kc) {
     const int s = kc % NSTAGE;
     uint8_t* st = smem + s * SM::STAGE;
     if (kc >= NSTAGE) mbar_wait(smem_u32(bars + s), (uint32_t)((kc / NSTAGE - 1) & 1));   // MMAs of slab kc-NSTAGE retired
-    load_slab<TC_BM>(A, q.a_sr, q.a_sk, m0, q.m_rows, kc * TC_BK, p.K, st, st + SM::A_PLANE);
-    load_slab<BN>(B, q.b_sr, q.b_sk, n0, p.N, kc * TC_BK, p.K, st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
+    ra.st(a_kc, st, st + SM::A_PLANE);
+    rb.st(b_kc, st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
+    if (kc + 1 < nk) {          // next slab's global loads fly during the barrier, the MMA issue and the next wait
+      ra.ld(A, q.a_sr, q.a_sk, m0, q.m_rows, (kc + 1) * TC_BK, p.K);
+      rb.ld(B, q.b_sr, q.b_sk, n0, p.N, (kc + 1) * TC_BK, p.K);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -204,40 +217,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(TcP q) {
   mbar_wait(smem_u32(bars + NSTAGE), 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns of half (w/4) ----------------------
-  const int row = m0 + (warp & 3) * 32 + lane;
-  const int chalf = (warp >> 2) * (BN / 2);
+  // ---- epilogue -------------------------------------------------------------------------------
+  // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column group w/4.  Phase 1: tcgen05.ld gives each
+  // thread 32 consecutive columns of ITS row; they are parked in a warp-private padded smem patch (the
+  // operand stages are free once the last MMA has retired).  Phase 2: the warp walks the patch row-wise so
+  // that bias/addend/aux reads and the C stores are coalesced 16-byte accesses.
+  constexpr int NGRP = (BN / 32) < (TC_THREADS / 128) ? (BN / 32) : (TC_THREADS / 128);   // column groups
+  constexpr int GCOLS = BN / NGRP;                 // columns per warp (32 or 64)
+  constexpr int PSTR = GCOLS + 4;                  // padded patch row stride (floats), keeps 16-byte alignment
+  const int grp = warp >> 2;
   const float* bias = p.bias ? p.bias + agent * p.sba + net * p.sbn : nullptr;
   const float* addend = p.addend ? p.addend + offC : nullptr;
   const float* aux = p.aux ? p.aux + offC : nullptr;
   float* __restrict__ C = p.C + offC;
+  if (grp < NGRP) {
+    float* patch = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * PSTR;
+    const int cbase = grp * GCOLS;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-    uint32_t v[32];
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf + c0);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row < q.m_rows) {
-      const int gn0 = n0 + chalf + c0;
-      const long long o0 = (long long)row * p.ldc + gn0;
+    for (int c0 = 0; c0 < GCOLS; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + c0);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                   "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                   "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                     "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                     "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                     "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                   : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float4* dst = reinterpret_cast<float4*>(patch + lane * PSTR + c0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gn = gn0 + j;
-        if (gn < p.N) {
-          float x = __uint_as_float(v[j]);
-          if (bias) x += __ldg(bias + gn);
-          if (addend) x += addend[o0 + j];
-          if (p.epi == EPI_ACT) x = apply_act(p.act, x);
-          else if (p.epi == EPI_MUL_DACT) x *= dact_from_out(p.act, aux[o0 + j]);
-          C[o0 + j] = x;
-        }
+      for (int j = 0; j < 8; ++j)
+        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+    }
+    __syncwarp();
+    constexpr int LPR = GCOLS / 4;                 // lanes per row (float4 each)
+    constexpr int RPI = 32 / LPR;                  // rows per warp instruction
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                        (!addend || (reinterpret_cast<uintptr_t>(addend) & 15) == 0) &&
+                        (!aux || (reinterpret_cast<uintptr_t>(aux) & 15) == 0);
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr += RPI) {
+      const int r = rr + lr;
+      const int grow = m0 + (warp & 3) * 32 + r;
+      const int gn = n0 + cbase + lc;
+      if (grow >= q.m_rows || gn >= p.N) continue;
+      const float4 acc = *reinterpret_cast<const float4*>(patch + r * PSTR + lc);
+      float x[4] = {acc.x, acc.y, acc.z, acc.w};
+      const long long o = (long long)grow * p.ldc + gn;
+      const bool full = vec_ok && (gn + 4 <= p.N);
+      float ad[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+      if (full) {
+        if (addend) { const float4 t4 = *reinterpret_cast<const float4*>(addend + o); ad[0] = t4.x; ad[1] = t4.y; ad[2] = t4.z; ad[3] = t4.w; }
+        if (aux) { const float4 t4 = *reinterpret_cast<const float4*>(aux + o); ax[0] = t4.x; ax[1] = t4.y; ax[2] = t4.z; ax[3] = t4.w; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (gn + j < p.N) { if (addend) ad[j] = addend[o + j]; if (aux) ax[j] = aux[o + j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (bias && gn + j < p.N) x[j] += __ldg(bias + gn + j);
+        x[j] += ad[j];
+        if (p.epi == EPI_ACT) x[j] = apply_act(p.act, x[j]);
+        else if (p.epi == EPI_MUL_DACT) x[j] *= dact_from_out(p.act, ax[j]);
+      }
+      if (full) *reinterpret_cast<float4*>(C + o) = make_float4(x[0], x[1], x[2], x[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (gn + j < p.N) C[o + j] = x[j];
       }
     }
   }

@@ -1,0 +1,216 @@
+"""CPU tests pinning the ORACLE (it is the checker for the CUDA path; the reference ships no tests and
+cannot run here - parity unpinned, see oracle/sac_eo_oracle.py header): fp32 vs fp64 twin, autograd vs the
+hand-derived backward, both Fisher-vector forms, the committed golden fixtures, and one test per reference
+quirk (SURVEY.md §8a closing list)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sac_eo_oracle as O
+from oracle.analytic import analytic_update, fvp_gn
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+CFGS = {
+    "saceo2": O.NetCfg(S=11, A=3, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(96, 96)),
+    "one_model_state_indep": O.NetCfg(S=7, A=2, actor_hidden=(32, 48), critic_hidden=(40, 32), model_hidden=(64, 32),
+                                      per_state_std=False, num_models=1, actor_acts=("tanh", "tanh"),
+                                      critic_acts=("elu", "tanh"), model_acts=("relu", "elu"), delta_clip_pred=0.05),
+    "plain": O.NetCfg(S=5, A=2, actor_hidden=(32, 32), critic_hidden=(32, 32), num_models=0),
+}
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def problem(cfg, B=48, E=10, seed=1):
+    st, replay, expert, hyper = O.make_problem(cfg, B=B, E=E, N=400, seed=seed, perturb=0.05)
+    hyper["eps"] = 0.3
+    return st, replay, expert, hyper, O.draw_batch(cfg, replay, expert, B, seed=seed + 1)
+
+
+@pytest.mark.parametrize("name", list(CFGS))
+def test_fp32_vs_fp64_and_analytic(name):
+    cfg = CFGS[name]
+    st, replay, expert, hyper, batch = problem(cfg)
+    o64 = O.sac_eo_update(cfg, O.to_torch_state(st, torch.float64), batch, hyper)
+    o32 = O.sac_eo_update(cfg, O.to_torch_state(st, torch.float32), batch, hyper)
+    a64 = analytic_update(cfg, st, batch, hyper, dtype=np.float64)
+    for k in ("y", "L_q1", "L_q2", "L_pi", "mse", "p_loss", "alpha_loss", "g_alpha"):
+        assert rel(a64[k], o64[k].numpy()) < 1e-12, k
+        assert rel(o32[k].numpy(), o64[k].numpy()) < 2e-5, k
+    for k in ("g_q1", "g_q2", "g_actor"):
+        for x, y, z in zip(a64[k], o64[k], o32[k]):
+            assert rel(x, y.numpy()) < 1e-11, k
+            assert rel(z.numpy(), y.numpy()) < 5e-5, k
+    for k in ("q1", "q2", "actor", "t1", "t2"):
+        for x, y in zip(a64["new"][k], o64["new"][k]):
+            assert rel(x, y.numpy()) < 1e-12, k
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_fisher_vector_forms_agree(per_state_std):
+    cfg = O.NetCfg(S=6, A=2, actor_hidden=(32, 24), critic_hidden=(8, 8), num_models=0, per_state_std=per_state_std,
+                   actor_acts=("tanh", "elu"), std_mult=0.6)
+    st, replay, _, _ = O.make_problem(cfg, 8, 2, 200, seed=4, perturb=0.1)
+    th = O.to_torch_state(st, torch.float64)
+    s_all = replay["s"][:64]
+    F1 = O.make_F(cfg, th["actor"], s_all, th, 0.01)
+    F2 = O.make_F_gn(cfg, th["actor"], s_all, th, 0.01)
+    x = torch.randn(sum(w.numel() for w in th["actor"]), dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    ref = F1(x).numpy()
+    assert rel(F2(x).numpy(), ref) < 1e-12
+    assert rel(fvp_gn(cfg, st["actor"], x.numpy(), s_all, st, 0.01, dtype=np.float64), ref) < 1e-12
+    # F is symmetric positive definite (+damp): x.F(y) == y.F(x), CG reduces the residual, x.F(x) > 0
+    y2 = torch.randn_like(x)
+    assert abs(float(x.dot(F1(y2)) - y2.dot(F1(x)))) < 1e-9 * float(x.norm() * y2.norm())
+    b = torch.randn_like(x) * 0.1
+    sol, vFv, step = O.trpo_step(F1, b, delta=0.02, cg_iters=40)
+    assert float(vFv) > 0 and rel(F1(sol).numpy(), b.numpy()) < 0.2      # 40 CG iterations: residual well down
+
+
+def test_golden_update_fixtures():
+    pend = np.load(os.path.join(GOLD, "pendulum_templog0.npz"))
+    aw = [pend[f"actor_{i}"] for i in range(7)]
+    assert [w.shape for w in aw] == [(3, 64), (64,), (64, 64), (64,), (64, 1), (1,), (1, 1)]
+    for tag, nm in (("sac", 0), ("saceo", 2)):
+        gold = np.load(os.path.join(GOLD, f"golden_pendulum_{tag}.npz"))
+        cfg = O.NetCfg(S=3, A=1, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(64, 64),
+                       actor_acts=("tanh", "tanh"), critic_acts=("tanh", "tanh"), per_state_std=False, num_models=nm)
+        st, replay, expert, hyper = O.make_problem(cfg, B=32, E=8, N=300, seed=123, perturb=0.02)
+        st["actor"] = [w.copy() for w in aw]
+        st["adam_actor"] = dict(m=[np.zeros_like(w) for w in aw], v=[np.zeros_like(w) for w in aw], t=0)
+        st.update(s_mean=pend["s_mean"], s_std=pend["s_std"], a_mean=pend["a_mean"], a_std=pend["a_std"],
+                  ret_std=pend["ret_std"], m_s_mean=pend["s_mean"], m_s_std=pend["s_std"], m_a_mean=pend["a_mean"],
+                  m_a_std=pend["a_std"], m_d_mean=pend["d_mean"], m_d_std=pend["d_std"])
+        hyper["eps"] = 0.25
+        batch = O.draw_batch(cfg, replay, expert, 32, seed=321)
+        for dt, tol in ((torch.float64, 1e-12), (torch.float32, 3e-4)):
+            o = O.sac_eo_update(cfg, O.to_torch_state(st, dt), batch, hyper)
+            for k in ("y", "L_q1", "L_q2", "L_pi", "mse", "p_loss", "alpha_loss", "g_alpha"):
+                assert rel(o[k].numpy(), gold[k]) < tol, (tag, k)
+            for k in ("g_q1", "g_q2", "g_actor"):
+                assert rel(O.flat(o[k]).numpy(), gold[k]) < tol, (tag, k)
+            assert rel(O.flat(o["new"]["actor"]).numpy(), gold["new_actor"]) < tol
+            assert rel(O.flat(o["new"]["t1"]).numpy(), gold["new_t1"]) < tol
+
+
+def test_golden_fvp_fixture():
+    pend = np.load(os.path.join(GOLD, "pendulum_templog0.npz"))
+    gold = np.load(os.path.join(GOLD, "golden_pendulum_fvp.npz"))
+    aw = [pend[f"actor_{i}"] for i in range(7)]
+    cfg = O.NetCfg(S=3, A=1, actor_hidden=(64, 64), critic_hidden=(8, 8), actor_acts=("tanh", "tanh"),
+                   per_state_std=False, num_models=0)
+    st = dict(actor=aw, s_mean=pend["s_mean"], s_std=pend["s_std"])
+    th = O.to_torch_state(st, torch.float64)
+    F = O.make_F(cfg, th["actor"], gold["states"], th, damp=0.01)
+    assert rel(F(torch.from_numpy(gold["x"])).numpy(), gold["Fx"]) < 1e-12
+    assert rel(fvp_gn(cfg, aw, gold["x"], gold["states"], st, 0.01, dtype=np.float64), gold["Fx"]) < 1e-10
+    sol = O.cg(F, torch.from_numpy(gold["b"]), cg_iters=20)
+    assert rel(sol.numpy(), gold["cg_x"]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------- quirks
+def test_quirk_keras_adam_epsilon_outside_bias_correction():
+    th, g = [torch.tensor([1.0, -2.0])], [torch.tensor([1e-6, 3e-7])]
+    new, m, v, t = O.keras_adam(th, g, [torch.zeros(2)], [torch.zeros(2)], 0, 1e-3)
+    lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    expect = th[0] - lr_t * (0.1 * g[0]) / (torch.sqrt(0.001 * g[0] ** 2) + 1e-7)
+    assert torch.allclose(new[0], expect, rtol=1e-6) and t == 1
+    # torch.optim.Adam (eps inside the corrected denominator) gives a different step at this gradient scale
+    p = torch.nn.Parameter(th[0].clone()); p.grad = g[0].clone()
+    torch.optim.Adam([p], lr=1e-3, eps=1e-7).step()
+    assert not torch.allclose(p.detach() - th[0], new[0] - th[0], rtol=1e-2, atol=0)
+
+
+def test_quirk_raw_alpha_and_mixed_normalisation():
+    cfg = CFGS["plain"]
+    st, replay, expert, hyper, batch = problem(cfg)
+    assert st["alpha"] > 0          # perturbed problem
+    st["alpha"] = np.float32(math.log(0.1))       # SAC_expert.py:106 - raw, negative, used without exp
+    o = O.sac_eo_update(cfg, O.to_torch_state(st, torch.float64), batch, hyper)
+    T = O.to_torch_state(st, torch.float64)
+    sp = torch.as_tensor(batch["sp"]).double()
+    a1, nlp1 = O.head(cfg, T["actor"], sp, torch.as_tensor(batch["u1"]), T)
+    minq = torch.minimum(O.q_value(cfg, T["t1"], sp, a1, T), O.q_value(cfg, T["t2"], sp, a1, T))
+    y = torch.as_tensor(batch["r"]).double() + hyper["gamma"] * (1 - torch.as_tensor(batch["d"])) * (minq + math.log(0.1) * nlp1)
+    assert rel(o["y"].numpy(), y.numpy()) < 1e-6
+    # critic loss: NORMALISED prediction vs DENORMALISED target (ret_std != 1 makes the two differ)
+    q = O.q_forward(cfg, T["q1"], torch.as_tensor(batch["s"]).double(), torch.as_tensor(batch["a"]).double(), T)
+    assert rel(o["L_q1"].numpy(), (0.5 * (q[:, 0] - o["y"]) ** 2).mean().numpy()) < 1e-12
+    assert float(T["ret_std"]) != 1.0
+    # alpha is clamped at 1e-5 after its step (SAC_expert.py:348)
+    assert float(o["new"]["alpha"]) == pytest.approx(1e-5)
+
+
+def test_quirk_head_ignores_std_mult_and_clips_logstd():
+    cfg = O.NetCfg(S=4, A=2, actor_hidden=(8, 8), critic_hidden=(8, 8), num_models=0, std_mult=0.3)
+    st, *_ = O.make_problem(cfg, 8, 2, 50, seed=0, identity_norm=True)
+    T = O.to_torch_state(st, torch.float64)
+    T["actor"][5] = torch.tensor([0.0, 0.0, 9.0, -9.0], dtype=torch.float64)     # logstd biases far outside [-5, 2]
+    x = torch.zeros(3, 4, dtype=torch.float64); u = torch.ones(3, 2, dtype=torch.float64)
+    pi, nlp = O.head(cfg, T["actor"], x, u, T)
+    z = torch.atanh(pi)
+    mean = O.mlp(T["actor"], x, cfg.actor_acts)[:, :2]
+    assert torch.allclose(z - mean, torch.tensor([math.exp(2.0), math.exp(-5.0)], dtype=torch.float64).expand(3, 2), rtol=1e-6)
+    cfg2 = O.NetCfg(S=4, A=2, actor_hidden=(8, 8), critic_hidden=(8, 8), num_models=0, std_mult=1.0)
+    pi2, _ = O.head(cfg2, T["actor"], x, u, T)
+    assert torch.equal(pi, pi2)      # std_mult / logstd_init play no role in evaluate()/sample()
+
+
+def test_quirk_reduce_min_splits_ties_and_clip_passes_gradient_on_the_boundary():
+    a = torch.tensor([1.0, 2.0], requires_grad=True); b = torch.tensor([1.0, 3.0], requires_grad=True)
+    torch.minimum(a, b).sum().backward()
+    assert a.grad.tolist() == [0.5, 1.0] and b.grad.tolist() == [0.5, 0.0]
+    x = torch.tensor([-5.0, 2.0, 2.1], requires_grad=True)
+    torch.clamp(x, O.MIN_LOG_STD, O.MAX_LOG_STD).sum().backward()
+    assert x.grad.tolist() == [1.0, 1.0, 0.0]
+
+
+def test_quirk_polyak_gate_and_fp32_rounding():
+    cfg = CFGS["plain"]
+    st, replay, expert, hyper, batch = problem(cfg)
+    hyper["do_polyak"] = False
+    o = O.sac_eo_update(cfg, O.to_torch_state(st), batch, hyper)
+    assert all(torch.equal(a, torch.as_tensor(b)) for a, b in zip(o["new"]["t1"], st["t1"]))
+    hyper["do_polyak"] = True
+    o = O.sac_eo_update(cfg, O.to_torch_state(st), batch, hyper)
+    tau = np.float32(hyper["tau"]); om = np.float32(1.0 - hyper["tau"])
+    want = st["t1"][0] * om + o["new"]["q1"][0].numpy() * tau           # NumPy fp32: two products, one sum
+    assert np.array_equal(o["new"]["t1"][0].numpy(), want)
+
+
+def test_quirk_two_models_need_even_expert_rows():
+    cfg = CFGS["saceo2"]
+    st, replay, expert, hyper = O.make_problem(cfg, B=16, E=7, N=100, seed=0)
+    batch = O.draw_batch(cfg, replay, expert, 16, seed=1)
+    with pytest.raises(RuntimeError):       # unequal halves cannot be added (SAC_expert.py:329-332)
+        O.sac_eo_update(cfg, O.to_torch_state(st), batch, hyper)
+
+
+def test_adaptive_epsilon():
+    assert O.adaptive_epsilon(1e-3) == 1e-3
+    e = O.adaptive_epsilon(0.5, scale_by_true_mse=True, mse_cf=4.0)
+    assert e == pytest.approx(1 / 3)
+    e2 = O.adaptive_epsilon(0.5, scale_by_true_mse=True, mse_cf=4.0, j_cur=50.0, j_exp=100.0, min_mult=True, mult_coeff=1.0)
+    assert e2 == pytest.approx((1 / 3) * 0.5)
+    e3 = O.adaptive_epsilon(0.5, scale_by_true_mse=True, mse_cf=4.0, j_cur=50.0, j_exp=100.0, exp_mult=True, mult_coeff=2.0)
+    assert e3 == pytest.approx((1 / 3) * math.exp(-1.0))
+    assert O.adaptive_epsilon(2.0, disc_mode="max", disc=np.array([1.0, 3.0])) == pytest.approx(1 / 7)
+    assert O.adaptive_epsilon(2.0, disc_mode="median", disc=np.array([1.0, 3.0, 5.0])) == pytest.approx(1 / 7)
+    assert O.adaptive_epsilon(2.0, disc_mode="total", disc=np.array([1.0, 3.0])) == pytest.approx(1 / 9)
+
+
+def test_gather_semantics_with_replacement():
+    rng = np.random.default_rng(0)
+    rep = dict(s=rng.standard_normal((9, 3)).astype(np.float32), a=rng.standard_normal((9, 2)).astype(np.float32),
+               sp=rng.standard_normal((9, 3)).astype(np.float32), r=rng.standard_normal(9).astype(np.float32),
+               d=(rng.random(9) < 0.5).astype(np.float64))
+    idx = np.array([8, 8, 0, 3, 3, 3])
+    s, a, sp, r, d = O.gather(rep, idx)
+    assert s.shape == (6, 3) and d.dtype == np.float64 and np.array_equal(s[0], s[1]) and np.array_equal(r[3:], rep["r"][[3, 3, 3]])
