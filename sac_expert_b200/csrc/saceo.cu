@@ -11,6 +11,7 @@
 
 #include "../../include/saceo.h"
 #include "gemm_simt.cuh"
+#include "gemm_skinny.cuh"
 #include "elem.cuh"
 #include "fvp.cuh"
 #include "tc_gemm.cuh"
@@ -287,20 +288,40 @@ extern "C" int64_t saceo_launch_count(const saceo_ctx* x) { return x ? x->launch
 // ------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ------------------------------------------------------------------------------------------
-static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
-  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
-  if (x && x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && tc_gemm_eligible(TA, TB, ONES, p)) {
-    int rc = tc_gemm_launch(TA, TB, ONES, p, nagents, st);
-    if (rc == 0) { if (x) x->launches += tc_gemm_launches_per_call(); return 0; }
-    if (rc < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
-  }
+static void simt_launch(bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
   dim3 grid(cdiv(p.N, SG_BN), cdiv(p.M - p.m_off, SG_BM), nagents * p.nnet), block(SG_THREADS);
   if (!TA && !TB) k_gemm_simt<false, false, false><<<grid, block, 0, st>>>(p);
   else if (!TA && TB) k_gemm_simt<false, true, false><<<grid, block, 0, st>>>(p);
   else if (TA && !TB && ONES) k_gemm_simt<true, false, true><<<grid, block, 0, st>>>(p);
   else if (TA && !TB) k_gemm_simt<true, false, false><<<grid, block, 0, st>>>(p);
   else k_gemm_simt<true, true, false><<<grid, block, 0, st>>>(p);
-  if (x) x->launches++;
+}
+
+// Engine choice per GEMM: tensor cores for 128-row tiles of wide layers, the skinny kernel when one
+// output dimension is <= 32 (expert rows, heads, bias rows, row tails), the tiled SIMT kernel otherwise.
+static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+  int row0 = 0;
+  if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && tc_gemm_eligible(TA, TB, ONES, p)) {
+    if (tc_gemm_launch(TA, TB, ONES, p, nagents, st) < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
+    x->launches++;
+    row0 = tc_rows(ONES, p);
+    if (row0 >= p.M) return 0;
+  }
+  if (p.M - row0 <= 32) {
+    skinny_launch(skinny_rows(TA, TB, ONES, p, row0), nagents, st);
+  } else if (p.M - row0 <= 64 && p.N > 32) {          // e.g. [dW0; db0] with S+A+1 = 36 rows: two 32-row passes
+    SkinnyP s1 = skinny_rows(TA, TB, ONES, p, row0); s1.Ms = row0 + 32;
+    skinny_launch(s1, nagents, st);
+    skinny_launch(skinny_rows(TA, TB, ONES, p, row0 + 32), nagents, st);
+    x->launches++;
+  } else if (row0 == 0 && p.N <= 32) {
+    skinny_launch(skinny_cols(TA, TB, ONES, p), nagents, st);
+  } else {
+    GemmP t = p; t.m_off = row0;
+    simt_launch(TA, TB, ONES, t, nagents, st);
+  }
+  x->launches++;
   return 0;
 }
 

@@ -76,15 +76,17 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// fp32 -> (bf16 hi, bf16 lo) for 8 consecutive-k values, packed conversions (cvt.rn.bf16x2.f32):
+// hi = rn(x), lo = rn(x - hi); 6 instructions per pair.
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);      // low half = x[2i]
+    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+    const float f0 = __uint_as_float(h[i] << 16), f1 = __uint_as_float(h[i] & 0xFFFF0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(x[2 * i] - f0, x[2 * i + 1] - f1);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -92,52 +94,69 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 // Register-staged slab loader.  A ROWS x 64 slab of a fp32 operand (element (r,k) at src[r*sr + k*sk],
 // zero outside [0,rlim) x [0,klim)) is cut into ROWS*8 items of 8 consecutive k; thread t owns items
-// t, t+TC_THREADS, ...  ld() only ISSUES the global loads (so the next slab is in flight while the
-// tensor core works on the current one); st() splits fp32 -> bf16 hi/lo and stores both planes in the
-// K-major SWIZZLE_128B layout (conflict-free 16-byte stores for either storage order).
+// t, t+TC_THREADS, ...  The item -> (row, k-chunk) map, the global base pointer and the swizzled smem
+// offset of every item are fixed for the whole K loop and computed once (init); ld() only ISSUES the
+// global loads of one slab (so the next slab is in flight while the tensor core works on the current
+// one); st() splits fp32 -> bf16 hi/lo and stores both planes in the K-major SWIZZLE_128B layout
+// (conflict-free 16-byte stores for either storage order).
 template <int ROWS>
 struct Slab {
   static constexpr int ITEMS = ROWS * 8;
   static constexpr int PER = (ITEMS + TC_THREADS - 1) / TC_THREADS;
   float x[PER][8];
+  const float* ptr[PER];     // element (row, kc*8) of slab 0
+  int soff[PER];             // byte offset of the item's 16-byte chunk inside a plane; -1: item out of range
+  int kc8[PER];              // kc*8
+  long long sk;
+  bool kcontig, vec;
 
-  __device__ __forceinline__ static void coords(int it, bool kcontig, int& r, int& kc) {
-    if (kcontig) { kc = it & 7; r = it >> 3; }          // 8 lanes cover one row's 256 contiguous bytes
-    else { r = it % ROWS; kc = it / ROWS; }               // lanes walk rows: each scalar load is coalesced
-  }
-  __device__ __forceinline__ void ld(const float* __restrict__ src, long long sr, long long sk, int r0, int rlim,
-                                     int k0, int klim) {
-    const bool kcontig = (sk == 1);
-    const bool vec = kcontig && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  __device__ __forceinline__ void init(const float* __restrict__ src, long long sr, long long sk_, int r0, int rlim) {
+    sk = sk_;
+    kcontig = (sk_ == 1);
+    vec = kcontig && ((sr & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       const int it = threadIdx.x + i * TC_THREADS;
-      int r, kc; coords(it, kcontig, r, kc);
-      const int gr = r0 + r, gk = k0 + kc * 8;
-      const bool rin = (it < ITEMS) && (gr < rlim);
-      if (vec && rin && gk + 8 <= klim) {
-        const float4* p4 = reinterpret_cast<const float4*>(src + (long long)gr * sr + gk);
-        const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-        x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w;
-        x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+      int r, kc;
+      if (kcontig) { kc = it & 7; r = it >> 3; }          // 8 lanes cover one row's 256 contiguous bytes
+      else { r = it % ROWS; kc = it / ROWS; }               // lanes walk rows: each scalar load is coalesced
+      const int gr = r0 + r;
+      const bool ok = (it < ITEMS);
+      kc8[i] = kc * 8;
+      ptr[i] = (ok && gr < rlim) ? src + (long long)gr * sr + (long long)(kc * 8) * sk_ : nullptr;
+      soff[i] = ok ? (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4) : -1;
+    }
+  }
+  __device__ __forceinline__ void ld(int k0, int klim) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float* p = ptr[i];
+      const int gk = k0 + kc8[i];
+      if (p != nullptr && gk + 8 <= klim) {
+        p += (long long)k0 * sk;
+        if (vec) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+          x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w;
+          x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = __ldg(p + j * sk);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          x[i][j] = (rin && gk + j < klim) ? __ldg(src + (long long)gr * sr + (long long)(gk + j) * sk) : 0.f;
+          x[i][j] = (p != nullptr && gk + j < klim) ? __ldg(p + ((long long)k0 + j) * sk) : 0.f;
       }
     }
   }
-  __device__ __forceinline__ void st(bool kcontig, uint8_t* hi, uint8_t* lo) const {
+  __device__ __forceinline__ void st(uint8_t* hi, uint8_t* lo) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      const int it = threadIdx.x + i * TC_THREADS;
-      if (it >= ITEMS) break;
-      int r, kc; coords(it, kcontig, r, kc);
+      if (soff[i] < 0) continue;
       uint4 h, l;
       split8(x[i], h, l);
-      const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(lo + off) = l;
+      *reinterpret_cast<uint4*>(hi + soff[i]) = h;
+      *reinterpret_cast<uint4*>(lo + soff[i]) = l;
     }
   }
 };
@@ -184,18 +203,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(TcP q) {
   constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
   Slab<TC_BM> ra;
   Slab<BN> rb;
-  const bool a_kc = (q.a_sk == 1), b_kc = (q.b_sk == 1);
-  ra.ld(A, q.a_sr, q.a_sk, m0, q.m_rows, 0, p.K);
-  rb.ld(B, q.b_sr, q.b_sk, n0, p.N, 0, p.K);
+  ra.init(A, q.a_sr, q.a_sk, m0, q.m_rows);
+  rb.init(B, q.b_sr, q.b_sk, n0, p.N);
+  ra.ld(0, p.K);
+  rb.ld(0, p.K);
   for (int kc = 0; kc < nk; ++kc) {
     const int s = kc % NSTAGE;
     uint8_t* st = smem + s * SM::STAGE;
     if (kc >= NSTAGE) mbar_wait(smem_u32(bars + s), (uint32_t)((kc / NSTAGE - 1) & 1));   // MMAs of slab kc-NSTAGE retired
-    ra.st(a_kc, st, st + SM::A_PLANE);
-    rb.st(b_kc, st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
+    ra.st(st, st + SM::A_PLANE);
+    rb.st(st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
     if (kc + 1 < nk) {          // next slab's global loads fly during the barrier, the MMA issue and the next wait
-      ra.ld(A, q.a_sr, q.a_sk, m0, q.m_rows, (kc + 1) * TC_BK, p.K);
-      rb.ld(B, q.b_sr, q.b_sk, n0, p.N, (kc + 1) * TC_BK, p.K);
+      ra.ld((kc + 1) * TC_BK, p.K);
+      rb.ld((kc + 1) * TC_BK, p.K);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     __syncthreads();
@@ -324,17 +344,14 @@ static inline bool tc_gemm_eligible(bool TA, bool TB, bool ONES, const GemmP& p)
   (void)TA; (void)TB;
   return p.m_off == 0 && tc_rows(ONES, p) >= TC_BM - 32 && p.N >= 64 && p.K >= 8;
 }
-static thread_local int g_tc_launches = 1;
-static inline int tc_gemm_launches_per_call() { return g_tc_launches; }
 
-// returns 0 on success (whole GEMM done, SIMT tail included), <0 on a launch error
+// launches the tensor-core part (rows [0, tc_rows)); the caller finishes rows [tc_rows, M). <0 on a launch error
 static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, int nagents, cudaStream_t st) {
   TcP q; q.g = p;
   q.m_rows = tc_rows(ONES, p);
   q.a_sr = TA ? 1 : p.lda; q.a_sk = TA ? p.lda : 1;
   q.b_sr = TB ? p.ldb : 1; q.b_sk = TB ? 1 : p.ldb;
   const int mt = (q.m_rows + TC_BM - 1) / TC_BM;
-  g_tc_launches = 1;
   if (p.N > 128) {
     dim3 grid((p.N + 255) / 256, mt, nagents * p.nnet);
     k_gemm_tc<256, 2><<<grid, TC_THREADS, TcSmem<256, 2>::BYTES, st>>>(q);
@@ -346,17 +363,6 @@ static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, in
     k_gemm_tc<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::BYTES, st>>>(q);
   }
   if (cudaPeekAtLastError() != cudaSuccess) return -1;
-  if (q.m_rows < p.M) {     // tail rows (expert rows / ones-row) on the SIMT engine
-    GemmP t = p; t.m_off = q.m_rows;
-    dim3 grid((p.N + SG_BN - 1) / SG_BN, (p.M - t.m_off + SG_BM - 1) / SG_BM, nagents * p.nnet), block(SG_THREADS);
-    if (!TA && !TB) k_gemm_simt<false, false, false><<<grid, block, 0, st>>>(t);
-    else if (!TA && TB) k_gemm_simt<false, true, false><<<grid, block, 0, st>>>(t);
-    else if (TA && !TB && ONES) k_gemm_simt<true, false, true><<<grid, block, 0, st>>>(t);
-    else if (TA && !TB) k_gemm_simt<true, false, false><<<grid, block, 0, st>>>(t);
-    else k_gemm_simt<true, true, false><<<grid, block, 0, st>>>(t);
-    g_tc_launches = 2;
-    if (cudaPeekAtLastError() != cudaSuccess) return -1;
-  }
   return 0;
 }
 
