@@ -303,7 +303,7 @@ static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int n
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   int row0 = 0;
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && tc_gemm_eligible(TA, TB, ONES, p)) {
-    if (tc_gemm_launch(TA, TB, ONES, p, nagents, st) < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
+    if (tc_gemm_launch(TA, TB, ONES, p, nagents, x->cfg.reserved[0], st) < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
     x->launches++;
     row0 = tc_rows(ONES, p);
     if (row0 >= p.M) return 0;
@@ -849,8 +849,8 @@ extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int3
   GemmP p{}; p.nnet = 1; p.A = A; p.B = Bm; p.C = C; p.M = M; p.N = N; p.K = K;
   p.lda = transA ? M : K; p.ldb = transB ? K : N; p.ldc = N;
   p.sAa = (long long)M * K; p.sBa = (long long)K * N; p.sCa = (long long)M * N; p.epi = EPI_NONE;
-  saceo_ctx tmp; tmp.cfg.gemm_mode = gemm_mode; tmp.cfg.n_agents = batch;
-  if (gemm_mode == SACEO_GEMM_TCGEN05_BF16X3) {
+  saceo_ctx tmp; tmp.cfg.gemm_mode = gemm_mode & 0xff; tmp.cfg.reserved[0] = (gemm_mode >> 8) & 0xff; tmp.cfg.n_agents = batch;
+  if ((gemm_mode & 0xff) == SACEO_GEMM_TCGEN05_BF16X3) {
     CU(tc_gemm_init());
     if (!tc_gemm_eligible(transA != 0, transB != 0, false, p))
       return fail(SACEO_E_INVALID, "shape not eligible for the tcgen05 engine");

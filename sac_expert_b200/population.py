@@ -44,6 +44,7 @@ class PopulationSpec:
     fvp_rows: int = 0
     std_mult: float = 1.0
     gemm_mode: int = _l.GEMM_FP32_SIMT
+    tc_variant: int = 0            # tcgen05 tile variant (0: 128x256 1 CTA/SM, 1: 128x128 2 CTAs/SM)
     use_graph: bool = False
     device: int = 0
 
@@ -73,6 +74,7 @@ class PopulationSpec:
         c.std_mult = self.std_mult
         c.gemm_mode = self.gemm_mode
         c.use_graph = int(self.use_graph)
+        c.reserved[0] = self.tc_variant
         return c
 
 

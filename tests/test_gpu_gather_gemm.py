@@ -85,7 +85,8 @@ def test_simt_gemm(ta, tb, M, N, K):
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 256), (276, 256, 27), (256, 64, 35), (257, 128, 276),
                                    (100, 96, 16), (384, 512, 130)])
-def test_tcgen05_bf16x3_gemm(ta, tb, M, N, K):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_tcgen05_bf16x3_gemm(ta, tb, M, N, K, variant):
     """tcgen05 engine (bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM) vs an fp64 matmul."""
     lib = L.load()
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K)
@@ -95,7 +96,7 @@ def test_tcgen05_bf16x3_gemm(ta, tb, M, N, K):
     ref = torch.matmul((A.transpose(1, 2) if ta else A).double(), (B.transpose(1, 2) if tb else B).double())
     Ad, Bd = A.cuda().contiguous(), B.cuda().contiguous()
     Cd = torch.full((batch, M, N), float("nan"), device="cuda")
-    L.check(lib.saceo_test_gemm(L.GEMM_TCGEN05_BF16X3, batch, M, N, K, ta, tb, Ad.data_ptr(), Bd.data_ptr(),
+    L.check(lib.saceo_test_gemm(L.GEMM_TCGEN05_BF16X3 | (variant << 8), batch, M, N, K, ta, tb, Ad.data_ptr(), Bd.data_ptr(),
                                 Cd.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     err = (Cd.cpu().double() - ref).norm() / ref.norm()

@@ -9,7 +9,7 @@ lib = L.load()
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 shapes = [(256, 256, 256), (256, 256, 35), (276, 256, 256), (256, 256, 276)]
 st = torch.cuda.current_stream().cuda_stream
-for mode in (0, 1):
+for mode in [int(m) for m in (sys.argv[2].split(',') if len(sys.argv) > 2 else ['0', '1', '257'])]:
     for (M, N, K) in shapes:
         for ta, tb in ((0, 0), (0, 1), (1, 0)):
             A = torch.randn(batch, *((K, M) if ta else (M, K)), device="cuda")
