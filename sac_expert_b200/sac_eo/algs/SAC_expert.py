@@ -1,0 +1,105 @@
+"""``SAC_exp`` - SAC with the expert-observation term and the adaptive weight, reference interface
+(``/root/reference/sac_eo/algs/SAC_expert.py``).  ``_update(num_timesteps, expert_reg)`` is the seam the CUDA
+path sits behind; ``expert_reg = (s_expert, a_expert, sp_expert, epsilon_coef, use_expert_actions)`` as built by
+``_expert_preprocess`` (:375-424)."""
+import numpy as np
+import torch
+
+from .SAC import SAC
+from ..common.buffers import TrajectoryBuffer
+from ..common.normalizer import RunningNormalizers
+
+
+class SAC_exp(SAC):
+    def __init__(self, idx, env, env_eval, env_expert, actor, expert, init_expert_rms_stats, v_critic, q_targets,
+                 q_critics, models, alg_kwargs, mf_update_kwargs):
+        self.env_expert, self.expert, self.init_expert_rms_stats = env_expert, expert, init_expert_rms_stats
+        self._kw_pre = alg_kwargs
+        super().__init__(idx, env, env_eval, actor, v_critic, q_targets, q_critics, models, alg_kwargs, mf_update_kwargs)
+        kw = self.alg_kwargs
+        self.scale_epsilon_by_true_MSE, self.use_expert_actions = kw["scale_epsilon_by_true_MSE"], kw["use_expert_actions"]
+        self.scale_max_disc, self.scale_median_disc, self.scale_total_disc = (kw["scale_max_disc"], kw["scale_median_disc"],
+                                                                              kw["scale_total_disc"])
+        self.exp_mult, self.min_mult, self.mult_coeff = kw["exp_mult"], kw["min_mult"], kw["mult_coeff"]
+        self.expert_data = TrajectoryBuffer(self.s_dim, self.a_dim, self.gamma, self.lam, self.expert_buffer_size)
+        self.model_data = TrajectoryBuffer(self.s_dim, self.a_dim, self.gamma, self.lam, int(kw["model_buffer_size"]))
+        self.expert_normalizer = RunningNormalizers(self.s_dim, self.a_dim, self.gamma, init_expert_rms_stats)
+        self.model_MSE_on_expert_data = []
+        self.model_MSE_on_expert_counterfactual_action = []
+        self.expert_reward = 1.0
+        self.B = len(self.models)
+        self._last_expert = None
+
+    def _n_models(self):
+        n = len(self.models)
+        if n < 1:
+            raise ValueError("SAC_exp needs at least one dynamics model")
+        return min(n, 2)                      # only models[0] and models[1] are ever used (:325-326)
+
+    def _expert_rows(self):
+        kw = {**self._kw_pre}
+        e = kw.get("expert_batch_size") or kw.get("expert_buffer_size") or 20
+        return int(e)
+
+    # ------------------------------------------------------------------ hot path
+    def _update(self, num_timesteps, expert_reg):
+        """``SAC_exp._update`` (:463-477)."""
+        s_expert, _, sp_expert, epsilon, _ = expert_reg
+        s_expert, sp_expert = np.asarray(s_expert, np.float32), np.asarray(sp_expert, np.float32)
+        if len(s_expert) != self.pop.spec.E:
+            raise ValueError(f"expert_reg carries {len(s_expert)} rows, the device population was built for {self.pop.spec.E}")
+        key = (id(expert_reg[0]), id(expert_reg[2]), float(epsilon))
+        if key != self._last_expert:          # expert_reg only changes once per episode (:774)
+            self.pop.set_expert(0, s_expert, sp_expert)
+            self.pop.set_hyper(0, eps=float(epsilon))
+            self._last_expert = key
+        self.last_losses = out = self._device_update(num_timesteps, expert_reg)
+        self.logger.log_train({"alpha_loss": out["alpha_loss"], "p_loss": out["p_loss"], "epsilon": epsilon})   # :351-356
+
+    # ------------------------------------------------------------------ adaptive weight (host, once per episode)
+    def _expert_mse_bookkeeping(self):
+        """MSE of the models on the expert transitions with expert actions and with one shared stochastic actor
+        draw (:579-608); feeds ``scale_epsilon_by_true_MSE``."""
+        sE, aE, spE, _ = self.expert_data.get_model_info()
+        mse = lambda pred: float((0.5 * ((np.asarray(pred) - spE) ** 2).sum(-1)).mean())
+        n = self._n_models()
+        on_exp = np.mean([mse(self.models[k].sample(sE, aE, deterministic=True).numpy()) for k in range(n)])
+        self.model_MSE_on_expert_data.append(on_exp)
+        if self.use_expert_actions:
+            cf = on_exp
+        else:
+            a_cf = self.actor.sample(sE, deterministic=False).numpy()
+            cf = np.mean([mse(self.models[k].sample(sE, a_cf, deterministic=True).numpy()) for k in range(n)])
+        self.model_MSE_on_expert_counterfactual_action.append(cf)
+        return on_exp, cf
+
+    def _calc_disc(self, s_expert, a_expert, sp_expert):
+        """Model-disagreement statistics over the expert rows (:427-460)."""
+        if self.use_expert_actions:
+            act = a_expert
+        else:
+            act = self.actor.tf_clip(self.actor.sample(s_expert, deterministic=False)).numpy()
+        p0 = self.models[0].sample(s_expert, act, deterministic=True).numpy()
+        p1 = self.models[1].sample(s_expert, act, deterministic=True).numpy()
+        s_disc = np.linalg.norm(p0 - p1, axis=1)
+        total = float(np.sum(s_disc))
+        return s_disc / total, float(np.max(s_disc)), float(np.median(s_disc)), total
+
+    def _expert_preprocess(self):
+        """``_expert_preprocess`` (:375-424): adaptive expert weight + optional expert minibatch."""
+        eps = self.epsilon
+        s_expert, a_expert, sp_expert, r_expert = self.expert_data.get_model_info()
+        if self.scale_epsilon_by_true_MSE:
+            eps = 1 / (self.epsilon * self.model_MSE_on_expert_counterfactual_action[-1] + 1)
+            cur = self.current_reward
+            if cur > 0:
+                if self.min_mult:
+                    eps = eps * (-min(self.mult_coeff * (cur / self.expert_reward) - 1, 0))
+                if self.exp_mult:
+                    eps = eps * np.exp(-self.mult_coeff * cur / self.expert_reward)
+        elif self.scale_max_disc or self.scale_median_disc or self.scale_total_disc:
+            _, mx, med, tot = self._calc_disc(s_expert, a_expert, sp_expert)
+            eps = 1 / (self.epsilon * (mx if self.scale_max_disc else med if self.scale_median_disc else tot) + 1)
+        if self.expert_batch_size:
+            s_expert, a_expert, sp_expert, r_expert = self.expert_data.get_model_info(batch_size=self.expert_batch_size)
+        return (s_expert, a_expert, sp_expert, eps, self.use_expert_actions)

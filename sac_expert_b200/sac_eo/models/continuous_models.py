@@ -1,0 +1,75 @@
+"""Learned dynamics models with the reference's interface
+(``/root/reference/sac_eo/models/continuous_models.py``, ``base_world_model.py``): ``sample(s, a,
+deterministic=True)`` = ``s + denorm_delta(MLP([norm(s), norm(a)])[:, :S])``.  Inside the SAC-EO update the
+weights are frozen and only the gradient to the action input is needed; model FITTING (``get_loss``) is the
+first "next" row of SURVEY.md §8f and is not built yet."""
+import numpy as np
+import torch
+
+from ..common.device_net import DeviceNet
+from ..common.nn_utils import broadcast_activations, check_two_hidden, create_nn_weights
+from ..envs.synthetic import flatdim
+
+
+class MSEModel(DeviceNet):
+    gaussian = False
+
+    def __init__(self, env, model_layers, model_activations, model_gain, reward_layers, reward_activations,
+                 reward_gain, model_setup_kwargs, std_mult=1.0):
+        super().__init__()
+        self.s_dim, self.a_dim = flatdim(env.observation_space), flatdim(env.action_space)
+        self.layers = check_two_hidden(model_layers)
+        self.activations = broadcast_activations(model_layers, model_activations)
+        self.separate_reward_nn = bool(model_setup_kwargs.get("separate_reward_nn", False))
+        self.delta_clip_pred = model_setup_kwargs.get("delta_clip_pred", None)
+        self.reward_clip_pred = model_setup_kwargs.get("reward_clip_pred", None)
+        out = self.s_dim if self.separate_reward_nn else self.s_dim + 1
+        self._host_weights = create_nn_weights(self.s_dim + self.a_dim, out, self.layers, model_gain)
+        self._reward_weights = (create_nn_weights(self.s_dim + self.a_dim, 1, check_two_hidden(reward_layers), reward_gain)
+                                if self.separate_reward_nn else None)
+        self._logstd = np.ones((1, self.s_dim), np.float32) * np.log(std_mult) if self.gaussian else None
+        self.trainable = ["W0", "b0", "W1", "b1", "W2", "b2"] + (["logstd"] if self.gaussian else [])
+
+    def set_rms(self, normalizer):
+        self._rms = normalizer.get_rms()
+        self.s_rms, self.a_rms, self.r_rms, self.delta_rms, _ = self._rms
+        self._push_rms()
+
+    def _push_rms(self):
+        if self._pop is not None and self._rms is not None:
+            self._pop.set_norm(self._agent, m_s_mean=self.s_rms.mean, m_s_std=self.s_rms.std, m_a_mean=self.a_rms.mean,
+                               m_a_std=self.a_rms.std, m_d_mean=self.delta_rms.mean, m_d_std=self.delta_rms.std)
+
+    def get_weights(self, flat=False):
+        ws = super().get_weights(False)
+        return ws + [self._logstd.copy()] if self.gaussian else ws
+
+    def set_weights(self, weights, from_flat=False, increment=False):
+        if self.gaussian and not from_flat:
+            self._logstd = np.asarray(weights[-1], np.float32)
+            weights = weights[:-1]
+        super().set_weights(weights, from_flat, increment)
+
+    def get_reward_weights(self):
+        return self._reward_weights
+
+    def set_reward_weights(self, weights):
+        if self.separate_reward_nn:
+            self._reward_weights = [np.asarray(w, np.float32) for w in weights]
+
+    def sample(self, s, a, deterministic=True):
+        if self.gaussian and not deterministic:
+            raise NotImplementedError("stochastic GaussianModel rollouts are not on the SAC-EO update path")
+        pop = self._need_device()
+        net = int(self._table[1]) - 1
+        s_, a_ = self._as_rows(s, self.s_dim), self._as_rows(np.asarray(a), self.a_dim)
+        sp = pop.model_eval(torch.from_numpy(s_)[None], torch.from_numpy(a_)[None])
+        out = self._host(sp[0, net])
+        return out[0] if out.shape[0] == 1 else out
+
+    def get_loss(self, s, sp, a, r):
+        raise NotImplementedError("model fitting is SURVEY.md §8f 'next' row 1 (not part of the update hot path)")
+
+
+class GaussianModel(MSEModel):
+    gaussian = True

@@ -1,0 +1,149 @@
+"""GPU: the reference-compatible class interface (init_actor / init_critics / init_world_models / init_alg,
+alg._update) against the oracle, with the NumPy RNG streams consumed exactly like the reference does."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac_eo_oracle import NetCfg, sac_eo_update, to_torch_state
+from sac_expert_b200 import lib as L
+from sac_expert_b200.sac_eo.actors.init_actor import init_actor
+from sac_expert_b200.sac_eo.algs.init_alg import init_alg
+from sac_expert_b200.sac_eo.common.update_utils import cg, make_F
+from sac_expert_b200.sac_eo.critics.init_critic import init_critics
+from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
+from sac_expert_b200.sac_eo.models.init_world_models import init_world_models
+from tests.helpers import rel
+
+pytestmark = pytest.mark.gpu
+
+SETUP = dict(separate_reward_nn=False, reward_loss_coef=1.0, scale_model_loss=False, delta_clip_loss=None,
+             reward_clip_loss=None, delta_clip_pred=None, reward_clip_pred=None)
+
+
+def build_alg(alg_type, S=11, A=3, B=32, E=8, per_state_std=True):
+    np.random.seed(0)
+    env = SyntheticEnv(S, A)
+    actor = init_actor(env, [32, 32], ["relu"], 0.01, 1.0, "orthogonal", False, None, per_state_std, True, False)
+    critics, q_targets, q_critics = init_critics(env, [32, 32], ["relu"], 1.0, None, 2, False, "orthogonal", False)
+    models = init_world_models(env, [48, 48], ["relu"], 0.01, 1.0, None, [48, 48], ["relu"], 0.01, None, 2, False, SETUP)
+    kw = dict(alg_type=alg_type, sac_batch_size=B, expert_buffer_size=E, gamma=0.99, alg_seed=5, epsilon=0.2,
+              device_replay_capacity=1000, gemm_mode=L.GEMM_FP32_SIMT)
+    alg = init_alg(0, env, env, env, actor, critics, q_targets, q_critics, models, kw, {}, None, None)
+    rng = np.random.default_rng(1)
+    n = 300
+    alg.env_data.add(rng.standard_normal((n, S)).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                     rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32),
+                     rng.random(n) < 0.05)
+    return alg, rng
+
+
+def snapshot(alg, cfg):
+    st = dict(actor=alg.actor.get_weights(), q1=alg.q_critics[0].get_weights(), q2=alg.q_critics[1].get_weights(),
+              t1=alg.q_targets[0].get_weights(), t2=alg.q_targets[1].get_weights(), alpha=np.float32(alg.alpha))
+    if cfg.num_models:
+        st["m1"], st["m2"] = alg.models[0].get_weights(), alg.models[1].get_weights()
+    for k in ("q1", "q2", "actor"):
+        st["adam_" + k] = dict(m=[np.zeros_like(w) for w in st[k]], v=[np.zeros_like(w) for w in st[k]], t=0)
+    st["adam_alpha"] = dict(m=np.float32(0), v=np.float32(0), t=0)
+    S, A = cfg.S, cfg.A
+    z, o = (lambda n: np.zeros(n, np.float32)), (lambda n: np.ones(n, np.float32))
+    st.update(s_mean=z(S), s_std=o(S), a_mean=z(A), a_std=o(A), ret_std=np.float32(1), m_s_mean=z(S), m_s_std=o(S),
+              m_a_mean=z(A), m_a_std=o(A), m_d_mean=z(S), m_d_std=o(S), act_limit=o(A))
+    return st
+
+
+@pytest.mark.parametrize("alg_type", ["sac", "sac_imit"])
+def test_alg_update_matches_oracle_with_reference_rng_order(alg_type):
+    S, A, B, E = 11, 3, 32, 8
+    alg, rng = build_alg(alg_type, S, A, B, E)
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48),
+                 num_models=2 if alg_type == "sac_imit" else 0)
+    st = snapshot(alg, cfg)
+    hyper = dict(gamma=0.99, tau=5e-3, lr_q=3e-4, lr_pi=1e-4, lr_alpha=1e-4, eps=0.2, target_entropy=float(-A),
+                 do_polyak=True)
+    expert_reg = None
+    if alg_type == "sac_imit":
+        alg.expert_data.add(rng.standard_normal((E, S)).astype(np.float32), rng.uniform(-1, 1, (E, A)).astype(np.float32),
+                            rng.standard_normal(E).astype(np.float32), rng.standard_normal((E, S)).astype(np.float32),
+                            np.zeros(E, bool))
+        expert_reg = alg._expert_preprocess()
+        assert expert_reg[3] == 0.2 and expert_reg[4] is False
+    # ---- device update, global RNG seeded
+    np.random.seed(123)
+    if expert_reg is None:
+        alg._update(0)
+    else:
+        alg._update(0, expert_reg)
+    # ---- replay the reference's draw order for the oracle
+    np.random.seed(123)
+    idx = np.random.randint(alg.env_data.current_size, size=B)
+    assert np.array_equal(idx, alg.last_idx)
+    u1 = np.random.normal(size=(B, A))
+    batch = dict(idx=idx, s=alg.env_data.s_all[idx], a=alg.env_data.a_all[idx], sp=alg.env_data.sp_all[idx],
+                 r=alg.env_data.r_all[idx], d=alg.env_data.d_all[idx], u1=u1)
+    if expert_reg is not None:
+        order = np.arange(E)
+        np.random.default_rng(5).shuffle(order)           # alg_seed=5 -> self.rng
+        I1, I2 = np.array_split(order, 2)
+        batch.update(I1=I1, I2=I2, sE=expert_reg[0], spE=expert_reg[2])
+    batch["u2"] = np.random.normal(size=(B, A))
+    if expert_reg is not None:
+        batch["u3"], batch["u4"] = np.random.normal(size=(E // 2, A)), np.random.normal(size=(E // 2, A))
+    batch["u5"] = np.random.normal(size=(B, A))
+    o = sac_eo_update(cfg, to_torch_state(st), batch, hyper)
+    assert abs(alg.last_losses["p_loss"] - float(o["p_loss"])) < 1e-4 * max(1, abs(float(o["p_loss"])))
+    assert abs(alg.last_losses["alpha_loss"] - float(o["alpha_loss"])) < 1e-4 * max(1, abs(float(o["alpha_loss"])))
+    for name, net in (("actor", alg.actor), ("q1", alg.q_critics[0]), ("q2", alg.q_critics[1]),
+                      ("t1", alg.q_targets[0]), ("t2", alg.q_targets[1])):
+        for got, new, old in zip(net.get_weights(), o["new"][name], st[name]):
+            d_ref = new.numpy() - old
+            if np.linalg.norm(d_ref) > 0:
+                assert rel(got - old, d_ref) < 1e-3, name
+    assert alg.alpha == pytest.approx(float(o["new"]["alpha"]), rel=1e-5)
+    if expert_reg is not None:
+        assert alg.logger.train_dict["epsilon"] == [0.2]
+
+
+def test_actor_critic_model_forwards_match_oracle():
+    from oracle.sac_eo_oracle import head, model_sample, q_forward, q_value
+    S, A = 11, 3
+    alg, rng = build_alg("sac_imit", S, A)
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48))
+    st = to_torch_state(snapshot(alg, cfg))
+    s = rng.standard_normal((5, S)).astype(np.float32)
+    a = rng.uniform(-1, 1, (5, A)).astype(np.float32)
+    np.random.seed(9)
+    pi, nlp = alg.actor.evaluate(s)
+    np.random.seed(9)
+    u = np.random.normal(size=(5, A))
+    pi_ref, nlp_ref = head(cfg, st["actor"], torch.from_numpy(s), torch.from_numpy(u), st)
+    assert rel(pi.numpy(), pi_ref.numpy()) < 1e-5 and rel(nlp.numpy(), nlp_ref.numpy()) < 1e-5
+    det = alg.actor.sample(s[0], deterministic=True)
+    assert det.shape == (A,)
+    assert rel(alg.q_critics[1]._forward(s, a).numpy(), q_forward(cfg, st["q2"], torch.from_numpy(s), torch.from_numpy(a), st).numpy()) < 1e-5
+    assert rel(alg.q_targets[0].value(s, a).numpy(), q_value(cfg, st["t1"], torch.from_numpy(s), torch.from_numpy(a), st).numpy()) < 1e-5
+    assert rel(alg.models[1].sample(s, a).numpy(), model_sample(cfg, st["m2"], torch.from_numpy(s), torch.from_numpy(a), st).numpy()) < 1e-5
+
+
+def test_make_F_and_cg_interface_on_golden_pendulum_actor():
+    """Reference-shaped call sequence of trpo.py:179-187 on the REAL trained Pendulum actor shipped in the
+    reference's TEMPLOG_0 (tests/golden/pendulum_templog0.npz), against the committed fp64 oracle outputs."""
+    import os
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    pend, gold = np.load(os.path.join(g, "pendulum_templog0.npz")), np.load(os.path.join(g, "golden_pendulum_fvp.npz"))
+    env = SyntheticEnv(3, 1)
+    actor = init_actor(env, [64, 64], ["tanh"], 0.01, 1.0, "orthogonal", False, [pend[f"actor_{i}"] for i in range(7)],
+                       False, True, False)
+
+    class _N:   # normaliser carrying the pickled running statistics
+        def get_rms(self):
+            from sac_expert_b200.sac_eo.common.normalizer import RunningNormalizer
+            r = RunningNormalizer(3); r.mean, r.std = pend["s_mean"], pend["s_std"]
+            return r, None, None, None, None
+    actor.set_rms(_N())
+    F = make_F(actor, gold["states"], trust_sub=1, trust_damp=0.01)
+    assert rel(F(gold["x"]).numpy(), gold["Fx"]) < 1e-3
+    v = cg(F, gold["b"].astype(np.float32), cg_iters=20)
+    vFv = float(np.dot(v, F(v).numpy()))
+    assert rel(v, gold["cg_x"]) < 2e-2            # 20 fp32 CG iterations vs the fp64 oracle
+    assert vFv == pytest.approx(float(gold["vFv"]), rel=2e-2)
