@@ -78,4 +78,4 @@ def dp_update(pop, num_timesteps: int = 0, group=None) -> torch.Tensor:
     g_a.view(pop.spec.n_agents, -1)[:, -1] = last
     pop.update_phase(5, num_timesteps)        # alpha Adam + clamp
     average_(losses, group)
-    return losses
+    return losses.view(pop.spec.n_agents, -1)
