@@ -249,6 +249,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
     CU(cudaMemcpy(k.perm, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   CU(tc_gemm_init());
+  CU(mlp_fwd_tc_init());
   *out = x;
   return 0;
 }
@@ -325,31 +326,59 @@ static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int n
   return 0;
 }
 
-// forward through one population of 3-layer MLPs (nn_utils.py:101-136)
-static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
-                       int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
-                       long long sOa, long long sOn, cudaStream_t st) {
+// forward through one population of 3-layer MLPs (nn_utils.py:101-136), rows [row0, rows), unfused: three GEMMs
+static int mlp_forward_unfused(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
+                               int row0, int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
+                               long long sOa, long long sOn, cudaStream_t st) {
   const int na = x->cfg.n_agents;
   GemmP p{}; p.nnet = n.nnet;
+  const int M = rows - row0;
   // layer 0
-  p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
+  p.A = X + (long long)row0 * ldx; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
   p.B = n.theta + n.oW0(); p.ldb = n.h1; p.sBa = n.sa; p.sBn = n.sn;
   p.bias = n.theta + n.ob0(); p.sba = n.sa; p.sbn = n.sn;
-  p.C = H1; p.ldc = n.h1; p.sCa = (long long)n.nnet * rowsAllocH * n.h1; p.sCn = rowsAllocH * n.h1;
-  p.M = rows; p.N = n.h1; p.K = n.in; p.epi = EPI_ACT; p.act = n.act0;
+  p.C = H1 + (long long)row0 * n.h1; p.ldc = n.h1; p.sCa = (long long)n.nnet * rowsAllocH * n.h1; p.sCn = rowsAllocH * n.h1;
+  p.M = M; p.N = n.h1; p.K = n.in; p.epi = EPI_ACT; p.act = n.act0;
   int rc = gemm(x, false, false, false, p, na, st); if (rc) return rc;
   // layer 1
-  p.A = H1; p.lda = n.h1; p.sAa = p.sCa; p.sAn = p.sCn;
+  p.A = p.C; p.lda = n.h1; p.sAa = p.sCa; p.sAn = p.sCn;
   p.B = n.theta + n.oW1(); p.ldb = n.h2; p.bias = n.theta + n.ob1();
-  p.C = H2; p.ldc = n.h2; p.sCa = (long long)n.nnet * rowsAllocH * n.h2; p.sCn = rowsAllocH * n.h2;
-  p.M = rows; p.N = n.h2; p.K = n.h1; p.act = n.act1;
+  p.C = H2 + (long long)row0 * n.h2; p.ldc = n.h2; p.sCa = (long long)n.nnet * rowsAllocH * n.h2; p.sCn = rowsAllocH * n.h2;
+  p.M = M; p.N = n.h2; p.K = n.h1; p.act = n.act1;
   rc = gemm(x, false, false, false, p, na, st); if (rc) return rc;
   // layer 2 (linear)
-  p.A = H2; p.lda = n.h2; p.sAa = p.sCa; p.sAn = p.sCn;
+  p.A = p.C; p.lda = n.h2; p.sAa = p.sCa; p.sAn = p.sCn;
   p.B = n.theta + n.oW2(); p.ldb = n.out; p.bias = n.theta + n.ob2();
-  p.C = Out; p.ldc = ldo; p.sCa = sOa; p.sCn = sOn;
-  p.M = rows; p.N = n.out; p.K = n.h2; p.epi = EPI_NONE; p.act = ACT_LINEAR;
+  p.C = Out + (long long)row0 * ldo; p.ldc = ldo; p.sCa = sOa; p.sCn = sOn;
+  p.M = M; p.N = n.out; p.K = n.h2; p.epi = EPI_NONE; p.act = ACT_LINEAR;
   return gemm(x, false, false, false, p, na, st);
+}
+
+// Forward pass dispatcher: full 128-row tiles of 2x256 nets go through the fused tcgen05 kernel (activations
+// stay in TMEM between layers; h1/h2 reach HBM only when save_h), leftover rows through the GEMM chain.
+static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
+                       int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
+                       long long sOa, long long sOn, cudaStream_t st, bool save_h = true) {
+  int row0 = 0;
+  if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[1] == 0 &&
+      mlp_fwd_tc_eligible(n.h1, n.h2, n.out, rows, n.theta, n.sa, n.sn, n.in)) {
+    int tiles = rows / TC_BM;
+    if (rows % TC_BM >= 96) tiles += 1;
+    FwdP f{};
+    f.X = X; f.ldx = ldx; f.sXa = sXa; f.sXn = sXn;
+    f.theta = n.theta; f.sTa = n.sa; f.sTn = n.sn;
+    f.H1 = save_h ? H1 : nullptr; f.H2 = save_h ? H2 : nullptr;
+    f.sHa = (long long)n.nnet * rowsAllocH * n.h1; f.sHn = rowsAllocH * n.h1;
+    f.Out = Out; f.ldo = ldo; f.sOa = sOa; f.sOn = sOn;
+    f.rows = tiles * TC_BM < rows ? tiles * TC_BM : rows;
+    f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    dim3 grid(tiles, x->cfg.n_agents * n.nnet);
+    k_mlp_fwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
+    x->launches++;
+    row0 = f.rows;
+    if (row0 >= rows) return 0;
+  }
+  return mlp_forward_unfused(x, n, X, ldx, sXa, sXn, row0, rows, H1, H2, rowsAllocH, Out, ldo, sOa, sOn, st);
 }
 
 // backward through the same MLPs.  grads (nullable): flat [W|b] blocks via the ones-row trick.
@@ -452,10 +481,10 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
   NetD an = actor_net(x), tn = critic_net(x, true), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)B * S, 256), n), 256, 0, st, k, 0);
   rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                   (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+                   (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 0, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
-  rc = mlp_forward(x, tn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  rc = mlp_forward(x, tn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
   LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
   LAUNCH(x, k_stage, dim3(cdiv((long long)B * SA, 256), n), 256, 0, st, k, 1);
   rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
@@ -555,7 +584,7 @@ static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
   const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A;
   NetD an = actor_net(x);
   int rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                       (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+                       (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 2 * B + k.E, 0,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   LAUNCH(x, k_alpha_step, dim3(n), 256, 0, st, k, apply);
@@ -718,7 +747,7 @@ extern "C" int saceo_actor_forward(saceo_ctx* x, const float* obs, int32_t rows,
     LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xpi, k.S,
            (long long)k.R * k.S, 0);
     int rc = mlp_forward(x, an, k.Xpi, k.S, (long long)k.R * k.S, 0, nr, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                         (long long)k.R * k.Ao, 0, st); if (rc) return rc;
+                         (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
     LAUNCH(x, k_head_fwd, dim3(cdiv(nr, 128), n), 128, 0, st, k, nr, nr, noise, (long long)rows * k.A, r0, 0,
            act_out, neglogp_out, (long long)rows, r0);
   }
@@ -738,7 +767,7 @@ extern "C" int saceo_critic_forward(saceo_ctx* x, int32_t which, const float* ob
     LAUNCH(x, k_stage_act, dim3(cdiv((long long)nr * k.A, 256), n), 256, 0, st, k, act, rows, r0, nr, k.Xc, SA,
            (long long)k.B * SA, 0);
     int rc = mlp_forward(x, qn, k.Xc, SA, (long long)k.B * SA, 0, nr, k.cH1, k.cH2, k.B, q_out + r0, 1,
-                         2LL * rows, rows, st); if (rc) return rc;
+                         2LL * rows, rows, st, false); if (rc) return rc;
   }
   if (scale_ret) LAUNCH(x, k_scale_ret, dim3(cdiv(2LL * rows, 256), n), 256, 0, st, k, q_out, rows);
   return check_launch();

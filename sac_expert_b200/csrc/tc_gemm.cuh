@@ -573,3 +573,268 @@ static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, in
 }
 
 }  // namespace saceo
+
+// ==========================================================================================
+// Fused three-layer MLP forward for one (agent, net, 128-row tile):
+//     h1 = act0(X W0 + b0);  h2 = act1(h1 W1 + b1);  out = h2 W2 + b2          (nn_utils.py:101-136)
+// The activation tile never leaves the SM between layers: the fp32 accumulator (TMEM columns [0,256)) is read
+// back with tcgen05.ld, bias + activation are applied, the result is split into bf16 hi/lo and written with
+// tcgen05.st into TMEM columns [256,512) where the next layer's tcgen05.mma reads it as its A operand
+// (A-from-TMEM form).  W1 (the 256 KB that dominates traffic) streams through the cp.async ring; its first two
+// slabs are already in flight while layer 0 runs.  h1 / h2 are written to global memory only when the caller
+// needs them for the backward pass.  Requires hidden = (256, 256), out <= 32.
+// ==========================================================================================
+namespace saceo {
+
+struct FwdP {
+  const float* X; int ldx; long long sXa, sXn;      // input rows [rows, K0]
+  const float* theta; long long sTa, sTn;           // flat nets
+  float* H1; float* H2; long long sHa, sHn;         // optional [rows, 256] outputs (nullable)
+  float* Out; int ldo; long long sOa, sOn;          // [rows, nout]
+  int rows, K0, nout, nnet, act0, act1;
+};
+
+constexpr int FW_H = 256, FW_NT = 512;
+constexpr int FW_R1 = 98304;                         // L0 stage / B stage + patches
+constexpr int FW_R2 = 2 * FW_H * TS_BK * 4;          // raw ring: 2 x 32 KB
+constexpr int FW_MAIN = FW_R1 + FW_R2;
+constexpr int FW_BYTES = FW_MAIN + 1024 + 64;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// hidden-layer epilogue: D (TMEM cols [0,256)) -> bias + act -> [global H] + bf16 hi/lo A operand (TMEM cols 256.., 384..)
+__device__ __forceinline__ void fw_hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ bias, int act,
+                                                   float* __restrict__ Hout, int row0, int rows, int warp, int lane) {
+  const int q = warp & 3, grp = warp >> 2;                 // lane quarter, 64-column group
+  constexpr int PSTR = 36;
+  const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    const int col = grp * 64 + c0;
+    uint32_t v[32];
+    tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + col + 2 * j);
+      float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + col + 2 * j + 1);
+      x0 = apply_act(act, x0); x1 = apply_act(act, x1);
+      v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
+      const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&hp);
+      const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
+      const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
+    tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
+    tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
+    if (Hout) {      // coalesced global write through the warp-private patch
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      __syncwarp();
+      const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int r = rr + lr;
+        const int grow = row0 + q * 32 + r;
+        if (grow < rows) {
+          const float4 t4 = lds128(patch + (uint32_t)(r * PSTR + lc) * 4);
+          *reinterpret_cast<float4*>(Hout + (long long)grow * FW_H + col + lc) = t4;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t r1 = sb, r2 = sb + FW_R1;
+  const uint32_t bars = sb + FW_MAIN;                  // [0],[1] half free, [2] layer0, [3] layer1, [4] layer2
+  const uint32_t tmem_slot = bars + 40;
+  const int z = blockIdx.y;
+  const int agent = z / f.nnet, net = z - agent * f.nnet;
+  const int row0 = blockIdx.x * TC_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ X = f.X + agent * f.sXa + net * f.sXn;
+  const float* __restrict__ th = f.theta + agent * f.sTa + net * f.sTn;
+  const long long oW0 = 0, ob0 = (long long)f.K0 * FW_H, oW1 = ob0 + FW_H, ob1 = oW1 + (long long)FW_H * FW_H,
+                  oW2 = ob1 + FW_H, ob2 = oW2 + (long long)FW_H * f.nout;
+  float* H1 = f.H1 ? f.H1 + agent * f.sHa + net * f.sHn : nullptr;
+  float* H2 = f.H2 ? f.H2 + agent * f.sHa + net * f.sHn : nullptr;
+  float* Out = f.Out + agent * f.sOa + net * f.sOn;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 5; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // W1 slabs 0 and 1 start flying now (ring r2), they are consumed after layer 0 and its epilogue
+  TsPlan<FW_H, false> pw1;
+  pw1.init(th + oW1, 1, FW_H, 0);
+  pw1.issue(r2);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  pw1.issue(r2 + FW_H * TS_BK * 4);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // ---------------- layer 0: D = X . W0   (register-staged slabs, SS MMAs) ----------------
+  Slab<TC_BM, FW_NT> sx;
+  Slab<FW_H, FW_NT> sw;
+  sx.init(X, f.ldx, 1, row0, f.rows);
+  sw.init(th + oW0, 1, FW_H, 0, FW_H);
+  const int nk0 = (f.K0 + TC_BK - 1) / TC_BK;
+  sx.ld(0, f.K0); sw.ld(0, f.K0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = lds_u32(tmem_slot);
+  constexpr uint32_t IDESC = umma_idesc(TC_BM, FW_H);
+  {
+    const uint32_t a_hi = r1, a_lo = r1 + 16384, b_hi = r1 + 32768, b_lo = r1 + 65536;
+    for (int kc = 0; kc < nk0; ++kc) {
+      if (kc > 0) mbar_wait(bars + 16, (uint32_t)((kc - 1) & 1));
+      sx.st(a_hi, a_lo); sw.st(b_hi, b_lo);
+      if (kc + 1 < nk0) { sx.ld((kc + 1) * TC_BK, f.K0); sw.ld((kc + 1) * TC_BK, f.K0); }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 32;
+          umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_hi + ko), IDESC, (kc | kk) ? 1u : 0u);
+          umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_lo + ko), IDESC, 1u);
+          umma_f16(tmem, umma_desc(a_lo + ko), umma_desc(b_hi + ko), IDESC, 1u);
+        }
+        umma_commit(bars + 16);
+      }
+    }
+    mbar_wait(bars + 16, (uint32_t)((nk0 - 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // W2 (tiny) into registers now, staged to smem after layer 1
+  Slab<32, FW_NT> sw2;
+  sw2.init(th + oW2, 1, f.nout, 0, f.nout);
+
+  // ---------------- epilogue 0: h1 ----------------
+  fw_hidden_epilogue(tmem, r1, th + ob0, f.act0, H1, row0, f.rows, warp, lane);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  // ---------------- layer 1: D = h1 . W1   (A from TMEM, W1 streamed) ----------------
+  const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
+  constexpr int NS1 = FW_H / TS_BK;    // 8 slabs
+  for (int j = 0; j < NS1; ++j) {
+    const int h = j & 1;
+    const uint32_t raw = r2 + h * (FW_H * TS_BK * 4);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
+    pw1.convert(raw, h, b_hi, b_lo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (j + 2 < NS1) pw1.issue(raw);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = j * 2 + kk;                            // k16 step inside K = 256
+        const uint32_t ko = (uint32_t)(h * 2 + kk) * 32;
+        const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+        umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
+        umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
+        umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
+      }
+      umma_commit(bars + 8 * h);
+      if (j == NS1 - 1) umma_commit(bars + 24);
+    }
+  }
+  mbar_wait(bars + 24, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---------------- epilogue 1: h2 ; stage W2 ----------------
+  fw_hidden_epilogue(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane);
+  __syncthreads();                                            // patches (r1) no longer read
+  // W2 as B operand: 4 chunks of 64 k, each [32 rows x 128 B] hi plane + lo plane (8 KB per chunk)
+  const uint32_t w2s = r1;
+#pragma unroll 1
+  for (int kc = 0; kc < 4; ++kc) {
+    sw2.ld(kc * TC_BK, FW_H);
+    sw2.st(w2s + kc * 8192, w2s + kc * 8192 + 4096);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  // ---------------- layer 2: D[:, :npad] = h2 . W2 ----------------
+  const int npad = f.nout <= 16 ? 16 : 32;
+  if (threadIdx.x == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc2 = umma_idesc(TC_BM, npad);
+    for (int ks = 0; ks < 16; ++ks) {
+      const uint32_t cb = w2s + (ks >> 2) * 8192 + (ks & 3) * 32;
+      const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+      umma_f16_ts(tmem, ta_hi, umma_desc(cb), idesc2, ks ? 1u : 0u);
+      umma_f16_ts(tmem, ta_hi, umma_desc(cb + 4096), idesc2, 1u);
+      umma_f16_ts(tmem, ta_lo, umma_desc(cb), idesc2, 1u);
+    }
+    umma_commit(bars + 32);
+  }
+  mbar_wait(bars + 32, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 4) {                                             // one warp per lane quarter reads the 32 output columns
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+    const int grow = row0 + warp * 32 + lane;
+    if (grow < f.rows) {
+      for (int n = 0; n < f.nout; ++n) Out[(long long)grow * f.ldo + n] = __uint_as_float(v[n]) + __ldg(th + ob2 + n);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+static inline bool mlp_fwd_tc_eligible(int h1, int h2, int nout, int rows, const float* theta, long long sTa, long long sTn, int K0) {
+  return h1 == FW_H && h2 == FW_H && nout >= 1 && nout <= 32 && rows >= TC_BM && K0 >= 1 &&
+         ((reinterpret_cast<uintptr_t>(theta) & 15) == 0) && ((sTa & 3) == 0) && ((sTn & 3) == 0);
+}
+static inline cudaError_t mlp_fwd_tc_init() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_BYTES);
+  if (e == cudaSuccess) done = true;
+  return e;
+}
+
+}  // namespace saceo

@@ -45,6 +45,7 @@ class PopulationSpec:
     std_mult: float = 1.0
     gemm_mode: int = _l.GEMM_FP32_SIMT
     tc_variant: int = 0            # tcgen05 tile variant (0: 128x256 1 CTA/SM, 1: 128x128 2 CTAs/SM)
+    fuse_forward: bool = True      # fused 3-layer tcgen05 forward (activations resident in TMEM)
     use_graph: bool = False
     device: int = 0
 
@@ -75,6 +76,7 @@ class PopulationSpec:
         c.gemm_mode = self.gemm_mode
         c.use_graph = int(self.use_graph)
         c.reserved[0] = self.tc_variant
+        c.reserved[1] = 0 if self.fuse_forward else 1
         return c
 
 
