@@ -363,7 +363,7 @@ static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lon
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[1] == 0 &&
       mlp_fwd_tc_eligible(n.h1, n.h2, n.out, rows, n.theta, n.sa, n.sn, n.in)) {
     int tiles = rows / TC_BM;
-    if (rows % TC_BM >= 96) tiles += 1;
+    if (rows % TC_BM >= 16) tiles += 1;
     FwdP f{};
     f.X = X; f.ldx = ldx; f.sXa = sXa; f.sXn = sXn;
     f.theta = n.theta; f.sTa = n.sa; f.sTn = n.sn;
@@ -872,6 +872,9 @@ extern "C" int saceo_cg_solve(saceo_ctx* x, const float* b, int32_t iters, float
 // ------------------------------------------------------------------------------------------
 // standalone GEMM self-test surface
 // ------------------------------------------------------------------------------------------
+// test-only: per-CTA phase timestamps of the tcgen05 streaming kernel (dbg = device buffer, 8 u64 per CTA)
+extern "C" int saceo_test_set_tc_debug(void* dbg) { g_tc_dbg = (unsigned long long*)dbg; return 0; }
+
 extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int32_t N, int32_t K, int32_t transA,
                                int32_t transB, const float* A, const float* Bm, float* C, void* stream) {
   if (!A || !Bm || !C || batch < 1) return fail(SACEO_E_INVALID, "bad argument");

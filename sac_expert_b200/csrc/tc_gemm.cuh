@@ -31,6 +31,7 @@ struct TcP {
   GemmP g;
   int m_rows;          // valid rows of op(A) handled by the tensor-core launch
   long long a_sr, a_sk, b_sr, b_sk;   // element strides of op(A)(m,k) and op(B)(k,n): (row=m|n, k)
+  unsigned long long* dbg;            // optional per-CTA phase timestamps (globaltimer ns), 8 per CTA
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -364,6 +365,13 @@ constexpr int TS_APLANE = TC_BM * 128, TS_BPLANE = TS_BN * 128, TS_STAGE = 2 * T
 constexpr int TS_MAIN = 2 * TS_RAW + TS_STAGE;
 constexpr int TS_BYTES = TS_MAIN + 1024 + 64;
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) do { if (q.dbg && threadIdx.x == 0) q.dbg[(size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -437,6 +445,7 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
   const uint32_t bars = sb + TS_MAIN;                              // [2] half free + [1] done
   const uint32_t tmem_slot = bars + 24;
 
+  TC_STAMP(0);
   const GemmP& p = q.g;
   const int z = blockIdx.z;
   const int agent = z / p.nnet, net = z - agent * p.nnet;
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = lds_u32(tmem_slot);
+  TC_STAMP(1);
   constexpr uint32_t IDESC = umma_idesc(TC_BM, TS_BN);
   const uint32_t a_hi = stage, a_lo = stage + TS_APLANE, b_hi = stage + 2 * TS_APLANE, b_lo = b_hi + TS_BPLANE;
 
@@ -496,11 +506,15 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
       if (j == nslab - 1) umma_commit(bars + 16);
     }
   }
+  TC_STAMP(2);
   mbar_wait(bars + 16, 0);
+  TC_STAMP(3);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   tc_epilogue<TS_BN, TS_NT>(q, sb, tmem, agent, net, offC, m0, n0, warp, lane);
+  TC_STAMP(4);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  TC_STAMP(5);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TS_BN) : "memory");
   }
@@ -531,22 +545,27 @@ static inline cudaError_t tc_gemm_init() {
   return cudaSuccess;
 }
 
-// rows of op(A) that go to the tensor-core launch (multiple of 128, or everything when the tail is >= 96 rows)
+// rows of op(A) that go to the tensor-core launch.  The MMA itself is nearly free next to the operand traffic,
+// so a partly empty 128-row tile (zero-filled rows) beats a CUDA-core tail as soon as the tail has >= 16 rows
+// (the E expert rows, [dW0; db0] with S+A rows); only tiny tails (the single ones-row) stay off the tensor core.
 static inline int tc_rows(bool ONES, const GemmP& p) {
   const int mmain = ONES ? p.M - 1 : p.M;
   int tiles = mmain / TC_BM;
-  if (mmain % TC_BM >= 96) tiles += 1;
+  if (mmain % TC_BM >= 16) tiles += 1;
   const int r = tiles * TC_BM;
   return r < mmain ? r : mmain;
 }
 static inline bool tc_gemm_eligible(bool TA, bool TB, bool ONES, const GemmP& p) {
   (void)TA; (void)TB;
-  return p.m_off == 0 && tc_rows(ONES, p) >= TC_BM - 32 && p.N >= 64 && p.K >= 8;
+  const int r = tc_rows(ONES, p);
+  // full tiles always; a lone partial tile only when the weight panel is big enough to amortise a 512-thread CTA
+  return p.m_off == 0 && p.N >= 64 && p.K >= 8 && (r >= 96 || (r >= 16 && (long long)p.N * p.K >= 128 * 128));
 }
 
+static unsigned long long* g_tc_dbg = nullptr;   // set by saceo_test_gemm_timed only
 // launches the tensor-core part (rows [0, tc_rows)); the caller finishes rows [tc_rows, M). <0 on a launch error
 static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, int nagents, int variant, cudaStream_t st) {
-  TcP q; q.g = p;
+  TcP q; q.g = p; q.dbg = g_tc_dbg;
   q.m_rows = tc_rows(ONES, p);
   q.a_sr = TA ? 1 : p.lda; q.a_sk = TA ? p.lda : 1;
   q.b_sr = TB ? p.ldb : 1; q.b_sk = TB ? 1 : p.ldb;
