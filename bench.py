@@ -33,6 +33,7 @@ def parse():
     p.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 bf16x3 (default: best available)")
     p.add_argument("--tc-variant", type=int, default=0)
     p.add_argument("--no-fuse-forward", action="store_true")
+    p.add_argument("--no-fuse-backward", action="store_true")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -170,7 +171,7 @@ def run_b200(a):
     S, A, B = SHAPES[a.shape]
     gemm_mode = a.gemm_mode if a.gemm_mode is not None else lib.GEMM_TCGEN05_BF16X3
     spec = PopulationSpec(n_agents=a.agents, S=S, A=A, B=B, E=20, num_models=0 if a.plain_sac else 2,
-                          replay_capacity=a.replay_rows, gemm_mode=gemm_mode, tc_variant=a.tc_variant, fuse_forward=not a.no_fuse_forward, use_graph=not a.no_graph, device=local)
+                          replay_capacity=a.replay_rows, gemm_mode=gemm_mode, tc_variant=a.tc_variant, fuse_forward=not a.no_fuse_forward, fuse_backward=not a.no_fuse_backward, use_graph=not a.no_graph, device=local)
     pop = Population(spec)
     fill_synthetic(pop, seed=1234 + rank)
 

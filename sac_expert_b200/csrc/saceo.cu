@@ -393,6 +393,23 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   const long long sH2a = (long long)n.nnet * rowsAllocH * n.h2, sH2n = rowsAllocH * n.h2;
   int rc;
   GemmP p{};
+  // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
+  bool fused = false;
+  if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[2] == 0 && n.h1 == FW_H && n.h2 == FW_H &&
+      out_cols >= 1 && out_cols <= 32 && rows >= TC_BM && (rows % TC_BM == 0 || rows % TC_BM >= 16) &&
+      (!dXa || A_cols <= 32) && ((reinterpret_cast<uintptr_t>(n.theta) & 15) == 0) && ((n.sa & 3) == 0) && ((n.sn & 3) == 0)) {
+    BwdP f{};
+    f.dOut = dOut; f.ldd = ldd; f.sDa = sDa; f.sDn = sDn; f.kout = out_cols;
+    f.theta = n.theta; f.sTa = n.sa; f.sTn = n.sn; f.K0 = n.in; f.nout = n.out;
+    f.H1 = H1; f.H2 = H2; f.sHa = sH1a; f.sHn = sH1n;
+    f.dH2 = grads ? dH2 : nullptr; f.dH1 = grads ? dH1 : nullptr;
+    f.dXa = dXa; f.s_cols = S_cols; f.a_cols = A_cols; f.sXa = sXaA; f.sXn = sXaN;
+    f.rows = rows; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    dim3 grid((rows + TC_BM - 1) / TC_BM, na * n.nnet);
+    k_mlp_bwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
+    x->launches++;
+    fused = true;
+  }
   if (grads) {   // [dW2; db2] = [H2,1]^T . dOut
     p = GemmP{}; p.nnet = n.nnet;
     p.A = H2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
@@ -401,6 +418,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.M = n.h2 + 1; p.N = n.out; p.K = rows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
+  if (!fused) {
   // dH2 = (dOut . W2[:, :out_cols]^T) * act1'(H2)
   p = GemmP{}; p.nnet = n.nnet;
   p.A = dOut; p.lda = ldd; p.sAa = sDa; p.sAn = sDn;
@@ -408,6 +426,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   p.C = dH2; p.ldc = n.h2; p.sCa = sH2a; p.sCn = sH2n; p.aux = H2;
   p.M = rows; p.N = n.h2; p.K = out_cols; p.epi = EPI_MUL_DACT; p.act = n.act1;
   rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
+  }
   if (grads) {   // [dW1; db1] = [H1,1]^T . dH2
     p = GemmP{}; p.nnet = n.nnet;
     p.A = H1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
@@ -416,6 +435,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.M = n.h1 + 1; p.N = n.h2; p.K = rows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
+  if (!fused) {
   // dH1 = (dH2 . W1^T) * act0'(H1)
   p = GemmP{}; p.nnet = n.nnet;
   p.A = dH2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
@@ -423,6 +443,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   p.C = dH1; p.ldc = n.h1; p.sCa = sH1a; p.sCn = sH1n; p.aux = H1;
   p.M = rows; p.N = n.h1; p.K = n.h2; p.epi = EPI_MUL_DACT; p.act = n.act0;
   rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
+  }
   if (grads) {   // [dW0; db0] = [X,1]^T . dH1
     p = GemmP{}; p.nnet = n.nnet;
     p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
@@ -431,7 +452,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.M = n.in + 1; p.N = n.h1; p.K = rows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
-  if (dXa) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
+  if (dXa && !fused) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
     p = GemmP{}; p.nnet = n.nnet;
     p.A = dH1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
     p.B = n.theta + n.oW0() + (long long)S_cols * n.h1; p.ldb = n.h1; p.sBa = n.sa; p.sBn = n.sn;

@@ -834,7 +834,232 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
     const int grow = row0 + warp * 32 + lane;
     if (grow < f.rows) {
-      for (int n = 0; n < f.nout; ++n) Out[(long long)grow * f.ldo + n] = __uint_as_float(v[n]) + __ldg(th + ob2 + n);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) if (n < f.nout) Out[(long long)grow * f.ldo + n] = __uint_as_float(v[n]) + __ldg(th + ob2 + n);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// ==========================================================================================
+// Fused backward chain through one (agent, net, 128-row tile) of a 2x256 MLP (weights fixed):
+//     dH2 = (dOut W2[:, :kout]^T) * act1'(H2);  dH1 = (dH2 W1^T) * act0'(H1);  dXa = dH1 W0[S:S+A, :]^T
+// Same structure as the fused forward: the gradient tile stays in TMEM between layers (fp32 accumulator ->
+// tcgen05.ld -> multiply by the activation derivative taken from the SAVED post-activation tile -> bf16 hi/lo
+// -> tcgen05.st -> A operand of the next MMA); W1 streams through the cp.async ring, read K-contiguously
+// (B(n=i, k=j) = W1[i, j]), so no transposed copy of the weights is ever made.  dH2 / dH1 are written to
+// global memory only when the weight-gradient GEMMs need them; for the actor-phase critics (gradient to the
+// action only) nothing but dXa [rows, A] leaves the SM.
+// ==========================================================================================
+struct BwdP {
+  const float* dOut; int ldd; long long sDa, sDn; int kout;   // upstream gradient [rows, >=kout]
+  const float* theta; long long sTa, sTn; int K0, nout;       // flat nets (W2 leading dim = nout)
+  const float* H1; const float* H2; long long sHa, sHn;       // saved activations [rows, 256]
+  float* dH2; float* dH1;                                      // optional outputs, strides as H
+  float* dXa; int s_cols, a_cols; long long sXa, sXn;         // optional [rows, a_cols]
+  int rows, nnet, act0, act1;
+};
+
+// gradient epilogue: D -> * act'(H) -> [global dH] + bf16 hi/lo A operand in TMEM
+__device__ __forceinline__ void bw_hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ Hsaved, int act,
+                                                   float* __restrict__ dHout, int row0, int rows, int warp, int lane) {
+  const int q = warp & 3, grp = warp >> 2;
+  constexpr int PSTR = 36;
+  const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const int grow_own = row0 + q * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    const int col = grp * 64 + c0;
+    uint32_t v[32];
+    tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+    float hv[32];
+    if (grow_own < rows) {
+      const float4* hp = reinterpret_cast<const float4*>(Hsaved + (long long)grow_own * FW_H + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 t4 = __ldg(hp + j); hv[4 * j] = t4.x; hv[4 * j + 1] = t4.y; hv[4 * j + 2] = t4.z; hv[4 * j + 3] = t4.w; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hv[j] = 0.f;
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x0 = __uint_as_float(v[2 * j]) * dact_from_out(act, hv[2 * j]);
+      const float x1 = __uint_as_float(v[2 * j + 1]) * dact_from_out(act, hv[2 * j + 1]);
+      v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
+      const __nv_bfloat162 hp2 = __floats2bfloat162_rn(x0, x1);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&hp2);
+      const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
+      const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
+    tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
+    tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
+    if (dHout) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      __syncwarp();
+      const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int r = rr + lr;
+        const int grow = row0 + q * 32 + r;
+        if (grow < rows) {
+          const float4 t4 = lds128(patch + (uint32_t)(r * PSTR + lc) * 4);
+          *reinterpret_cast<float4*>(dHout + (long long)grow * FW_H + col + lc) = t4;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t r1 = sb, r2 = sb + FW_R1;
+  const uint32_t bars = sb + FW_MAIN;                  // [0],[1] half free, [2] layer2^T, [3] layer1^T, [4] layer0^T
+  const uint32_t tmem_slot = bars + 40;
+  const int z = blockIdx.y;
+  const int agent = z / f.nnet, net = z - agent * f.nnet;
+  const int row0 = blockIdx.x * TC_BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ dOut = f.dOut + agent * f.sDa + net * f.sDn;
+  const float* __restrict__ th = f.theta + agent * f.sTa + net * f.sTn;
+  const long long oW0 = 0, ob0 = (long long)f.K0 * FW_H, oW1 = ob0 + FW_H, ob1 = oW1 + (long long)FW_H * FW_H, oW2 = ob1 + FW_H;
+  const float* H1 = f.H1 + agent * f.sHa + net * f.sHn;
+  const float* H2 = f.H2 + agent * f.sHa + net * f.sHn;
+  float* dH1 = f.dH1 ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
+  float* dH2 = f.dH2 ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 5; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // W1 read K-contiguously as B(n = input index i, k = output index j): first two slabs in flight now
+  TsPlan<FW_H, true> pw1;
+  pw1.init(th + oW1, FW_H, 1, 0);
+  pw1.issue(r2);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  pw1.issue(r2 + FW_H * TS_BK * 4);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // ---------------- layer 2 transposed: D = dOut[:, :kout] . W2[:, :kout]^T  (one 64-wide slab, kout <= 32) ----------------
+  Slab<TC_BM, FW_NT> sx;
+  Slab<FW_H, FW_NT> sw;
+  sx.init(dOut, f.ldd, 1, row0, f.rows);
+  sw.init(th + oW2, f.nout, 1, 0, FW_H);            // B(n = hidden j, k = out c) = W2[j*nout + c]
+  sx.ld(0, f.kout); sw.ld(0, f.kout);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = lds_u32(tmem_slot);
+  constexpr uint32_t IDESC = umma_idesc(TC_BM, FW_H);
+  {
+    const uint32_t a_hi = r1, a_lo = r1 + 16384, b_hi = r1 + 32768, b_lo = r1 + 65536;
+    sx.st(a_hi, a_lo); sw.st(b_hi, b_lo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nks = (f.kout + 15) >> 4;
+      for (int kk = 0; kk < nks; ++kk) {
+        const uint32_t ko = kk * 32;
+        umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_hi + ko), IDESC, kk ? 1u : 0u);
+        umma_f16(tmem, umma_desc(a_hi + ko), umma_desc(b_lo + ko), IDESC, 1u);
+        umma_f16(tmem, umma_desc(a_lo + ko), umma_desc(b_hi + ko), IDESC, 1u);
+      }
+      umma_commit(bars + 16);
+    }
+    mbar_wait(bars + 16, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // action rows of W0 (tiny) into registers now, staged after layer 1^T
+  Slab<32, FW_NT> sw0;
+  if (f.dXa) sw0.init(th + oW0 + (long long)f.s_cols * FW_H, FW_H, 1, 0, f.a_cols);   // B(n = a, k = j) = W0[(S+a)*256 + j]
+
+  bw_hidden_epilogue(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  // ---------------- layer 1 transposed: D = dH2 . W1^T ----------------
+  const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
+  constexpr int NS1 = FW_H / TS_BK;
+  for (int j = 0; j < NS1; ++j) {
+    const int h = j & 1;
+    const uint32_t raw = r2 + h * (FW_H * TS_BK * 4);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
+    pw1.convert(raw, h, b_hi, b_lo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (j + 2 < NS1) pw1.issue(raw);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = j * 2 + kk;
+        const uint32_t ko = (uint32_t)(h * 2 + kk) * 32;
+        const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+        umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
+        umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
+        umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
+      }
+      umma_commit(bars + 8 * h);
+      if (j == NS1 - 1) umma_commit(bars + 24);
+    }
+  }
+  mbar_wait(bars + 24, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  bw_hidden_epilogue(tmem, r1, H1, f.act0, dH1, row0, f.rows, warp, lane);
+  if (f.dXa) {
+    __syncthreads();
+    const uint32_t w0s = r1;
+#pragma unroll 1
+    for (int kc = 0; kc < 4; ++kc) {
+      sw0.ld(kc * TC_BK, FW_H);
+      sw0.st(w0s + kc * 8192, w0s + kc * 8192 + 4096);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const int npad = f.a_cols <= 16 ? 16 : 32;
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t idesc2 = umma_idesc(TC_BM, npad);
+      for (int ks = 0; ks < 16; ++ks) {
+        const uint32_t cb = w0s + (ks >> 2) * 8192 + (ks & 3) * 32;
+        const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+        umma_f16_ts(tmem, ta_hi, umma_desc(cb), idesc2, ks ? 1u : 0u);
+        umma_f16_ts(tmem, ta_hi, umma_desc(cb + 4096), idesc2, 1u);
+        umma_f16_ts(tmem, ta_lo, umma_desc(cb), idesc2, 1u);
+      }
+      umma_commit(bars + 32);
+    }
+    mbar_wait(bars + 32, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+      const int grow = row0 + warp * 32 + lane;
+      if (grow < f.rows) {
+        float* o = f.dXa + agent * f.sXa + net * f.sXn + (long long)grow * f.a_cols;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) if (n < f.a_cols) o[n] = __uint_as_float(v[n]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -852,6 +1077,8 @@ static inline cudaError_t mlp_fwd_tc_init() {
   static bool done = false;
   if (done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_BYTES);
   if (e == cudaSuccess) done = true;
   return e;
 }

@@ -46,6 +46,7 @@ class PopulationSpec:
     gemm_mode: int = _l.GEMM_FP32_SIMT
     tc_variant: int = 0            # tcgen05 tile variant (0: 128x256 1 CTA/SM, 1: 128x128 2 CTAs/SM)
     fuse_forward: bool = True      # fused 3-layer tcgen05 forward (activations resident in TMEM)
+    fuse_backward: bool = True     # fused tcgen05 gradient chain dOut -> dH2 -> dH1 -> dXa
     use_graph: bool = False
     device: int = 0
 
@@ -77,6 +78,7 @@ class PopulationSpec:
         c.use_graph = int(self.use_graph)
         c.reserved[0] = self.tc_variant
         c.reserved[1] = 0 if self.fuse_forward else 1
+        c.reserved[2] = 0 if self.fuse_backward else 1
         return c
 
 
