@@ -371,7 +371,7 @@ static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lon
     f.sHa = (long long)n.nnet * rowsAllocH * n.h1; f.sHn = rowsAllocH * n.h1;
     f.Out = Out; f.ldo = ldo; f.sOa = sOa; f.sOn = sOn;
     f.rows = tiles * TC_BM < rows ? tiles * TC_BM : rows;
-    f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1; f.dbg = g_tc_dbg;
     dim3 grid(tiles, x->cfg.n_agents * n.nnet);
     k_mlp_fwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
     x->launches++;

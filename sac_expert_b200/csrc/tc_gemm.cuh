@@ -611,11 +611,13 @@ struct FwdP {
   float* H1; float* H2; long long sHa, sHn;         // optional [rows, 256] outputs (nullable)
   float* Out; int ldo; long long sOa, sOn;          // [rows, nout]
   int rows, K0, nout, nnet, act0, act1;
+  unsigned long long* dbg;
 };
+#define FW_STAMP(i) do { if (f.dbg && threadIdx.x == 0) f.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
 
 constexpr int FW_H = 256, FW_NT = 512;
 constexpr int FW_R1 = 98304;                         // L0 stage / B stage + patches
-constexpr int FW_R2 = 2 * FW_H * TS_BK * 4;          // raw ring: 2 x 32 KB
+constexpr int FW_R2 = 3 * FW_H * TS_BK * 4;          // raw ring: 3 x 32 KB (slab j+2 is issued before slab j is consumed)
 constexpr int FW_MAIN = FW_R1 + FW_R2;
 constexpr int FW_BYTES = FW_MAIN + 1024 + 64;
 
@@ -642,34 +644,60 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// hidden-layer epilogue: D (TMEM cols [0,256)) -> bias + act -> [global H] + bf16 hi/lo A operand (TMEM cols 256.., 384..)
-__device__ __forceinline__ void fw_hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ bias, int act,
-                                                   float* __restrict__ Hout, int row0, int rows, int warp, int lane) {
+// element-wise part of the hidden epilogues, specialised on the activation so the inner loops are branch-free
+//   FWD: x = act(acc + bias)        BWD: x = acc * act'(h_saved)
+template <int ACT, bool BWD>
+__device__ __forceinline__ void hidden_math(uint32_t (&v)[32], const float (&aux)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+    if (BWD) { x0 *= dact_from_out(ACT, aux[2 * j]); x1 *= dact_from_out(ACT, aux[2 * j + 1]); }
+    else { x0 = apply_act(ACT, x0 + aux[2 * j]); x1 = apply_act(ACT, x1 + aux[2 * j + 1]); }
+    v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+    hi[j] = *reinterpret_cast<const uint32_t*>(&hp);
+    const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+    lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+}
+template <bool BWD>
+__device__ __forceinline__ void hidden_math_dispatch(int act, uint32_t (&v)[32], const float (&aux)[32], uint32_t (&hi)[16],
+                                                     uint32_t (&lo)[16]) {
+  if (act == ACT_RELU) hidden_math<ACT_RELU, BWD>(v, aux, hi, lo);
+  else if (act == ACT_TANH) hidden_math<ACT_TANH, BWD>(v, aux, hi, lo);
+  else hidden_math<ACT_ELU, BWD>(v, aux, hi, lo);
+}
+
+// hidden epilogue (forward and backward): D (TMEM cols [0,256)) -> element-wise op -> [global tile] + bf16 hi/lo A
+// operand (TMEM cols 256.., 384..).  FWD: aux = bias[col..col+31] (same for every row); BWD: aux = saved H[row][col..].
+template <bool BWD>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ auxp, int act,
+                                                float* __restrict__ Gout, int row0, int rows, int warp, int lane) {
   const int q = warp & 3, grp = warp >> 2;                 // lane quarter, 64-column group
   constexpr int PSTR = 36;
   const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const int grow_own = row0 + q * 32 + lane;
 #pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 32) {
     const int col = grp * 64 + c0;
+    float aux[32];
+    if (!BWD || grow_own < rows) {
+      const float4* ap = reinterpret_cast<const float4*>(BWD ? auxp + (long long)grow_own * FW_H + col : auxp + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 t4 = __ldg(ap + j); aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) aux[j] = 0.f;
+    }
     uint32_t v[32];
     tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
     uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + col + 2 * j);
-      float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + col + 2 * j + 1);
-      x0 = apply_act(act, x0); x1 = apply_act(act, x1);
-      v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
-      const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
-      hi[j] = *reinterpret_cast<const uint32_t*>(&hp);
-      const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
-      const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
-      lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
-    }
+    hidden_math_dispatch<BWD>(act, v, aux, hi, lo);
     tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
     tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
-    if (Hout) {      // coalesced global write through the warp-private patch
+    if (Gout) {      // coalesced global write through the warp-private patch
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       __syncwarp();
@@ -680,7 +708,7 @@ __device__ __forceinline__ void fw_hidden_epilogue(uint32_t tmem, uint32_t patch
         const int grow = row0 + q * 32 + r;
         if (grow < rows) {
           const float4 t4 = lds128(patch + (uint32_t)(r * PSTR + lc) * 4);
-          *reinterpret_cast<float4*>(Hout + (long long)grow * FW_H + col + lc) = t4;
+          *reinterpret_cast<float4*>(Gout + (long long)grow * FW_H + col + lc) = t4;
         }
       }
       __syncwarp();
@@ -695,6 +723,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   const uint32_t r1 = sb, r2 = sb + FW_R1;
   const uint32_t bars = sb + FW_MAIN;                  // [0],[1] half free, [2] layer0, [3] layer1, [4] layer2
   const uint32_t tmem_slot = bars + 40;
+  FW_STAMP(0);
   const int z = blockIdx.y;
   const int agent = z / f.nnet, net = z - agent * f.nnet;
   const int row0 = blockIdx.x * TC_BM;
@@ -758,29 +787,41 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
     mbar_wait(bars + 16, (uint32_t)((nk0 - 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  // W2 (tiny) into registers now, staged to smem after layer 1
-  Slab<32, FW_NT> sw2;
-  sw2.init(th + oW2, 1, f.nout, 0, f.nout);
+  FW_STAMP(1);
+  // W2 (tiny): four 64-k slabs, loaded into registers before epilogue 1 and staged to smem after it
+  Slab<32, FW_NT> sw2[4];
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) sw2[kc].init(th + oW2, 1, f.nout, 0, f.nout);
 
   // ---------------- epilogue 0: h1 ----------------
-  fw_hidden_epilogue(tmem, r1, th + ob0, f.act0, H1, row0, f.rows, warp, lane);
+  hidden_epilogue<false>(tmem, r1, th + ob0, f.act0, H1, row0, f.rows, warp, lane);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 
+  FW_STAMP(2);
   // ---------------- layer 1: D = h1 . W1   (A from TMEM, W1 streamed) ----------------
   const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
   constexpr int NS1 = FW_H / TS_BK;    // 8 slabs
+  unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};
   for (int j = 0; j < NS1; ++j) {
     const int h = j & 1;
-    const uint32_t raw = r2 + h * (FW_H * TS_BK * 4);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const uint32_t raw = r2 + (j % 3) * (FW_H * TS_BK * 4);
+    unsigned long long c0 = clock64();
+    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // buffer of slab j-1: free since last iteration
+    asm volatile("cp.async.commit_group;" ::: "memory");       // (possibly empty) keeps the group count uniform
+    unsigned long long c1 = clock64();
+    asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
+    unsigned long long c2 = clock64();
     __syncthreads();
+    unsigned long long c3 = clock64();
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
+    unsigned long long c4 = clock64();
     pw1.convert(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    unsigned long long c5 = clock64();
     __syncthreads();
-    if (j + 2 < NS1) pw1.issue(raw);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    unsigned long long c6 = clock64();
+    tacc[0] += c1 - c0; tacc[1] += c2 - c1; tacc[2] += c3 - c2; tacc[3] += c4 - c3; tacc[4] += c5 - c4; tacc[5] += c6 - c5;
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -796,23 +837,27 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
       if (j == NS1 - 1) umma_commit(bars + 24);
     }
   }
+  if (f.dbg && threadIdx.x == 32) {
+    for (int i = 0; i < 6; ++i) f.dbg[(size_t)(gridDim.x * gridDim.y) * 8 + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + i] = tacc[i];
+  }
   mbar_wait(bars + 24, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+  FW_STAMP(3);
   // ---------------- epilogue 1: h2 ; stage W2 ----------------
-  fw_hidden_epilogue(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane);
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) sw2[kc].ld(kc * TC_BK, FW_H);      // in flight during the epilogue
+  hidden_epilogue<false>(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane);
   __syncthreads();                                            // patches (r1) no longer read
   // W2 as B operand: 4 chunks of 64 k, each [32 rows x 128 B] hi plane + lo plane (8 KB per chunk)
   const uint32_t w2s = r1;
-#pragma unroll 1
-  for (int kc = 0; kc < 4; ++kc) {
-    sw2.ld(kc * TC_BK, FW_H);
-    sw2.st(w2s + kc * 8192, w2s + kc * 8192 + 4096);
-  }
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) sw2[kc].st(w2s + kc * 8192, w2s + kc * 8192 + 4096);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 
+  FW_STAMP(4);
   // ---------------- layer 2: D[:, :npad] = h2 . W2 ----------------
   const int npad = f.nout <= 16 ? 16 : 32;
   if (threadIdx.x == 0) {
@@ -829,6 +874,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   }
   mbar_wait(bars + 32, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  FW_STAMP(5);
   if (warp < 4) {                                             // one warp per lane quarter reads the 32 output columns
     uint32_t v[32];
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
@@ -840,6 +886,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  FW_STAMP(6);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
@@ -863,62 +910,6 @@ struct BwdP {
   float* dXa; int s_cols, a_cols; long long sXa, sXn;         // optional [rows, a_cols]
   int rows, nnet, act0, act1;
 };
-
-// gradient epilogue: D -> * act'(H) -> [global dH] + bf16 hi/lo A operand in TMEM
-__device__ __forceinline__ void bw_hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ Hsaved, int act,
-                                                   float* __restrict__ dHout, int row0, int rows, int warp, int lane) {
-  const int q = warp & 3, grp = warp >> 2;
-  constexpr int PSTR = 36;
-  const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
-  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const int grow_own = row0 + q * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 64; c0 += 32) {
-    const int col = grp * 64 + c0;
-    uint32_t v[32];
-    tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
-    float hv[32];
-    if (grow_own < rows) {
-      const float4* hp = reinterpret_cast<const float4*>(Hsaved + (long long)grow_own * FW_H + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float4 t4 = __ldg(hp + j); hv[4 * j] = t4.x; hv[4 * j + 1] = t4.y; hv[4 * j + 2] = t4.z; hv[4 * j + 3] = t4.w; }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) hv[j] = 0.f;
-    }
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float x0 = __uint_as_float(v[2 * j]) * dact_from_out(act, hv[2 * j]);
-      const float x1 = __uint_as_float(v[2 * j + 1]) * dact_from_out(act, hv[2 * j + 1]);
-      v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
-      const __nv_bfloat162 hp2 = __floats2bfloat162_rn(x0, x1);
-      hi[j] = *reinterpret_cast<const uint32_t*>(&hp2);
-      const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
-      const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
-      lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
-    }
-    tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
-    tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
-    if (dHout) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-      __syncwarp();
-      const int lr = lane >> 3, lc = (lane & 7) * 4;
-#pragma unroll
-      for (int rr = 0; rr < 32; rr += 4) {
-        const int r = rr + lr;
-        const int grow = row0 + q * 32 + r;
-        if (grow < rows) {
-          const float4 t4 = lds128(patch + (uint32_t)(r * PSTR + lc) * 4);
-          *reinterpret_cast<float4*>(dHout + (long long)grow * FW_H + col + lc) = t4;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   extern __shared__ uint8_t smem_raw[];
@@ -985,10 +976,13 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   // action rows of W0 (tiny) into registers now, staged after layer 1^T
-  Slab<32, FW_NT> sw0;
-  if (f.dXa) sw0.init(th + oW0 + (long long)f.s_cols * FW_H, FW_H, 1, 0, f.a_cols);   // B(n = a, k = j) = W0[(S+a)*256 + j]
+  Slab<32, FW_NT> sw0[4];
+  if (f.dXa) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) sw0[kc].init(th + oW0 + (long long)f.s_cols * FW_H, FW_H, 1, 0, f.a_cols);   // B(n = a, k = j) = W0[(S+a)*256 + j]
+  }
 
-  bw_hidden_epilogue(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane);
+  hidden_epilogue<true>(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 
@@ -997,15 +991,15 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   constexpr int NS1 = FW_H / TS_BK;
   for (int j = 0; j < NS1; ++j) {
     const int h = j & 1;
-    const uint32_t raw = r2 + h * (FW_H * TS_BK * 4);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const uint32_t raw = r2 + (j % 3) * (FW_H * TS_BK * 4);
+    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // buffer of slab j-1: free since last iteration
+    asm volatile("cp.async.commit_group;" ::: "memory");       // (possibly empty) keeps the group count uniform
+    asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
     __syncthreads();
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
     pw1.convert(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (j + 2 < NS1) pw1.issue(raw);
-    asm volatile("cp.async.commit_group;" ::: "memory");
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -1024,15 +1018,16 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   mbar_wait(bars + 24, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  bw_hidden_epilogue(tmem, r1, H1, f.act0, dH1, row0, f.rows, warp, lane);
+  if (f.dXa) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) sw0[kc].ld(kc * TC_BK, FW_H);
+  }
+  hidden_epilogue<true>(tmem, r1, H1, f.act0, dH1, row0, f.rows, warp, lane);
   if (f.dXa) {
     __syncthreads();
     const uint32_t w0s = r1;
-#pragma unroll 1
-    for (int kc = 0; kc < 4; ++kc) {
-      sw0.ld(kc * TC_BK, FW_H);
-      sw0.st(w0s + kc * 8192, w0s + kc * 8192 + 4096);
-    }
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) sw0[kc].st(w0s + kc * 8192, w0s + kc * 8192 + 4096);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
