@@ -27,7 +27,7 @@ struct KCtx {
   float *Xm, *mH1, *mH2, *mOut, *mdOut, *mdH2, *mdH1, *mdXa;
   float *y, *nlp;
   float *g_q, *g_actor;
-  float *lrt, *losses;
+  float *lrt, *losses, *mse_part;
   unsigned long long* step_ctr;
   // expert rows actually used (bound table or host-staged copy)
   const float *expert_s, *expert_sp;
@@ -380,7 +380,7 @@ __global__ void k_model_loss(KCtx c) {
     c.mdOut[(((long long)agent * 2 + net) * E + il) * S + j] = (-err * inv * eps) * sd * cm;
   }
   acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) c.losses[(long long)agent * c.L.n_losses + 3] = acc * inv;
+  if (threadIdx.x == 0) { c.mse_part[agent * 2] = acc * inv; c.mse_part[agent * 2 + 1] = 0.f; }
 }
 
 // head backward: dL/d(out) from dL/d(pi) and dL/d(neglogp).  One thread per row.
@@ -484,6 +484,7 @@ __global__ void k_alpha_step(KCtx c, int apply) {
     const float g = -mean_term;
     ls[5] = -alpha * mean_term;
     const float eps = hy[5];
+    if (c.nmod > 0) ls[3] = c.mse_part[agent * 2] + (c.nmod == 2 ? c.mse_part[agent * 2 + 1] : 0.f);   // fixed order
     ls[4] = c.nmod > 0 ? (1.f - eps) * ls[2] + eps * ls[3] : ls[2];
     ls[7] = eps;
     c.g_actor[(long long)agent * c.L.na_stride + c.L.na_stride - 1] = g;   // last padded word: g_alpha (DP all-reduce rides along)

@@ -15,6 +15,7 @@
 #include "elem.cuh"
 #include "fvp.cuh"
 #include "tc_gemm.cuh"
+#include "model_term.cuh"
 
 using namespace saceo;
 
@@ -169,6 +170,7 @@ static void carve(saceo_ctx* x, char* base) {
   k.g_actor = b.get<float>("g_actor", n * L.na_stride);
   k.lrt = b.get<float>("lrt", n * 4);
   k.losses = b.get<float>("losses", n * L.n_losses);
+  k.mse_part = b.get<float>("mse_part", n * 2);
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
   x->exp_stage = b.get<float>("exp_stage", n * 2 * e1 * S);
   x->idx_stage = b.get<long long>("idx_stage", n * B);
@@ -250,6 +252,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   }
   CU(tc_gemm_init());
   CU(mlp_fwd_tc_init());
+  CU(model_term_init());
   *out = x;
   return 0;
 }
@@ -538,7 +541,11 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
   rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                     k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
   if (rc) return rc;
-  if (k.nmod > 0) {
+  if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
+    // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
+    if (model_term_launch(k, k.mse_part, st) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
+    x->launches++;
+  } else if (k.nmod > 0) {
     const int half = k.nmod == 2 ? E / 2 : E;
     NetD mn = model_net(x, k.nmod);
     // model buffers are laid out [agent][2][E rows]; net strides are fixed at E rows regardless of nmod

@@ -47,6 +47,7 @@ class PopulationSpec:
     tc_variant: int = 0            # tcgen05 tile variant (0: 128x256 1 CTA/SM, 1: 128x128 2 CTAs/SM)
     fuse_forward: bool = True      # fused 3-layer tcgen05 forward (activations resident in TMEM)
     fuse_backward: bool = True     # fused tcgen05 gradient chain dOut -> dH2 -> dH1 -> dXa
+    fuse_model: bool = True        # fused expert-observation term (model forward + MSE + backward to action)
     use_graph: bool = False
     device: int = 0
 
@@ -79,6 +80,7 @@ class PopulationSpec:
         c.reserved[0] = self.tc_variant
         c.reserved[1] = 0 if self.fuse_forward else 1
         c.reserved[2] = 0 if self.fuse_backward else 1
+        c.reserved[3] = 0 if self.fuse_model else 1
         return c
 
 
