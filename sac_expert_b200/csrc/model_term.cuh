@@ -14,7 +14,7 @@ namespace saceo {
 constexpr int MT_THREADS = 512;
 
 template <int MS>
-__global__ void __launch_bounds__(MT_THREADS) k_model_term(KCtx c, float* __restrict__ mse_part) {
+__global__ void __launch_bounds__(MT_THREADS, 2) k_model_term(KCtx c, float* __restrict__ mse_part) {
   extern __shared__ float msm[];
   const int net = blockIdx.x, agent = blockIdx.y;
   const int S = c.S, A = c.A, SA = S + A, H1 = c.mh1, H2 = c.mh2, mo = c.mo, E = c.E;
@@ -162,16 +162,22 @@ __global__ void __launch_bounds__(MT_THREADS) k_model_term(KCtx c, float* __rest
   }
   __syncthreads();
   // ---- layer 1 transposed: one warp per input index i, lanes walk the contiguous W1 row ------
-  for (int i = warp; i < H1; i += nwarp) {
-    float acc[MS];
+  for (int i = warp; i < H1; i += 2 * nwarp) {
+    const int i2 = i + nwarp;                         // second output index handled in the same pass
+    const bool has2 = i2 < H1;
+    float acc[MS], acc2[MS];
 #pragma unroll
-    for (int r = 0; r < MS; ++r) acc[r] = 0.f;
+    for (int r = 0; r < MS; ++r) { acc[r] = 0.f; acc2[r] = 0.f; }
     const float* wrow = W1 + (long long)i * H2;
+    const float* wrow2 = W1 + (long long)(has2 ? i2 : i) * H2;
     for (int j0 = lane * 4; j0 < H2; j0 += 512) {
-      float4 w[4];
+      float4 w[4], w2[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        w[u] = (j0 + 128 * u < H2) ? __ldg(reinterpret_cast<const float4*>(wrow + j0 + 128 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = j0 + 128 * u < H2;
+        w[u] = ok ? __ldg(reinterpret_cast<const float4*>(wrow + j0 + 128 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w2[u] = ok ? __ldg(reinterpret_cast<const float4*>(wrow2 + j0 + 128 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (j0 + 128 * u < H2) {
@@ -180,15 +186,20 @@ __global__ void __launch_bounds__(MT_THREADS) k_model_term(KCtx c, float* __rest
             const float4 g = *reinterpret_cast<const float4*>(h2 + r * H2 + j0 + 128 * u);
             acc[r] = fmaf(g.x, w[u].x, acc[r]); acc[r] = fmaf(g.y, w[u].y, acc[r]);
             acc[r] = fmaf(g.z, w[u].z, acc[r]); acc[r] = fmaf(g.w, w[u].w, acc[r]);
+            acc2[r] = fmaf(g.x, w2[u].x, acc2[r]); acc2[r] = fmaf(g.y, w2[u].y, acc2[r]);
+            acc2[r] = fmaf(g.z, w2[u].z, acc2[r]); acc2[r] = fmaf(g.w, w2[u].w, acc2[r]);
           }
         }
       }
     }
 #pragma unroll
     for (int r = 0; r < MS; ++r) {
-      float v = acc[r];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) h1[r * H1 + i] = v * dact_from_out(c.mact0, h1[r * H1 + i]);     // only this warp touches column i
+      float v = acc[r], v2 = acc2[r];
+      for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); v2 += __shfl_xor_sync(0xffffffffu, v2, o); }
+      if (lane == 0) {
+        h1[r * H1 + i] = v * dact_from_out(c.mact0, h1[r * H1 + i]);     // only this warp touches columns i, i2
+        if (has2) h1[r * H1 + i2] = v2 * dact_from_out(c.mact0, h1[r * H1 + i2]);
+      }
     }
   }
   __syncthreads();
