@@ -211,7 +211,7 @@ def run_b200(a):
     # ---- end-to-end through the host-buffer API ("e2e") -------------------------------------
     rng = np.random.default_rng(7 + rank)
     sizes = pop._host_size
-    expert = np.concatenate([pop.t["expert_s"].cpu().numpy()[:, None], pop.t["expert_sp"].cpu().numpy()[:, None]], 1) \
+    expert = np.stack([pop.t["expert_s"].cpu().numpy(), pop.t["expert_sp"].cpu().numpy()], 0) \
         if spec.num_models > 0 else None
     e2e_steps = max(3, min(a.steps, 20))
     for w in range(2):

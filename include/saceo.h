@@ -81,7 +81,9 @@ typedef struct saceo_config {
   float   std_mult;           /* --actor_std_mult, only used by the GaussianActor._forward (CG) path */
   int32_t gemm_mode;          /* SACEO_GEMM_* */
   int32_t use_graph;          /* capture one update into a CUDA graph and replay it */
-  int32_t reserved[8];
+  int32_t reserved[8];        /* tuning switches, 0 = default: [0] tcgen05 tile variant (0: 128x256 tile, 1: 128x128 2 CTAs/SM,
+                                 2: force the register-staged kernel); [1] != 0 disables the fused 3-layer forward kernel;
+                                 [2] != 0 disables the fused backward-chain kernel; [3] != 0 disables the fused model-term kernel */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */
@@ -162,7 +164,7 @@ int saceo_update(saceo_ctx *ctx, int32_t n_steps, int64_t num_timesteps, int32_t
                  uint64_t seed, float *losses_out, void *stream);
 
 /* Same, through HOST buffers (the call the Python `_update` makes per step): copies idx_host
- * [n,B] int64 (may be NULL => device RNG) and expert_host [n, 2, E, S] f32 (sE then s'E; may be
+ * [n,B] int64 (may be NULL => device RNG) and expert_host [2, n, E, S] f32 (all sE rows, then all s'E rows; may be
  * NULL => keep bound tables) host->device, runs one update, copies losses [n, n_losses] back into
  * losses_host and synchronises the stream. */
 int saceo_update_host(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,

@@ -688,13 +688,8 @@ extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t s
   cudaStream_t st = (cudaStream_t)stream; KCtx& k = x->k;
   if (expert_host && k.E > 0) {
     const long long ne = (long long)k.n_agents * k.E * k.S;
-    // host layout [n, 2, E, S] -> two device planes
-    for (int a = 0; a < k.n_agents; ++a) {
-      CU(cudaMemcpyAsync(x->exp_stage + (long long)a * k.E * k.S, expert_host + (long long)a * 2 * k.E * k.S,
-                         sizeof(float) * k.E * k.S, cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(x->exp_stage + ne + (long long)a * k.E * k.S, expert_host + ((long long)a * 2 + 1) * k.E * k.S,
-                         sizeof(float) * k.E * k.S, cudaMemcpyHostToDevice, st));
-    }
+    // host layout [2, n, E, S] (all sE rows, then all s'E rows): one contiguous copy, two device planes
+    CU(cudaMemcpyAsync(x->exp_stage, expert_host, sizeof(float) * 2 * ne, cudaMemcpyHostToDevice, st));
     if (k.expert_s != x->exp_stage) {
       k.expert_s = x->exp_stage; k.expert_sp = x->exp_stage + ne;
       for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)

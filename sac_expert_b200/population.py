@@ -349,7 +349,7 @@ class Population:
             ip = self._pin_idx.data_ptr()
         if expert_host is not None:
             if self._pin_exp is None:
-                self._pin_exp = torch.empty(n, 2, sp_.E, sp_.S, pin_memory=True)
+                self._pin_exp = torch.empty(2, n, sp_.E, sp_.S, pin_memory=True)
             self._pin_exp.numpy()[...] = expert_host
             ep = self._pin_exp.data_ptr()
         st = self._enter()
