@@ -155,9 +155,10 @@ int saceo_set_draws(saceo_ctx *ctx, const int64_t *idx, const float *noise,
                     const int32_t *expert_perm, void *stream);
 
 /* SAC_exp._update / SAC._update (SAC_expert.py:463-477, SAC.py:236-250) for every agent,
- * n_steps times.  use_device_rng != 0: idx/noise/permutation are drawn in-kernel (Philox4x32-10
- * keyed by seed, agent, step) before each step; otherwise the draws last injected with
- * saceo_set_draws() are consumed (n_steps should then be 1).  num_timesteps gates the Polyak
+ * n_steps times.  use_device_rng = 1: idx/noise/permutation are drawn in-kernel (Philox4x32-10
+ * keyed by seed, agent, step) before each step; 2: only noise and permutation are drawn in-kernel, the
+ * minibatch indices already in the context (set_draws / update_host) are kept; 0: the draws last injected
+ * with saceo_set_draws() are consumed (n_steps should then be 1).  num_timesteps gates the Polyak
  * update of step i on (num_timesteps + i) % target_update_int == 0.  losses_out (device,
  * [n_agents, n_losses], may be NULL) receives the values of the LAST step. */
 int saceo_update(saceo_ctx *ctx, int32_t n_steps, int64_t num_timesteps, int32_t use_device_rng,

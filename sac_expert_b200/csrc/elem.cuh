@@ -82,7 +82,7 @@ __global__ void k_step_begin(KCtx c, int advance_rng) {
 // in-kernel draws (perf mode): idx, noise, expert permutation.  grid: (ceil(max_items/256), n_agents)
 // ------------------------------------------------------------------------------------------
 __global__ void k_set_seed(KCtx c, unsigned long long seed) { c.step_ctr[1] = seed; }
-__global__ void k_rng_fill(KCtx c) {
+__global__ void k_rng_fill(KCtx c, int skip_idx) {
   const unsigned long long seed = c.step_ctr[1];
   const int agent = blockIdx.y;
   const unsigned step = (unsigned)c.step_ctr[0];
@@ -92,7 +92,7 @@ __global__ void k_rng_fill(KCtx c) {
   const int n_noise = (3 * c.B + c.E) * c.A;
   const int n_noise4 = (n_noise + 3) / 4;
   uint32_t r[4];
-  if (q < n_idx4) {
+  if (q < n_idx4 && !skip_idx) {      // skip_idx: the minibatch indices come from the host (np.random.randint)
     Philox::gen(seed, (uint32_t)q, (uint32_t)agent, step, 0u, r);
     for (int j = 0; j < 4; ++j) {
       const int b = 4 * q + j;

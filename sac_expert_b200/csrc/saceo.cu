@@ -59,8 +59,8 @@ struct saceo_ctx {
   float *exp_stage = nullptr;          // [n, 2, E, S] host-staged expert rows
   long long* idx_stage = nullptr;
   long long launches = 0;
-  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [rng][polyak]
-  long long graph_nodes[2][2] = {{0, 0}, {0, 0}};
+  cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [rng mode][polyak]
+  long long graph_nodes[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 };
 
 #define LAUNCH(ctx, kern, grid, block, smem, st, ...) do { \
@@ -259,7 +259,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
 
 extern "C" int saceo_destroy(saceo_ctx* x) {
   if (!x) return 0;
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
   if (x->ws) cudaFree(x->ws);
   delete x;
   return 0;
@@ -275,7 +275,7 @@ extern "C" int saceo_bind(saceo_ctx* x, const saceo_tables* t) {
   x->k.T = *t;
   x->k.expert_s = t->expert_s; x->k.expert_sp = t->expert_sp;
   x->bound = true;
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j)
     if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
   return 0;
 }
@@ -625,7 +625,7 @@ static int step_once(saceo_ctx* x, int use_rng, int do_polyak, cudaStream_t st) 
   LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, use_rng);
   if (use_rng) {
     const int items = ((3 * k.B + k.E) * k.A + 3) / 4;
-    LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k);
+    LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k, use_rng == 2 ? 1 : 0);
   }
   if ((rc = phase_gather(x, st))) return rc;
   if ((rc = phase_critic_grads(x, st))) return rc;
@@ -652,7 +652,7 @@ extern "C" int saceo_update(saceo_ctx* x, int32_t n_steps, int64_t num_timesteps
   if (!x->k.T.replay || !x->k.T.replay_size) return fail(SACEO_E_UNBOUND, "replay tables are not bound");
   if (n_steps < 1) return fail(SACEO_E_INVALID, "n_steps must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
-  const int rng = use_device_rng ? 1 : 0;
+  const int rng = use_device_rng == 2 ? 2 : (use_device_rng ? 1 : 0);   // 2: device noise/permutation, indices already in place
   if (rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, x->k, (unsigned long long)seed);
   for (int i = 0; i < n_steps; ++i) {
     const int pol = ((num_timesteps + i) % x->cfg.target_update_int) == 0 ? 1 : 0;
@@ -692,31 +692,15 @@ extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t s
     CU(cudaMemcpyAsync(x->exp_stage, expert_host, sizeof(float) * 2 * ne, cudaMemcpyHostToDevice, st));
     if (k.expert_s != x->exp_stage) {
       k.expert_s = x->exp_stage; k.expert_sp = x->exp_stage + ne;
-      for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j)
         if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
     }
   }
-  int rng = 1;
-  if (idx_host) {
-    CU(cudaMemcpyAsync(k.idx, idx_host, sizeof(long long) * k.n_agents * k.B, cudaMemcpyHostToDevice, st));
-    rng = 2;   // host indices, device noise/permutation
-  }
   int rc;
-  if (rng == 2) {
-    // noise + permutation from the device generator, indices from the host: run the generator first,
-    // then overwrite idx (stream order keeps the host copy last)
-    LAUNCH(x, k_set_seed, 1, 1, 0, st, k, (unsigned long long)seed);
-    const int pol = (num_timesteps % x->cfg.target_update_int) == 0 ? 1 : 0;
-    LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, 1);
-    const int items = ((3 * k.B + k.E) * k.A + 3) / 4;
-    LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k);
+  if (idx_host) {
+    // host indices (np.random.randint, buffers.py:135) + device noise / expert shuffle
     CU(cudaMemcpyAsync(k.idx, idx_host, sizeof(long long) * k.n_agents * k.B, cudaMemcpyHostToDevice, st));
-    if ((rc = phase_gather(x, st))) return rc;
-    if ((rc = phase_critic_grads(x, st))) return rc;
-    if ((rc = phase_critic_apply(x, pol, st))) return rc;
-    if ((rc = phase_actor_grads(x, st))) return rc;
-    if ((rc = phase_actor_apply(x, st))) return rc;
-    if ((rc = phase_alpha(x, 1, st))) return rc;
+    rc = saceo_update(x, 1, num_timesteps, 2, seed, nullptr, stream); if (rc) return rc;
   } else {
     rc = saceo_update(x, 1, num_timesteps, 1, seed, nullptr, stream); if (rc) return rc;
   }

@@ -671,14 +671,21 @@ __device__ __forceinline__ void hidden_math_dispatch(int act, uint32_t (&v)[32],
 
 // hidden epilogue (forward and backward): D (TMEM cols [0,256)) -> element-wise op -> [global tile] + bf16 hi/lo A
 // operand (TMEM cols 256.., 384..).  FWD: aux = bias[col..col+31] (same for every row); BWD: aux = saved H[row][col..].
+//   outer_w != null (critic backward, single output): the incoming tile is the outer product outer_s[row] * outer_w[col]
+//                    (dq . W2^T has K = 1), formed in registers instead of by an MMA.
+//   qdot_w  != null (critic forward, single output): q[row] = h2[row,:] . qdot_w is accumulated here on CUDA cores
+//                    (returned per thread, partial over this warp's 64 columns); the tile is then NOT written to TMEM.
 template <bool BWD>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ auxp, int act,
-                                                float* __restrict__ Gout, int row0, int rows, int warp, int lane) {
+__device__ __forceinline__ float hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ auxp, int act,
+                                                 float* __restrict__ Gout, int row0, int rows, int warp, int lane,
+                                                 const float* __restrict__ outer_w = nullptr, float outer_s = 0.f,
+                                                 const float* __restrict__ qdot_w = nullptr) {
   const int q = warp & 3, grp = warp >> 2;                 // lane quarter, 64-column group
   constexpr int PSTR = 36;
   const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const int grow_own = row0 + q * 32 + lane;
+  float qacc = 0.f;
 #pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 32) {
     const int col = grp * 64 + c0;
@@ -692,11 +699,31 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem, uint32_t patch_ba
       for (int j = 0; j < 32; ++j) aux[j] = 0.f;
     }
     uint32_t v[32];
-    tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+    if (outer_w) {
+      const float4* wp = reinterpret_cast<const float4*>(outer_w + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t4 = __ldg(wp + j);
+        v[4 * j] = __float_as_uint(outer_s * t4.x); v[4 * j + 1] = __float_as_uint(outer_s * t4.y);
+        v[4 * j + 2] = __float_as_uint(outer_s * t4.z); v[4 * j + 3] = __float_as_uint(outer_s * t4.w);
+      }
+    } else {
+      tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+    }
     uint32_t hi[16], lo[16];
     hidden_math_dispatch<BWD>(act, v, aux, hi, lo);
-    tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
-    tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
+    if (qdot_w) {
+      const float4* wp = reinterpret_cast<const float4*>(qdot_w + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t4 = __ldg(wp + j);
+        qacc = fmaf(__uint_as_float(v[4 * j]), t4.x, qacc); qacc = fmaf(__uint_as_float(v[4 * j + 1]), t4.y, qacc);
+        qacc = fmaf(__uint_as_float(v[4 * j + 2]), t4.z, qacc); qacc = fmaf(__uint_as_float(v[4 * j + 3]), t4.w, qacc);
+      }
+    } else {
+      tmem_st16(tmem + lane_addr + (uint32_t)(256 + (col >> 1)), hi);
+      tmem_st16(tmem + lane_addr + (uint32_t)(384 + (col >> 1)), lo);
+    }
     if (Gout) {      // coalesced global write through the warp-private patch
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
@@ -715,6 +742,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem, uint32_t patch_ba
     }
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  return qacc;
 }
 
 __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
@@ -802,26 +830,17 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   // ---------------- layer 1: D = h1 . W1   (A from TMEM, W1 streamed) ----------------
   const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
   constexpr int NS1 = FW_H / TS_BK;    // 8 slabs
-  unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};
   for (int j = 0; j < NS1; ++j) {
     const int h = j & 1;
     const uint32_t raw = r2 + (j % 3) * (FW_H * TS_BK * 4);
-    unsigned long long c0 = clock64();
     if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // buffer of slab j-1: free since last iteration
     asm volatile("cp.async.commit_group;" ::: "memory");       // (possibly empty) keeps the group count uniform
-    unsigned long long c1 = clock64();
     asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
-    unsigned long long c2 = clock64();
     __syncthreads();
-    unsigned long long c3 = clock64();
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
-    unsigned long long c4 = clock64();
     pw1.convert(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    unsigned long long c5 = clock64();
     __syncthreads();
-    unsigned long long c6 = clock64();
-    tacc[0] += c1 - c0; tacc[1] += c2 - c1; tacc[2] += c3 - c2; tacc[3] += c4 - c3; tacc[4] += c5 - c4; tacc[5] += c6 - c5;
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -837,14 +856,30 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
       if (j == NS1 - 1) umma_commit(bars + 24);
     }
   }
-  if (f.dbg && threadIdx.x == 32) {
-    for (int i = 0; i < 6; ++i) f.dbg[(size_t)(gridDim.x * gridDim.y) * 8 + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + i] = tacc[i];
-  }
   mbar_wait(bars + 24, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   FW_STAMP(3);
   // ---------------- epilogue 1: h2 ; stage W2 ----------------
+  if (f.nout == 1) {
+    // single output (critics): q = h2 . w2 + b2 on CUDA cores inside the epilogue - no MMA, no TMEM round trip
+    const float qp = hidden_epilogue<false>(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane, nullptr, 0.f, th + oW2);
+    __syncthreads();                                          // patches (r1) no longer read
+    float* qs = reinterpret_cast<float*>(smem_raw) + ((sb - smem_u32(smem_raw)) >> 2);     // [4 groups][128 rows] in r1
+    qs[(warp >> 2) * TC_BM + (warp & 3) * 32 + lane] = qp;
+    __syncthreads();
+    if (warp < 4) {
+      const int r = warp * 32 + lane, grow = row0 + r;
+      if (grow < f.rows) Out[(long long)grow * f.ldo] = ((qs[r] + qs[TC_BM + r]) + (qs[2 * TC_BM + r] + qs[3 * TC_BM + r])) + __ldg(th + ob2);
+    }
+    FW_STAMP(6);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+    return;
+  }
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc) sw2[kc].ld(kc * TC_BK, FW_H);      // in flight during the epilogue
   hidden_epilogue<false>(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane);
@@ -946,17 +981,20 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---------------- layer 2 transposed: D = dOut[:, :kout] . W2[:, :kout]^T  (one 64-wide slab, kout <= 32) ----------------
+  const bool outer = (f.kout == 1 && f.nout == 1);     // critics: K = 1, the "GEMM" is an outer product formed in the epilogue
   Slab<TC_BM, FW_NT> sx;
   Slab<FW_H, FW_NT> sw;
-  sx.init(dOut, f.ldd, 1, row0, f.rows);
-  sw.init(th + oW2, f.nout, 1, 0, FW_H);            // B(n = hidden j, k = out c) = W2[j*nout + c]
-  sx.ld(0, f.kout); sw.ld(0, f.kout);
+  if (!outer) {
+    sx.init(dOut, f.ldd, 1, row0, f.rows);
+    sw.init(th + oW2, f.nout, 1, 0, FW_H);            // B(n = hidden j, k = out c) = W2[j*nout + c]
+    sx.ld(0, f.kout); sw.ld(0, f.kout);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = lds_u32(tmem_slot);
   constexpr uint32_t IDESC = umma_idesc(TC_BM, FW_H);
-  {
+  if (!outer) {
     const uint32_t a_hi = r1, a_lo = r1 + 16384, b_hi = r1 + 32768, b_lo = r1 + 65536;
     sx.st(a_hi, a_lo); sw.st(b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -982,7 +1020,11 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
     for (int kc = 0; kc < 4; ++kc) sw0[kc].init(th + oW0 + (long long)f.s_cols * FW_H, FW_H, 1, 0, f.a_cols);   // B(n = a, k = j) = W0[(S+a)*256 + j]
   }
 
-  hidden_epilogue<true>(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane);
+  {
+    const int grow = row0 + (warp & 3) * 32 + lane;
+    const float dq = (outer && grow < f.rows) ? __ldg(dOut + (long long)grow * f.ldd) : 0.f;
+    hidden_epilogue<true>(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane, outer ? th + oW2 : nullptr, dq);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 

@@ -22,8 +22,7 @@ torch.cuda.synchronize()
 lib.saceo_test_set_tc_debug(None)
 raw = dbg.cpu().numpy()
 t = raw[:nct * 8].reshape(nct, 8).astype(np.float64)
-cyc = raw[nct * 8:].reshape(nct, 8)[:, :6].astype(np.float64).mean(0) / 8
-print('L1 loop, cycles per slab (warp 1 lane 0): issue %.0f | wait_group %.0f | sync1 %.0f | mbar %.0f | convert+fence %.0f | sync2 %.0f' % tuple(cyc))
+
 names = ["setup+L0 (X,W0 load, MMA)", "epilogue0", "misc", "L1 stream (8 slabs)", "epilogue1 + W2 stage", "L2 MMA", "epilogue2"]
 d = np.diff(t[:, :7], axis=1)
 print("kernel span %.1f us, CTA mean %.2f us" % ((t[:, 6].max() - t[:, 0].min()) / 1e3, (t[:, 6] - t[:, 0]).mean() / 1e3))
