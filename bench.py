@@ -240,6 +240,11 @@ def run_b200(a):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    if os.path.exists(tj) and a.shape == "ant" and not a.plain_sac:
+        tr = json.load(open(tj))          # ncu dram__bytes_{read,write}.sum summed over the 36 launches of one step
+        traffic = (tr["dram_read_bytes_per_step"] + tr["dram_write_bytes_per_step"]) / tr["agents"] * a.agents
     bytes_step = algorithmic_bytes(spec, pop.L) * a.agents
     achieved = bytes_step / (ms / a.steps * 1e-3) / 1e9
     flops_step = algorithmic_flops(spec) * a.agents
@@ -248,7 +253,7 @@ def run_b200(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "agents_per_gpu": a.agents, "batch": B,
-                   "gemm_engine": "tcgen05 bf16x3 (fp32 accum in TMEM)" if gemm_mode == 1 else "fp32 SIMT",
+                   "gemm_engine": "tcgen05 bf16x3 (fp32 accum in TMEM), fused 3-layer forward/backward kernels" if gemm_mode == 1 else "fp32 SIMT",
                    "cuda_graph": not a.no_graph, "rng": "in-kernel Philox4x32-10",
                    "l2_note": f"population state {bytes_step / 1e9:.2f} GB/step >> 126 MB L2; no explicit flush"},
         "clocks": clocks,
@@ -257,8 +262,10 @@ def run_b200(a):
                                             "copied H2D from pinned memory every step, losses copied D2H, stream sync"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "scope": "whole update step (sequence of kernels, per-kernel shares in profiles/); algorithmic bytes "
+                     "traffic": traffic, "traffic_note": "DRAM bytes per step from profiles/r1_step_traffic.json (ncu, all launches of one step)",
+                     "peak_source": peak_src,
+                     "achieved_note": "algorithmic bytes per step / CUDA-event step time",
+                     "scope": "whole update step (36 kernel launches, per-kernel shares in profiles/r1_launches_final_ncu.csv); algorithmic bytes "
                               f"{algorithmic_bytes(spec, pop.L) / 1e6:.2f} MB/agent-update",
                      "algorithmic_tflops": flops_step / (ms / a.steps * 1e-3) / 1e12},
     }
