@@ -33,6 +33,7 @@ struct GemmP {
   int nnet;
   int epi, act;
   int m_off;            // first output row handled by this launch (tail launches after a tensor-core main part)
+  int f16;              // tensor-core engine only: split operands into fp16 planes (forward passes) instead of bf16
 };
 
 __device__ __forceinline__ float apply_act(int act, float v) {

@@ -334,7 +334,7 @@ static int mlp_forward_unfused(saceo_ctx* x, const NetD& n, const float* X, int 
                                int row0, int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
                                long long sOa, long long sOn, cudaStream_t st) {
   const int na = x->cfg.n_agents;
-  GemmP p{}; p.nnet = n.nnet;
+  GemmP p{}; p.nnet = n.nnet; p.f16 = 1;     // forward operands are O(1): fp16 planes (tc_gemm.cuh split8)
   const int M = rows - row0;
   // layer 0
   p.A = X + (long long)row0 * ldx; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;

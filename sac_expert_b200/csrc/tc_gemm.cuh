@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include "gemm_simt.cuh"
 
@@ -89,8 +90,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return d;
 }
 // instruction descriptor: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, A/B K-major, N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// fmt: 1 = bf16 operands (default), 0 = fp16 operands (forward passes, see split8)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, uint32_t fmt = 1u) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -101,17 +103,32 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// fp32 -> (bf16 hi, bf16 lo) for 8 consecutive-k values, packed conversions (cvt.rn.bf16x2.f32):
-// hi = rn(x), lo = rn(x - hi); 6 instructions per pair.
+// fp32 -> (hi, lo) 16-bit pair for 8 consecutive-k values, packed conversions; hi = rn(x), lo = rn(x - hi).
+//   F16 = false: bf16 planes (8 + 8 mantissa bits, residual 2^-17, full fp32 exponent range) - used wherever the
+//                operand can be tiny (gradients).
+//   F16 = true:  fp16 planes (11 + 11 bits, residual 2^-23 for |x| >= 2^-3, absolute 2^-25 below; saturating at
+//                65504) - used by the FORWARD kernels, whose operands (normalised inputs, activations, weights) are
+//                O(1): the pre-activations then carry fp32-level error, so ReLU masks / min(Q1,Q2) selections flip
+//                no more often than between two fp32 implementations.  With bf16 planes (1e-5 forward error) a
+//                handful of masks per layer flip and single gradient tensors can miss the 1e-3 parity bar.
+template <bool F16 = false>
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);      // low half = x[2i]
-    h[i] = *reinterpret_cast<const uint32_t*>(&hp);
-    const float f0 = __uint_as_float(h[i] << 16), f1 = __uint_as_float(h[i] & 0xFFFF0000u);
-    const __nv_bfloat162 lp = __floats2bfloat162_rn(x[2 * i] - f0, x[2 * i + 1] - f1);
-    l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+    if (F16) {
+      uint32_t hb, lb;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lb) : "f"(x[2 * i + 1] - hf.y), "f"(x[2 * i] - hf.x));
+      h[i] = hb; l[i] = lb;
+    } else {
+      const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);      // low half = x[2i]
+      h[i] = *reinterpret_cast<const uint32_t*>(&hp);
+      const float f0 = __uint_as_float(h[i] << 16), f1 = __uint_as_float(h[i] & 0xFFFF0000u);
+      const __nv_bfloat162 lp = __floats2bfloat162_rn(x[2 * i] - f0, x[2 * i + 1] - f1);
+      l[i] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -174,12 +191,13 @@ struct Slab {
       }
     }
   }
+  template <bool F16 = false>
   __device__ __forceinline__ void st(uint32_t hi, uint32_t lo) const {
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       if (soff[i] < 0) continue;
       uint4 h, l;
-      split8(x[i], h, l);
+      split8<F16>(x[i], h, l);
       sts128(hi + soff[i], h);
       sts128(lo + soff[i], l);
     }
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(NT, MINB) k_gemm_tc(TcP q) {
   const uint32_t tmem = lds_u32(tmem_slot);
 
   const int nk = (p.K + TC_BK - 1) / TC_BK;
-  constexpr uint32_t IDESC = umma_idesc(TC_BM, BN);
+  const uint32_t IDESC = umma_idesc(TC_BM, BN, p.f16 ? 0u : 1u);
   Slab<TC_BM, NT> ra;
   Slab<BN, NT> rb;
   ra.init(A, q.a_sr, q.a_sk, m0, q.m_rows);
@@ -316,8 +334,8 @@ __global__ void __launch_bounds__(NT, MINB) k_gemm_tc(TcP q) {
     const int s = kc % NSTAGE;
     const uint32_t st = sb + s * SM::STAGE;
     if (kc >= NSTAGE) mbar_wait(bars + 8 * s, (uint32_t)((kc / NSTAGE - 1) & 1));   // MMAs of slab kc-NSTAGE retired
-    ra.st(st, st + SM::A_PLANE);
-    rb.st(st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE);
+    if (p.f16) { ra.template st<true>(st, st + SM::A_PLANE); rb.template st<true>(st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE); }
+    else       { ra.template st<false>(st, st + SM::A_PLANE); rb.template st<false>(st + 2 * SM::A_PLANE, st + 2 * SM::A_PLANE + SM::B_PLANE); }
     if (kc + 1 < nk) {          // next slab's global loads fly during the barrier, the MMA issue and the next wait
       ra.ld((kc + 1) * TC_BK, p.K);
       rb.ld((kc + 1) * TC_BK, p.K);
@@ -417,6 +435,7 @@ struct TsPlan {
 #pragma unroll
     for (int i = 0; i < NP; ++i) { cp_async16(raw + dst[i], src[i]); src[i] += kstep; }
   }
+  template <bool F16 = false>
   __device__ __forceinline__ void convert(uint32_t raw, int h, uint32_t hi, uint32_t lo) const {
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -429,7 +448,7 @@ struct TsPlan {
         for (int j = 0; j < 8; ++j) x[j] = lds32(raw + rd[i] + j * (ROWS * 4));
       }
       uint4 hh, ll;
-      split8(x, hh, ll);
+      split8<F16>(x, hh, ll);
       const uint32_t off = wr[i] ^ (uint32_t)(h << 6);
       sts128(hi + off, hh);
       sts128(lo + off, ll);
@@ -478,7 +497,7 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = lds_u32(tmem_slot);
   TC_STAMP(1);
-  constexpr uint32_t IDESC = umma_idesc(TC_BM, TS_BN);
+  const uint32_t IDESC = umma_idesc(TC_BM, TS_BN, p.f16 ? 0u : 1u);
   const uint32_t a_hi = stage, a_lo = stage + TS_APLANE, b_hi = stage + 2 * TS_APLANE, b_lo = b_hi + TS_BPLANE;
 
   for (int j = 0; j < nslab; ++j) {
@@ -487,8 +506,8 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's copies of slab j have landed
     __syncthreads();                                            // ... and everybody else's
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));     // MMAs that read half h (slab j-2) retired
-    pa.convert(raw, h, a_hi, a_lo);
-    pb.convert(raw + TS_RAW_A, h, b_hi, b_lo);
+    if (p.f16) { pa.template convert<true>(raw, h, a_hi, a_lo); pb.template convert<true>(raw + TS_RAW_A, h, b_hi, b_lo); }
+    else       { pa.template convert<false>(raw, h, a_hi, a_lo); pb.template convert<false>(raw + TS_RAW_A, h, b_hi, b_lo); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();                                            // stage half written, raw[h] free again
     if (j + 2 < nslab) { pa.issue(raw); pb.issue(raw + TS_RAW_A); }
@@ -654,11 +673,17 @@ __device__ __forceinline__ void hidden_math(uint32_t (&v)[32], const float (&aux
     if (BWD) { x0 *= dact_from_out(ACT, aux[2 * j]); x1 *= dact_from_out(ACT, aux[2 * j + 1]); }
     else { x0 = apply_act(ACT, x0 + aux[2 * j]); x1 = apply_act(ACT, x1 + aux[2 * j + 1]); }
     v[2 * j] = __float_as_uint(x0); v[2 * j + 1] = __float_as_uint(x1);
-    const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
-    hi[j] = *reinterpret_cast<const uint32_t*>(&hp);
-    const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
-    const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
-    lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
+    if (!BWD) {       // forward activations: fp16 hi/lo (see split8)
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(x1), "f"(x0));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    } else {          // gradients: bf16 hi/lo (range)
+      const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&hp);
+      const float f0 = __uint_as_float(hi[j] << 16), f1 = __uint_as_float(hi[j] & 0xFFFF0000u);
+      const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
   }
 }
 template <bool BWD>
@@ -791,12 +816,12 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = lds_u32(tmem_slot);
-  constexpr uint32_t IDESC = umma_idesc(TC_BM, FW_H);
+  constexpr uint32_t IDESC = umma_idesc(TC_BM, FW_H, 0u);      // fp16 operands
   {
     const uint32_t a_hi = r1, a_lo = r1 + 16384, b_hi = r1 + 32768, b_lo = r1 + 65536;
     for (int kc = 0; kc < nk0; ++kc) {
       if (kc > 0) mbar_wait(bars + 16, (uint32_t)((kc - 1) & 1));
-      sx.st(a_hi, a_lo); sw.st(b_hi, b_lo);
+      sx.st<true>(a_hi, a_lo); sw.st<true>(b_hi, b_lo);
       if (kc + 1 < nk0) { sx.ld((kc + 1) * TC_BK, f.K0); sw.ld((kc + 1) * TC_BK, f.K0); }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
@@ -838,7 +863,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
     asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
     __syncthreads();
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
-    pw1.convert(raw, h, b_hi, b_lo);
+    pw1.convert<true>(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -887,7 +912,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   // W2 as B operand: 4 chunks of 64 k, each [32 rows x 128 B] hi plane + lo plane (8 KB per chunk)
   const uint32_t w2s = r1;
 #pragma unroll
-  for (int kc = 0; kc < 4; ++kc) sw2[kc].st(w2s + kc * 8192, w2s + kc * 8192 + 4096);
+  for (int kc = 0; kc < 4; ++kc) sw2[kc].st<true>(w2s + kc * 8192, w2s + kc * 8192 + 4096);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -897,7 +922,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   const int npad = f.nout <= 16 ? 16 : 32;
   if (threadIdx.x == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t idesc2 = umma_idesc(TC_BM, npad);
+    const uint32_t idesc2 = umma_idesc(TC_BM, npad, 0u);
     for (int ks = 0; ks < 16; ++ks) {
       const uint32_t cb = w2s + (ks >> 2) * 8192 + (ks & 3) * 32;
       const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
