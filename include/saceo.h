@@ -193,6 +193,33 @@ int saceo_critic_forward(saceo_ctx *ctx, int32_t which, const float *obs, const 
 int saceo_model_eval(saceo_ctx *ctx, const float *obs, const float *act, int32_t rows,
                      float *sp_out, void *stream);
 
+/* ---- dynamics-model fitting -------------------------------------------------
+ * MBRLOnPolicyAlg._apply_model_grads (sac_eo/algs/mbrl_onpolicy_alg.py:301-319) as driven by
+ * SAC_exp._update_models (sac_eo/algs/SAC_expert.py:480-556), loss MSEModel.get_loss
+ * (sac_eo/models/continuous_models.py:280-302) on BaseWorldModel._forward(clip=False)
+ * (sac_eo/models/base_world_model.py:65-87).  Replaces self.model_optimizer (one tf.keras Adam over the
+ * tensors of ALL models, mbrl_onpolicy_alg.py:48-49) and tf.clip_by_global_norm (:315-317).
+ * Single-network models only (separate_reward_nn == 0).  fit_hyper per agent (8 floats):
+ *   [0] model_lr  [1] reward_loss_coef  [2] delta_clip_loss (0 = off)  [3] reward_clip_loss (0 = off)
+ *   [4] model_max_grad_norm (0 = None)  [5] r_rms mean  [6] r_rms std  [7] pad                      */
+#define SACEO_FIT_HYPER 8
+typedef struct saceo_fit_tables {
+  float *model;                /* [n_agents, 2, nm_stride] trainable; normally the table bound as saceo_tables.model */
+  float *model_m, *model_v;    /* Adam slots, same shape */
+  int32_t *model_t;            /* [n_agents] step count of the joint optimiser */
+  const float *fit_hyper;      /* [n_agents, SACEO_FIT_HYPER] */
+} saceo_fit_tables;
+
+/* Binds the fit tables and allocates the fitting workspace for minibatches of model_batch rows
+ * (--model_batch_size, 200).  use_grad_clip != 0 enables the global-norm pass (agents whose
+ * model_max_grad_norm is 0 are still left unclipped).  Requires saceo_bind (replay + normalisers). */
+int saceo_fit_bind(saceo_ctx *ctx, const saceo_fit_tables *t, int32_t model_batch, int32_t use_grad_clip);
+
+/* n_steps joint gradient steps.  idx: device int64 [n_steps, n_agents, num_models, model_batch] logical
+ * replay rows - the columns of the reference's per-model shuffled index matrix (SAC_expert.py:524-545).
+ * losses_out (device, nullable): [n_steps, n_agents, num_models] minibatch loss of each model before the step. */
+int saceo_model_fit(saceo_ctx *ctx, int32_t n_steps, const int64_t *idx, float *losses_out, void *stream);
+
 /* TRPO._make_F closure (model_free/trpo.py:200-227): Fx = d/dtheta((d/dtheta mean KL) . x) + damp x
  * on the bound fvp_states, x and Fx [n_agents, na_stride] device. */
 int saceo_fvp(saceo_ctx *ctx, const float *x, float damp, float *Fx, void *stream);

@@ -325,6 +325,88 @@ def sac_eo_update(cfg: NetCfg, state: Dict, batch: Dict, hyper: Dict) -> Dict:
 
 
 # --------------------------------------------------------------------------------------
+# dynamics-model fitting  mbrl_onpolicy_alg.py:301-319, SAC_expert.py:480-556
+# --------------------------------------------------------------------------------------
+def model_loss(cfg: NetCfg, theta_m, s_: Tensor, a_: Tensor, sp_: Tensor, r_: Tensor, st: Dict,
+               reward_loss_coef: float = 1.0, delta_clip_loss: float = 0.0,
+               reward_clip_loss: float = 0.0) -> Tensor:
+    """``MSEModel.get_loss`` (continuous_models.py:280-302) on ``BaseWorldModel._forward(s, a,
+    clip=False)`` (base_world_model.py:65-87): the net predicts the NORMALISED state delta in its
+    first S outputs and the normalised reward in the last one; targets are normalised with the
+    model's ``delta_rms`` / ``r_rms`` and optionally clipped; loss = mean_b(0.5*sum_j (dn-dp)^2 +
+    coef*0.5*(rn-rp)^2).  Single-network models only (``separate_reward_nn`` is not restated)."""
+    if cfg.separate_reward_nn:
+        raise ValueError("model fitting with separate_reward_nn is not restated")
+    sa = torch.cat([normalize(s_, st["m_s_mean"], st["m_s_std"]),
+                    normalize(a_, st["m_a_mean"], st["m_a_std"])], -1)
+    pred = mlp(theta_m, sa.to(s_.dtype), cfg.model_acts)
+    delta_pred, r_pred = pred[:, :-1], pred[:, -1]
+    delta_norm = normalize(sp_ - s_, st["m_d_mean"], st["m_d_std"])
+    if delta_clip_loss:
+        delta_norm = torch.clamp(delta_norm, -delta_clip_loss, delta_clip_loss)
+    delta_loss = 0.5 * ((delta_norm - delta_pred) ** 2).sum(-1)
+    r_norm = normalize(r_, st.get("m_r_mean", 0.0), st.get("m_r_std", 1.0))
+    if reward_clip_loss:
+        r_norm = torch.clamp(r_norm, -reward_clip_loss, reward_clip_loss)
+    r_loss = 0.5 * (r_norm - r_pred) ** 2
+    return (delta_loss + reward_loss_coef * r_loss).mean()
+
+
+def apply_model_grads(cfg: NetCfg, models: List[List[Tensor]], adam: Dict, batches: List[Dict], st: Dict,
+                      fit: Dict) -> Dict:
+    """``MBRLOnPolicyAlg._apply_model_grads`` (mbrl_onpolicy_alg.py:301-319): the losses of ALL models
+    (each on its own minibatch) are summed under one tape, the gradient list is optionally clipped
+    with ``tf.clip_by_global_norm(grads, model_max_grad_norm * num_models)`` and ONE Keras Adam
+    (lr ``model_lr``, one shared step counter) applies it to every model's tensors.
+    ``adam`` = dict(m=[per model lists], v=[...], t=int); ``batches[k]`` = dict(s,a,sp,r) tensors."""
+    dt = models[0][0].dtype
+    live = [[w.detach().clone().requires_grad_(True) for w in th] for th in models]
+    losses = []
+    for k, th in enumerate(live):
+        b = batches[k]
+        losses.append(model_loss(cfg, th, b["s"].to(dt), b["a"].to(dt), b["sp"].to(dt), b["r"].to(dt), st,
+                                 fit.get("reward_loss_coef", 1.0), fit.get("delta_clip_loss", 0.0),
+                                 fit.get("reward_clip_loss", 0.0)))
+    flat_params = [w for th in live for w in th]
+    grads = list(torch.autograd.grad(sum(losses), flat_params))
+    gnorm = torch.sqrt(sum((g ** 2).sum() for g in grads))
+    mgn = fit.get("model_max_grad_norm", 0.0)
+    if mgn:                                   # tf.clip_by_global_norm: g * clip * min(1/norm, 1/clip)
+        clip = torch.as_tensor(mgn * len(models), dtype=dt)
+        scale = clip * torch.minimum(1.0 / gnorm, 1.0 / clip)
+        grads = [g * scale for g in grads]
+    flat_m = [x for ml in adam["m"] for x in ml]
+    flat_v = [x for vl in adam["v"] for x in vl]
+    new_theta, new_m, new_v, t = keras_adam([w.detach() for w in flat_params], grads, flat_m, flat_v,
+                                            adam["t"], fit.get("model_lr", 1e-3))
+    n = len(models[0])
+    split = lambda xs: [xs[i * n:(i + 1) * n] for i in range(len(models))]
+    return dict(losses=[l.detach() for l in losses], grads=split(grads), gnorm=gnorm.detach(),
+                models=split(new_theta), m=split(new_m), v=split(new_v), t=t)
+
+
+def model_fit_batches(n_train: int, num_models: int, model_batch_size: int, batch_shuffle: bool,
+                      rng=np.random) -> List[np.ndarray]:
+    """One epoch of minibatch indices the way ``_update_models`` draws them (SAC_expert.py:524-540):
+    per-model independent ``np.random.shuffle`` when ``model_batch_shuffle`` else one shared shuffle
+    tiled over the models; split every ``model_batch_size`` columns, dropping a ragged last batch.
+    Returns a list of ``[num_models, model_batch_size]`` int arrays."""
+    idx = np.arange(n_train)
+    if batch_shuffle:
+        idx = np.tile(idx, (num_models, 1))
+        for row in idx:
+            rng.shuffle(row)
+    else:
+        rng.shuffle(idx)
+        idx = np.tile(idx, (num_models, 1))
+    sections = np.arange(0, n_train, model_batch_size)[1:]
+    batches = np.array_split(idx, sections, axis=1)
+    if n_train % model_batch_size != 0:
+        batches = batches[:-1]
+    return batches
+
+
+# --------------------------------------------------------------------------------------
 # adaptive expert weight (host side, once per episode)  SAC_expert.py:375-460, 579-608
 # --------------------------------------------------------------------------------------
 def model_mse_on_expert(cfg: NetCfg, state: Dict, sE, aE, spE, u=None, use_expert_actions=False):

@@ -1,0 +1,148 @@
+// Dynamics-model fitting for the whole population:
+//   MBRLOnPolicyAlg._apply_model_grads   sac_eo/algs/mbrl_onpolicy_alg.py:301-319
+//   MSEModel.get_loss                    sac_eo/models/continuous_models.py:280-302
+//   BaseWorldModel._forward(clip=False)  sac_eo/models/base_world_model.py:65-87
+// One "fit step" = for every agent: every model's loss on its own minibatch of replay rows, summed;
+// optional tf.clip_by_global_norm over ALL models' tensors; one joint Keras Adam step.
+// The MLP forward / backward / weight-gradient GEMMs are the generic ones of saceo.cu; this file holds
+// the row staging, the loss + output gradient, the global-norm reduction and the Adam step.
+#pragma once
+#include "elem.cuh"
+
+namespace saceo {
+
+enum { FIT_LR = 0, FIT_RCOEF = 1, FIT_DCLIP = 2, FIT_RCLIP = 3, FIT_MAXNORM = 4, FIT_RMEAN = 5, FIT_RSTD = 6, FIT_HYPER = 8 };
+
+struct FitCtx {
+  // caller tables (saceo_fit_tables)
+  float *model, *m, *v; int* t; const float* hyper;
+  // workspace, all [n_agents, 2, ...]
+  float *X, *T, *H1, *H2, *Out, *dOut, *dH2, *dH1, *g;
+  float *loss_part;      // [n_agents, 2]
+  float *gscale;         // [n_agents] gradient scale of clip_by_global_norm (1 when clipping is off)
+  float *gnorm;          // [n_agents] global gradient norm (diagnostic)
+  float *lrt;            // [n_agents] bias-corrected Adam step size
+  int mb, nmod, use_clip;
+  long long nm, nm_stride;
+};
+
+// Adam step counter and step size of the joint model optimiser.  grid: ceil(n_agents/128)
+__global__ void k_fit_begin(FitCtx f, int n_agents) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_agents) return;
+  const int t = f.t[i] + 1;
+  f.t[i] = t;
+  const float lr = f.hyper[i * FIT_HYPER + FIT_LR];
+  const double b1t = pow((double)kB1, (double)t), b2t = pow((double)kB2, (double)t);
+  f.lrt[i] = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  f.gscale[i] = 1.f;
+}
+
+// Gathers the minibatch rows of every (agent, model) from the device replay table (same logical ->
+// physical ring mapping as k_gather) and stages the normalised network input and regression target:
+//   X[row] = [ N_s(s) | N_a(a) ]                         base_world_model.py:67-70
+//   T[row] = [ clip(N_delta(sp - s)) | clip(N_r(r)) ]    continuous_models.py:284-296
+// grid: (ceil(mb*(2S+A+1)/256), nmod, n_agents)
+__global__ void k_fit_stage(KCtx c, FitCtx f, const long long* __restrict__ idx) {
+  const int agent = blockIdx.z, net = blockIdx.y;
+  const int S = c.S, A = c.A, SA = S + A, W = SA + S + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= f.mb * W) return;
+  const int row = e / W, col = e - row * W;
+  const long long an = (long long)agent * 2 + net;
+  const long long li = idx[((long long)agent * f.nmod + net) * f.mb + row];
+  const int start = c.T.replay_start ? c.T.replay_start[agent] : 0;
+  long long phys = li + start;
+  if (phys >= c.cap) phys -= c.cap;
+  const float* __restrict__ src = c.T.replay + ((long long)agent * c.cap + phys) * c.L.row_words;
+  const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
+  const float* hy = f.hyper + (long long)agent * FIT_HYPER;
+  if (col < S) {
+    f.X[(an * f.mb + row) * SA + col] = (src[c.L.off_s + col] - nr[c.L.off_m_s_mean + col]) / nstd(nr[c.L.off_m_s_std + col]);
+  } else if (col < SA) {
+    const int j = col - S;
+    f.X[(an * f.mb + row) * SA + col] = (src[c.L.off_a + j] - nr[c.L.off_m_a_mean + j]) / nstd(nr[c.L.off_m_a_std + j]);
+  } else if (col < SA + S) {
+    const int j = col - SA;
+    const float d = src[c.L.off_sp + j] - src[c.L.off_s + j];
+    float dn = (d - nr[c.L.off_m_d_mean + j]) / nstd(nr[c.L.off_m_d_std + j]);
+    const float cl = hy[FIT_DCLIP];
+    if (cl > 0.f) dn = fminf(fmaxf(dn, -cl), cl);
+    f.T[(an * f.mb + row) * (S + 1) + j] = dn;
+  } else {
+    float rn = (src[c.L.off_r] - hy[FIT_RMEAN]) / nstd(hy[FIT_RSTD]);
+    const float cl = hy[FIT_RCLIP];
+    if (cl > 0.f) rn = fminf(fmaxf(rn, -cl), cl);
+    f.T[(an * f.mb + row) * (S + 1) + S] = rn;
+  }
+}
+
+// loss and its gradient w.r.t. the network output.  grid: (nmod, n_agents), block 256
+//   L = mean_b( 0.5*sum_j (T_j - P_j)^2 + coef*0.5*(T_r - P_r)^2 );  dP = w_j (P - T) / mb
+__global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
+  __shared__ float sh[32];
+  const int agent = blockIdx.y, net = blockIdx.x;
+  const int mo = c.S + 1;
+  const long long an = (long long)agent * 2 + net;
+  const float coef = f.hyper[(long long)agent * FIT_HYPER + FIT_RCOEF];
+  const float inv = 1.f / (float)f.mb;
+  float acc = 0.f;
+  for (int row = threadIdx.x; row < f.mb; row += blockDim.x) {
+    const float* P = f.Out + (an * f.mb + row) * mo;
+    const float* T = f.T + (an * f.mb + row) * mo;
+    float* dP = f.dOut + (an * f.mb + row) * mo;
+    float dl = 0.f;
+    for (int j = 0; j < c.S; ++j) {
+      const float e = P[j] - T[j];
+      dl += e * e;
+      dP[j] = e * inv;
+    }
+    const float er = P[c.S] - T[c.S];
+    dP[c.S] = coef * er * inv;
+    acc += 0.5f * dl + coef * (0.5f * er * er);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const float L = acc * inv;
+    f.loss_part[an] = L;
+    if (losses_out) losses_out[(long long)agent * f.nmod + net] = L;
+  }
+}
+
+// tf.clip_by_global_norm over every tensor of every model of one agent (mbrl_onpolicy_alg.py:315-317):
+// scale = clip * min(1/||g||, 1/clip), clip = model_max_grad_norm * num_models.  grid: (n_agents), block 1024
+__global__ void k_fit_gnorm(FitCtx f) {
+  __shared__ float sh[32];
+  const int agent = blockIdx.x;
+  float acc = 0.f;
+  for (int net = 0; net < f.nmod; ++net) {
+    const float* g = f.g + ((long long)agent * 2 + net) * f.nm_stride;
+    for (long long i = threadIdx.x; i < f.nm; i += blockDim.x) { const float x = g[i]; acc += x * x; }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const float norm = sqrtf(acc);
+    f.gnorm[agent] = norm;
+    const float mgn = f.hyper[(long long)agent * FIT_HYPER + FIT_MAXNORM];
+    if (mgn > 0.f) {
+      const float clip = mgn * (float)f.nmod;
+      f.gscale[agent] = clip * fminf(1.f / norm, 1.f / clip);
+    }
+  }
+}
+
+// joint Keras Adam over all model tensors (one step counter per agent).  grid: (ceil(nm/256), nmod, n_agents)
+__global__ void k_fit_adam(FitCtx f) {
+  const int agent = blockIdx.z, net = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f.nm) return;
+  const long long o = ((long long)agent * 2 + net) * f.nm_stride + i;
+  const float lr_t = f.lrt[agent];
+  const float gi = f.g[o] * f.gscale[agent];
+  const float mi = kB1 * f.m[o] + (1.f - kB1) * gi;
+  const float vi = kB2 * f.v[o] + (1.f - kB2) * gi * gi;
+  f.model[o] = f.model[o] - lr_t * mi / (sqrtf(vi) + kAdamEps);
+  f.m[o] = mi; f.v[o] = vi;
+}
+
+}  // namespace saceo

@@ -16,6 +16,7 @@
 #include "fvp.cuh"
 #include "tc_gemm.cuh"
 #include "model_term.cuh"
+#include "model_fit.cuh"
 
 using namespace saceo;
 
@@ -58,6 +59,9 @@ struct saceo_ctx {
   std::map<std::string, std::pair<void*, long long>> names;
   float *exp_stage = nullptr;          // [n, 2, E, S] host-staged expert rows
   long long* idx_stage = nullptr;
+  FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
+  bool fit_bound = false;
+  void* fit_ws = nullptr;
   long long launches = 0;
   cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [rng mode][polyak]
   long long graph_nodes[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -224,7 +228,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   saceo_ctx* x = new saceo_ctx();
   x->cfg = *cfg;
   fill_layout(cfg, &x->L);
-  memset(&x->k, 0, sizeof(KCtx)); memset(&x->f, 0, sizeof(FvpWs));
+  memset(&x->k, 0, sizeof(KCtx)); memset(&x->f, 0, sizeof(FvpWs)); memset(&x->fit, 0, sizeof(FitCtx));
   carve(x, nullptr);
   x->L.workspace_bytes = x->ws_bytes;
   if (cudaMalloc(&x->ws, (size_t)x->ws_bytes) != cudaSuccess) {
@@ -261,6 +265,7 @@ extern "C" int saceo_destroy(saceo_ctx* x) {
   if (!x) return 0;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
   if (x->ws) cudaFree(x->ws);
+  if (x->fit_ws) cudaFree(x->fit_ws);
   delete x;
   return 0;
 }
@@ -797,6 +802,78 @@ extern "C" int saceo_model_eval(saceo_ctx* x, const float* obs, const float* act
     int rc = mlp_forward(x, mn, k.Xm, SA, 2LL * E * SA, 0, nr, k.mH1, k.mH2, E, k.mOut, mn.out,
                          2LL * E * mn.out, (long long)E * mn.out, st); if (rc) return rc;
     LAUNCH(x, k_model_out, dim3(cdiv((long long)nr * k.S, 256), n, k.nmod), 256, 0, st, k, obs, rows, r0, nr, sp_out);
+  }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// dynamics-model fitting (mbrl_onpolicy_alg.py:301-319; SAC_expert.py:480-556)
+// ------------------------------------------------------------------------------------------
+extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t model_batch, int32_t use_grad_clip) {
+  if (!x || !t) return fail(SACEO_E_INVALID, "null argument");
+  if (x->cfg.num_models < 1) return fail(SACEO_E_INVALID, "model fitting needs num_models >= 1");
+  if (x->cfg.separate_reward_nn) return fail(SACEO_E_INVALID, "model fitting with separate_reward_nn is not supported");
+  if (model_batch < 1) return fail(SACEO_E_INVALID, "model_batch must be >= 1");
+  if (!t->model || !t->model_m || !t->model_v || !t->model_t || !t->fit_hyper)
+    return fail(SACEO_E_INVALID, "a required fit table pointer is NULL");
+  CU(cudaSetDevice(x->cfg.device));
+  if (x->fit_ws) { CU(cudaDeviceSynchronize()); cudaFree(x->fit_ws); x->fit_ws = nullptr; x->fit_bound = false; }
+  const saceo_config& c = x->cfg;
+  FitCtx& f = x->fit;
+  memset(&f, 0, sizeof(f));
+  f.model = t->model; f.m = t->model_m; f.v = t->model_v; f.t = t->model_t; f.hyper = t->fit_hyper;
+  f.mb = model_batch; f.nmod = c.num_models; f.use_clip = use_grad_clip;
+  f.nm = x->L.nm; f.nm_stride = x->L.nm_stride;
+  const long long n2 = 2LL * c.n_agents, mb = model_batch, SA = c.S + c.A, mo = x->L.model_out;
+  for (int pass = 0; pass < 2; ++pass) {
+    Bump b{pass ? (char*)x->fit_ws : nullptr, 0, pass ? &x->names : nullptr};
+    f.X = b.get<float>("fit_X", n2 * mb * SA);        f.T = b.get<float>("fit_T", n2 * mb * mo);
+    f.H1 = b.get<float>("fit_H1", n2 * mb * c.model_hidden[0]); f.H2 = b.get<float>("fit_H2", n2 * mb * c.model_hidden[1]);
+    f.Out = b.get<float>("fit_Out", n2 * mb * mo);    f.dOut = b.get<float>("fit_dOut", n2 * mb * mo);
+    f.dH2 = b.get<float>("fit_dH2", n2 * mb * c.model_hidden[1]); f.dH1 = b.get<float>("fit_dH1", n2 * mb * c.model_hidden[0]);
+    f.g = b.get<float>("g_model", n2 * x->L.nm_stride);
+    f.loss_part = b.get<float>("fit_loss", n2);
+    f.gscale = b.get<float>("fit_gscale", c.n_agents); f.gnorm = b.get<float>("fit_gnorm", c.n_agents);
+    f.lrt = b.get<float>("fit_lrt", c.n_agents);
+    if (!pass) {
+      const long long bytes = rup(b.off, 256);
+      if (cudaMalloc(&x->fit_ws, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError(); x->fit_ws = nullptr;
+        return fail(SACEO_E_NOMEM, "cudaMalloc of %lld model-fit workspace bytes failed", bytes);
+      }
+      CU(cudaMemset(x->fit_ws, 0, (size_t)bytes));
+    }
+  }
+  x->fit_bound = true;
+  return 0;
+}
+
+// One joint gradient step on every agent's models per entry of idx ([n_steps, n_agents, num_models, model_batch]
+// logical replay rows).  losses_out (nullable): [n_steps, n_agents, num_models] per-model minibatch losses.
+extern "C" int saceo_model_fit(saceo_ctx* x, int32_t n_steps, const int64_t* idx, float* losses_out, void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null context");
+  if (!x->bound || !x->fit_bound) return fail(SACEO_E_UNBOUND, "saceo_bind and saceo_fit_bind must precede saceo_model_fit");
+  if (!idx || n_steps < 0) return fail(SACEO_E_INVALID, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const KCtx& k = x->k; const FitCtx& f = x->fit;
+  const int n = k.n_agents, mb = f.mb, SA = k.S + k.A, mo = x->L.model_out;
+  NetD net{f.model, 2 * x->L.nm_stride, x->L.nm_stride, f.nmod, SA, x->cfg.model_hidden[0], x->cfg.model_hidden[1], mo,
+           x->cfg.model_act[0], x->cfg.model_act[1]};
+  for (int s = 0; s < n_steps; ++s) {
+    const long long* ix = reinterpret_cast<const long long*>(idx) + (long long)s * n * f.nmod * mb;
+    LAUNCH(x, k_fit_begin, cdiv(n, 128), 128, 0, st, f, n);
+    LAUNCH(x, k_fit_stage, dim3(cdiv((long long)mb * (SA + k.S + 1), 256), f.nmod, n), 256, 0, st, k, f, ix);
+    int rc = mlp_forward(x, net, f.X, SA, 2LL * mb * SA, (long long)mb * SA, mb, f.H1, f.H2, mb, f.Out, mo,
+                         2LL * mb * mo, (long long)mb * mo, st, true);
+    if (rc) return rc;
+    LAUNCH(x, k_fit_loss, dim3(f.nmod, n), 256, 0, st, k, f,
+           losses_out ? losses_out + (long long)s * n * f.nmod : (float*)nullptr);
+    rc = mlp_backward(x, net, f.X, SA, 2LL * mb * SA, (long long)mb * SA, mb, f.H1, f.H2, mb, f.dOut, mo,
+                      2LL * mb * mo, (long long)mb * mo, mo, f.dH2, f.dH1, f.g, 2 * x->L.nm_stride, x->L.nm_stride,
+                      nullptr, 0, 0, 0, 0, st);
+    if (rc) return rc;
+    if (f.use_clip) LAUNCH(x, k_fit_gnorm, n, 1024, 0, st, f);
+    LAUNCH(x, k_fit_adam, dim3(cdiv(f.nm, 256), f.nmod, n), 256, 0, st, f);
   }
   return check_launch();
 }

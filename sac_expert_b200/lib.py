@@ -61,6 +61,15 @@ class Tables(C.Structure):
         "replay", "replay_size", "replay_start", "expert_s", "expert_sp", "fvp_states")]
 
 
+class FitTables(C.Structure):
+    """saceo_fit_tables (include/saceo.h): dynamics-model fitting state."""
+    _fields_ = [(n, C.c_void_p) for n in ("model", "model_m", "model_v", "model_t", "fit_hyper")]
+
+
+FIT_HYPER = 8
+FIT_HYPER_NAMES = ("model_lr", "reward_loss_coef", "delta_clip_loss", "reward_clip_loss", "model_max_grad_norm",
+                   "r_mean", "r_std")
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/saceo.h declares (tests/test_abi.py checks the library exports them all)
@@ -68,6 +77,7 @@ EXPORTS = [
     "saceo_query_layout", "saceo_create", "saceo_destroy", "saceo_bind", "saceo_gather",
     "saceo_set_draws", "saceo_update", "saceo_update_host", "saceo_update_phase",
     "saceo_actor_forward", "saceo_critic_forward", "saceo_model_eval", "saceo_fvp", "saceo_cg_solve",
+    "saceo_fit_bind", "saceo_model_fit",
     "saceo_debug_ptr", "saceo_launch_count", "saceo_test_gemm", "saceo_last_error", "saceo_abi_version",
 ]
 
@@ -96,6 +106,8 @@ def load() -> C.CDLL:
         "saceo_actor_forward": (C.c_int, [vp, vp, i32, vp, vp, vp, vp]),
         "saceo_critic_forward": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp]),
         "saceo_model_eval": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "saceo_fit_bind": (C.c_int, [vp, C.POINTER(FitTables), i32, i32]),
+        "saceo_model_fit": (C.c_int, [vp, i32, vp, vp, vp]),
         "saceo_fvp": (C.c_int, [vp, vp, f32, vp, vp]),
         "saceo_cg_solve": (C.c_int, [vp, vp, i32, f32, f32, vp, vp, vp]),
         "saceo_debug_ptr": (vp, [vp, C.c_char_p, C.POINTER(i64)]),

@@ -401,6 +401,48 @@ class Population:
         self._exit()
         return out
 
+    # ------------------------------------------------------------------ dynamics-model fitting
+    def fit_bind(self, model_batch: int = 200, use_grad_clip: bool = False):
+        """Allocates the joint model optimiser's slots (``self.model_optimizer``, mbrl_onpolicy_alg.py:48-49)
+        and the fitting workspace for minibatches of ``model_batch`` rows (--model_batch_size)."""
+        n, L = self.spec.n_agents, self.L
+        z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)
+        self.t.update(model_m=z(n, 2, L.nm_stride), model_v=z(n, 2, L.nm_stride), model_t=z(n, dt=torch.int32),
+                      fit_hyper=z(n, _l.FIT_HYPER))
+        self.t["fit_hyper"][:, 0] = 1e-3      # --model_lr
+        self.t["fit_hyper"][:, 1] = 1.0       # --reward_loss_coef
+        self.t["fit_hyper"][:, 6] = 1.0       # identity r_rms
+        ft = _l.FitTables()
+        for name, _ in _l.FitTables._fields_:
+            setattr(ft, name, self.t[name].data_ptr())
+        torch.cuda.synchronize(self.dev)
+        _l.check(self.lib.saceo_fit_bind(self.ctx, C.byref(ft), int(model_batch), int(bool(use_grad_clip))))
+        self.model_batch = int(model_batch)
+
+    def set_fit_hyper(self, agent: int, **hy):
+        """model_lr, reward_loss_coef, delta_clip_loss, reward_clip_loss, model_max_grad_norm (0/None = off), r_mean, r_std."""
+        row = self.t["fit_hyper"][agent]
+        for key, val in hy.items():
+            row[_l.FIT_HYPER_NAMES.index(key)] = float(val or 0.0)
+
+    def reset_model_optimizer(self):
+        """``reset_model_optimizer`` (SAC_expert.py:551-553): fresh Adam slots and step count."""
+        for k in ("model_m", "model_v", "model_t"):
+            self.t[k].zero_()
+
+    def model_fit(self, idx, want_losses: bool = True) -> Optional[torch.Tensor]:
+        """``_apply_model_grads`` for every entry of ``idx`` ([n_steps, n_agents, num_models, model_batch] or
+        [n_agents, num_models, model_batch] logical replay rows).  Returns the per-model minibatch losses
+        [n_steps, n_agents, num_models]."""
+        n, nm = self.spec.n_agents, self.spec.num_models
+        idx = torch.as_tensor(idx).to(self.dev, torch.int64).contiguous().view(-1, n, nm, self.model_batch)
+        steps = idx.shape[0]
+        losses = torch.zeros(steps, n, nm, device=self.dev) if want_losses else None
+        st = self._enter()
+        _l.check(self.lib.saceo_model_fit(self.ctx, steps, idx.data_ptr(), losses.data_ptr() if want_losses else None, st))
+        self._exit()
+        return losses
+
     # ------------------------------------------------------------------ CG / Fisher-vector
     def fvp(self, x: torch.Tensor, damp: float) -> torch.Tensor:
         x = x.to(self.dev, torch.float32).contiguous()

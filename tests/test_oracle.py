@@ -214,3 +214,48 @@ def test_gather_semantics_with_replacement():
     idx = np.array([8, 8, 0, 3, 3, 3])
     s, a, sp, r, d = O.gather(rep, idx)
     assert s.shape == (6, 3) and d.dtype == np.float64 and np.array_equal(s[0], s[1]) and np.array_equal(r[3:], rep["r"][[3, 3, 3]])
+
+
+def test_model_fit_restatement():
+    """apply_model_grads: joint Adam over both models, clip_by_global_norm semantics, batch index shapes
+    (mbrl_onpolicy_alg.py:301-319, SAC_expert.py:524-540)."""
+    from oracle.sac_eo_oracle import (NetCfg, apply_model_grads, make_problem, model_fit_batches, model_loss,
+                                      to_torch_state)
+    cfg = NetCfg(S=5, A=2, model_hidden=(16, 16), model_acts=("tanh", "tanh"))
+    st, replay, expert, hyper = make_problem(cfg, 8, 4, 103, seed=4, perturb=0.05)
+    bs = model_fit_batches(103, 2, 20, True, np.random.default_rng(0))
+    assert len(bs) == 5 and all(b.shape == (2, 20) for b in bs)            # ragged tail batch dropped
+    assert not np.array_equal(bs[0][0], bs[0][1])                          # per-model shuffles
+    shared = model_fit_batches(100, 2, 20, False, np.random.default_rng(0))
+    assert len(shared) == 5 and np.array_equal(shared[0][0], shared[0][1])  # one shuffle tiled over the models
+    for dt in (torch.float32, torch.float64):
+        T = to_torch_state(st, dt)
+        models = [T["m1"], T["m2"]]
+        zeros = lambda: [[torch.zeros_like(w) for w in m] for m in models]
+        b = [{k: torch.as_tensor(replay[k][bs[0][i]]).to(dt) for k in ("s", "a", "sp", "r")} for i in range(2)]
+        free = apply_model_grads(cfg, models, dict(m=zeros(), v=zeros(), t=0), b, T, dict(model_lr=1e-3))
+        clip = apply_model_grads(cfg, models, dict(m=zeros(), v=zeros(), t=0), b, T,
+                                 dict(model_lr=1e-3, model_max_grad_norm=0.25))
+        gn = float(free["gnorm"])
+        assert gn > 0.5                                                     # clipping active: norm -> 0.25 * num_models
+        got = float(torch.sqrt(sum((g ** 2).sum() for gl in clip["grads"] for g in gl)))
+        assert abs(got - 0.5) < 1e-4
+        big = apply_model_grads(cfg, models, dict(m=zeros(), v=zeros(), t=0), b, T,
+                                dict(model_lr=1e-3, model_max_grad_norm=1e6))
+        for a_, b_ in zip(big["grads"][0], free["grads"][0]):               # norm below the clip: unchanged
+            assert torch.allclose(a_, b_, rtol=1e-6, atol=0)
+        assert free["t"] == 1
+        # model k's gradient only depends on model k's loss (sum of independent losses)
+        l0 = model_loss(cfg, [w.clone().requires_grad_(True) for w in models[0]], b[0]["s"], b[0]["a"], b[0]["sp"], b[0]["r"], T)
+        assert abs(float(l0.detach()) - float(free["losses"][0])) < 1e-5 * abs(float(l0.detach()))
+    # fp32 vs fp64 gradients
+    T32, T64 = to_torch_state(st), to_torch_state(st, torch.float64)
+    outs = []
+    for T in (T32, T64):
+        models = [T["m1"], T["m2"]]
+        zeros = lambda: [[torch.zeros_like(w) for w in m] for m in models]
+        b = [{k: torch.as_tensor(replay[k][bs[0][i]]) for k in ("s", "a", "sp", "r")} for i in range(2)]
+        outs.append(apply_model_grads(cfg, models, dict(m=zeros(), v=zeros(), t=0), b, T,
+                                      dict(model_lr=1e-3, reward_loss_coef=0.5, delta_clip_loss=1.0, reward_clip_loss=1.0)))
+    for g32, g64 in zip(outs[0]["grads"][1], outs[1]["grads"][1]):
+        assert float((g32.double() - g64).norm() / g64.norm()) < 1e-5
