@@ -56,6 +56,85 @@ class SAC_exp(SAC):
         self.last_losses = out = self._device_update(num_timesteps, expert_reg)
         self.logger.log_train({"alpha_loss": out["alpha_loss"], "p_loss": out["p_loss"], "epsilon": epsilon})   # :351-356
 
+    # ------------------------------------------------------------------ dynamics-model fitting (device)
+    def _setup_model_fit(self):
+        """``MBRLOnPolicyAlg._setup`` (mbrl_onpolicy_alg.py:35-59): one joint Adam over every model's tensors."""
+        kw = self.alg_kwargs
+        g = lambda k, d: kw[k] if kw.get(k) is not None else d
+        self.model_lr, self.model_num_epochs = g("model_lr", 1e-3), int(g("model_num_epochs", 10))
+        self.model_batch_size, self.model_batch_shuffle = int(g("model_batch_size", 200)), bool(g("model_batch_shuffle", True))
+        self.model_max_updates, self.model_max_grad_norm = g("model_max_updates", 1e5), kw.get("model_max_grad_norm")
+        self.model_holdout_ratio = g("model_holdout_ratio", 0.0)
+        self.reset_model_optimizer = bool(g("reset_model_optimizer", False))
+        if len(self.models) != self._n_models():
+            raise NotImplementedError("the device joint optimiser covers the two models of the update path")
+        m = self.models[0]
+        self.pop.fit_bind(self.model_batch_size, use_grad_clip=self.model_max_grad_norm is not None)
+        self._fit_ready = True
+        self._push_fit_hyper()
+
+    def _push_fit_hyper(self):
+        m = self.models[0]
+        r_rms = getattr(m, "r_rms", None)
+        self.pop.set_fit_hyper(0, model_lr=self.model_lr, reward_loss_coef=getattr(m, "reward_loss_coef", 1.0),
+                               delta_clip_loss=getattr(m, "delta_clip_loss", None), reward_clip_loss=getattr(m, "reward_clip_loss", None),
+                               model_max_grad_norm=self.model_max_grad_norm,
+                               r_mean=float(np.ravel(r_rms.mean)[0]) if r_rms is not None else 0.0,
+                               r_std=float(np.ravel(r_rms.std)[0]) if r_rms is not None else 1.0)
+
+    def _apply_model_grads(self, batch_idx):
+        """``_apply_model_grads`` (mbrl_onpolicy_alg.py:301-319) for one or more minibatches.  The reference passes
+        the gathered rows ``s_batch[B, mb, S]``...; the rows already live in the device replay table, so the device
+        version takes the index matrix ``batch_idx[(steps,) B, mb]`` into ``model_data`` that produced them."""
+        if not getattr(self, "_fit_ready", False):
+            self._setup_model_fit()
+        off = self.env_data.current_size - self.model_data.current_size
+        if off < 0 or self.env_data.steps_total != self.model_data.steps_total:
+            raise NotImplementedError("model_data must be a suffix window of the device-resident env_data rows")
+        idx = np.asarray(batch_idx, np.int64)
+        idx = idx.reshape((-1, 1) + idx.shape[-2:]) + off
+        losses = self.pop.model_fit(idx)
+        self.last_model_losses = losses[-1, 0].cpu().numpy()
+        return losses
+
+    def _update_models(self):
+        """``SAC_exp._update_models`` (:480-609): holdout split, per-epoch (per-model) shuffles with the global NumPy
+        RNG in the reference's order, ragged tail batch dropped, ``model_max_updates`` cap, optional optimiser
+        reset, then the expert-data MSE bookkeeping.  All gradient steps of the call run back to back on the device."""
+        if not getattr(self, "_fit_ready", False):
+            self._setup_model_fit()
+        self._push_fit_hyper()
+
+        def shuffled(n):                       # one np.random.shuffle of arange(n): the reference's only RNG use here
+            order = np.arange(n)
+            np.random.shuffle(order)
+            return order
+
+        n_total = self.model_data.current_size
+        # holdout rows are only withheld from training; the reference's holdout evaluation is commented out (:556-576)
+        rows = shuffled(n_total)[: int(n_total * (1 - self.model_holdout_ratio))] if self.model_holdout_ratio > 0.0 \
+            else np.arange(n_total)
+        mb, nb = self.model_batch_size, len(rows) // self.model_batch_size      # ragged tail batch dropped (:538-540)
+        budget = int(min(self.model_max_updates, self.model_num_epochs * nb))
+        steps, ep = [], 0
+        for ep in range(self.model_num_epochs):
+            if self.model_batch_shuffle:       # every model sees its own order (:526-529)
+                order = np.stack([shuffled(len(rows)) for _ in range(self.B)])
+            else:                              # one order shared by all models (:530-532)
+                order = np.repeat(shuffled(len(rows))[None], self.B, 0)
+            epoch = rows[order[:, : nb * mb]].reshape(self.B, nb, mb).transpose(1, 0, 2)      # [nb, B, mb]
+            steps.extend(epoch[: budget - len(steps)])
+            if nb and len(steps) >= budget:
+                break
+        num_updates = len(steps)
+        if steps:
+            self._apply_model_grads(np.stack(steps))
+        if self.reset_model_optimizer:
+            self.pop.reset_model_optimizer()
+        self._expert_mse_bookkeeping()
+        self.logger.log_train({"model_loss_epochs": ep + 1, "model_updates": num_updates})
+        return num_updates
+
     # ------------------------------------------------------------------ adaptive weight (host, once per episode)
     def _expert_mse_bookkeeping(self):
         """MSE of the models on the expert transitions with expert actions and with one shared stochastic actor

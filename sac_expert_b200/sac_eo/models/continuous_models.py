@@ -1,8 +1,8 @@
 """Learned dynamics models with the reference's interface
 (``/root/reference/sac_eo/models/continuous_models.py``, ``base_world_model.py``): ``sample(s, a,
 deterministic=True)`` = ``s + denorm_delta(MLP([norm(s), norm(a)])[:, :S])``.  Inside the SAC-EO update the
-weights are frozen and only the gradient to the action input is needed; model FITTING (``get_loss``) is the
-first "next" row of SURVEY.md §8f and is not built yet."""
+weights are frozen and only the gradient to the action input is needed; model FITTING runs on the device through
+``SAC_exp._update_models`` / ``Population.model_fit`` (joint optimiser over both models)."""
 import numpy as np
 import torch
 
@@ -23,6 +23,9 @@ class MSEModel(DeviceNet):
         self.separate_reward_nn = bool(model_setup_kwargs.get("separate_reward_nn", False))
         self.delta_clip_pred = model_setup_kwargs.get("delta_clip_pred", None)
         self.reward_clip_pred = model_setup_kwargs.get("reward_clip_pred", None)
+        self.reward_loss_coef = model_setup_kwargs.get("reward_loss_coef", 1.0)
+        self.delta_clip_loss = model_setup_kwargs.get("delta_clip_loss", None)
+        self.reward_clip_loss = model_setup_kwargs.get("reward_clip_loss", None)
         out = self.s_dim if self.separate_reward_nn else self.s_dim + 1
         self._host_weights = create_nn_weights(self.s_dim + self.a_dim, out, self.layers, model_gain)
         self._reward_weights = (create_nn_weights(self.s_dim + self.a_dim, 1, check_two_hidden(reward_layers), reward_gain)
@@ -68,7 +71,8 @@ class MSEModel(DeviceNet):
         return out[0] if out.shape[0] == 1 else out
 
     def get_loss(self, s, sp, a, r):
-        raise NotImplementedError("model fitting is SURVEY.md §8f 'next' row 1 (not part of the update hot path)")
+        raise NotImplementedError("per-model losses are evaluated inside the joint device step: use "
+                                  "SAC_exp._apply_model_grads / Population.model_fit (returns the minibatch losses)")
 
 
 class GaussianModel(MSEModel):

@@ -147,3 +147,62 @@ def test_make_F_and_cg_interface_on_golden_pendulum_actor():
     vFv = float(np.dot(v, F(v).numpy()))
     assert rel(v, gold["cg_x"]) < 2e-2            # 20 fp32 CG iterations vs the fp64 oracle
     assert vFv == pytest.approx(float(gold["vFv"]), rel=2e-2)
+
+
+@pytest.mark.parametrize("shuffle,holdout", [(True, 0.0), (False, 0.0), (True, 0.2)])
+def test_update_models_matches_oracle_with_reference_rng_order(shuffle, holdout):
+    """SAC_exp._update_models (SAC_expert.py:480-609): the index stream (holdout shuffle, per-epoch per-model
+    shuffles, ragged tail dropped, model_max_updates cap) comes from the global NumPy RNG like the reference's,
+    the gradient steps run on the device; the oracle replays the same stream step by step."""
+    from oracle.sac_eo_oracle import apply_model_grads
+    S, A, B, E = 11, 3, 32, 8
+    alg, rng = build_alg("sac_imit", S, A, B, E)
+    alg.alg_kwargs.update(model_num_epochs=2, model_batch_size=50, model_batch_shuffle=shuffle, model_lr=2e-3,
+                          model_max_updates=9, model_max_grad_norm=0.5, model_holdout_ratio=holdout)
+    d = alg.env_data
+    alg.model_data.add(d.s_all, d.a_all, d.r_all, d.sp_all, d.d_all)
+    alg.expert_data.add(rng.standard_normal((E, S)).astype(np.float32), rng.uniform(-1, 1, (E, A)).astype(np.float32),
+                        rng.standard_normal(E).astype(np.float32), rng.standard_normal((E, S)).astype(np.float32),
+                        np.zeros(E, bool))
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48))
+    st = to_torch_state(snapshot(alg, cfg))
+    np.random.seed(77)
+    n_upd = alg._update_models()
+    n = d.current_size
+    n_train = int(n * (1 - holdout)) if holdout else n
+    assert n_upd == min(9, 2 * (n_train // 50))
+    # ---- replay with the oracle
+    np.random.seed(77)
+    rows = np.arange(n)
+    if holdout:
+        perm = np.arange(n)
+        np.random.shuffle(perm)
+        rows = perm[:n_train]
+    models = [st["m1"], st["m2"]]
+    adam = dict(m=[[torch.zeros_like(w) for w in m] for m in models], v=[[torch.zeros_like(w) for w in m] for m in models], t=0)
+    done = 0
+    for ep in range(2):
+        if shuffle:
+            order = []
+            for _ in range(2):
+                o_ = np.arange(n_train)
+                np.random.shuffle(o_)
+                order.append(o_)
+        else:
+            o_ = np.arange(n_train)
+            np.random.shuffle(o_)
+            order = [o_, o_]
+        for k in range(n_train // 50):
+            if done >= 9:
+                break
+            b = [{key: torch.as_tensor(getattr(d, key + "_all")[rows[order[m][50 * k:50 * (k + 1)]]]) for key in ("s", "a", "sp", "r")}
+                 for m in range(2)]
+            out = apply_model_grads(cfg, models, adam, b, st, dict(model_lr=2e-3, model_max_grad_norm=0.5))
+            models, adam = out["models"], dict(m=out["m"], v=out["v"], t=out["t"])
+            done += 1
+    assert done == n_upd and int(alg.pop.t["model_t"][0]) == done
+    for m in range(2):
+        assert abs(float(alg.last_model_losses[m]) - float(out["losses"][m])) < 1e-3 * abs(float(out["losses"][m]))
+        for got, ref, old in zip(alg.models[m].get_weights(), models[m], st["m%d" % (m + 1)]):
+            assert rel(got - old.numpy(), ref.numpy() - old.numpy()) < 2e-3, m     # 9 compounded Adam steps
+    assert len(alg.model_MSE_on_expert_data) == 1 and len(alg.model_MSE_on_expert_counterfactual_action) == 1
