@@ -965,7 +965,7 @@ extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int3
   GemmP p{}; p.nnet = 1; p.A = A; p.B = Bm; p.C = C; p.M = M; p.N = N; p.K = K;
   p.lda = transA ? M : K; p.ldb = transB ? K : N; p.ldc = N;
   p.sAa = (long long)M * K; p.sBa = (long long)K * N; p.sCa = (long long)M * N; p.epi = EPI_NONE;
-  saceo_ctx tmp; tmp.cfg.gemm_mode = gemm_mode & 0xff; tmp.cfg.reserved[0] = (gemm_mode >> 8) & 0xff; tmp.cfg.n_agents = batch;
+  saceo_ctx tmp; memset(&tmp.cfg, 0, sizeof(tmp.cfg)); tmp.cfg.gemm_mode = gemm_mode & 0xff; tmp.cfg.reserved[0] = (gemm_mode >> 8) & 0xff; tmp.cfg.n_agents = batch;
   if ((gemm_mode & 0xff) == SACEO_GEMM_TCGEN05_BF16X3) {
     CU(tc_gemm_init());
     if (!tc_gemm_eligible(transA != 0, transB != 0, false, p))

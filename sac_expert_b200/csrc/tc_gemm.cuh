@@ -855,32 +855,36 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   // ---------------- layer 1: D = h1 . W1   (A from TMEM, W1 streamed) ----------------
   const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
   constexpr int NS1 = FW_H / TS_BK;    // 8 slabs
+  // One block barrier per slab: it publishes slab j's raw data AND the planes of slab j-1, whose MMAs the elected
+  // thread then issues while everybody converts slab j (the issue cost is off the convert -> barrier chain).
+  auto issue_l1 = [&](int js) {
+    const int hs = js & 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = js * 2 + kk;                             // k16 step inside K = 256
+      const uint32_t ko = (uint32_t)(hs * 2 + kk) * 32;
+      const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+      umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
+      umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
+      umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
+    }
+    umma_commit(bars + 8 * hs);
+  };
   for (int j = 0; j < NS1; ++j) {
     const int h = j & 1;
     const uint32_t raw = r2 + (j % 3) * (FW_H * TS_BK * 4);
-    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // buffer of slab j-1: free since last iteration
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's pieces of slab j have landed
+    __syncthreads();                                            // ... everybody's; planes of slab j-1 are complete
+    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // raw buffer of slab j-1 is free now
     asm volatile("cp.async.commit_group;" ::: "memory");       // (possibly empty) keeps the group count uniform
-    asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
-    __syncthreads();
-    if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
+    if (threadIdx.x == 0 && j >= 1) issue_l1(j - 1);
+    if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));      // MMAs of slab j-2 released plane half h
     pw1.convert<true>(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = j * 2 + kk;                            // k16 step inside K = 256
-        const uint32_t ko = (uint32_t)(h * 2 + kk) * 32;
-        const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
-        umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
-        umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
-        umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
-      }
-      umma_commit(bars + 8 * h);
-      if (j == NS1 - 1) umma_commit(bars + 24);
-    }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) { issue_l1(NS1 - 1); umma_commit(bars + 24); }
   mbar_wait(bars + 24, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -1056,32 +1060,35 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   // ---------------- layer 1 transposed: D = dH2 . W1^T ----------------
   const uint32_t b_hi = r1, b_lo = r1 + TS_BPLANE;
   constexpr int NS1 = FW_H / TS_BK;
+  // one block barrier per slab (see k_mlp_fwd_tc): it publishes raw slab j and the planes of slab j-1
+  auto issue_l1 = [&](int js) {
+    const int hs = js & 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int ks = js * 2 + kk;
+      const uint32_t ko = (uint32_t)(hs * 2 + kk) * 32;
+      const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
+      umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
+      umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
+      umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
+    }
+    umma_commit(bars + 8 * hs);
+  };
   for (int j = 0; j < NS1; ++j) {
     const int h = j & 1;
     const uint32_t raw = r2 + (j % 3) * (FW_H * TS_BK * 4);
-    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // buffer of slab j-1: free since last iteration
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's pieces of slab j have landed
+    __syncthreads();                                            // ... everybody's; planes of slab j-1 are complete
+    if (j + 2 < NS1) pw1.issue(r2 + ((j + 2) % 3) * (FW_H * TS_BK * 4));   // raw buffer of slab j-1 is free now
     asm volatile("cp.async.commit_group;" ::: "memory");       // (possibly empty) keeps the group count uniform
-    asm volatile("cp.async.wait_group 2;" ::: "memory");       // slab j has landed (j+1, j+2 may still fly)
-    __syncthreads();
+    if (threadIdx.x == 0 && j >= 1) issue_l1(j - 1);
     if (j >= 2) mbar_wait(bars + 8 * h, (uint32_t)((j / 2 - 1) & 1));
     pw1.convert(raw, h, b_hi, b_lo);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = j * 2 + kk;
-        const uint32_t ko = (uint32_t)(h * 2 + kk) * 32;
-        const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
-        umma_f16_ts(tmem, ta_hi, umma_desc(b_hi + ko), IDESC, ks ? 1u : 0u);
-        umma_f16_ts(tmem, ta_hi, umma_desc(b_lo + ko), IDESC, 1u);
-        umma_f16_ts(tmem, ta_lo, umma_desc(b_hi + ko), IDESC, 1u);
-      }
-      umma_commit(bars + 8 * h);
-      if (j == NS1 - 1) umma_commit(bars + 24);
-    }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) { issue_l1(NS1 - 1); umma_commit(bars + 24); }
   mbar_wait(bars + 24, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 

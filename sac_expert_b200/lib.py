@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsaceo.so")
+LIB_PATH = os.environ.get("SACEO_LIB") or os.path.join(_HERE, "libsaceo.so")     # SACEO_LIB: alternative build (experiments)
 
 ABI_VERSION = 1
 ACT_IDS = {"relu": 0, "tanh": 1, "elu": 2}

@@ -65,7 +65,8 @@ def test_gather_ring_truncation():
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(64, 64, 16), (276, 256, 11), (10, 512, 35), (257, 1, 256), (33, 7, 129),
-                                   (20, 256, 256), (256, 16, 64), (1, 300, 70), (300, 8, 256), (32, 32, 32), (40, 33, 100)])
+                                   (20, 256, 256), (256, 16, 64), (1, 300, 70), (300, 8, 256), (32, 32, 32), (40, 33, 100),
+                                   (36, 256, 256), (36, 256, 276), (63, 100, 70), (12, 512, 200), (49, 64, 31)])
 def test_simt_gemm(ta, tb, M, N, K):
     lib = L.load()
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
