@@ -214,14 +214,20 @@ def run_b200(a):
     expert = np.stack([pop.t["expert_s"].cpu().numpy(), pop.t["expert_sp"].cpu().numpy()], 0) \
         if spec.num_models > 0 else None
     e2e_steps = max(3, min(a.steps, 20))
-    for w in range(2):
+    for w in range(4):                         # warm-up: both pinned staging sets allocated, graphs instantiated
         idx = rng.integers(0, sizes[:, None], size=(a.agents, B)).astype(np.int64)
-        pop.update_host(w, 5, idx, expert)
+        pop.update_host_async(w, 5, idx, expert, slot=w & 1)
+        pop.wait_host(w & 1)
     barrier()
     t0 = time.perf_counter()
+    prev = None
     for sidx in range(e2e_steps):
         idx = rng.integers(0, sizes[:, None], size=(a.agents, B)).astype(np.int64)   # np.random.randint, buffers.py:135
-        out = pop.update_host(sidx, 5, idx, expert)                                 # H2D idx+expert rows, D2H losses
+        pop.update_host_async(sidx, 5, idx, expert, slot=sidx & 1)                  # H2D idx+expert rows, update, D2H losses
+        if prev is not None:
+            out = pop.wait_host(prev)          # the previous step's losses are consumed on the host while this one runs
+        prev = sidx & 1
+    out = pop.wait_host(prev)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
@@ -258,8 +264,9 @@ def run_b200(a):
                    "l2_note": f"population state {bytes_step / 1e9:.2f} GB/step >> 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "note": "Population.update_host: host np.random.randint indices + host expert rows "
-                                            "copied H2D from pinned memory every step, losses copied D2H, stream sync"},
+                "steps": e2e_steps, "note": "Population.update_host_async/wait_host: every step copies host np.random.randint indices + host expert "
+                                            "rows H2D from pinned memory and the losses D2H; two pinned staging sets, so the host draws "
+                                            "step t+1 while the device runs step t"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_note": "DRAM bytes per step from profiles/r1_step_traffic.json (ncu, all launches of one step)",

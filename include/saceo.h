@@ -171,6 +171,13 @@ int saceo_update(saceo_ctx *ctx, int32_t n_steps, int64_t num_timesteps, int32_t
 int saceo_update_host(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,
                       const float *expert_host, float *losses_host, void *stream);
 
+/* Same without the final synchronisation: the copies and the update are only enqueued on `stream`.  The host
+ * buffers (pinned) must stay untouched until the stream reaches this point (record an event after the call);
+ * with two sets of host buffers the caller prepares step t+1 (np.random.randint, env stepping) while the device
+ * runs step t.  The device-side staging is single-buffered and stream-ordered, so calls may be queued back to back. */
+int saceo_update_host_async(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,
+                      const float *expert_host, float *losses_host, void *stream);
+
 /* Phase-split form of one update for the optional single-agent data-parallel mode (gradients are
  * all-reduced by the caller between *_grads and *_apply; torch.distributed/NCCL does the
  * collective).  phase: 0 = TD target + critic grads, 1 = critic Adam(+Polyak), 2 = actor grads,

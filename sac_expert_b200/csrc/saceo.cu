@@ -686,8 +686,8 @@ extern "C" int saceo_update(saceo_ctx* x, int32_t n_steps, int64_t num_timesteps
   return 0;
 }
 
-extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,
-                                 const float* expert_host, float* losses_host, void* stream) {
+static int update_host_impl(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,
+                            const float* expert_host, float* losses_host, void* stream, bool sync) {
   if (!x) return fail(SACEO_E_INVALID, "null ctx");
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; KCtx& k = x->k;
@@ -711,8 +711,16 @@ extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t s
   }
   if (losses_host)
     CU(cudaMemcpyAsync(losses_host, k.losses, sizeof(float) * k.n_agents * x->L.n_losses, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  if (sync) CU(cudaStreamSynchronize(st));
   return 0;
+}
+extern "C" int saceo_update_host(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,
+                                 const float* expert_host, float* losses_host, void* stream) {
+  return update_host_impl(x, num_timesteps, seed, idx_host, expert_host, losses_host, stream, true);
+}
+extern "C" int saceo_update_host_async(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,
+                                       const float* expert_host, float* losses_host, void* stream) {
+  return update_host_impl(x, num_timesteps, seed, idx_host, expert_host, losses_host, stream, false);
 }
 
 extern "C" int saceo_update_phase(saceo_ctx* x, int32_t phase, int64_t num_timesteps, void* stream) {

@@ -357,6 +357,37 @@ class Population:
         self._exit()
         return self._pin_loss.numpy()
 
+    def update_host_async(self, num_timesteps: int, seed: int, idx_host: Optional[np.ndarray] = None,
+                          expert_host: Optional[np.ndarray] = None, slot: int = 0) -> None:
+        """Enqueues one update through HOST buffers without waiting for it.  ``slot`` (0/1) selects one of two pinned
+        staging sets, so the caller can prepare step t+1 on the host (index draws, environment steps) while the
+        device runs step t; ``wait_host(slot)`` returns that step's losses.  A slot must be waited for before reuse."""
+        n, sp_ = self.spec.n_agents, self.spec
+        if not hasattr(self, "_slots"):
+            self._slots = [dict(loss=torch.empty(n, self.L.n_losses, pin_memory=True), idx=None, exp=None,
+                                ev=torch.cuda.Event()) for _ in range(2)]
+        sl = self._slots[slot]
+        ip = ep = None
+        if idx_host is not None:
+            if sl["idx"] is None:
+                sl["idx"] = torch.empty(n, sp_.B, dtype=torch.int64, pin_memory=True)
+            sl["idx"].numpy()[...] = idx_host
+            ip = sl["idx"].data_ptr()
+        if expert_host is not None:
+            if sl["exp"] is None:
+                sl["exp"] = torch.empty(2, n, sp_.E, sp_.S, pin_memory=True)
+            sl["exp"].numpy()[...] = expert_host
+            ep = sl["exp"].data_ptr()
+        st = self._enter()
+        _l.check(self.lib.saceo_update_host_async(self.ctx, num_timesteps, seed, ip, ep, sl["loss"].data_ptr(), st))
+        sl["ev"].record(self.stream)
+
+    def wait_host(self, slot: int = 0) -> np.ndarray:
+        """Blocks until the update enqueued with ``slot`` has finished; returns its losses [n_agents, n_losses] (host)."""
+        sl = self._slots[slot]
+        sl["ev"].synchronize()
+        return sl["loss"].numpy()
+
     def update_phase(self, phase: int, num_timesteps: int = 0):
         st = self._enter()
         _l.check(self.lib.saceo_update_phase(self.ctx, phase, num_timesteps, st))

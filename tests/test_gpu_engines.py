@@ -92,3 +92,37 @@ def test_relu_mask_stability_tcgen05(seed, fuse):
     for k in ("g_q1", "g_q2", "g_actor", "y", "L_pi"):
         assert w[k] < 2e-4, (k, w[k])
     assert max(w.values()) < TOL, w
+
+
+def test_host_buffer_paths_agree():
+    """update_host (synchronous) vs update_host_async/wait_host (double-buffered, queued) vs update() with the same
+    indices injected on the device: identical losses and parameters, bit for bit."""
+    cfg = NetCfg(S=11, A=3, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(64, 64))
+    n, B, E, N, steps = 3, 64, 8, 500, 5
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, N, size=(steps, n, B)).astype(np.int64)
+    outs = []
+    for mode in ("sync", "async", "device"):
+        pop, probs = build(cfg, n_agents=n, B=B, E=E, N=N, seed=4, gemm_mode=L.GEMM_FP32_SIMT)
+        expert = np.stack([pop.t["expert_s"].cpu().numpy(), pop.t["expert_sp"].cpu().numpy()], 0)
+        losses = []
+        if mode == "sync":
+            for s in range(steps):
+                losses.append(pop.update_host(s, 11, idx[s], expert).copy())
+        elif mode == "async":
+            for s in range(steps):
+                pop.update_host_async(s, 11, idx[s], expert, slot=s & 1)
+                if s:
+                    losses.append(pop.wait_host((s - 1) & 1).copy())
+            losses.append(pop.wait_host((steps - 1) & 1).copy())
+        else:
+            for s in range(steps):
+                pop.set_draws(idx=idx[s])
+                losses.append(pop.update(1, num_timesteps=s, use_device_rng=2, seed=11).cpu().numpy().copy())
+        torch.cuda.synchronize()
+        outs.append((np.stack(losses), {k: pop.t[k].cpu().numpy().copy() for k in ("actor", "q", "qt", "alpha")}))
+        pop.close()
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0])
+        for k in outs[0][1]:
+            assert np.array_equal(outs[0][1][k], other[1][k]), k
