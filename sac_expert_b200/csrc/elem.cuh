@@ -13,6 +13,7 @@ namespace saceo {
 
 struct KCtx {
   int n_agents, S, A, Ao, mo, B, E, R, nmod, per_state_std, sep_reward;
+  int Rs;   // row stride of the per-agent [R rows] actor buffers (R rounded up to 32; the pad rows stay zero)
   int ah1, ah2, ch1, ch2, mh1, mh2;
   int aact0, aact1, cact0, cact1, mact0, mact1;
   float delta_clip;
@@ -182,7 +183,7 @@ __global__ void k_stage(KCtx c, int phase) {
     if (e >= B * S) return;
     const int b = e / S, j = e - b * S;
     const float v = (c.mb_sp[((long long)agent * B + b) * S + j] - smean[j]) / nstd(sstd[j]);
-    c.Xpi[((long long)agent * c.R + b) * S + j] = v;
+    c.Xpi[((long long)agent * c.Rs + b) * S + j] = v;
     c.Xc[((long long)agent * B + b) * SA + j] = v;
   } else if (phase == 1) {
     if (e >= B * SA) return;
@@ -196,13 +197,13 @@ __global__ void k_stage(KCtx c, int phase) {
     if (e >= c.R * S) return;
     const int row = e / S, j = e - row * S;
     if (row < B) {
-      c.Xpi[((long long)agent * c.R + row) * S + j] =
+      c.Xpi[((long long)agent * c.Rs + row) * S + j] =
           (c.mb_s[((long long)agent * B + row) * S + j] - smean[j]) / nstd(sstd[j]);
     } else {
       const int i = row - B;
       const int src = c.perm[(long long)agent * c.E + i];
       const float x = c.expert_s[((long long)agent * c.E + src) * S + j];
-      c.Xpi[((long long)agent * c.R + row) * S + j] = (x - smean[j]) / nstd(sstd[j]);
+      c.Xpi[((long long)agent * c.Rs + row) * S + j] = (x - smean[j]) / nstd(sstd[j]);
       const int half = c.nmod == 2 ? c.E / 2 : c.E;
       const int net = i / half, il = i - net * half;
       c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + j] =
@@ -255,7 +256,7 @@ __global__ void k_head_fwd(KCtx c, int nrows, int nmain, const float* __restrict
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows) return;
   const int A = c.A, Ao = c.Ao, S = c.S, SA = S + A;
-  const float* out = c.aOut + ((long long)agent * c.R + row) * Ao;
+  const float* out = c.aOut + ((long long)agent * c.Rs + row) * Ao;
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   const float* lsv = c.T.actor + (long long)agent * c.L.na_stride + (c.L.na - A);
   const float* u = noise ? noise + agent * noise_agent_stride + (long long)(noise_row0 + row) * A : nullptr;
@@ -288,7 +289,7 @@ __global__ void k_head_fwd(KCtx c, int nrows, int nmain, const float* __restrict
     }
   }
   const float nlp = 0.5f * acc_g + acc_c;
-  if (!expert) c.nlp[(long long)agent * c.R + row] = nlp;
+  if (!expert) c.nlp[(long long)agent * c.Rs + row] = nlp;
   if (nlp_out) nlp_out[(long long)agent * out_agent_stride_rows + out_row0 + row] = nlp;
 }
 
@@ -304,7 +305,7 @@ __global__ void k_td_target(KCtx c) {
   const float alpha = c.T.alpha[agent];
   const float q0 = c.cQ[((long long)agent * 2 + 0) * c.B + b] * ret;
   const float q1 = c.cQ[((long long)agent * 2 + 1) * c.B + b] * ret;
-  const float nv = fminf(q0, q1) + alpha * c.nlp[(long long)agent * c.R + b];
+  const float nv = fminf(q0, q1) + alpha * c.nlp[(long long)agent * c.Rs + b];
   const long long o = (long long)agent * c.B + b;
   c.y[o] = c.mb_r[o] + gamma * (c.mb_omd[o] * nv);
 }
@@ -342,7 +343,7 @@ __global__ void k_actor_q(KCtx c) {
     const float s0 = q0 < q1 ? 1.f : (q0 == q1 ? 0.5f : 0.f);
     c.cdQ[((long long)agent * 2 + 0) * c.B + b] = sc * s0;
     c.cdQ[((long long)agent * 2 + 1) * c.B + b] = sc * (1.f - s0);
-    acc += -alpha * c.nlp[(long long)agent * c.R + b] - fminf(q0, q1);
+    acc += -alpha * c.nlp[(long long)agent * c.Rs + b] - fminf(q0, q1);
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
@@ -392,8 +393,8 @@ __global__ void k_head_bwd(KCtx c, int nrows) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows) return;
   const int A = c.A, Ao = c.Ao, B = c.B;
-  const float* out = c.aOut + ((long long)agent * c.R + row) * Ao;
-  float* dout = c.daOut + ((long long)agent * c.R + row) * Ao;
+  const float* out = c.aOut + ((long long)agent * c.Rs + row) * Ao;
+  float* dout = c.daOut + ((long long)agent * c.Rs + row) * Ao;
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   const float* lsv = c.T.actor + (long long)agent * c.L.na_stride + (c.L.na - A);
   const float alpha = c.T.alpha[agent];
@@ -429,7 +430,7 @@ __global__ void k_head_bwd(KCtx c, int nrows) {
     const float dl = (dz * sd * u[j] + g_nlp) * mask;
     dout[j] = dz;
     if (c.per_state_std) dout[A + j] = dl;
-    else c.dls[((long long)agent * c.R + row) * A + j] = dl;
+    else c.dls[((long long)agent * c.Rs + row) * A + j] = dl;
   }
 }
 
@@ -439,7 +440,7 @@ __global__ void k_lsv_reduce(KCtx c, int nrows) {
   const int agent = blockIdx.x, j = threadIdx.x;
   if (j >= c.A) return;
   float acc = 0.f;
-  for (int r = 0; r < nrows; ++r) acc += c.dls[((long long)agent * c.R + r) * c.A + j];
+  for (int r = 0; r < nrows; ++r) acc += c.dls[((long long)agent * c.Rs + r) * c.A + j];
   c.g_actor[(long long)agent * c.L.na_stride + (c.L.na - c.A) + j] = acc;
 }
 
@@ -475,7 +476,7 @@ __global__ void k_alpha_step(KCtx c, int apply) {
   const float* hy = c.T.hyper + (long long)agent * c.L.hyper_stride;
   const float te = hy[6];
   float acc = 0.f;
-  for (int b = threadIdx.x; b < c.B; b += blockDim.x) acc += -c.nlp[(long long)agent * c.R + b] + te;
+  for (int b = threadIdx.x; b < c.B; b += blockDim.x) acc += -c.nlp[(long long)agent * c.Rs + b] + te;
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
     float* ls = c.losses + (long long)agent * c.L.n_losses;

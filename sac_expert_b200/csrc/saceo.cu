@@ -144,7 +144,7 @@ static void carve(saceo_ctx* x, char* base) {
   KCtx& k = x->k;
   Bump b{base, 0, base ? &x->names : nullptr};
   const long long n = c.n_agents;
-  const int S = c.S, A = c.A, B = c.B, E = c.num_models > 0 ? c.E : 0, R = B + E;
+  const int S = c.S, A = c.A, B = c.B, E = c.num_models > 0 ? c.E : 0, R = (int)rup(B + E, 32);   // padded row stride
   const int SA = S + A;
   k.idx = b.get<long long>("idx", n * B);
   k.noise = b.get<float>("noise", n * (3LL * B + E) * A);
@@ -239,7 +239,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   carve(x, (char*)x->ws);
   KCtx& k = x->k;
   k.n_agents = cfg->n_agents; k.S = cfg->S; k.A = cfg->A; k.Ao = x->L.Ao; k.mo = x->L.model_out;
-  k.B = cfg->B; k.E = cfg->num_models > 0 ? cfg->E : 0; k.R = k.B + k.E; k.nmod = cfg->num_models;
+  k.B = cfg->B; k.E = cfg->num_models > 0 ? cfg->E : 0; k.R = k.B + k.E; k.Rs = (int)rup(k.R, 32); k.nmod = cfg->num_models;
   k.per_state_std = cfg->per_state_std; k.sep_reward = cfg->separate_reward_nn;
   k.ah1 = cfg->actor_hidden[0]; k.ah2 = cfg->actor_hidden[1];
   k.ch1 = cfg->critic_hidden[0]; k.ch2 = cfg->critic_hidden[1];
@@ -395,8 +395,12 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
                         int rows, const float* H1, const float* H2, long long rowsAllocH,
                         const float* dOut, int ldd, long long sDa, long long sDn, int out_cols,
                         float* dH2, float* dH1, float* grads, long long sGa, long long sGn,
-                        float* dXa, int S_cols, int A_cols, long long sXaA, long long sXaN, cudaStream_t st) {
+                        float* dXa, int S_cols, int A_cols, long long sXaA, long long sXaN, cudaStream_t st,
+                        bool kpad = false) {
   const int na = x->cfg.n_agents;
+  // kpad: the caller guarantees that rows [rows, rowsAllocH) of X, H1, H2, dOut, dH2, dH1 are zero, so the
+  // weight-gradient contractions may run over a row count rounded up to the 32-row slabs of the streaming kernel
+  const int krows = (kpad && rup(rows, 32) <= rowsAllocH) ? (int)rup(rows, 32) : rows;
   const long long sH1a = (long long)n.nnet * rowsAllocH * n.h1, sH1n = rowsAllocH * n.h1;
   const long long sH2a = (long long)n.nnet * rowsAllocH * n.h2, sH2n = rowsAllocH * n.h2;
   int rc;
@@ -423,7 +427,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.A = H2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
     p.B = dOut; p.ldb = ldd; p.sBa = sDa; p.sBn = sDn;
     p.C = grads + n.oW2(); p.ldc = n.out; p.sCa = sGa; p.sCn = sGn;
-    p.M = n.h2 + 1; p.N = n.out; p.K = rows; p.epi = EPI_NONE;
+    p.M = n.h2 + 1; p.N = n.out; p.K = krows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
   if (!fused) {
@@ -440,7 +444,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.A = H1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
     p.B = dH2; p.ldb = n.h2; p.sBa = sH2a; p.sBn = sH2n;
     p.C = grads + n.oW1(); p.ldc = n.h2; p.sCa = sGa; p.sCn = sGn;
-    p.M = n.h1 + 1; p.N = n.h2; p.K = rows; p.epi = EPI_NONE;
+    p.M = n.h1 + 1; p.N = n.h2; p.K = krows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
   if (!fused) {
@@ -457,7 +461,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
     p.B = dH1; p.ldb = n.h1; p.sBa = sH1a; p.sBn = sH1n;
     p.C = grads + n.oW0(); p.ldc = n.h1; p.sCa = sGa; p.sCn = sGn;
-    p.M = n.in + 1; p.N = n.h1; p.K = rows; p.epi = EPI_NONE;
+    p.M = n.in + 1; p.N = n.h1; p.K = krows; p.epi = EPI_NONE;
     rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
   }
   if (dXa && !fused) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
@@ -509,8 +513,8 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
   int rc;
   NetD an = actor_net(x), tn = critic_net(x, true), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)B * S, 256), n), 256, 0, st, k, 0);
-  rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                   (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
+  rc = mlp_forward(x, an, k.Xpi, S, (long long)k.Rs * S, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+                   (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 0, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   rc = mlp_forward(x, tn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
@@ -533,11 +537,11 @@ static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
 
 // phase 2: actor gradients (policy loss through the UPDATED critics + expert-observation term)
 static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
-  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E;
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
   int rc;
   NetD an = actor_net(x), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
-  rc = mlp_forward(x, an, k.Xpi, S, (long long)R * S, 0, R, k.aH1, k.aH2, R, k.aOut, k.Ao, (long long)R * k.Ao, 0, st);
+  rc = mlp_forward(x, an, k.Xpi, S, (long long)Rs * S, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
@@ -598,8 +602,8 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
     }
   }
   LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
-  rc = mlp_backward(x, an, k.Xpi, S, (long long)R * S, 0, R, k.aH1, k.aH2, R, k.daOut, k.Ao, (long long)R * k.Ao, 0,
-                    k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st);
+  rc = mlp_backward(x, an, k.Xpi, S, (long long)Rs * S, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
+                    k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
   return check_launch();
@@ -616,8 +620,8 @@ static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
 static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
   const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A;
   NetD an = actor_net(x);
-  int rc = mlp_forward(x, an, k.Xpi, S, (long long)k.R * S, 0, B, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                       (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
+  int rc = mlp_forward(x, an, k.Xpi, S, (long long)k.Rs * S, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+                       (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 2 * B + k.E, 0,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   LAUNCH(x, k_alpha_step, dim3(n), 256, 0, st, k, apply);
@@ -765,9 +769,9 @@ extern "C" int saceo_actor_forward(saceo_ctx* x, const float* obs, int32_t rows,
   for (int r0 = 0; r0 < rows; r0 += k.B) {
     const int nr = rows - r0 < k.B ? rows - r0 : k.B;
     LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xpi, k.S,
-           (long long)k.R * k.S, 0);
-    int rc = mlp_forward(x, an, k.Xpi, k.S, (long long)k.R * k.S, 0, nr, k.aH1, k.aH2, k.R, k.aOut, k.Ao,
-                         (long long)k.R * k.Ao, 0, st, false); if (rc) return rc;
+           (long long)k.Rs * k.S, 0);
+    int rc = mlp_forward(x, an, k.Xpi, k.S, (long long)k.Rs * k.S, 0, nr, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+                         (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
     LAUNCH(x, k_head_fwd, dim3(cdiv(nr, 128), n), 128, 0, st, k, nr, nr, noise, (long long)rows * k.A, r0, 0,
            act_out, neglogp_out, (long long)rows, r0);
   }
