@@ -22,7 +22,7 @@ struct FitCtx {
   float *gscale;         // [n_agents] gradient scale of clip_by_global_norm (1 when clipping is off)
   float *gnorm;          // [n_agents] global gradient norm (diagnostic)
   float *lrt;            // [n_agents] bias-corrected Adam step size
-  int mb, nmod, use_clip;
+  int mb, mbs, nmod, use_clip;     // mbs: row stride of the minibatch buffers (mb rounded up to 32, pad rows stay zero)
   long long nm, nm_stride;
 };
 
@@ -58,22 +58,22 @@ __global__ void k_fit_stage(KCtx c, FitCtx f, const long long* __restrict__ idx)
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   const float* hy = f.hyper + (long long)agent * FIT_HYPER;
   if (col < S) {
-    f.X[(an * f.mb + row) * SA + col] = (src[c.L.off_s + col] - nr[c.L.off_m_s_mean + col]) / nstd(nr[c.L.off_m_s_std + col]);
+    f.X[(an * f.mbs + row) * SA + col] = (src[c.L.off_s + col] - nr[c.L.off_m_s_mean + col]) / nstd(nr[c.L.off_m_s_std + col]);
   } else if (col < SA) {
     const int j = col - S;
-    f.X[(an * f.mb + row) * SA + col] = (src[c.L.off_a + j] - nr[c.L.off_m_a_mean + j]) / nstd(nr[c.L.off_m_a_std + j]);
+    f.X[(an * f.mbs + row) * SA + col] = (src[c.L.off_a + j] - nr[c.L.off_m_a_mean + j]) / nstd(nr[c.L.off_m_a_std + j]);
   } else if (col < SA + S) {
     const int j = col - SA;
     const float d = src[c.L.off_sp + j] - src[c.L.off_s + j];
     float dn = (d - nr[c.L.off_m_d_mean + j]) / nstd(nr[c.L.off_m_d_std + j]);
     const float cl = hy[FIT_DCLIP];
     if (cl > 0.f) dn = fminf(fmaxf(dn, -cl), cl);
-    f.T[(an * f.mb + row) * (S + 1) + j] = dn;
+    f.T[(an * f.mbs + row) * (S + 1) + j] = dn;
   } else {
     float rn = (src[c.L.off_r] - hy[FIT_RMEAN]) / nstd(hy[FIT_RSTD]);
     const float cl = hy[FIT_RCLIP];
     if (cl > 0.f) rn = fminf(fmaxf(rn, -cl), cl);
-    f.T[(an * f.mb + row) * (S + 1) + S] = rn;
+    f.T[(an * f.mbs + row) * (S + 1) + S] = rn;
   }
 }
 
@@ -88,9 +88,9 @@ __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
   const float inv = 1.f / (float)f.mb;
   float acc = 0.f;
   for (int row = threadIdx.x; row < f.mb; row += blockDim.x) {
-    const float* P = f.Out + (an * f.mb + row) * mo;
-    const float* T = f.T + (an * f.mb + row) * mo;
-    float* dP = f.dOut + (an * f.mb + row) * mo;
+    const float* P = f.Out + (an * f.mbs + row) * mo;
+    const float* T = f.T + (an * f.mbs + row) * mo;
+    float* dP = f.dOut + (an * f.mbs + row) * mo;
     float dl = 0.f;
     for (int j = 0; j < c.S; ++j) {
       const float e = P[j] - T[j];

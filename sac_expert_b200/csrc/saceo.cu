@@ -834,9 +834,9 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
   FitCtx& f = x->fit;
   memset(&f, 0, sizeof(f));
   f.model = t->model; f.m = t->model_m; f.v = t->model_v; f.t = t->model_t; f.hyper = t->fit_hyper;
-  f.mb = model_batch; f.nmod = c.num_models; f.use_clip = use_grad_clip;
+  f.mb = model_batch; f.mbs = (int)rup(model_batch, 32); f.nmod = c.num_models; f.use_clip = use_grad_clip;
   f.nm = x->L.nm; f.nm_stride = x->L.nm_stride;
-  const long long n2 = 2LL * c.n_agents, mb = model_batch, SA = c.S + c.A, mo = x->L.model_out;
+  const long long n2 = 2LL * c.n_agents, mb = f.mbs, SA = c.S + c.A, mo = x->L.model_out;
   for (int pass = 0; pass < 2; ++pass) {
     Bump b{pass ? (char*)x->fit_ws : nullptr, 0, pass ? &x->names : nullptr};
     f.X = b.get<float>("fit_X", n2 * mb * SA);        f.T = b.get<float>("fit_T", n2 * mb * mo);
@@ -868,21 +868,21 @@ extern "C" int saceo_model_fit(saceo_ctx* x, int32_t n_steps, const int64_t* idx
   if (!idx || n_steps < 0) return fail(SACEO_E_INVALID, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const KCtx& k = x->k; const FitCtx& f = x->fit;
-  const int n = k.n_agents, mb = f.mb, SA = k.S + k.A, mo = x->L.model_out;
+  const int n = k.n_agents, mb = f.mb, ms = f.mbs, SA = k.S + k.A, mo = x->L.model_out;
   NetD net{f.model, 2 * x->L.nm_stride, x->L.nm_stride, f.nmod, SA, x->cfg.model_hidden[0], x->cfg.model_hidden[1], mo,
            x->cfg.model_act[0], x->cfg.model_act[1]};
   for (int s = 0; s < n_steps; ++s) {
     const long long* ix = reinterpret_cast<const long long*>(idx) + (long long)s * n * f.nmod * mb;
     LAUNCH(x, k_fit_begin, cdiv(n, 128), 128, 0, st, f, n);
     LAUNCH(x, k_fit_stage, dim3(cdiv((long long)mb * (SA + k.S + 1), 256), f.nmod, n), 256, 0, st, k, f, ix);
-    int rc = mlp_forward(x, net, f.X, SA, 2LL * mb * SA, (long long)mb * SA, mb, f.H1, f.H2, mb, f.Out, mo,
-                         2LL * mb * mo, (long long)mb * mo, st, true);
+    int rc = mlp_forward(x, net, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.H1, f.H2, ms, f.Out, mo,
+                         2LL * ms * mo, (long long)ms * mo, st, true);
     if (rc) return rc;
     LAUNCH(x, k_fit_loss, dim3(f.nmod, n), 256, 0, st, k, f,
            losses_out ? losses_out + (long long)s * n * f.nmod : (float*)nullptr);
-    rc = mlp_backward(x, net, f.X, SA, 2LL * mb * SA, (long long)mb * SA, mb, f.H1, f.H2, mb, f.dOut, mo,
-                      2LL * mb * mo, (long long)mb * mo, mo, f.dH2, f.dH1, f.g, 2 * x->L.nm_stride, x->L.nm_stride,
-                      nullptr, 0, 0, 0, 0, st);
+    rc = mlp_backward(x, net, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.H1, f.H2, ms, f.dOut, mo,
+                      2LL * ms * mo, (long long)ms * mo, mo, f.dH2, f.dH1, f.g, 2 * x->L.nm_stride, x->L.nm_stride,
+                      nullptr, 0, 0, 0, 0, st, false);    // K = 200 on the register-staged kernel beats K = 224 streamed (measured)
     if (rc) return rc;
     if (f.use_clip) LAUNCH(x, k_fit_gnorm, n, 1024, 0, st, f);
     LAUNCH(x, k_fit_adam, dim3(cdiv(f.nm, 256), f.nmod, n), 256, 0, st, f);
