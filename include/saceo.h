@@ -83,7 +83,8 @@ typedef struct saceo_config {
   int32_t use_graph;          /* capture one update into a CUDA graph and replay it */
   int32_t reserved[8];        /* tuning switches, 0 = default: [0] tcgen05 tile variant (0: 128x256 tile, 1: 128x128 2 CTAs/SM,
                                  2: force the register-staged kernel); [1] != 0 disables the fused 3-layer forward kernel;
-                                 [2] != 0 disables the fused backward-chain kernel; [3] != 0 disables the fused model-term kernel */
+                                 [2] != 0 disables the fused backward-chain kernel; [3] != 0 disables the fused model-term kernel;
+                                 [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */

@@ -59,6 +59,7 @@ struct saceo_ctx {
   std::map<std::string, std::pair<void*, long long>> names;
   float *exp_stage = nullptr;          // [n, 2, E, S] host-staged expert rows
   long long* idx_stage = nullptr;
+  float* dbpart = nullptr;             // per-tile bias-gradient partials of the fused backward kernel
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -175,6 +176,7 @@ static void carve(saceo_ctx* x, char* base) {
   k.lrt = b.get<float>("lrt", n * 4);
   k.losses = b.get<float>("losses", n * L.n_losses);
   k.mse_part = b.get<float>("mse_part", n * 2);
+  x->dbpart = b.get<float>("dbpart", n * 2 * cdiv(R > B ? R : B, TC_BM) * 2 * FW_H);
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
   x->exp_stage = b.get<float>("exp_stage", n * 2 * e1 * S);
   x->idx_stage = b.get<long long>("idx_stage", n * B);
@@ -406,7 +408,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   int rc;
   GemmP p{};
   // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
-  bool fused = false;
+  bool fused = false, bias_done = false;
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[2] == 0 && n.h1 == FW_H && n.h2 == FW_H &&
       out_cols >= 1 && out_cols <= 32 && rows >= TC_BM && (rows % TC_BM == 0 || rows % TC_BM >= 16) &&
       (!dXa || A_cols <= 32) && ((reinterpret_cast<uintptr_t>(n.theta) & 15) == 0) && ((n.sa & 3) == 0) && ((n.sn & 3) == 0)) {
@@ -417,10 +419,16 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     f.dH2 = grads ? dH2 : nullptr; f.dH1 = grads ? dH1 : nullptr;
     f.dXa = dXa; f.s_cols = S_cols; f.a_cols = A_cols; f.sXa = sXaA; f.sXn = sXaN;
     f.rows = rows; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    f.dbpart = (grads && x->dbpart && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
     dim3 grid((rows + TC_BM - 1) / TC_BM, na * n.nnet);
     k_mlp_bwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
     x->launches++;
     fused = true;
+    if (f.dbpart) {     // bias gradients of the two hidden layers come from the kernel's column sums
+      k_bias_finish<<<na * n.nnet, 2 * FW_H, 0, st>>>(f.dbpart, (int)grid.x, grads, sGa, sGn, n.nnet, n.ob1(), n.ob0());
+      x->launches++;
+      bias_done = true;
+    }
   }
   if (grads) {   // [dW2; db2] = [H2,1]^T . dOut
     p = GemmP{}; p.nnet = n.nnet;
@@ -444,8 +452,8 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.A = H1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
     p.B = dH2; p.ldb = n.h2; p.sBa = sH2a; p.sBn = sH2n;
     p.C = grads + n.oW1(); p.ldc = n.h2; p.sCa = sGa; p.sCn = sGn;
-    p.M = n.h1 + 1; p.N = n.h2; p.K = krows; p.epi = EPI_NONE;
-    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+    p.M = bias_done ? n.h1 : n.h1 + 1; p.N = n.h2; p.K = krows; p.epi = EPI_NONE;
+    rc = gemm(x, true, false, !bias_done, p, na, st); if (rc) return rc;
   }
   if (!fused) {
   // dH1 = (dH2 . W1^T) * act0'(H1)
@@ -461,8 +469,8 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
     p.B = dH1; p.ldb = n.h1; p.sBa = sH1a; p.sBn = sH1n;
     p.C = grads + n.oW0(); p.ldc = n.h1; p.sCa = sGa; p.sCn = sGn;
-    p.M = n.in + 1; p.N = n.h1; p.K = krows; p.epi = EPI_NONE;
-    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+    p.M = bias_done ? n.in : n.in + 1; p.N = n.h1; p.K = krows; p.epi = EPI_NONE;
+    rc = gemm(x, true, false, !bias_done, p, na, st); if (rc) return rc;
   }
   if (dXa && !fused) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
     p = GemmP{}; p.nnet = n.nnet;

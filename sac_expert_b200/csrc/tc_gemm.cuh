@@ -704,7 +704,9 @@ template <bool BWD>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tmem, uint32_t patch_base, const float* __restrict__ auxp, int act,
                                                  float* __restrict__ Gout, int row0, int rows, int warp, int lane,
                                                  const float* __restrict__ outer_w = nullptr, float outer_s = 0.f,
-                                                 const float* __restrict__ qdot_w = nullptr) {
+                                                 const float* __restrict__ qdot_w = nullptr, uint32_t cs_base = 0) {
+  // cs_base != 0 (needs Gout): column sums of the tile over this warp's 32 rows go to smem [4 quarters][256] (floats) -
+  // the bias gradients of the layer below, so that no separate pass has to re-read the tile from global memory.
   const int q = warp & 3, grp = warp >> 2;                 // lane quarter, 64-column group
   constexpr int PSTR = 36;
   const uint32_t patch = patch_base + (uint32_t)warp * 32 * PSTR * 4;
@@ -762,6 +764,13 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tmem, uint32_t patch_b
           const float4 t4 = lds128(patch + (uint32_t)(r * PSTR + lc) * 4);
           *reinterpret_cast<float4*>(Gout + (long long)grow * FW_H + col + lc) = t4;
         }
+      }
+      if (cs_base) {
+        const int nvalid = rows - (row0 + q * 32);
+        float cs = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) { const float t = lds32(patch + (uint32_t)(r * PSTR + lane) * 4); cs += r < nvalid ? t : 0.f; }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cs_base + (uint32_t)(q * FW_H + col + lane) * 4), "f"(cs) : "memory");
       }
       __syncwarp();
     }
@@ -973,6 +982,7 @@ struct BwdP {
   float* dH2; float* dH1;                                      // optional outputs, strides as H
   float* dXa; int s_cols, a_cols; long long sXa, sXn;         // optional [rows, a_cols]
   int rows, nnet, act0, act1;
+  float* dbpart;      // optional [agent*nnet+net][tile][2][256]: column sums of dH2 (slot 0) and dH1 (slot 1) per row tile
 };
 
 __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
@@ -981,6 +991,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   const uint32_t r1 = sb, r2 = sb + FW_R1;
   const uint32_t bars = sb + FW_MAIN;                  // [0],[1] half free, [2] layer2^T, [3] layer1^T, [4] layer0^T
   const uint32_t tmem_slot = bars + 40;
+  const uint32_t cs2 = r1 + 80 * 1024, cs1 = cs2 + 4096;    // column-sum scratch, beyond the patches / planes / W0 stage
   const int z = blockIdx.y;
   const int agent = z / f.nnet, net = z - agent * f.nnet;
   const int row0 = blockIdx.x * TC_BM;
@@ -1052,7 +1063,8 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   {
     const int grow = row0 + (warp & 3) * 32 + lane;
     const float dq = (outer && grow < f.rows) ? __ldg(dOut + (long long)grow * f.ldd) : 0.f;
-    hidden_epilogue<true>(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane, outer ? th + oW2 : nullptr, dq);
+    hidden_epilogue<true>(tmem, r1, H2, f.act1, dH2, row0, f.rows, warp, lane, outer ? th + oW2 : nullptr, dq, nullptr,
+                          (f.dbpart && dH2) ? cs2 : 0u);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -1096,7 +1108,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) sw0[kc].ld(kc * TC_BK, FW_H);
   }
-  hidden_epilogue<true>(tmem, r1, H1, f.act0, dH1, row0, f.rows, warp, lane);
+  hidden_epilogue<true>(tmem, r1, H1, f.act0, dH1, row0, f.rows, warp, lane, nullptr, 0.f, nullptr, (f.dbpart && dH1) ? cs1 : 0u);
   if (f.dXa) {
     __syncthreads();
     const uint32_t w0s = r1;
@@ -1133,9 +1145,26 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (f.dbpart && f.dH2 && f.dH1) {      // fixed-order sum of the four row quarters -> per-tile bias-gradient partials
+    const int t = threadIdx.x & (FW_H - 1), which = threadIdx.x >> 8;
+    const uint32_t b = (which ? cs1 : cs2) + (uint32_t)t * 4;
+    const float v = ((lds32(b) + lds32(b + FW_H * 4)) + lds32(b + 2 * FW_H * 4)) + lds32(b + 3 * FW_H * 4);
+    f.dbpart[(((long long)z * gridDim.x + blockIdx.x) * 2 + which) * FW_H + t] = v;
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
+}
+
+// g[ob1 + c] = sum_tiles dbpart[.][tile][0][c],  g[ob0 + c] = sum_tiles dbpart[.][tile][1][c]   (fixed tile order)
+// grid: (n_agents * nnet), block 512
+__global__ void k_bias_finish(const float* __restrict__ dbpart, int ntiles, float* __restrict__ g, long long sGa, long long sGn,
+                              int nnet, long long ob1, long long ob0) {
+  const int z = blockIdx.x, agent = z / nnet, net = z - agent * nnet;
+  const int t = threadIdx.x & (FW_H - 1), which = threadIdx.x >> 8;
+  float acc = 0.f;
+  for (int tile = 0; tile < ntiles; ++tile) acc += dbpart[(((long long)z * ntiles + tile) * 2 + which) * FW_H + t];
+  g[agent * sGa + net * sGn + (which ? ob0 : ob1) + t] = acc;
 }
 
 static inline bool mlp_fwd_tc_eligible(int h1, int h2, int nout, int rows, const float* theta, long long sTa, long long sTn, int K0) {
