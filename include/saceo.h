@@ -207,15 +207,19 @@ int saceo_model_eval(saceo_ctx *ctx, const float *obs, const float *act, int32_t
  * (sac_eo/models/continuous_models.py:280-302) on BaseWorldModel._forward(clip=False)
  * (sac_eo/models/base_world_model.py:65-87).  Replaces self.model_optimizer (one tf.keras Adam over the
  * tensors of ALL models, mbrl_onpolicy_alg.py:48-49) and tf.clip_by_global_norm (:315-317).
+ * GaussianModel.get_loss (continuous_models.py:101-131) is used instead when the logstd tables are given.
  * Single-network models only (separate_reward_nn == 0).  fit_hyper per agent (8 floats):
  *   [0] model_lr  [1] reward_loss_coef  [2] delta_clip_loss (0 = off)  [3] reward_clip_loss (0 = off)
- *   [4] model_max_grad_norm (0 = None)  [5] r_rms mean  [6] r_rms std  [7] pad                      */
+ *   [4] model_max_grad_norm (0 = None)  [5] r_rms mean  [6] r_rms std  [7] scale_model_loss (0/1, Gaussian only) */
 #define SACEO_FIT_HYPER 8
 typedef struct saceo_fit_tables {
   float *model;                /* [n_agents, 2, nm_stride] trainable; normally the table bound as saceo_tables.model */
   float *model_m, *model_v;    /* Adam slots, same shape */
   int32_t *model_t;            /* [n_agents] step count of the joint optimiser */
   const float *fit_hyper;      /* [n_agents, SACEO_FIT_HYPER] */
+  /* GaussianModel only (all three NULL => MSEModel loss): the trainable logstd variable [n_agents, 2, S]
+   * (continuous_models.py:24-27, initial value log(std_mult)) and its Adam slots; part of the same joint optimiser */
+  float *model_logstd, *model_logstd_m, *model_logstd_v;
 } saceo_fit_tables;
 
 /* Binds the fit tables and allocates the fitting workspace for minibatches of model_batch rows

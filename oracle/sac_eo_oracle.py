@@ -329,12 +329,17 @@ def sac_eo_update(cfg: NetCfg, state: Dict, batch: Dict, hyper: Dict) -> Dict:
 # --------------------------------------------------------------------------------------
 def model_loss(cfg: NetCfg, theta_m, s_: Tensor, a_: Tensor, sp_: Tensor, r_: Tensor, st: Dict,
                reward_loss_coef: float = 1.0, delta_clip_loss: float = 0.0,
-               reward_clip_loss: float = 0.0) -> Tensor:
-    """``MSEModel.get_loss`` (continuous_models.py:280-302) on ``BaseWorldModel._forward(s, a,
-    clip=False)`` (base_world_model.py:65-87): the net predicts the NORMALISED state delta in its
-    first S outputs and the normalised reward in the last one; targets are normalised with the
-    model's ``delta_rms`` / ``r_rms`` and optionally clipped; loss = mean_b(0.5*sum_j (dn-dp)^2 +
-    coef*0.5*(rn-rp)^2).  Single-network models only (``separate_reward_nn`` is not restated)."""
+               reward_clip_loss: float = 0.0, logstd: Optional[Tensor] = None,
+               scale_model_loss: bool = False) -> Tensor:
+    """``MSEModel.get_loss`` (continuous_models.py:280-302) / ``GaussianModel.get_loss`` (:101-131) on
+    ``BaseWorldModel._forward(s, a, clip=False)`` (base_world_model.py:65-87): the net predicts the
+    NORMALISED state delta in its first S outputs and the normalised reward in the last one; targets
+    are normalised with the model's ``delta_rms`` / ``r_rms`` and optionally clipped.
+    MSE:      loss = mean_b(0.5*sum_j (dn-dp)^2 + coef*0.5*(rn-rp)^2)
+    Gaussian: ``logstd`` [1,S] (trainable, NOT clipped): neglogp = 0.5*sum_j(((dn-dp)/exp(ls))^2 + 2 ls +
+              log 2pi); loss = mean_b(scale*neglogp + coef*0.5*(rn-rp)^2), scale = stop_gradient(mean(
+              exp(ls)^2)) with ``scale_model_loss`` else 1.
+    Single-network models only (``separate_reward_nn`` is not restated)."""
     if cfg.separate_reward_nn:
         raise ValueError("model fitting with separate_reward_nn is not restated")
     sa = torch.cat([normalize(s_, st["m_s_mean"], st["m_s_std"]),
@@ -344,7 +349,13 @@ def model_loss(cfg: NetCfg, theta_m, s_: Tensor, a_: Tensor, sp_: Tensor, r_: Te
     delta_norm = normalize(sp_ - s_, st["m_d_mean"], st["m_d_std"])
     if delta_clip_loss:
         delta_norm = torch.clamp(delta_norm, -delta_clip_loss, delta_clip_loss)
-    delta_loss = 0.5 * ((delta_norm - delta_pred) ** 2).sum(-1)
+    if logstd is None:
+        delta_loss = 0.5 * ((delta_norm - delta_pred) ** 2).sum(-1)
+    else:
+        vec = ((delta_norm - delta_pred) / torch.exp(logstd)) ** 2 + 2 * logstd + math.log(2 * math.pi)
+        delta_loss = 0.5 * vec.sum(-1)
+        if scale_model_loss:
+            delta_loss = (torch.exp(logstd) ** 2).mean().detach() * delta_loss
     r_norm = normalize(r_, st.get("m_r_mean", 0.0), st.get("m_r_std", 1.0))
     if reward_clip_loss:
         r_norm = torch.clamp(r_norm, -reward_clip_loss, reward_clip_loss)
@@ -358,15 +369,19 @@ def apply_model_grads(cfg: NetCfg, models: List[List[Tensor]], adam: Dict, batch
     (each on its own minibatch) are summed under one tape, the gradient list is optionally clipped
     with ``tf.clip_by_global_norm(grads, model_max_grad_norm * num_models)`` and ONE Keras Adam
     (lr ``model_lr``, one shared step counter) applies it to every model's tensors.
-    ``adam`` = dict(m=[per model lists], v=[...], t=int); ``batches[k]`` = dict(s,a,sp,r) tensors."""
+    ``adam`` = dict(m=[per model lists], v=[...], t=int); ``batches[k]`` = dict(s,a,sp,r) tensors.
+    ``GaussianModel``: pass each model's tensor list with the ``logstd`` [1,S] variable appended
+    (``model_trainable = nn weights + [logstd]``, continuous_models.py:27) and ``fit["gaussian"] = True``."""
     dt = models[0][0].dtype
+    gauss = bool(fit.get("gaussian", False))
     live = [[w.detach().clone().requires_grad_(True) for w in th] for th in models]
     losses = []
     for k, th in enumerate(live):
         b = batches[k]
-        losses.append(model_loss(cfg, th, b["s"].to(dt), b["a"].to(dt), b["sp"].to(dt), b["r"].to(dt), st,
-                                 fit.get("reward_loss_coef", 1.0), fit.get("delta_clip_loss", 0.0),
-                                 fit.get("reward_clip_loss", 0.0)))
+        losses.append(model_loss(cfg, th[:-1] if gauss else th, b["s"].to(dt), b["a"].to(dt), b["sp"].to(dt),
+                                 b["r"].to(dt), st, fit.get("reward_loss_coef", 1.0), fit.get("delta_clip_loss", 0.0),
+                                 fit.get("reward_clip_loss", 0.0), th[-1] if gauss else None,
+                                 bool(fit.get("scale_model_loss", False))))
     flat_params = [w for th in live for w in th]
     grads = list(torch.autograd.grad(sum(losses), flat_params))
     gnorm = torch.sqrt(sum((g ** 2).sum() for g in grads))

@@ -11,18 +11,20 @@
 
 namespace saceo {
 
-enum { FIT_LR = 0, FIT_RCOEF = 1, FIT_DCLIP = 2, FIT_RCLIP = 3, FIT_MAXNORM = 4, FIT_RMEAN = 5, FIT_RSTD = 6, FIT_HYPER = 8 };
+enum { FIT_LR = 0, FIT_RCOEF = 1, FIT_DCLIP = 2, FIT_RCLIP = 3, FIT_MAXNORM = 4, FIT_RMEAN = 5, FIT_RSTD = 6, FIT_SCALE = 7, FIT_HYPER = 8 };
 
 struct FitCtx {
   // caller tables (saceo_fit_tables)
   float *model, *m, *v; int* t; const float* hyper;
+  float *ls, *ls_m, *ls_v;   // GaussianModel.logstd [n_agents, 2, S] and its Adam slots (NULL: MSEModel loss)
+  float *g_ls;               // workspace: gradient of logstd [n_agents, 2, S]
   // workspace, all [n_agents, 2, ...]
   float *X, *T, *H1, *H2, *Out, *dOut, *dH2, *dH1, *g;
   float *loss_part;      // [n_agents, 2]
   float *gscale;         // [n_agents] gradient scale of clip_by_global_norm (1 when clipping is off)
   float *gnorm;          // [n_agents] global gradient norm (diagnostic)
   float *lrt;            // [n_agents] bias-corrected Adam step size
-  int mb, mbs, nmod, use_clip;     // mbs: row stride of the minibatch buffers (mb rounded up to 32, pad rows stay zero)
+  int S, mb, mbs, nmod, use_clip;     // mbs: row stride of the minibatch buffers (mb rounded up to 32, pad rows stay zero)
   long long nm, nm_stride;
 };
 
@@ -78,34 +80,67 @@ __global__ void k_fit_stage(KCtx c, FitCtx f, const long long* __restrict__ idx)
 }
 
 // loss and its gradient w.r.t. the network output.  grid: (nmod, n_agents), block 256
-//   L = mean_b( 0.5*sum_j (T_j - P_j)^2 + coef*0.5*(T_r - P_r)^2 );  dP = w_j (P - T) / mb
+//   MSEModel (continuous_models.py:280-302):
+//     L = mean_b( 0.5*sum_j (T_j - P_j)^2 + coef*0.5*(T_r - P_r)^2 );  dP_j = (P_j - T_j) / mb
+//   GaussianModel (continuous_models.py:101-131), logstd ls[S] trainable and unclipped:
+//     L = mean_b( sc*0.5*sum_j(((T_j - P_j)/exp(ls_j))^2 + 2 ls_j + log 2pi) + coef*0.5*(T_r - P_r)^2 )
+//     sc = stop_gradient(mean_j exp(ls_j)^2) if scale_model_loss else 1
+//     dP_j = sc (P_j - T_j) exp(-2 ls_j) / mb;   dL/dls_j = sc * mean_b(1 - (T_j - P_j)^2 exp(-2 ls_j))
 __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
   __shared__ float sh[32];
+  __shared__ float w[512];              // exp(-2 ls_j) per output column (S <= 512 checked at bind time)
+  __shared__ float sc_s, lsum_s;
   const int agent = blockIdx.y, net = blockIdx.x;
-  const int mo = c.S + 1;
+  const int S = c.S, mo = S + 1;
   const long long an = (long long)agent * 2 + net;
-  const float coef = f.hyper[(long long)agent * FIT_HYPER + FIT_RCOEF];
+  const float* hy = f.hyper + (long long)agent * FIT_HYPER;
+  const float coef = hy[FIT_RCOEF];
   const float inv = 1.f / (float)f.mb;
+  const float* ls = f.ls ? f.ls + an * S : nullptr;
+  if (ls) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) w[j] = expf(-2.f * ls[j]);
+    if (threadIdx.x == 0) {             // fixed-order scalars
+      float var = 0.f, lsum = 0.f;
+      for (int j = 0; j < S; ++j) { const float sd = expf(ls[j]); var += sd * sd; lsum += 2.f * ls[j] + kLog2Pi; }
+      sc_s = hy[FIT_SCALE] != 0.f ? var / (float)S : 1.f;
+      lsum_s = lsum;
+    }
+  } else {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) w[j] = 1.f;
+    if (threadIdx.x == 0) { sc_s = 1.f; lsum_s = 0.f; }
+  }
+  __syncthreads();
+  const float sc = sc_s;
   float acc = 0.f;
   for (int row = threadIdx.x; row < f.mb; row += blockDim.x) {
     const float* P = f.Out + (an * f.mbs + row) * mo;
     const float* T = f.T + (an * f.mbs + row) * mo;
     float* dP = f.dOut + (an * f.mbs + row) * mo;
     float dl = 0.f;
-    for (int j = 0; j < c.S; ++j) {
+    for (int j = 0; j < S; ++j) {
       const float e = P[j] - T[j];
-      dl += e * e;
-      dP[j] = e * inv;
+      dl += e * e * w[j];
+      dP[j] = sc * e * w[j] * inv;
     }
-    const float er = P[c.S] - T[c.S];
-    dP[c.S] = coef * er * inv;
-    acc += 0.5f * dl + coef * (0.5f * er * er);
+    const float er = P[S] - T[S];
+    dP[S] = coef * er * inv;
+    acc += sc * (0.5f * (dl + lsum_s)) + coef * (0.5f * er * er);
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
     const float L = acc * inv;
     f.loss_part[an] = L;
     if (losses_out) losses_out[(long long)agent * f.nmod + net] = L;
+  }
+  if (ls) {                             // dL/dls_j: one thread per column, rows in fixed order
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      float g = 0.f;
+      for (int row = 0; row < f.mb; ++row) {
+        const float e = f.Out[(an * f.mbs + row) * mo + j] - f.T[(an * f.mbs + row) * mo + j];
+        g += 1.f - e * e * w[j];
+      }
+      f.g_ls[an * S + j] = sc * g * inv;
+    }
   }
 }
 
@@ -118,6 +153,10 @@ __global__ void k_fit_gnorm(FitCtx f) {
   for (int net = 0; net < f.nmod; ++net) {
     const float* g = f.g + ((long long)agent * 2 + net) * f.nm_stride;
     for (long long i = threadIdx.x; i < f.nm; i += blockDim.x) { const float x = g[i]; acc += x * x; }
+    if (f.ls) {
+      const float* gl = f.g_ls + ((long long)agent * 2 + net) * f.S;
+      for (int i = threadIdx.x; i < f.S; i += blockDim.x) { const float x = gl[i]; acc += x * x; }
+    }
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
@@ -135,9 +174,19 @@ __global__ void k_fit_gnorm(FitCtx f) {
 __global__ void k_fit_adam(FitCtx f) {
   const int agent = blockIdx.z, net = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float lr_t = f.lrt[agent];
+  if (f.ls && blockIdx.x == 0) {                           // the logstd variable rides in the first block
+    for (int j = threadIdx.x; j < f.S; j += blockDim.x) {
+      const long long o = ((long long)agent * 2 + net) * f.S + j;
+      const float gi = f.g_ls[o] * f.gscale[agent];
+      const float mi = kB1 * f.ls_m[o] + (1.f - kB1) * gi;
+      const float vi = kB2 * f.ls_v[o] + (1.f - kB2) * gi * gi;
+      f.ls[o] = f.ls[o] - lr_t * mi / (sqrtf(vi) + kAdamEps);
+      f.ls_m[o] = mi; f.ls_v[o] = vi;
+    }
+  }
   if (i >= f.nm) return;
   const long long o = ((long long)agent * 2 + net) * f.nm_stride + i;
-  const float lr_t = f.lrt[agent];
   const float gi = f.g[o] * f.gscale[agent];
   const float mi = kB1 * f.m[o] + (1.f - kB1) * gi;
   const float vi = kB2 * f.v[o] + (1.f - kB2) * gi * gi;

@@ -836,12 +836,16 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
   if (model_batch < 1) return fail(SACEO_E_INVALID, "model_batch must be >= 1");
   if (!t->model || !t->model_m || !t->model_v || !t->model_t || !t->fit_hyper)
     return fail(SACEO_E_INVALID, "a required fit table pointer is NULL");
+  const int nls = (t->model_logstd != nullptr) + (t->model_logstd_m != nullptr) + (t->model_logstd_v != nullptr);
+  if (nls != 0 && nls != 3) return fail(SACEO_E_INVALID, "model_logstd, model_logstd_m and model_logstd_v must be given together");
+  if (nls && x->cfg.S > 512) return fail(SACEO_E_INVALID, "Gaussian model loss supports S <= 512");
   CU(cudaSetDevice(x->cfg.device));
   if (x->fit_ws) { CU(cudaDeviceSynchronize()); cudaFree(x->fit_ws); x->fit_ws = nullptr; x->fit_bound = false; }
   const saceo_config& c = x->cfg;
   FitCtx& f = x->fit;
   memset(&f, 0, sizeof(f));
   f.model = t->model; f.m = t->model_m; f.v = t->model_v; f.t = t->model_t; f.hyper = t->fit_hyper;
+  f.ls = t->model_logstd; f.ls_m = t->model_logstd_m; f.ls_v = t->model_logstd_v; f.S = c.S;
   f.mb = model_batch; f.mbs = (int)rup(model_batch, 32); f.nmod = c.num_models; f.use_clip = use_grad_clip;
   f.nm = x->L.nm; f.nm_stride = x->L.nm_stride;
   const long long n2 = 2LL * c.n_agents, mb = f.mbs, SA = c.S + c.A, mo = x->L.model_out;
@@ -853,6 +857,7 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
     f.dH2 = b.get<float>("fit_dH2", n2 * mb * c.model_hidden[1]); f.dH1 = b.get<float>("fit_dH1", n2 * mb * c.model_hidden[0]);
     f.g = b.get<float>("g_model", n2 * x->L.nm_stride);
     f.loss_part = b.get<float>("fit_loss", n2);
+    f.g_ls = b.get<float>("g_model_logstd", n2 * c.S);
     f.gscale = b.get<float>("fit_gscale", c.n_agents); f.gnorm = b.get<float>("fit_gnorm", c.n_agents);
     f.lrt = b.get<float>("fit_lrt", c.n_agents);
     if (!pass) {

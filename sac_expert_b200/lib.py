@@ -63,12 +63,13 @@ class Tables(C.Structure):
 
 class FitTables(C.Structure):
     """saceo_fit_tables (include/saceo.h): dynamics-model fitting state."""
-    _fields_ = [(n, C.c_void_p) for n in ("model", "model_m", "model_v", "model_t", "fit_hyper")]
+    _fields_ = [(n, C.c_void_p) for n in ("model", "model_m", "model_v", "model_t", "fit_hyper",
+                                          "model_logstd", "model_logstd_m", "model_logstd_v")]
 
 
 FIT_HYPER = 8
 FIT_HYPER_NAMES = ("model_lr", "reward_loss_coef", "delta_clip_loss", "reward_clip_loss", "model_max_grad_norm",
-                   "r_mean", "r_std")
+                   "r_mean", "r_std", "scale_model_loss")
 
 _lib: Optional[C.CDLL] = None
 

@@ -433,9 +433,11 @@ class Population:
         return out
 
     # ------------------------------------------------------------------ dynamics-model fitting
-    def fit_bind(self, model_batch: int = 200, use_grad_clip: bool = False):
+    def fit_bind(self, model_batch: int = 200, use_grad_clip: bool = False, gaussian: bool = False, std_mult: float = 1.0):
         """Allocates the joint model optimiser's slots (``self.model_optimizer``, mbrl_onpolicy_alg.py:48-49)
-        and the fitting workspace for minibatches of ``model_batch`` rows (--model_batch_size)."""
+        and the fitting workspace for minibatches of ``model_batch`` rows (--model_batch_size).  ``gaussian``:
+        ``GaussianModel`` loss with the trainable ``logstd`` variable initialised to log(std_mult)
+        (continuous_models.py:24-25)."""
         n, L = self.spec.n_agents, self.L
         z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)
         self.t.update(model_m=z(n, 2, L.nm_stride), model_v=z(n, 2, L.nm_stride), model_t=z(n, dt=torch.int32),
@@ -443,23 +445,31 @@ class Population:
         self.t["fit_hyper"][:, 0] = 1e-3      # --model_lr
         self.t["fit_hyper"][:, 1] = 1.0       # --reward_loss_coef
         self.t["fit_hyper"][:, 6] = 1.0       # identity r_rms
+        if gaussian:
+            self.t.update(model_logstd=torch.full((n, 2, self.spec.S), float(np.log(std_mult)), device=self.dev),
+                          model_logstd_m=z(n, 2, self.spec.S), model_logstd_v=z(n, 2, self.spec.S))
+        else:
+            for k in ("model_logstd", "model_logstd_m", "model_logstd_v"):
+                self.t.pop(k, None)
         ft = _l.FitTables()
         for name, _ in _l.FitTables._fields_:
-            setattr(ft, name, self.t[name].data_ptr())
+            setattr(ft, name, self.t[name].data_ptr() if name in self.t else None)
         torch.cuda.synchronize(self.dev)
         _l.check(self.lib.saceo_fit_bind(self.ctx, C.byref(ft), int(model_batch), int(bool(use_grad_clip))))
         self.model_batch = int(model_batch)
 
     def set_fit_hyper(self, agent: int, **hy):
-        """model_lr, reward_loss_coef, delta_clip_loss, reward_clip_loss, model_max_grad_norm (0/None = off), r_mean, r_std."""
+        """model_lr, reward_loss_coef, delta_clip_loss, reward_clip_loss, model_max_grad_norm (0/None = off), r_mean, r_std,
+        scale_model_loss (Gaussian loss only)."""
         row = self.t["fit_hyper"][agent]
         for key, val in hy.items():
             row[_l.FIT_HYPER_NAMES.index(key)] = float(val or 0.0)
 
     def reset_model_optimizer(self):
         """``reset_model_optimizer`` (SAC_expert.py:551-553): fresh Adam slots and step count."""
-        for k in ("model_m", "model_v", "model_t"):
-            self.t[k].zero_()
+        for k in ("model_m", "model_v", "model_t", "model_logstd_m", "model_logstd_v"):
+            if k in self.t:
+                self.t[k].zero_()
 
     def model_fit(self, idx, want_losses: bool = True) -> Optional[torch.Tensor]:
         """``_apply_model_grads`` for every entry of ``idx`` ([n_steps, n_agents, num_models, model_batch] or

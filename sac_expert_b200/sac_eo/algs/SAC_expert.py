@@ -68,8 +68,11 @@ class SAC_exp(SAC):
         self.reset_model_optimizer = bool(g("reset_model_optimizer", False))
         if len(self.models) != self._n_models():
             raise NotImplementedError("the device joint optimiser covers the two models of the update path")
-        m = self.models[0]
-        self.pop.fit_bind(self.model_batch_size, use_grad_clip=self.model_max_grad_norm is not None)
+        gaussian = bool(getattr(self.models[0], "gaussian", False))
+        self.pop.fit_bind(self.model_batch_size, use_grad_clip=self.model_max_grad_norm is not None, gaussian=gaussian)
+        if gaussian:                           # GaussianModel.logstd (continuous_models.py:24-25) joins the device optimiser
+            for k in range(self._n_models()):
+                self.pop.t["model_logstd"][0, k].copy_(torch.from_numpy(np.asarray(self.models[k]._logstd, np.float32)[0]))
         self._fit_ready = True
         self._push_fit_hyper()
 
@@ -79,6 +82,7 @@ class SAC_exp(SAC):
         self.pop.set_fit_hyper(0, model_lr=self.model_lr, reward_loss_coef=getattr(m, "reward_loss_coef", 1.0),
                                delta_clip_loss=getattr(m, "delta_clip_loss", None), reward_clip_loss=getattr(m, "reward_clip_loss", None),
                                model_max_grad_norm=self.model_max_grad_norm,
+                               scale_model_loss=float(getattr(m, "scale_model_loss", False)),
                                r_mean=float(np.ravel(r_rms.mean)[0]) if r_rms is not None else 0.0,
                                r_std=float(np.ravel(r_rms.std)[0]) if r_rms is not None else 1.0)
 

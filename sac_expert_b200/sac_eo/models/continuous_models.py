@@ -26,6 +26,7 @@ class MSEModel(DeviceNet):
         self.reward_loss_coef = model_setup_kwargs.get("reward_loss_coef", 1.0)
         self.delta_clip_loss = model_setup_kwargs.get("delta_clip_loss", None)
         self.reward_clip_loss = model_setup_kwargs.get("reward_clip_loss", None)
+        self.scale_model_loss = bool(model_setup_kwargs.get("scale_model_loss", False))
         out = self.s_dim if self.separate_reward_nn else self.s_dim + 1
         self._host_weights = create_nn_weights(self.s_dim + self.a_dim, out, self.layers, model_gain)
         self._reward_weights = (create_nn_weights(self.s_dim + self.a_dim, 1, check_two_hidden(reward_layers), reward_gain)
@@ -43,14 +44,28 @@ class MSEModel(DeviceNet):
             self._pop.set_norm(self._agent, m_s_mean=self.s_rms.mean, m_s_std=self.s_rms.std, m_a_mean=self.a_rms.mean,
                                m_a_std=self.a_rms.std, m_d_mean=self.delta_rms.mean, m_d_std=self.delta_rms.std)
 
+    def _device_logstd(self):
+        """The trainable logstd lives in the device fit tables once the joint optimiser is bound."""
+        if self.gaussian and self._pop is not None and "model_logstd" in self._pop.t:
+            return self._pop.t["model_logstd"][self._agent, int(self._table[1]) - 1]
+        return None
+
     def get_weights(self, flat=False):
         ws = super().get_weights(False)
-        return ws + [self._logstd.copy()] if self.gaussian else ws
+        if not self.gaussian:
+            return ws
+        dev = self._device_logstd()
+        if dev is not None:
+            self._logstd = dev.detach().cpu().numpy()[None].astype(np.float32)
+        return ws + [self._logstd.copy()]
 
     def set_weights(self, weights, from_flat=False, increment=False):
         if self.gaussian and not from_flat:
-            self._logstd = np.asarray(weights[-1], np.float32)
+            self._logstd = np.asarray(weights[-1], np.float32).reshape(1, -1)
             weights = weights[:-1]
+            dev = self._device_logstd()
+            if dev is not None:
+                dev.copy_(torch.from_numpy(self._logstd[0]))
         super().set_weights(weights, from_flat, increment)
 
     def get_reward_weights(self):

@@ -206,3 +206,41 @@ def test_update_models_matches_oracle_with_reference_rng_order(shuffle, holdout)
         for got, ref, old in zip(alg.models[m].get_weights(), models[m], st["m%d" % (m + 1)]):
             assert rel(got - old.numpy(), ref.numpy() - old.numpy()) < 2e-3, m     # 9 compounded Adam steps
     assert len(alg.model_MSE_on_expert_data) == 1 and len(alg.model_MSE_on_expert_counterfactual_action) == 1
+
+
+def test_update_models_gaussian_mirror():
+    """GaussianModel through the class interface: logstd joins the device optimiser, get_weights() returns it,
+    and one _apply_model_grads call matches the oracle's Gaussian NLL step."""
+    from oracle.sac_eo_oracle import apply_model_grads
+    S, A, B, E = 11, 3, 32, 8
+    np.random.seed(0)
+    env = SyntheticEnv(S, A)
+    actor = init_actor(env, [32, 32], ["relu"], 0.01, 1.0, "orthogonal", False, None, True, True, False)
+    critics, q_targets, q_critics = init_critics(env, [32, 32], ["relu"], 1.0, None, 2, False, "orthogonal", False)
+    setup = dict(SETUP, scale_model_loss=True, reward_loss_coef=0.8)
+    models = init_world_models(env, [48, 48], ["tanh"], 0.01, 0.5, None, [48, 48], ["relu"], 0.01, None, 2, True, setup)
+    kw = dict(alg_type="sac_imit", sac_batch_size=B, expert_buffer_size=E, gamma=0.99, alg_seed=5, epsilon=0.2,
+              device_replay_capacity=1000, gemm_mode=L.GEMM_FP32_SIMT, model_batch_size=40, model_lr=1e-3)
+    alg = init_alg(0, env, env, env, actor, critics, q_targets, q_critics, models, kw, {}, None, None)
+    rng = np.random.default_rng(1)
+    n = 200
+    rows = (rng.standard_normal((n, S)).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32),
+            rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32), rng.random(n) < 0.05)
+    alg.env_data.add(*rows)
+    alg.model_data.add(*rows)
+    w0 = [m.get_weights() for m in alg.models]
+    assert len(w0[0]) == 7 and np.allclose(w0[0][-1], np.log(0.5))          # logstd initialised to log(std_mult)
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48), model_acts=("tanh", "tanh"))
+    st = to_torch_state(snapshot(alg, cfg))
+    idx = np.stack([rng.permutation(n)[:40] for _ in range(2)])
+    losses = alg._apply_model_grads(idx)
+    mods = [[torch.from_numpy(np.asarray(w, np.float32)) for w in ws] for ws in w0]
+    adam = dict(m=[[torch.zeros_like(w) for w in m] for m in mods], v=[[torch.zeros_like(w) for w in m] for m in mods], t=0)
+    d = alg.model_data
+    b = [{k: torch.as_tensor(getattr(d, k + "_all")[idx[m]]) for k in ("s", "a", "sp", "r")} for m in range(2)]
+    out = apply_model_grads(cfg, mods, adam, b, st, dict(model_lr=1e-3, gaussian=True, scale_model_loss=True, reward_loss_coef=0.8))
+    for m in range(2):
+        assert abs(float(losses[0, 0, m]) - float(out["losses"][m])) < 1e-4 * abs(float(out["losses"][m]))
+        got = alg.models[m].get_weights()
+        for gw, ref, old in zip(got, out["models"][m], w0[m]):
+            assert rel(np.asarray(gw) - np.asarray(old), ref.numpy() - np.asarray(old)) < 1e-3

@@ -17,7 +17,10 @@ TOL = 1e-3
 
 def _setup(cfg, n_agents, mb, N, seed, fit, gemm_mode, capacity=None, **kw):
     pop = Population(spec_from_cfg(cfg, n_agents, 32, 4, capacity or N, gemm_mode=gemm_mode, **kw))
-    pop.fit_bind(mb, use_grad_clip=bool(fit.get("model_max_grad_norm")))
+    pop.fit_bind(mb, use_grad_clip=bool(fit.get("model_max_grad_norm")), gaussian=bool(fit.get("gaussian")), std_mult=0.7)
+    if fit.get("gaussian"):       # per-column, per-model logstd values instead of the constant initial value
+        g = torch.Generator().manual_seed(seed)
+        pop.t["model_logstd"].copy_((0.4 * torch.randn(n_agents, 2, cfg.S, generator=g) - 0.3).to(pop.dev))
     probs = []
     for i in range(n_agents):
         st, replay, expert, hyper = make_problem(cfg, 32, 4, N, seed=seed + 13 * i, perturb=0.05)
@@ -26,8 +29,11 @@ def _setup(cfg, n_agents, mb, N, seed, fit, gemm_mode, capacity=None, **kw):
         pop.load_agent(i, st, hyper)
         pop.append_rows(i, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
         f = dict(fit)
+        f.pop("gaussian", None)
         f["model_lr"] = fit.get("model_lr", 1e-3) * (1 + 0.5 * i)       # per-agent hyper-parameters differ
         pop.set_fit_hyper(i, r_mean=st["m_r_mean"], r_std=st["m_r_std"], **f)
+        if fit.get("gaussian"):
+            f["gaussian"] = True
         probs.append((st, replay, f))
     return pop, probs
 
@@ -44,6 +50,9 @@ def _run(cfg, pop, probs, mb, steps, seed, tol=TOL, window=None, verbose=False):
     for st, replay, f in probs:
         T = to_torch_state(st)
         models = [T["m%d" % (k + 1)] for k in range(nm)]
+        if probs[0][2].get("gaussian"):
+            ai = len(state)
+            models = [m + [pop.t["model_logstd"][ai, k].cpu().clone()[None]] for k, m in enumerate(models)]
         adam = dict(m=[[torch.zeros_like(w) for w in m] for m in models],
                     v=[[torch.zeros_like(w) for w in m] for m in models], t=0)
         state.append([T, models, adam])
@@ -59,9 +68,17 @@ def _run(cfg, pop, probs, mb, steps, seed, tol=TOL, window=None, verbose=False):
             o = apply_model_grads(cfg, models, adam, b, T, f)
             for m in range(nm):
                 upd("loss", abs(float(losses[0, i, m]) - float(o["losses"][m])) / abs(float(o["losses"][m])))
-                ref = np.concatenate([x.numpy().ravel() for x in o["grads"][m]])
+                gl = o["grads"][m][:-1] if f.get("gaussian") else o["grads"][m]
+                ref = np.concatenate([x.numpy().ravel() for x in gl])
                 scale = float(pop.debug("fit_gscale").cpu()[i]) if f.get("model_max_grad_norm") else 1.0
                 upd("grad", rel(g[i, m, :ref.size] * scale, ref))
+                if f.get("gaussian"):
+                    S_ = cfg.S
+                    gls = pop.debug("g_model_logstd").cpu().numpy().reshape(n, 2, S_)[i, m] * scale
+                    upd("grad_logstd", rel(gls, o["grads"][m][-1].numpy().ravel()))
+                    upd("logstd", rel(pop.t["model_logstd"][i, m].cpu().numpy(), o["models"][m][-1].numpy().ravel()))
+                    upd("logstd_m", rel(pop.t["model_logstd_m"][i, m].cpu().numpy(), o["m"][m][-1].numpy().ravel()))
+                    upd("logstd_v", rel(pop.t["model_logstd_v"][i, m].cpu().numpy(), o["v"][m][-1].numpy().ravel()))
                 name = "m%d" % (m + 1)
                 for ti, (gw, nw, ow) in enumerate(zip(pop.get_net(i, name), o["models"][m], models[m])):
                     upd("theta", rel(gw, nw.numpy()))
@@ -77,9 +94,10 @@ def _run(cfg, pop, probs, mb, steps, seed, tol=TOL, window=None, verbose=False):
                 upd("gnorm", abs(float(pop.debug("fit_gnorm").cpu()[i]) - float(o["gnorm"])) / float(o["gnorm"]))
             assert int(pop.t["model_t"][i]) == o["t"]
             # continue from the DEVICE state so that errors do not compound through the oracle's own trajectory
-            state[i][1] = [[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1))] for m in range(nm)]
-            state[i][2] = dict(m=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_m")] for m in range(nm)],
-                               v=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_v")] for m in range(nm)],
+            ex = (lambda tab, m: [pop.t[tab][i, m].cpu().clone()[None]]) if f.get("gaussian") else (lambda tab, m: [])
+            state[i][1] = [[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1))] + ex("model_logstd", m) for m in range(nm)]
+            state[i][2] = dict(m=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_m")] + ex("model_logstd_m", m) for m in range(nm)],
+                               v=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_v")] + ex("model_logstd_v", m) for m in range(nm)],
                                t=o["t"])
         if verbose:
             print(step, {k: "%.1e" % v for k, v in worst.items()})
@@ -94,6 +112,29 @@ def test_model_fit_small(gemm_mode, acts, clip):
     fit = dict(model_lr=1e-3, reward_loss_coef=0.7, model_max_grad_norm=clip)
     pop, probs = _setup(cfg, 3, 24, 120, seed=3, fit=fit, gemm_mode=gemm_mode)
     _run(cfg, pop, probs, 24, steps=3, seed=5)
+    pop.close()
+
+
+@pytest.mark.parametrize("gemm_mode", [L.GEMM_FP32_SIMT, L.GEMM_TCGEN05_BF16X3])
+@pytest.mark.parametrize("scale,clip", [(False, 0.0), (True, 0.6)])
+def test_model_fit_gaussian_nll(gemm_mode, scale, clip):
+    """GaussianModel.get_loss (continuous_models.py:101-131): trainable unclipped logstd in the joint optimiser,
+    optional scale_model_loss (stop-gradient mean variance) and the global-norm clip over weights AND logstd."""
+    cfg = NetCfg(S=7, A=3, model_hidden=(64, 64), model_acts=("tanh", "relu"))
+    fit = dict(model_lr=1e-3, reward_loss_coef=0.5, model_max_grad_norm=clip, gaussian=True, scale_model_loss=scale,
+               delta_clip_loss=2.5)
+    pop, probs = _setup(cfg, 2, 40, 160, seed=12, fit=fit, gemm_mode=gemm_mode)
+    w = _run(cfg, pop, probs, 40, steps=3, seed=2)
+    assert "grad_logstd" in w and "logstd" in w
+    pop.close()
+
+
+def test_model_fit_gaussian_full_size():
+    cfg = NetCfg(S=27, A=8, model_acts=("tanh", "tanh"))
+    fit = dict(model_lr=1e-3, gaussian=True, scale_model_loss=True)
+    pop, probs = _setup(cfg, 2, 200, 1000, seed=5, fit=fit, gemm_mode=L.GEMM_TCGEN05_BF16X3)
+    w = _run(cfg, pop, probs, 200, steps=2, seed=3)
+    assert w["grad"] < 2e-4 and w["grad_logstd"] < 2e-4, w
     pop.close()
 
 
