@@ -450,22 +450,36 @@ __global__ void k_adam(float* __restrict__ theta, float* __restrict__ m, float* 
                        const float* __restrict__ g, float* __restrict__ target,
                        const float* __restrict__ lrt, const float* __restrict__ hyper, int hyper_stride,
                        int opt0, long long n, long long stride, int nnet, int do_polyak) {
+  // one float4 (4 consecutive parameters) per thread: every table row is 128-byte aligned (strides are multiples of 32)
   const int agent = blockIdx.z, net = blockIdx.y;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const long long o = ((long long)agent * nnet + net) * stride + i;
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const long long o = ((long long)agent * nnet + net) * stride + i4;
   const float lr_t = lrt[agent * 4 + opt0 + net];
-  const float gi = g[o];
-  const float mi = kB1 * m[o] + (1.f - kB1) * gi;
-  const float vi = kB2 * v[o] + (1.f - kB2) * gi * gi;
-  const float th = theta[o] - lr_t * mi / (sqrtf(vi) + kAdamEps);
-  m[o] = mi; v[o] = vi; theta[o] = th;
-  if (do_polyak) {
-    const float tau = hyper[(long long)agent * hyper_stride + 1];
-    const float one_m = (float)(1.0 - (double)tau);
-    // NumPy fp32: two rounded products, one rounded sum (no FMA contraction)
-    target[o] = __fadd_rn(__fmul_rn(target[o], one_m), __fmul_rn(th, tau));
+  const float4 g4 = *reinterpret_cast<const float4*>(g + o);
+  float4 m4 = *reinterpret_cast<const float4*>(m + o);
+  float4 v4 = *reinterpret_cast<const float4*>(v + o);
+  float4 t4 = *reinterpret_cast<const float4*>(theta + o);
+  float4 q4 = do_polyak ? *reinterpret_cast<const float4*>(target + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float tau = do_polyak ? hyper[(long long)agent * hyper_stride + 1] : 0.f;
+  const float one_m = (float)(1.0 - (double)tau);
+  const float gi[4] = {g4.x, g4.y, g4.z, g4.w};
+  float mi[4] = {m4.x, m4.y, m4.z, m4.w}, vi[4] = {v4.x, v4.y, v4.z, v4.w}, th[4] = {t4.x, t4.y, t4.z, t4.w},
+        tg[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (i4 + j < n) {          // words past n are padding (the actor's last pad word carries g_alpha): left untouched
+      mi[j] = kB1 * mi[j] + (1.f - kB1) * gi[j];
+      vi[j] = kB2 * vi[j] + (1.f - kB2) * gi[j] * gi[j];
+      th[j] = th[j] - lr_t * mi[j] / (sqrtf(vi[j]) + kAdamEps);
+      // NumPy fp32: two rounded products, one rounded sum (no FMA contraction)
+      tg[j] = __fadd_rn(__fmul_rn(tg[j], one_m), __fmul_rn(th[j], tau));
+    }
   }
+  *reinterpret_cast<float4*>(m + o) = make_float4(mi[0], mi[1], mi[2], mi[3]);
+  *reinterpret_cast<float4*>(v + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  *reinterpret_cast<float4*>(theta + o) = make_float4(th[0], th[1], th[2], th[3]);
+  if (do_polyak) *reinterpret_cast<float4*>(target + o) = make_float4(tg[0], tg[1], tg[2], tg[3]);
 }
 
 // temperature step + loss bookkeeping (SAC_expert.py:341-356).  grid: (n_agents), block 256

@@ -538,7 +538,7 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
 
 static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
   const KCtx& k = x->k;
-  LAUNCH(x, k_adam, dim3(cdiv(x->L.nc, 256), 2, k.n_agents), 256, 0, st, k.T.q, k.T.q_m, k.T.q_v, k.g_q, k.T.qt,
+  LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.nc, 4), 256), 2, k.n_agents), 256, 0, st, k.T.q, k.T.q_m, k.T.q_v, k.g_q, k.T.qt,
          k.lrt, k.T.hyper, x->L.hyper_stride, 0, x->L.nc, x->L.nc_stride, 2, do_polyak);
   return check_launch();
 }
@@ -619,7 +619,7 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
 
 static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
   const KCtx& k = x->k;
-  LAUNCH(x, k_adam, dim3(cdiv(x->L.na, 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
+  LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.na, 4), 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
          k.g_actor, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0);
   return check_launch();
 }
