@@ -170,7 +170,7 @@ __global__ void k_fit_gnorm(FitCtx f) {
   }
 }
 
-// joint Keras Adam over all model tensors (one step counter per agent).  grid: (ceil(nm/256), nmod, n_agents)
+// joint Keras Adam over all model tensors (one step counter per agent).  grid: (ceil(ceil(nm/4)/256), nmod, n_agents)
 __global__ void k_fit_adam(FitCtx f) {
   const int agent = blockIdx.z, net = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,13 +185,27 @@ __global__ void k_fit_adam(FitCtx f) {
       f.ls_m[o] = mi; f.ls_v[o] = vi;
     }
   }
-  if (i >= f.nm) return;
-  const long long o = ((long long)agent * 2 + net) * f.nm_stride + i;
-  const float gi = f.g[o] * f.gscale[agent];
-  const float mi = kB1 * f.m[o] + (1.f - kB1) * gi;
-  const float vi = kB2 * f.v[o] + (1.f - kB2) * gi * gi;
-  f.model[o] = f.model[o] - lr_t * mi / (sqrtf(vi) + kAdamEps);
-  f.m[o] = mi; f.v[o] = vi;
+  const long long i4 = i * 4;             // one float4 per thread (rows are 128-byte aligned, nm_stride % 32 == 0)
+  if (i4 >= f.nm) return;
+  const long long o = ((long long)agent * 2 + net) * f.nm_stride + i4;
+  const float gs = f.gscale[agent];
+  const float4 g4 = *reinterpret_cast<const float4*>(f.g + o);
+  const float4 m4 = *reinterpret_cast<const float4*>(f.m + o);
+  const float4 v4 = *reinterpret_cast<const float4*>(f.v + o);
+  const float4 t4 = *reinterpret_cast<const float4*>(f.model + o);
+  const float gi[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs};
+  float mi[4] = {m4.x, m4.y, m4.z, m4.w}, vi[4] = {v4.x, v4.y, v4.z, v4.w}, th[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (i4 + j < f.nm) {
+      mi[j] = kB1 * mi[j] + (1.f - kB1) * gi[j];
+      vi[j] = kB2 * vi[j] + (1.f - kB2) * gi[j] * gi[j];
+      th[j] = th[j] - lr_t * mi[j] / (sqrtf(vi[j]) + kAdamEps);
+    }
+  }
+  *reinterpret_cast<float4*>(f.m + o) = make_float4(mi[0], mi[1], mi[2], mi[3]);
+  *reinterpret_cast<float4*>(f.v + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+  *reinterpret_cast<float4*>(f.model + o) = make_float4(th[0], th[1], th[2], th[3]);
 }
 
 }  // namespace saceo

@@ -898,7 +898,7 @@ extern "C" int saceo_model_fit(saceo_ctx* x, int32_t n_steps, const int64_t* idx
                       nullptr, 0, 0, 0, 0, st, false);    // K = 200 on the register-staged kernel beats K = 224 streamed (measured)
     if (rc) return rc;
     if (f.use_clip) LAUNCH(x, k_fit_gnorm, n, 1024, 0, st, f);
-    LAUNCH(x, k_fit_adam, dim3(cdiv(f.nm, 256), f.nmod, n), 256, 0, st, f);
+    LAUNCH(x, k_fit_adam, dim3(cdiv(cdiv(f.nm, 4), 256), f.nmod, n), 256, 0, st, f);
   }
   return check_launch();
 }
