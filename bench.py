@@ -249,7 +249,7 @@ def run_b200(a):
     traffic = None
     tj = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
     if os.path.exists(tj) and a.shape == "ant" and not a.plain_sac:
-        tr = json.load(open(tj))          # ncu dram__bytes_{read,write}.sum summed over the 36 launches of one step
+        tr = json.load(open(tj))          # ncu dram__bytes_{read,write}.sum summed over the launches of one step
         traffic = (tr["dram_read_bytes_per_step"] + tr["dram_write_bytes_per_step"]) / tr["agents"] * a.agents
     bytes_step = algorithmic_bytes(spec, pop.L) * a.agents
     achieved = bytes_step / (ms / a.steps * 1e-3) / 1e9
@@ -272,8 +272,8 @@ def run_b200(a):
                      "traffic": traffic, "traffic_note": "DRAM bytes per step from profiles/r1_step_traffic.json (ncu, all launches of one step)",
                      "peak_source": peak_src,
                      "achieved_note": "algorithmic bytes per step / CUDA-event step time",
-                     "scope": "whole update step (36 kernel launches, per-kernel shares in profiles/r1_launches_final_ncu.csv); algorithmic bytes "
-                              f"{algorithmic_bytes(spec, pop.L) / 1e6:.2f} MB/agent-update",
+                     "scope": f"whole update step ({int(launches) // max(a.steps, 1)} kernel launches, per-kernel shares in "
+                              f"profiles/r1_launches_final_ncu.csv); algorithmic bytes {algorithmic_bytes(spec, pop.L) / 1e6:.2f} MB/agent-update",
                      "algorithmic_tflops": flops_step / (ms / a.steps * 1e-3) / 1e12},
     }
     if not a.no_cpu_baseline:
