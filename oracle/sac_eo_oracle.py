@@ -325,6 +325,39 @@ def sac_eo_update(cfg: NetCfg, state: Dict, batch: Dict, hyper: Dict) -> Dict:
 
 
 # --------------------------------------------------------------------------------------
+# behaviour cloning from expert observations  BC.py:309-363  (the epsilon = 1 slice of the SAC-EO actor step)
+# --------------------------------------------------------------------------------------
+def bc_update(cfg: NetCfg, state: Dict, batch: Dict, hyper: Dict) -> Dict:
+    """``BC._update_actor`` (BC.py:309-363): ONLY the expert-observation term - counterfactual actions
+    ``actor.sample(sE, deterministic=False)`` go through the frozen model(s), loss = mean(0.5*sum (s'E - pred)^2)
+    (two models: both halves of a per-update shuffle summed row-wise, :329-354), one Keras-Adam step on the actor
+    (``self.actor_optimizer``, BC.py:113, learning rate ``lr_pi``).  Critics, temperature and targets are untouched.
+    ``batch``: sE, spE, u3 (and I1, I2, u4 for two models) exactly as in ``sac_eo_update``."""
+    st = state
+    dt = st["actor"][0].dtype
+    th_pi = _req(st["actor"])
+    sE = torch.as_tensor(batch["sE"]).to(dt)
+    spE = torch.as_tensor(batch["spE"]).to(dt)
+    if cfg.num_models == 1:
+        c, _ = head(cfg, th_pi, sE, torch.as_tensor(batch["u3"]), st)
+        mse = (0.5 * ((spE - model_sample(cfg, st["m1"], sE, c, st)) ** 2).sum(-1)).mean()
+    elif cfg.num_models == 2:
+        I1 = torch.as_tensor(np.asarray(batch["I1"]), dtype=torch.long)
+        I2 = torch.as_tensor(np.asarray(batch["I2"]), dtype=torch.long)
+        c1, _ = head(cfg, th_pi, sE[I1], torch.as_tensor(batch["u3"]), st)
+        c2, _ = head(cfg, th_pi, sE[I2], torch.as_tensor(batch["u4"]), st)
+        p1 = model_sample(cfg, st["m1"], sE[I1], c1, st)
+        p2 = model_sample(cfg, st["m2"], sE[I2], c2, st)
+        mse = (0.5 * (((spE[I1] - p1) ** 2).sum(-1) + ((spE[I2] - p2) ** 2).sum(-1))).mean()
+    else:
+        raise ValueError("BC needs one or two dynamics models")
+    g_pi = list(torch.autograd.grad(mse, th_pi))
+    ad = st["adam_actor"]
+    th_new, m_new, v_new, t_new = keras_adam([p.detach() for p in th_pi], g_pi, ad["m"], ad["v"], ad["t"], hyper["lr_pi"])
+    return dict(mse=mse.detach(), g_actor=g_pi, new=dict(actor=th_new, adam_actor=dict(m=m_new, v=v_new, t=t_new)))
+
+
+# --------------------------------------------------------------------------------------
 # dynamics-model fitting (SURVEY.md §8f rank 1)  mbrl_onpolicy_alg.py:301-319, SAC_expert.py:480-556
 # --------------------------------------------------------------------------------------
 def model_loss(cfg: NetCfg, theta_m, s_: Tensor, a_: Tensor, sp_: Tensor, r_: Tensor, st: Dict,
