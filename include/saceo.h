@@ -179,6 +179,15 @@ int saceo_update_host(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, cons
 int saceo_update_host_async(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,
                       const float *expert_host, float *losses_host, void *stream);
 
+/* Behaviour cloning from expert observations - BC._update_actor (sac_eo/algs/BC.py:309-363): the expert-observation
+ * term ALONE (counterfactual actions through the frozen models, MSE to the expert next states, i.e. the epsilon = 1
+ * slice of the SAC-EO actor step) and one Adam step of self.actor_optimizer (BC.py:113).  Critics, temperature,
+ * targets and their step counters are untouched.  Draws as in saceo_update: use_device_rng != 0 draws the expert
+ * noise / shuffle in-kernel, 0 consumes the noise block [u1|u2|uE|u5] and perm of saceo_set_draws (only uE is used).
+ * losses_out (device, [n_agents, n_losses], nullable): slots 3 and 4 hold BC_MSE_loss. */
+int saceo_bc_update(saceo_ctx *ctx, int32_t n_steps, int32_t use_device_rng, uint64_t seed, float *losses_out,
+                    void *stream);
+
 /* Phase-split form of one update for the optional single-agent data-parallel mode (gradients are
  * all-reduced by the caller between *_grads and *_apply; torch.distributed/NCCL does the
  * collective).  phase: 0 = TD target + critic grads, 1 = critic Adam(+Polyak), 2 = actor grads,

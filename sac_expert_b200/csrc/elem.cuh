@@ -13,6 +13,7 @@ namespace saceo {
 
 struct KCtx {
   int n_agents, S, A, Ao, mo, B, E, R, nmod, per_state_std, sep_reward;
+  float eps_force;   // >= 0: expert weight used instead of hyper[5] (behaviour cloning = 1), < 0: per-agent table value
   int Rs;   // row stride of the per-agent [R rows] actor buffers (R rounded up to 32; the pad rows stay zero)
   int ah1, ah2, ch1, ch2, mh1, mh2;
   int aact0, aact1, cact0, cact1, mact0, mact1;
@@ -33,6 +34,10 @@ struct KCtx {
   // expert rows actually used (bound table or host-staged copy)
   const float *expert_s, *expert_sp;
 };
+
+__device__ __forceinline__ float agent_eps(const KCtx& c, int agent) {
+  return c.eps_force >= 0.f ? c.eps_force : c.T.hyper[(long long)agent * c.L.hyper_stride + 5];
+}
 
 constexpr float kLog2Pi = 1.8378770664093453f;
 constexpr float kLog2 = 0.6931471805599453f;
@@ -77,6 +82,26 @@ __global__ void k_step_begin(KCtx c, int advance_rng) {
   const float lr = opt < 2 ? hy[2] : (opt == 2 ? hy[3] : hy[4]);
   const double b1t = pow((double)kB1, (double)t), b2t = pow((double)kB2, (double)t);
   c.lrt[i] = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+}
+
+// behaviour-cloning step (BC.py:309-363): only the actor optimiser advances.  grid: ceil(n_agents/128)
+__global__ void k_bc_begin(KCtx c, int advance_rng) {
+  const int agent = blockIdx.x * blockDim.x + threadIdx.x;
+  if (agent == 0 && advance_rng) c.step_ctr[0] += 1ull;
+  if (agent >= c.n_agents) return;
+  const int t = c.T.adam_t[agent * 4 + 2] + 1;
+  c.T.adam_t[agent * 4 + 2] = t;
+  const float lr = c.T.hyper[(long long)agent * c.L.hyper_stride + 3];
+  const double b1t = pow((double)kB1, (double)t), b2t = pow((double)kB2, (double)t);
+  c.lrt[agent * 4 + 2] = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+}
+// BC_MSE_loss bookkeeping (BC.py:360-363): losses[3] = losses[4] = MSE.  grid: ceil(n_agents/128)
+__global__ void k_bc_loss(KCtx c) {
+  const int agent = blockIdx.x * blockDim.x + threadIdx.x;
+  if (agent >= c.n_agents) return;
+  float* ls = c.losses + (long long)agent * c.L.n_losses;
+  const float mse = c.mse_part[agent * 2] + (c.nmod == 2 ? c.mse_part[agent * 2 + 1] : 0.f);
+  ls[3] = mse; ls[4] = mse; ls[7] = 1.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -333,7 +358,7 @@ __global__ void k_actor_q(KCtx c) {
   __shared__ float sh[32];
   const int agent = blockIdx.x;
   const float alpha = c.T.alpha[agent];
-  const float eps = c.T.hyper[(long long)agent * c.L.hyper_stride + 5];
+  const float eps = agent_eps(c, agent);
   const float wpi = c.nmod > 0 ? 1.f - eps : 1.f;
   const float sc = -wpi / (float)c.B;
   float acc = 0.f;
@@ -360,7 +385,7 @@ __global__ void k_model_loss(KCtx c) {
   const int agent = blockIdx.x;
   const int S = c.S, E = c.E;
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
-  const float eps = c.T.hyper[(long long)agent * c.L.hyper_stride + 5];
+  const float eps = agent_eps(c, agent);
   const int half = c.nmod == 2 ? E / 2 : E;
   const float inv = 1.f / (float)half;
   float acc = 0.f;
@@ -398,7 +423,7 @@ __global__ void k_head_bwd(KCtx c, int nrows) {
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   const float* lsv = c.T.actor + (long long)agent * c.L.na_stride + (c.L.na - A);
   const float alpha = c.T.alpha[agent];
-  const float eps = c.T.hyper[(long long)agent * c.L.hyper_stride + 5];
+  const float eps = agent_eps(c, agent);
   const float wpi = c.nmod > 0 ? 1.f - eps : 1.f;
   const bool expert = row >= B;
   const float g_nlp = expert ? 0.f : -alpha * wpi / (float)B;

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) k_model_term(KCtx c, float* __r
   }
   __syncthreads();
   // ---- loss and d(eps * MSE)/d(delta) -----------------------------------------------------------
-  const float eps = c.T.hyper[(long long)agent * c.L.hyper_stride + 5];
+  const float eps = agent_eps(c, agent);
   const float inv = 1.f / (float)half;
   float part = 0.f;
   for (int e = tid; e < MS * S; e += MT_THREADS) {

@@ -249,7 +249,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   k.aact0 = cfg->actor_act[0]; k.aact1 = cfg->actor_act[1];
   k.cact0 = cfg->critic_act[0]; k.cact1 = cfg->critic_act[1];
   k.mact0 = cfg->model_act[0]; k.mact1 = cfg->model_act[1];
-  k.delta_clip = cfg->delta_clip_pred; k.cap = cfg->replay_capacity; k.L = x->L;
+  k.delta_clip = cfg->delta_clip_pred; k.cap = cfg->replay_capacity; k.L = x->L; k.eps_force = -1.f;
   // identity expert permutation until draws are injected / generated
   if (k.E > 0) {
     std::vector<int> pm((size_t)cfg->n_agents * k.E);
@@ -544,8 +544,12 @@ static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
 }
 
 // phase 2: actor gradients (policy loss through the UPDATED critics + expert-observation term)
-static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
-  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
+// bc: behaviour cloning (BC.py:309-363) - the expert weight is forced to 1 and the policy-loss half (critic forward /
+// backward-to-action on the B minibatch rows) is skipped: those rows then carry exactly-zero output gradients.
+static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+  KCtx kk = x->k;
+  if (bc) kk.eps_force = 1.f;
+  const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
   int rc;
   NetD an = actor_net(x), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
@@ -553,11 +557,15 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st) {
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
-  rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
-  LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
-  rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
-                    k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
-  if (rc) return rc;
+  if (!bc) {
+    rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+    LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
+    rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+                      k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
+    if (rc) return rc;
+  } else {
+    CU(cudaMemsetAsync(k.cdXa, 0, sizeof(float) * (size_t)n * 2 * B * A, st));
+  }
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
     if (model_term_launch(k, k.mse_part, st) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
@@ -696,6 +704,31 @@ extern "C" int saceo_update(saceo_ctx* x, int32_t n_steps, int64_t num_timesteps
   if (losses_out)
     CU(cudaMemcpyAsync(losses_out, x->k.losses, sizeof(float) * x->k.n_agents * x->L.n_losses, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+// Behaviour cloning from expert observations: BC._update_actor (BC.py:309-363) = the expert-observation term alone
+// (epsilon = 1), one Adam step on the actor; critics, temperature, targets and their optimisers are not touched.
+extern "C" int saceo_bc_update(saceo_ctx* x, int32_t n_steps, int32_t use_device_rng, uint64_t seed, float* losses_out,
+                               void* stream) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  if (x->cfg.num_models < 1) return fail(SACEO_E_INVALID, "behaviour cloning needs num_models >= 1");
+  if (n_steps < 1) return fail(SACEO_E_INVALID, "n_steps must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  if (use_device_rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, k, (unsigned long long)seed);
+  for (int i = 0; i < n_steps; ++i) {
+    LAUNCH(x, k_bc_begin, cdiv(k.n_agents, 128), 128, 0, st, k, use_device_rng ? 1 : 0);
+    if (use_device_rng) {
+      const int items = ((3 * k.B + k.E) * k.A + 3) / 4;
+      LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k, 1);
+    }
+    int rc = phase_actor_grads(x, st, true); if (rc) return rc;
+    if ((rc = phase_actor_apply(x, st))) return rc;
+    LAUNCH(x, k_bc_loss, cdiv(k.n_agents, 128), 128, 0, st, k);
+  }
+  if (losses_out)
+    CU(cudaMemcpyAsync(losses_out, k.losses, sizeof(float) * k.n_agents * x->L.n_losses, cudaMemcpyDeviceToDevice, st));
+  return check_launch();
 }
 
 static int update_host_impl(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,

@@ -334,6 +334,13 @@ class Population:
         self._exit()
         return self.losses
 
+    def bc_update(self, n_steps: int = 1, use_device_rng: bool = True, seed: int = 0):
+        """``BC._update_actor`` (BC.py:309-363): actor step on the expert-observation MSE alone."""
+        st = self._enter()
+        _l.check(self.lib.saceo_bc_update(self.ctx, n_steps, int(use_device_rng), seed, self.losses.data_ptr(), st))
+        self._exit()
+        return self.losses
+
     def update_host(self, num_timesteps: int, seed: int, idx_host: Optional[np.ndarray] = None,
                     expert_host: Optional[np.ndarray] = None) -> np.ndarray:
         """One update through HOST buffers (pinned staging), synchronous - the per-step call of the

@@ -1,6 +1,7 @@
 """``init_alg`` with the reference's signature (``/root/reference/sac_eo/algs/init_alg.py:9-34``).  Only the
 algorithms whose update is the accelerated hot path are available."""
 from .SAC import SAC
+from .BC import BC
 from .SAC_expert import SAC_exp
 
 
@@ -12,6 +13,9 @@ def init_alg(idx, env, env_eval, env_expert, actor, critics, q_targets, q_critic
     if alg_type == "sac_imit":
         return SAC_exp(idx, env, env_eval, env_expert, actor, expert, init_expert_rms_stats, critics, q_targets,
                        q_critics, models, alg_kwargs, mf_update_kwargs)
-    if alg_type in ("mbrl", "bc"):
-        raise ValueError(f"alg_type '{alg_type}' is outside the accelerated hot path (SURVEY.md §2 rows 3-5)")
+    if alg_type == "bc":
+        return BC(idx, env, env_eval, env_expert, actor, expert, init_expert_rms_stats, critics, q_targets, q_critics,
+                  models, alg_kwargs, mf_update_kwargs)
+    if alg_type == "mbrl":
+        raise ValueError("alg_type 'mbrl' (on-policy model-based TRPO/PPO) is outside the accelerated hot path (SURVEY.md §2)")
     raise ValueError("invalid alg_type")

@@ -244,3 +244,32 @@ def test_update_models_gaussian_mirror():
         got = alg.models[m].get_weights()
         for gw, ref, old in zip(got, out["models"][m], w0[m]):
             assert rel(np.asarray(gw) - np.asarray(old), ref.numpy() - np.asarray(old)) < 1e-3
+
+
+def test_bc_alg_update_matches_oracle_with_reference_rng_order():
+    """init_alg(alg_type='bc'): BC._update -> _update_actor, RNG order of BC.py:329-341."""
+    from oracle.sac_eo_oracle import bc_update
+    S, A, B, E = 11, 3, 32, 8
+    alg, rng = build_alg("bc", S, A, B, E)
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48))
+    st = snapshot(alg, cfg)
+    alg.expert_data.add(rng.standard_normal((E, S)).astype(np.float32), rng.uniform(-1, 1, (E, A)).astype(np.float32),
+                        rng.standard_normal(E).astype(np.float32), rng.standard_normal((E, S)).astype(np.float32),
+                        np.zeros(E, bool))
+    expert_reg = alg._expert_preprocess()
+    q_before = alg.q_critics[0].get_weights()
+    np.random.seed(321)
+    alg._update(0, expert_reg)
+    np.random.seed(321)
+    order = np.arange(E)
+    np.random.default_rng(5).shuffle(order)               # alg_seed=5 -> self.rng
+    I1, I2 = np.array_split(order, 2)
+    batch = dict(sE=expert_reg[0], spE=expert_reg[2], I1=I1, I2=I2, u3=np.random.normal(size=(E // 2, A)),
+                 u4=np.random.normal(size=(E // 2, A)))
+    o = bc_update(cfg, to_torch_state(st), batch, dict(lr_pi=1e-4))
+    assert abs(alg.last_losses["BC_MSE_loss"] - float(o["mse"])) < 1e-4 * abs(float(o["mse"]))
+    for got, new, old in zip(alg.actor.get_weights(), o["new"]["actor"], st["actor"]):
+        assert rel(got - old, new.numpy() - old) < 1e-3
+    for a_, b_ in zip(q_before, alg.q_critics[0].get_weights()):
+        assert np.array_equal(a_, b_)
+    assert alg.logger.train_dict["BC_MSE_loss"] == [alg.last_losses["BC_MSE_loss"]] or len(alg.logger.train_dict["BC_MSE_loss"]) == 1
