@@ -188,6 +188,13 @@ int saceo_update_host_async(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed
 int saceo_bc_update(saceo_ctx *ctx, int32_t n_steps, int32_t use_device_rng, uint64_t seed, float *losses_out,
                     void *stream);
 
+/* Measurement aid: ONE update launched kernel by kernel (no CUDA graph) with a CUDA event after every launch.
+ * names_out [max_n][32] and us_out [max_n] receive the kernel name and the device time between consecutive events
+ * (so a launch gap is charged to the kernel that follows it); *n_out = launches recorded.  Synchronises the stream.
+ * Same arguments as saceo_update otherwise; the step is a real update (state advances). */
+int saceo_profile_step(saceo_ctx *ctx, int64_t num_timesteps, int32_t use_device_rng, uint64_t seed,
+                       char *names_out, float *us_out, int32_t max_n, int32_t *n_out, void *stream);
+
 /* Phase-split form of one update for the optional single-agent data-parallel mode (gradients are
  * all-reduced by the caller between *_grads and *_apply; torch.distributed/NCCL does the
  * collective).  phase: 0 = TD target + critic grads, 1 = critic Adam(+Polyak), 2 = actor grads,

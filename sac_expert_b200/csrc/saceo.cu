@@ -64,12 +64,28 @@ struct saceo_ctx {
   bool fit_bound = false;
   void* fit_ws = nullptr;
   long long launches = 0;
+  // per-launch CUDA-event profile of one un-graphed step (saceo_profile_step)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<const char*> prof_name;
+  size_t prof_n = 0;
   cudaGraphExec_t graph[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // [rng mode][polyak]
   long long graph_nodes[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 };
 
+// every kernel launch site reports here: launch counter + (profiling mode) an event right after the launch
+static inline void count_launch(saceo_ctx* x, const char* name, cudaStream_t st) {
+  x->launches++;
+  if (!x->prof) return;
+  if (x->prof_n == x->prof_ev.size()) {
+    cudaEvent_t e; cudaEventCreate(&e);
+    x->prof_ev.push_back(e); x->prof_name.push_back(name);
+  }
+  x->prof_name[x->prof_n] = name;
+  cudaEventRecord(x->prof_ev[x->prof_n++], st);
+}
 #define LAUNCH(ctx, kern, grid, block, smem, st, ...) do { \
-  kern<<<grid, block, smem, st>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+  kern<<<grid, block, smem, st>>>(__VA_ARGS__); count_launch((ctx), #kern, st); } while (0)
 
 // ------------------------------------------------------------------------------------------
 // layout
@@ -268,6 +284,7 @@ extern "C" int saceo_destroy(saceo_ctx* x) {
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
   if (x->ws) cudaFree(x->ws);
   if (x->fit_ws) cudaFree(x->fit_ws);
+  for (cudaEvent_t e : x->prof_ev) cudaEventDestroy(e);
   delete x;
   return 0;
 }
@@ -315,7 +332,7 @@ static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int n
   int row0 = 0;
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && tc_gemm_eligible(TA, TB, ONES, p)) {
     if (tc_gemm_launch(TA, TB, ONES, p, nagents, x->cfg.reserved[0], st) < 0) return fail(SACEO_E_CUDA, "tcgen05 gemm launch failed");
-    x->launches++;
+    count_launch(x, "k_gemm_tc", st);
     row0 = tc_rows(ONES, p);
     if (row0 >= p.M) return 0;
   }
@@ -324,15 +341,17 @@ static int gemm(saceo_ctx* x, bool TA, bool TB, bool ONES, const GemmP& p, int n
   } else if (p.M - row0 <= 64 && p.N > 32) {          // e.g. [dW0; db0] with S+A+1 = 36 rows: two 32-row passes
     SkinnyP s1 = skinny_rows(TA, TB, ONES, p, row0); s1.Ms = row0 + 32;
     skinny_launch(s1, nagents, st);
+    count_launch(x, "k_gemm_skinny", st);
     skinny_launch(skinny_rows(TA, TB, ONES, p, row0 + 32), nagents, st);
-    x->launches++;
   } else if (row0 == 0 && p.N <= 32) {
     skinny_launch(skinny_cols(TA, TB, ONES, p), nagents, st);
   } else {
     GemmP t = p; t.m_off = row0;
     simt_launch(TA, TB, ONES, t, nagents, st);
+    count_launch(x, "k_gemm_simt", st);
+    return 0;
   }
-  x->launches++;
+  count_launch(x, "k_gemm_skinny", st);
   return 0;
 }
 
@@ -384,7 +403,7 @@ static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lon
     f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1; f.dbg = g_tc_dbg;
     dim3 grid(tiles, x->cfg.n_agents * n.nnet);
     k_mlp_fwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
-    x->launches++;
+    count_launch(x, "k_mlp_fwd_tc", st);
     row0 = f.rows;
     if (row0 >= rows) return 0;
   }
@@ -422,11 +441,11 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     f.dbpart = (grads && x->dbpart && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
     dim3 grid((rows + TC_BM - 1) / TC_BM, na * n.nnet);
     k_mlp_bwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
-    x->launches++;
+    count_launch(x, "k_mlp_bwd_tc", st);
     fused = true;
     if (f.dbpart) {     // bias gradients of the two hidden layers come from the kernel's column sums
       k_bias_finish<<<na * n.nnet, 2 * FW_H, 0, st>>>(f.dbpart, (int)grid.x, grads, sGa, sGn, n.nnet, n.ob1(), n.ob0());
-      x->launches++;
+      count_launch(x, "k_bias_finish", st);
       bias_done = true;
     }
   }
@@ -569,7 +588,7 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
     if (model_term_launch(k, k.mse_part, st) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
-    x->launches++;
+    count_launch(x, "k_model_term", st);
   } else if (k.nmod > 0) {
     const int half = k.nmod == 2 ? E / 2 : E;
     NetD mn = model_net(x, k.nmod);
@@ -729,6 +748,38 @@ extern "C" int saceo_bc_update(saceo_ctx* x, int32_t n_steps, int32_t use_device
   if (losses_out)
     CU(cudaMemcpyAsync(losses_out, k.losses, sizeof(float) * k.n_agents * x->L.n_losses, cudaMemcpyDeviceToDevice, st));
   return check_launch();
+}
+
+// One update WITHOUT the CUDA graph, an event after every kernel launch: per-launch device times measured live
+// (bench.py's per-kernel roofline).  names_out: max_n x 32 chars, us_out: max_n floats; synchronises the stream.
+extern "C" int saceo_profile_step(saceo_ctx* x, int64_t num_timesteps, int32_t use_device_rng, uint64_t seed,
+                                  char* names_out, float* us_out, int32_t max_n, int32_t* n_out, void* stream) {
+  if (!x || !names_out || !us_out || !n_out || max_n < 1) return fail(SACEO_E_INVALID, "bad argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rng = use_device_rng == 2 ? 2 : (use_device_rng ? 1 : 0);
+  const int pol = (num_timesteps % x->cfg.target_update_int) == 0 ? 1 : 0;
+  if (rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, x->k, (unsigned long long)seed);
+  cudaEvent_t e0; CU(cudaEventCreate(&e0));
+  x->prof = true; x->prof_n = 0;
+  CU(cudaEventRecord(e0, st));
+  int rc = step_once(x, rng, pol, st);
+  x->prof = false;
+  if (rc) { cudaEventDestroy(e0); return rc; }
+  CU(cudaStreamSynchronize(st));
+  const int n = (int)x->prof_n < max_n ? (int)x->prof_n : max_n;
+  cudaEvent_t prev = e0;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prev, x->prof_ev[i]);
+    us_out[i] = ms * 1000.f;
+    strncpy(names_out + (size_t)i * 32, x->prof_name[i], 31);
+    names_out[(size_t)i * 32 + 31] = 0;
+    prev = x->prof_ev[i];
+  }
+  *n_out = n;
+  cudaEventDestroy(e0);
+  return 0;
 }
 
 static int update_host_impl(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, const int64_t* idx_host,

@@ -76,7 +76,7 @@ _lib: Optional[C.CDLL] = None
 # every symbol include/saceo.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
     "saceo_query_layout", "saceo_create", "saceo_destroy", "saceo_bind", "saceo_gather",
-    "saceo_set_draws", "saceo_update", "saceo_update_host", "saceo_update_host_async", "saceo_update_phase", "saceo_bc_update",
+    "saceo_set_draws", "saceo_update", "saceo_update_host", "saceo_update_host_async", "saceo_update_phase", "saceo_bc_update", "saceo_profile_step",
     "saceo_actor_forward", "saceo_critic_forward", "saceo_model_eval", "saceo_fvp", "saceo_cg_solve",
     "saceo_fit_bind", "saceo_model_fit",
     "saceo_debug_ptr", "saceo_launch_count", "saceo_test_gemm", "saceo_last_error", "saceo_abi_version",
@@ -106,6 +106,7 @@ def load() -> C.CDLL:
         "saceo_update_host_async": (C.c_int, [vp, i64, u64, vp, vp, vp, vp]),
         "saceo_update_phase": (C.c_int, [vp, i32, i64, vp]),
         "saceo_bc_update": (C.c_int, [vp, i32, i32, u64, vp, vp]),
+        "saceo_profile_step": (C.c_int, [vp, i64, i32, u64, C.c_char_p, vp, i32, C.POINTER(i32), vp]),
         "saceo_actor_forward": (C.c_int, [vp, vp, i32, vp, vp, vp, vp]),
         "saceo_critic_forward": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp]),
         "saceo_model_eval": (C.c_int, [vp, vp, vp, i32, vp, vp]),

@@ -334,6 +334,20 @@ class Population:
         self._exit()
         return self.losses
 
+    def profile_step(self, num_timesteps: int = 0, use_device_rng: bool = True, seed: int = 0):
+        """One real update launched kernel by kernel with a CUDA event after every launch.
+        Returns [(kernel name, microseconds)] in launch order."""
+        cap = 256
+        names = C.create_string_buffer(cap * 32)
+        us = (C.c_float * cap)()
+        n = C.c_int32(0)
+        st = self._enter()
+        _l.check(self.lib.saceo_profile_step(self.ctx, num_timesteps, int(use_device_rng), seed, names, C.cast(us, C.c_void_p),
+                                             cap, C.byref(n), st))
+        self._exit()
+        raw = names.raw
+        return [(raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode(), float(us[i])) for i in range(n.value)]
+
     def bc_update(self, n_steps: int = 1, use_device_rng: bool = True, seed: int = 0):
         """``BC._update_actor`` (BC.py:309-363): actor step on the expert-observation MSE alone."""
         st = self._enter()

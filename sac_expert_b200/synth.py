@@ -124,3 +124,27 @@ def algorithmic_bytes(sp, L) -> float:
     S, A, B, E = sp.S, sp.A, sp.B, (sp.E if sp.num_models > 0 else 0)
     nm = L.nm if sp.num_models > 0 else 0
     return float(4 * (2 * 6 * L.nc + 2 * 2 * L.nc + 6 * L.na + sp.num_models * nm) + 4 * B * (2 * S + A + 2) + 4 * E * 2 * S)
+
+
+def kernel_algorithmic_bytes(sp, L) -> dict:
+    """Compulsory HBM bytes PER AGENT-UPDATE of the launches of each hot kernel (what every launch must read and write
+    even with perfect on-chip reuse: the weights of the nets it applies once, its input rows, the outputs another kernel
+    consumes).  Used by bench.py for the per-kernel roofline next to the live per-launch times."""
+    S, A, B, SA = sp.S, sp.A, sp.B, sp.S + sp.A
+    E = sp.E if sp.num_models > 0 else 0
+    R, H, Ao = B + E, sp.critic_hidden[0], L.Ao
+    w = 4
+    fwd = (  # actor(sp) | Q-target(sp,a') | Q(s,a) + saved h1,h2 | actor(s,sE) + saved | Q(s,pi) + saved | actor(s) alpha pass
+        (L.na + B * S + B * Ao) + (2 * L.nc + B * SA + 2 * B) + (2 * L.nc + B * SA + 2 * B + 4 * B * H)
+        + (L.na + R * S + R * Ao + 2 * R * sp.actor_hidden[0]) + (2 * L.nc + B * SA + 2 * B + 4 * B * H) + (L.na + B * S + B * Ao))
+    bwd = (  # critic backward (dH2, dH1 out) | critic backward-to-action | actor backward
+        (2 * L.nc + 4 * B * H + 4 * B * H + 2 * B) + (2 * L.nc + 4 * B * H + 2 * B * A + 2 * B)
+        + (L.na + 2 * R * sp.actor_hidden[0] + 2 * R * sp.actor_hidden[0] + R * Ao))
+    dw = (2 * (B * SA + 4 * B * H + L.nc)) + (R * S + 4 * R * sp.actor_hidden[0] + R * Ao + L.na)   # activations in, gradients out
+    return {
+        "k_mlp_fwd_tc": float(w * fwd),
+        "k_mlp_bwd_tc": float(w * bwd),
+        "k_model_term": float(w * (sp.num_models * L.nm + E * (2 * S + A))) if sp.num_models > 0 else 0.0,
+        "k_adam": float(w * (2 * 9 * L.nc + 7 * L.na)),
+        "k_gemm_tc+k_gemm_skinny": float(w * dw),
+    }

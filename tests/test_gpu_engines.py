@@ -126,3 +126,25 @@ def test_host_buffer_paths_agree():
         assert np.array_equal(outs[0][0], other[0])
         for k in outs[0][1]:
             assert np.array_equal(outs[0][1][k], other[1][k]), k
+
+
+def test_profile_step_reports_every_launch():
+    """saceo_profile_step: one real update, kernel by kernel, with per-launch device times; same result as update()."""
+    cfg = NetCfg(S=11, A=3)
+    outs = []
+    for mode in ("profile", "plain"):
+        pop, probs = build(cfg, n_agents=2, B=256, E=20, N=800, seed=6, gemm_mode=L.GEMM_TCGEN05_BF16X3)
+        if mode == "profile":
+            l0 = pop.launches
+            prof = pop.profile_step(0, use_device_rng=False)
+            assert len(prof) == pop.launches - l0 and len(prof) >= 20
+            names = {n for n, _ in prof}
+            assert {"k_mlp_fwd_tc", "k_mlp_bwd_tc", "k_adam", "k_model_term", "k_gather"} <= names
+            assert all(us > 0 for _, us in prof) and sum(us for _, us in prof) < 1e6
+        else:
+            pop.update(1, num_timesteps=0, use_device_rng=False)
+        torch.cuda.synchronize()
+        outs.append({k: pop.t[k].cpu().numpy().copy() for k in ("actor", "q", "qt", "alpha")})
+        pop.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
