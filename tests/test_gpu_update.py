@@ -49,3 +49,27 @@ def test_full_size_tcgen05(shape):
     worst = compare_update(pop, cfg, probs, verbose=True)
     bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
     assert not bad, bad
+
+
+RAGGED = {
+    # batch / expert sizes that do not line up with the 128-row tensor-core tiles or the 32-row slabs
+    "B300_E6": (NetCfg(S=17, A=6, actor_acts=("tanh", "tanh"), critic_acts=("tanh", "tanh")), 300, 6),
+    "B129_one_model_state_indep_std": (NetCfg(S=11, A=3, per_state_std=False, num_models=1, actor_acts=("tanh", "tanh"),
+                                              critic_acts=("tanh", "tanh")), 129, 20),
+    "B144_plain_sac": (NetCfg(S=27, A=8, num_models=0, actor_acts=("elu", "elu"), critic_acts=("elu", "elu")), 144, 0),
+    "B512_E32_A1": (NetCfg(S=3, A=1, actor_acts=("tanh", "tanh"), critic_acts=("tanh", "tanh"), model_hidden=(256, 256)), 512, 32),
+}
+
+
+@pytest.mark.parametrize("name", list(RAGGED))
+def test_ragged_sizes_tcgen05(name):
+    """Partial row tiles, padded row strides, one-model / plain-SAC branches on the tensor-core engine (smooth activations:
+    the tolerance is not blurred by ReLU mask flips)."""
+    from sac_expert_b200 import lib as L
+    cfg, B, E = RAGGED[name]
+    pop, probs = build(cfg, n_agents=3, B=B, E=max(E, 2), N=900, seed=13, gemm_mode=L.GEMM_TCGEN05_BF16X3)
+    worst = compare_update(pop, cfg, probs)
+    bad = {k: v for k, v in worst.items() if v > TOL and not k.startswith("oracle32")}
+    assert not bad, bad
+    assert max(worst[k] for k in ("g_q1", "g_q2", "g_actor")) < 2e-4, worst
+    pop.close()
