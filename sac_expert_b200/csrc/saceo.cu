@@ -429,7 +429,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
   bool fused = false, bias_done = false;
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[2] == 0 && n.h1 == FW_H && n.h2 == FW_H &&
-      out_cols >= 1 && out_cols <= 32 && rows >= TC_BM && (rows % TC_BM == 0 || rows % TC_BM >= 16) &&
+      out_cols >= 1 && out_cols <= 64 && rows >= TC_BM && (rows % TC_BM == 0 || rows % TC_BM >= 16) &&
       (!dXa || A_cols <= 32) && ((reinterpret_cast<uintptr_t>(n.theta) & 15) == 0) && ((n.sa & 3) == 0) && ((n.sn & 3) == 0)) {
     BwdP f{};
     f.dOut = dOut; f.ldd = ldd; f.sDa = sDa; f.sDn = sDn; f.kout = out_cols;

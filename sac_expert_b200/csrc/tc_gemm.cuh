@@ -570,7 +570,8 @@ static inline cudaError_t tc_gemm_init() {
 static inline int tc_rows(bool ONES, const GemmP& p) {
   const int mmain = ONES ? p.M - 1 : p.M;
   int tiles = mmain / TC_BM;
-  if (mmain % TC_BM >= 16) tiles += 1;
+  const int rem = mmain % TC_BM;
+  if (rem >= 16 || (rem >= 4 && tiles >= 1)) tiles += 1;      // next to full tiles even a thin tail beats the CUDA-core pass
   const int r = tiles * TC_BM;
   return r < mmain ? r : mmain;
 }
@@ -620,7 +621,7 @@ static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, in
 // tcgen05.st into TMEM columns [256,512) where the next layer's tcgen05.mma reads it as its A operand
 // (A-from-TMEM form).  W1 (the 256 KB that dominates traffic) streams through the cp.async ring; its first two
 // slabs are already in flight while layer 0 runs.  h1 / h2 are written to global memory only when the caller
-// needs them for the backward pass.  Requires hidden = (256, 256), out <= 32.
+// needs them for the backward pass.  Requires hidden = (256, 256), out <= 64.
 // ==========================================================================================
 namespace saceo {
 
@@ -850,8 +851,8 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   FW_STAMP(1);
-  // W2 (tiny): four 64-k slabs, loaded into registers before epilogue 1 and staged to smem after it
-  Slab<32, FW_NT> sw2[4];
+  // W2 (tiny, nout <= 64): four 64-k slabs, loaded into registers before epilogue 1 and staged to smem after it
+  Slab<64, FW_NT> sw2[4];
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc) sw2[kc].init(th + oW2, 1, f.nout, 0, f.nout);
 
@@ -922,25 +923,25 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   for (int kc = 0; kc < 4; ++kc) sw2[kc].ld(kc * TC_BK, FW_H);      // in flight during the epilogue
   hidden_epilogue<false>(tmem, r1, th + ob1, f.act1, H2, row0, f.rows, warp, lane);
   __syncthreads();                                            // patches (r1) no longer read
-  // W2 as B operand: 4 chunks of 64 k, each [32 rows x 128 B] hi plane + lo plane (8 KB per chunk)
+  // W2 as B operand: 4 chunks of 64 k, each [64 rows x 128 B] hi plane + lo plane (16 KB per chunk)
   const uint32_t w2s = r1;
 #pragma unroll
-  for (int kc = 0; kc < 4; ++kc) sw2[kc].st<true>(w2s + kc * 8192, w2s + kc * 8192 + 4096);
+  for (int kc = 0; kc < 4; ++kc) sw2[kc].st<true>(w2s + kc * 16384, w2s + kc * 16384 + 8192);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 
   FW_STAMP(4);
   // ---------------- layer 2: D[:, :npad] = h2 . W2 ----------------
-  const int npad = f.nout <= 16 ? 16 : 32;
+  const int npad = f.nout <= 16 ? 16 : (f.nout <= 32 ? 32 : 64);
   if (threadIdx.x == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t idesc2 = umma_idesc(TC_BM, npad, 0u);
     for (int ks = 0; ks < 16; ++ks) {
-      const uint32_t cb = w2s + (ks >> 2) * 8192 + (ks & 3) * 32;
+      const uint32_t cb = w2s + (ks >> 2) * 16384 + (ks & 3) * 32;
       const uint32_t ta_hi = tmem + 256 + ks * 8, ta_lo = tmem + 384 + ks * 8;
       umma_f16_ts(tmem, ta_hi, umma_desc(cb), idesc2, ks ? 1u : 0u);
-      umma_f16_ts(tmem, ta_hi, umma_desc(cb + 4096), idesc2, 1u);
+      umma_f16_ts(tmem, ta_hi, umma_desc(cb + 8192), idesc2, 1u);
       umma_f16_ts(tmem, ta_lo, umma_desc(cb), idesc2, 1u);
     }
     umma_commit(bars + 32);
@@ -948,13 +949,15 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_fwd_tc(FwdP f) {
   mbar_wait(bars + 32, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   FW_STAMP(5);
-  if (warp < 4) {                                             // one warp per lane quarter reads the 32 output columns
-    uint32_t v[32];
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  if (warp < 4) {                                             // one warp per lane quarter reads the output columns
     const int grow = row0 + warp * 32 + lane;
-    if (grow < f.rows) {
+    for (int c0 = 0; c0 < npad; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (grow < f.rows) {
 #pragma unroll
-      for (int n = 0; n < 32; ++n) if (n < f.nout) Out[(long long)grow * f.ldo + n] = __uint_as_float(v[n]) + __ldg(th + ob2 + n);
+        for (int n = 0; n < 32; ++n) if (c0 + n < f.nout) Out[(long long)grow * f.ldo + c0 + n] = __uint_as_float(v[n]) + __ldg(th + ob2 + c0 + n);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1020,7 +1023,7 @@ __global__ void __launch_bounds__(FW_NT, 1) k_mlp_bwd_tc(BwdP f) {
   pw1.issue(r2 + FW_H * TS_BK * 4);
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  // ---------------- layer 2 transposed: D = dOut[:, :kout] . W2[:, :kout]^T  (one 64-wide slab, kout <= 32) ----------------
+  // ---------------- layer 2 transposed: D = dOut[:, :kout] . W2[:, :kout]^T  (one 64-wide slab, kout <= 64) ----------------
   const bool outer = (f.kout == 1 && f.nout == 1);     // critics: K = 1, the "GEMM" is an outer product formed in the epilogue
   Slab<TC_BM, FW_NT> sx;
   Slab<FW_H, FW_NT> sw;
@@ -1168,7 +1171,7 @@ __global__ void k_bias_finish(const float* __restrict__ dbpart, int ntiles, floa
 }
 
 static inline bool mlp_fwd_tc_eligible(int h1, int h2, int nout, int rows, const float* theta, long long sTa, long long sTn, int K0) {
-  return h1 == FW_H && h2 == FW_H && nout >= 1 && nout <= 32 && rows >= TC_BM && K0 >= 1 &&
+  return h1 == FW_H && h2 == FW_H && nout >= 1 && nout <= 64 && rows >= TC_BM && K0 >= 1 &&
          ((reinterpret_cast<uintptr_t>(theta) & 15) == 0) && ((sTa & 3) == 0) && ((sTn & 3) == 0);
 }
 static inline cudaError_t mlp_fwd_tc_init() {
