@@ -14,6 +14,7 @@ namespace saceo {
 struct KCtx {
   int n_agents, S, A, Ao, mo, B, E, R, nmod, per_state_std, sep_reward;
   float eps_force;   // >= 0: expert weight used instead of hyper[5] (behaviour cloning = 1), < 0: per-agent table value
+  int ldXc, ldXp;    // leading dimensions of Xc (S+A -> multiple of 4) and Xpi (S -> multiple of 4): 16-byte aligned rows, pad columns stay zero
   int Rs;   // row stride of the per-agent [R rows] actor buffers (R rounded up to 32; the pad rows stay zero)
   int ah1, ah2, ch1, ch2, mh1, mh2;
   int aact0, aact1, cact0, cact1, mact0, mact1;
@@ -208,8 +209,8 @@ __global__ void k_stage(KCtx c, int phase) {
     if (e >= B * S) return;
     const int b = e / S, j = e - b * S;
     const float v = (c.mb_sp[((long long)agent * B + b) * S + j] - smean[j]) / nstd(sstd[j]);
-    c.Xpi[((long long)agent * c.Rs + b) * S + j] = v;
-    c.Xc[((long long)agent * B + b) * SA + j] = v;
+    c.Xpi[((long long)agent * c.Rs + b) * c.ldXp + j] = v;
+    c.Xc[((long long)agent * B + b) * c.ldXc + j] = v;
   } else if (phase == 1) {
     if (e >= B * SA) return;
     const int b = e / SA, j = e - b * SA;
@@ -217,18 +218,18 @@ __global__ void k_stage(KCtx c, int phase) {
     if (j < S) v = (c.mb_s[((long long)agent * B + b) * S + j] - smean[j]) / nstd(sstd[j]);
     else v = (c.mb_a[((long long)agent * B + b) * A + (j - S)] - nr[c.L.off_a_mean + j - S]) /
              nstd(nr[c.L.off_a_std + j - S]);
-    c.Xc[((long long)agent * B + b) * SA + j] = v;
+    c.Xc[((long long)agent * B + b) * c.ldXc + j] = v;
   } else {
     if (e >= c.R * S) return;
     const int row = e / S, j = e - row * S;
     if (row < B) {
-      c.Xpi[((long long)agent * c.Rs + row) * S + j] =
+      c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] =
           (c.mb_s[((long long)agent * B + row) * S + j] - smean[j]) / nstd(sstd[j]);
     } else {
       const int i = row - B;
       const int src = c.perm[(long long)agent * c.E + i];
       const float x = c.expert_s[((long long)agent * c.E + src) * S + j];
-      c.Xpi[((long long)agent * c.Rs + row) * S + j] = (x - smean[j]) / nstd(sstd[j]);
+      c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] = (x - smean[j]) / nstd(sstd[j]);
       const int half = c.nmod == 2 ? c.E / 2 : c.E;
       const int net = i / half, il = i - net * half;
       c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + j] =
@@ -306,7 +307,7 @@ __global__ void k_head_fwd(KCtx c, int nrows, int nmain, const float* __restrict
     if (act_out) act_out[((long long)agent * out_agent_stride_rows + out_row0 + row) * A + j] = pi;
     if (!expert) {
       if (write_xc)
-        c.Xc[((long long)agent * c.B + row) * SA + S + j] =
+        c.Xc[((long long)agent * c.B + row) * c.ldXc + S + j] =
             (pi - nr[c.L.off_a_mean + j]) / nstd(nr[c.L.off_a_std + j]);
     } else {
       c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + S + j] =

@@ -169,12 +169,12 @@ static void carve(saceo_ctx* x, char* base) {
   k.mb_s = b.get<float>("mb_s", n * B * S);   k.mb_a = b.get<float>("mb_a", n * B * A);
   k.mb_sp = b.get<float>("mb_sp", n * B * S); k.mb_r = b.get<float>("mb_r", n * B);
   k.mb_omd = b.get<float>("mb_omd", n * B);
-  k.Xpi = b.get<float>("Xpi", n * R * S);
+  k.Xpi = b.get<float>("Xpi", n * R * rup(S, 4));
   k.aH1 = b.get<float>("aH1", n * R * c.actor_hidden[0]);  k.aH2 = b.get<float>("aH2", n * R * c.actor_hidden[1]);
   k.aOut = b.get<float>("aOut", n * R * L.Ao);             k.daOut = b.get<float>("daOut", n * R * L.Ao);
   k.daH2 = b.get<float>("daH2", n * R * c.actor_hidden[1]); k.daH1 = b.get<float>("daH1", n * R * c.actor_hidden[0]);
   k.dls = b.get<float>("dls", n * R * A);
-  k.Xc = b.get<float>("Xc", n * B * SA);
+  k.Xc = b.get<float>("Xc", n * B * rup(SA, 4));
   k.cH1 = b.get<float>("cH1", n * 2 * B * c.critic_hidden[0]);  k.cH2 = b.get<float>("cH2", n * 2 * B * c.critic_hidden[1]);
   k.cQ = b.get<float>("cQ", n * 2 * B);                          k.cdQ = b.get<float>("cdQ", n * 2 * B);
   k.cdH2 = b.get<float>("cdH2", n * 2 * B * c.critic_hidden[1]); k.cdH1 = b.get<float>("cdH1", n * 2 * B * c.critic_hidden[0]);
@@ -258,6 +258,7 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   KCtx& k = x->k;
   k.n_agents = cfg->n_agents; k.S = cfg->S; k.A = cfg->A; k.Ao = x->L.Ao; k.mo = x->L.model_out;
   k.B = cfg->B; k.E = cfg->num_models > 0 ? cfg->E : 0; k.R = k.B + k.E; k.Rs = (int)rup(k.R, 32); k.nmod = cfg->num_models;
+  k.ldXc = (int)rup(cfg->S + cfg->A, 4); k.ldXp = (int)rup(cfg->S, 4);
   k.per_state_std = cfg->per_state_std; k.sep_reward = cfg->separate_reward_nn;
   k.ah1 = cfg->actor_hidden[0]; k.ah2 = cfg->actor_hidden[1];
   k.ch1 = cfg->critic_hidden[0]; k.ch2 = cfg->critic_hidden[1];
@@ -540,16 +541,16 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
   int rc;
   NetD an = actor_net(x), tn = critic_net(x, true), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)B * S, 256), n), 256, 0, st, k, 0);
-  rc = mlp_forward(x, an, k.Xpi, S, (long long)k.Rs * S, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                    (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 0, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
-  rc = mlp_forward(x, tn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
+  rc = mlp_forward(x, tn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
   LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
   LAUNCH(x, k_stage, dim3(cdiv((long long)B * SA, 256), n), 256, 0, st, k, 1);
-  rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  rc = mlp_forward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
   LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
-  rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+  rc = mlp_backward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                     k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st);
   if (rc) return rc;
   return check_launch();
@@ -572,14 +573,14 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   int rc;
   NetD an = actor_net(x), qn = critic_net(x, false);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
-  rc = mlp_forward(x, an, k.Xpi, S, (long long)Rs * S, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
+  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   if (!bc) {
-    rc = mlp_forward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+    rc = mlp_forward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
     LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
-    rc = mlp_backward(x, qn, k.Xc, SA, (long long)B * SA, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+    rc = mlp_backward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                       k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
     if (rc) return rc;
   } else {
@@ -637,7 +638,7 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
     }
   }
   LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
-  rc = mlp_backward(x, an, k.Xpi, S, (long long)Rs * S, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
+  rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
                     k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
@@ -655,7 +656,7 @@ static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
 static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
   const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A;
   NetD an = actor_net(x);
-  int rc = mlp_forward(x, an, k.Xpi, S, (long long)k.Rs * S, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+  int rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                        (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 2 * B + k.E, 0,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
@@ -860,9 +861,9 @@ extern "C" int saceo_actor_forward(saceo_ctx* x, const float* obs, int32_t rows,
   // expert rows would be routed to the model input: use only the first B ("main") rows per chunk
   for (int r0 = 0; r0 < rows; r0 += k.B) {
     const int nr = rows - r0 < k.B ? rows - r0 : k.B;
-    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xpi, k.S,
-           (long long)k.Rs * k.S, 0);
-    int rc = mlp_forward(x, an, k.Xpi, k.S, (long long)k.Rs * k.S, 0, nr, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
+    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xpi, k.ldXp,
+           (long long)k.Rs * k.ldXp, 0);
+    int rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, nr, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                          (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
     LAUNCH(x, k_head_fwd, dim3(cdiv(nr, 128), n), 128, 0, st, k, nr, nr, noise, (long long)rows * k.A, r0, 0,
            act_out, neglogp_out, (long long)rows, r0);
@@ -878,11 +879,11 @@ extern "C" int saceo_critic_forward(saceo_ctx* x, int32_t which, const float* ob
   NetD qn = critic_net(x, which != 0);
   for (int r0 = 0; r0 < rows; r0 += k.B) {
     const int nr = rows - r0 < k.B ? rows - r0 : k.B;
-    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xc, SA,
-           (long long)k.B * SA, 0);
-    LAUNCH(x, k_stage_act, dim3(cdiv((long long)nr * k.A, 256), n), 256, 0, st, k, act, rows, r0, nr, k.Xc, SA,
-           (long long)k.B * SA, 0);
-    int rc = mlp_forward(x, qn, k.Xc, SA, (long long)k.B * SA, 0, nr, k.cH1, k.cH2, k.B, q_out + r0, 1,
+    LAUNCH(x, k_stage_obs, dim3(cdiv((long long)nr * k.S, 256), n), 256, 0, st, k, obs, rows, r0, nr, k.Xc, k.ldXc,
+           (long long)k.B * k.ldXc, 0);
+    LAUNCH(x, k_stage_act, dim3(cdiv((long long)nr * k.A, 256), n), 256, 0, st, k, act, rows, r0, nr, k.Xc, k.ldXc,
+           (long long)k.B * k.ldXc, 0);
+    int rc = mlp_forward(x, qn, k.Xc, k.ldXc, (long long)k.B * k.ldXc, 0, nr, k.cH1, k.cH2, k.B, q_out + r0, 1,
                          2LL * rows, rows, st, false); if (rc) return rc;
   }
   if (scale_ret) LAUNCH(x, k_scale_ret, dim3(cdiv(2LL * rows, 256), n), 256, 0, st, k, q_out, rows);
