@@ -393,6 +393,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// src_bytes = 0: nothing is read, the 16 destination bytes are zero-filled (rows past the end of a partial tile)
+__device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 
 // Per-thread copy/convert plan of one operand with ROWS rows; KC: storage contiguous along k.
 //   raw slab layout   KC: raw[r][32] (128 B per row)      else: raw[32][ROWS] (ROWS*4 B per k)
@@ -404,22 +408,30 @@ struct TsPlan {
   const float* src[NP];
   uint32_t dst[NP];
   uint32_t rd[NI], wr[NI];
+  uint32_t sz;               // bit i: piece i lies inside the operand (rows < rlim); other pieces are zero-filled
   long long kstep;
 
-  __device__ __forceinline__ void init(const float* __restrict__ base, long long sr, long long sk, int r0) {
+  // rlim: rows of the operand that exist (a partial last tile); the storage must be readable up to the 4-row group
+  // that contains row rlim-1 (KC = false: leading dimension >= rlim rounded up to 4)
+  __device__ __forceinline__ void init(const float* __restrict__ base, long long sr, long long sk, int r0, int rlim = 1 << 30) {
     kstep = KC ? TS_BK : (long long)TS_BK * sk;
+    sz = 0;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       const int pc = threadIdx.x + i * TS_NT;
       if (KC) {
         const int r = pc >> 3, c = pc & 7;
-        src[i] = base + (long long)(r0 + r) * sr + c * 4;
+        const bool ok = r0 + r < rlim;
+        src[i] = base + (long long)(ok ? r0 + r : r0) * sr + c * 4;
         dst[i] = (uint32_t)(r * 128 + c * 16);
+        sz |= ok ? (1u << i) : 0u;
       } else {
         constexpr int PPR = ROWS / 4;
         const int k = pc / PPR, c = pc % PPR;
-        src[i] = base + (long long)k * sk + r0 + c * 4;
+        const bool ok = r0 + c * 4 < rlim;
+        src[i] = base + (long long)k * sk + r0 + (ok ? c * 4 : 0);
         dst[i] = (uint32_t)(k * (ROWS * 4) + c * 16);
+        sz |= ok ? (1u << i) : 0u;
       }
     }
 #pragma unroll
@@ -433,7 +445,7 @@ struct TsPlan {
   }
   __device__ __forceinline__ void issue(uint32_t raw) {
 #pragma unroll
-    for (int i = 0; i < NP; ++i) { cp_async16(raw + dst[i], src[i]); src[i] += kstep; }
+    for (int i = 0; i < NP; ++i) { cp_async16z(raw + dst[i], src[i], (sz >> i) & 1u ? 16u : 0u); src[i] += kstep; }
   }
   template <bool F16 = false>
   __device__ __forceinline__ void convert(uint32_t raw, int h, uint32_t hi, uint32_t lo) const {
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
   }
   TsPlan<TC_BM, AKC> pa;
   TsPlan<TS_BN, BKC> pb;
-  pa.init(A, q.a_sr, q.a_sk, m0);
+  pa.init(A, q.a_sr, q.a_sk, m0, q.m_rows);        // a partial last row tile is zero-filled
   pb.init(B, q.b_sr, q.b_sk, n0);
   const int nslab = p.K / TS_BK;
   // prologue: two slabs in flight
@@ -594,7 +606,7 @@ static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, in
     k_gemm_tc<BN_, NS_, NT_, MB_><<<grid, NT_, TcSmem<BN_, NS_, NT_>::BYTES, st>>>(q); } while (0)
   const bool aligned = ((p.lda & 3) == 0) && ((p.ldb & 3) == 0) && (((p.sAa | p.sAn | p.sBa | p.sBn) & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
-  if (variant != 2 && aligned && (p.K % TS_BK) == 0 && (p.N % TS_BN) == 0 && (q.m_rows % TC_BM) == 0) {
+  if (variant != 2 && aligned && (p.K % TS_BK) == 0 && (p.N % TS_BN) == 0) {
     dim3 grid(p.N / TS_BN, mt, nagents * p.nnet);
     const bool akc = (q.a_sk == 1), bkc = (q.b_sk == 1);
     if (akc && bkc) k_gemm_tc_stream<true, true><<<grid, TS_NT, TS_BYTES, st>>>(q);
