@@ -591,7 +591,7 @@ static inline bool tc_gemm_eligible(bool TA, bool TB, bool ONES, const GemmP& p)
   (void)TA; (void)TB;
   const int r = tc_rows(ONES, p);
   // full tiles always; a lone partial tile only when the weight panel is big enough to amortise a 512-thread CTA
-  return p.m_off == 0 && p.N >= 64 && p.K >= 8 && (r >= 96 || (r >= 16 && (long long)p.N * p.K >= 128 * 128));
+  return p.m_off == 0 && p.N > 32 && p.K >= 8 && (r >= 96 || (r >= 16 && (long long)p.N * p.K >= 128 * 128));
 }
 
 static unsigned long long* g_tc_dbg = nullptr;   // set by saceo_test_gemm_timed only
