@@ -27,6 +27,7 @@ struct KCtx {
   float *mb_s, *mb_a, *mb_sp, *mb_r, *mb_omd;
   float *Xpi, *aH1, *aH2, *aOut, *daOut, *daH2, *daH1, *dls;
   float *Xc, *cH1, *cH2, *cQ, *cdQ, *cdH2, *cdH1, *cdXa;
+  float *Xc2;        // live-critic input [N_s(s) | N_a(a)] (Xc holds the target-critic input [N_s(sp) | N_a(a')])
   float *Xm, *mH1, *mH2, *mOut, *mdOut, *mdH2, *mdH1, *mdXa;
   float *y, *nlp;
   float *g_q, *g_actor;
@@ -153,11 +154,13 @@ __global__ void k_rng_fill(KCtx c, int skip_idx) {
 // replay row gather (buffers.py:135-142).  One warp per (agent, batch row): the AoS row is read
 // as contiguous 16-byte vectors and scattered to the SoA outputs.  Bit-exact word copies.
 // grid: (ceil(B/8), n_agents), block 256.  out_d (f64 raw words) xor omd (float 1-d) may be set.
+// stage != 0 (the update path): the normalised network inputs of the critic phase are written in the same pass
+// (normalizer.py:26-37, critics.py:89-93): Xpi[b] = Xc[b, :S] = N_s(sp[b]);  Xc2[b] = [N_s(s[b]) | N_a(a[b])].
 // ------------------------------------------------------------------------------------------
 __global__ void k_gather(KCtx c, const long long* __restrict__ idx, float* __restrict__ out_s,
                          float* __restrict__ out_a, float* __restrict__ out_sp,
                          float* __restrict__ out_r, double* __restrict__ out_d,
-                         float* __restrict__ out_omd) {
+                         float* __restrict__ out_omd, int stage) {
   const int agent = blockIdx.y;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -171,16 +174,29 @@ __global__ void k_gather(KCtx c, const long long* __restrict__ idx, float* __res
       c.T.replay + ((long long)agent * c.cap + phys) * rw);
   const long long ob = (long long)agent * c.B + b;
   const int S = c.S, A = c.A;
+  const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   for (int v = lane; v < (rw >> 2); v += 32) {
     const float4 q = __ldg(row + v);
     const float w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = 4 * v + j;
-      if (i < c.L.off_a) { if (out_s) out_s[ob * S + i] = w[j]; }
-      else if (i < c.L.off_sp) { if (out_a) out_a[ob * A + (i - c.L.off_a)] = w[j]; }
-      else if (i < c.L.off_r) { if (out_sp) out_sp[ob * S + (i - c.L.off_sp)] = w[j]; }
-      else if (i == c.L.off_r) { if (out_r) out_r[ob] = w[j]; }
+      if (i < c.L.off_a) {
+        if (out_s) out_s[ob * S + i] = w[j];
+        if (stage) c.Xc2[ob * c.ldXc + i] = (w[j] - nr[c.L.off_s_mean + i]) / nstd(nr[c.L.off_s_std + i]);
+      } else if (i < c.L.off_sp) {
+        const int a = i - c.L.off_a;
+        if (out_a) out_a[ob * A + a] = w[j];
+        if (stage) c.Xc2[ob * c.ldXc + S + a] = (w[j] - nr[c.L.off_a_mean + a]) / nstd(nr[c.L.off_a_std + a]);
+      } else if (i < c.L.off_r) {
+        const int t = i - c.L.off_sp;
+        if (out_sp) out_sp[ob * S + t] = w[j];
+        if (stage) {
+          const float x = (w[j] - nr[c.L.off_s_mean + t]) / nstd(nr[c.L.off_s_std + t]);
+          c.Xpi[((long long)agent * c.Rs + b) * c.ldXp + t] = x;
+          c.Xc[ob * c.ldXc + t] = x;
+        }
+      } else if (i == c.L.off_r) { if (out_r) out_r[ob] = w[j]; }
     }
     // d is an 8-byte-aligned f64 inside the row, so both words are in the same float4
     if (c.L.off_d >= 4 * v && c.L.off_d < 4 * v + 4) {
@@ -307,7 +323,7 @@ __global__ void k_head_fwd(KCtx c, int nrows, int nmain, const float* __restrict
     if (act_out) act_out[((long long)agent * out_agent_stride_rows + out_row0 + row) * A + j] = pi;
     if (!expert) {
       if (write_xc)
-        c.Xc[((long long)agent * c.B + row) * c.ldXc + S + j] =
+        (write_xc == 2 ? c.Xc2 : c.Xc)[((long long)agent * c.B + row) * c.ldXc + S + j] =
             (pi - nr[c.L.off_a_mean + j]) / nstd(nr[c.L.off_a_std + j]);
     } else {
       c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + S + j] =

@@ -175,6 +175,7 @@ static void carve(saceo_ctx* x, char* base) {
   k.daH2 = b.get<float>("daH2", n * R * c.actor_hidden[1]); k.daH1 = b.get<float>("daH1", n * R * c.actor_hidden[0]);
   k.dls = b.get<float>("dls", n * R * A);
   k.Xc = b.get<float>("Xc", n * B * rup(SA, 4));
+  k.Xc2 = b.get<float>("Xc2", n * B * rup(SA, 4));
   k.cH1 = b.get<float>("cH1", n * 2 * B * c.critic_hidden[0]);  k.cH2 = b.get<float>("cH2", n * 2 * B * c.critic_hidden[1]);
   k.cQ = b.get<float>("cQ", n * 2 * B);                          k.cdQ = b.get<float>("cdQ", n * 2 * B);
   k.cdH2 = b.get<float>("cdH2", n * 2 * B * c.critic_hidden[1]); k.cdH1 = b.get<float>("cdH1", n * 2 * B * c.critic_hidden[0]);
@@ -531,26 +532,25 @@ static int check_launch() {
 static int phase_gather(saceo_ctx* x, cudaStream_t st) {
   const KCtx& k = x->k;
   LAUNCH(x, k_gather, dim3(cdiv(k.B, 8), k.n_agents), 256, 0, st, k, k.idx, k.mb_s, k.mb_a, k.mb_sp, k.mb_r,
-         (double*)nullptr, k.mb_omd);
+         (double*)nullptr, k.mb_omd, 1);      // + normalised critic-phase inputs (Xpi, Xc[:, :S], Xc2)
   return check_launch();
 }
 
 // phase 0: TD target + critic gradients
 static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
-  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A;
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, A = k.A;
   int rc;
   NetD an = actor_net(x), tn = critic_net(x, true), qn = critic_net(x, false);
-  LAUNCH(x, k_stage, dim3(cdiv((long long)B * S, 256), n), 256, 0, st, k, 0);
+  // inputs were staged by the gather: Xpi = N_s(sp), Xc = [N_s(sp) | .], Xc2 = [N_s(s) | N_a(a)]
   rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                    (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(B, 128), n), 128, 0, st, k, B, B, k.noise, (3LL * B + k.E) * A, 0, 1,
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   rc = mlp_forward(x, tn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
   LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
-  LAUNCH(x, k_stage, dim3(cdiv((long long)B * SA, 256), n), 256, 0, st, k, 1);
-  rc = mlp_forward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
   LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
-  rc = mlp_backward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+  rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                     k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st);
   if (rc) return rc;
   return check_launch();
@@ -575,12 +575,12 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
   rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
   if (rc) return rc;
-  LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 1,
-         (float*)nullptr, (float*)nullptr, 0LL, 0);
+  LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
+         (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) replaces the action columns of Xc2
   if (!bc) {
-    rc = mlp_forward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+    rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
     LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
-    rc = mlp_backward(x, qn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+    rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                       k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
     if (rc) return rc;
   } else {
@@ -654,7 +654,7 @@ static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
 
 // phase 4/5: temperature (forward of the UPDATED actor on s with fresh noise u5)
 static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
-  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, S = k.S, A = k.A;
+  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, A = k.A;
   NetD an = actor_net(x);
   int rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                        (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
@@ -848,7 +848,7 @@ extern "C" int saceo_gather(saceo_ctx* x, const int64_t* idx, float* out_s, floa
   if (!x->bound || !x->k.T.replay) return fail(SACEO_E_UNBOUND, "replay table is not bound");
   const KCtx& k = x->k;
   LAUNCH(x, k_gather, dim3(cdiv(k.B, 8), k.n_agents), 256, 0, (cudaStream_t)stream, k, (const long long*)idx,
-         out_s, out_a, out_sp, out_r, out_d, (float*)nullptr);
+         out_s, out_a, out_sp, out_r, out_d, (float*)nullptr, 0);
   return check_launch();
 }
 
@@ -875,7 +875,7 @@ extern "C" int saceo_critic_forward(saceo_ctx* x, int32_t which, const float* ob
                                     int32_t scale_ret, float* q_out, void* stream) {
   if (!x || !obs || !act || !q_out || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
-  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents, SA = k.S + k.A;
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents;
   NetD qn = critic_net(x, which != 0);
   for (int r0 = 0; r0 < rows; r0 += k.B) {
     const int nr = rows - r0 < k.B ? rows - r0 : k.B;
