@@ -7,10 +7,12 @@ from sac_expert_b200.population import Population, PopulationSpec
 from sac_expert_b200.synth import fill_synthetic
 lib = L.load()
 lib.saceo_test_set_tc_debug.argtypes = [C.c_void_p]
-n = 256
-pop = Population(PopulationSpec(n_agents=n, S=27, A=8, B=256, E=20, replay_capacity=1000, gemm_mode=1))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 27
+A = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+pop = Population(PopulationSpec(n_agents=n, S=S, A=A, B=256, E=20, replay_capacity=1000, gemm_mode=1))
 fill_synthetic(pop, seed=1)
-obs = torch.randn(n, 256, 27, device="cuda")
+obs = torch.randn(n, 256, S, device="cuda")
 for _ in range(3):
     pop.actor_forward(obs, None)
 torch.cuda.synchronize()
