@@ -209,48 +209,30 @@ __global__ void k_gather(KCtx c, const long long* __restrict__ idx, float* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// input staging: normalise (+ concat) into the GEMM operand matrices
-//   phase 0 (target): Xpi[b] = N_s(sp[b]);  Xc[b,:S] = N_s(sp[b])
-//   phase 1 (critic): Xc[b] = [N_s(s[b]), N_a(a[b])]                       critics.py:89-93
-//   phase 2 (actor):  Xpi[b] = N_s(s[b]);  Xpi[B+i] = N_s(sE[perm i]);  Xm[net][il,:S] = N_s^M(sE[perm i])
-// grid: (ceil(R*(S+A)/256), n_agents)
+// input staging of the actor phase: normalise into the GEMM operand matrices (the critic-phase inputs are staged by
+// k_gather):  Xpi[b] = N_s(s[b]);  Xpi[B+i] = N_s(sE[perm i]);  Xm[net][il,:S] = N_s^M(sE[perm i])
+// grid: (ceil(R*S/256), n_agents)
 // ------------------------------------------------------------------------------------------
-__global__ void k_stage(KCtx c, int phase) {
+__global__ void k_stage(KCtx c) {
   const int agent = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int S = c.S, A = c.A, SA = S + A, B = c.B;
+  const int S = c.S, SA = S + c.A, B = c.B;
   const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
   const float* smean = nr + c.L.off_s_mean; const float* sstd = nr + c.L.off_s_std;
-  if (phase == 0) {
-    if (e >= B * S) return;
-    const int b = e / S, j = e - b * S;
-    const float v = (c.mb_sp[((long long)agent * B + b) * S + j] - smean[j]) / nstd(sstd[j]);
-    c.Xpi[((long long)agent * c.Rs + b) * c.ldXp + j] = v;
-    c.Xc[((long long)agent * B + b) * c.ldXc + j] = v;
-  } else if (phase == 1) {
-    if (e >= B * SA) return;
-    const int b = e / SA, j = e - b * SA;
-    float v;
-    if (j < S) v = (c.mb_s[((long long)agent * B + b) * S + j] - smean[j]) / nstd(sstd[j]);
-    else v = (c.mb_a[((long long)agent * B + b) * A + (j - S)] - nr[c.L.off_a_mean + j - S]) /
-             nstd(nr[c.L.off_a_std + j - S]);
-    c.Xc[((long long)agent * B + b) * c.ldXc + j] = v;
+  if (e >= c.R * S) return;
+  const int row = e / S, j = e - row * S;
+  if (row < B) {
+    c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] =
+        (c.mb_s[((long long)agent * B + row) * S + j] - smean[j]) / nstd(sstd[j]);
   } else {
-    if (e >= c.R * S) return;
-    const int row = e / S, j = e - row * S;
-    if (row < B) {
-      c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] =
-          (c.mb_s[((long long)agent * B + row) * S + j] - smean[j]) / nstd(sstd[j]);
-    } else {
-      const int i = row - B;
-      const int src = c.perm[(long long)agent * c.E + i];
-      const float x = c.expert_s[((long long)agent * c.E + src) * S + j];
-      c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] = (x - smean[j]) / nstd(sstd[j]);
-      const int half = c.nmod == 2 ? c.E / 2 : c.E;
-      const int net = i / half, il = i - net * half;
-      c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + j] =
-          (x - nr[c.L.off_m_s_mean + j]) / nstd(nr[c.L.off_m_s_std + j]);
-    }
+    const int i = row - B;
+    const int src = c.perm[(long long)agent * c.E + i];
+    const float x = c.expert_s[((long long)agent * c.E + src) * S + j];
+    c.Xpi[((long long)agent * c.Rs + row) * c.ldXp + j] = (x - smean[j]) / nstd(sstd[j]);
+    const int half = c.nmod == 2 ? c.E / 2 : c.E;
+    const int net = i / half, il = i - net * half;
+    c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + j] =
+        (x - nr[c.L.off_m_s_mean + j]) / nstd(nr[c.L.off_m_s_std + j]);
   }
 }
 

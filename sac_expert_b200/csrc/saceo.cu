@@ -572,7 +572,7 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
   int rc;
   NetD an = actor_net(x), qn = critic_net(x, false);
-  LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k, 2);
+  LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
   rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
