@@ -606,7 +606,10 @@ static inline int tc_gemm_launch(bool TA, bool TB, bool ONES, const GemmP& p, in
     k_gemm_tc<BN_, NS_, NT_, MB_><<<grid, NT_, TcSmem<BN_, NS_, NT_>::BYTES, st>>>(q); } while (0)
   const bool aligned = ((p.lda & 3) == 0) && ((p.ldb & 3) == 0) && (((p.sAa | p.sAn | p.sBa | p.sBn) & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
-  if (variant != 2 && aligned && (p.K % TS_BK) == 0 && (p.N % TS_BN) == 0) {
+  // both operands contiguous along k (dX = dY . W^T): the register-staged 64-k kernel reads whole 256-byte rows and wins
+  // (134 vs 160 us on 256^3 x 512, tools/gemm_bench.py); every other orientation streams
+  const bool both_kc = (q.a_sk == 1) && (q.b_sk == 1);
+  if (variant != 2 && aligned && !both_kc && (p.K % TS_BK) == 0 && (p.N % TS_BN) == 0) {
     dim3 grid(p.N / TS_BN, mt, nagents * p.nnet);
     const bool akc = (q.a_sk == 1), bkc = (q.b_sk == 1);
     if (akc && bkc) k_gemm_tc_stream<true, true><<<grid, TS_NT, TS_BYTES, st>>>(q);
