@@ -259,3 +259,46 @@ def test_model_fit_restatement():
                                       dict(model_lr=1e-3, reward_loss_coef=0.5, delta_clip_loss=1.0, reward_clip_loss=1.0)))
     for g32, g64 in zip(outs[0]["grads"][1], outs[1]["grads"][1]):
         assert float((g32.double() - g64).norm() / g64.norm()) < 1e-5
+
+
+def test_bc_is_the_unit_expert_weight_slice():
+    """BC._update_actor (BC.py:309-363) == the actor step of SAC_exp._update_actor_and_alpha with epsilon = 1
+    (SAC_expert.py:299-338): same MSE, same gradient, same Adam step; critics / temperature untouched by construction."""
+    from oracle.sac_eo_oracle import NetCfg, bc_update, draw_batch, make_problem, sac_eo_update, to_torch_state
+    for nm, per_state in ((2, True), (1, False)):
+        cfg = NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(16, 16), model_hidden=(16, 16), num_models=nm,
+                     per_state_std=per_state)
+        st, replay, expert, hyper = make_problem(cfg, 16, 4, 100, seed=1, perturb=0.05)
+        b = draw_batch(cfg, replay, expert, 16, seed=3)
+        T = to_torch_state(st, torch.float64)
+        o = bc_update(cfg, T, b, hyper)
+        h = dict(hyper); h["eps"] = 1.0
+        o2 = sac_eo_update(cfg, T, b, h)
+        assert abs(float(o["mse"]) - float(o2["mse"])) < 1e-12
+        for g1, g2 in zip(o["g_actor"], o2["g_actor"]):
+            assert float((g1 - g2).abs().max()) < 1e-12
+        for w1, w2 in zip(o["new"]["actor"], o2["new"]["actor"]):
+            assert float((w1 - w2).abs().max()) < 1e-14
+        assert o["new"]["adam_actor"]["t"] == st["adam_actor"]["t"] + 1
+
+
+def test_gaussian_model_loss_gradients():
+    """GaussianModel.get_loss (continuous_models.py:101-131): closed-form gradient w.r.t. the unclipped logstd and the
+    stop-gradient of scale_model_loss."""
+    from oracle.sac_eo_oracle import NetCfg, make_problem, model_loss, to_torch_state
+    cfg = NetCfg(S=4, A=2, model_hidden=(8, 8), model_acts=("tanh", "tanh"))
+    st, replay, _, _ = make_problem(cfg, 8, 4, 50, seed=2, perturb=0.05)
+    T = to_torch_state(st, torch.float64)
+    th = [w.clone().requires_grad_(True) for w in T["m1"]]
+    ls = (0.3 * torch.randn(1, 4, dtype=torch.float64)).requires_grad_(True)
+    b = {k: torch.as_tensor(replay[k][:20]).double() for k in ("s", "a", "sp", "r")}
+    for scale in (False, True):
+        L = model_loss(cfg, th, b["s"], b["a"], b["sp"], b["r"], T, 0.5, 0.0, 0.0, ls, scale)
+        (g,) = torch.autograd.grad(L, ls)
+        with torch.no_grad():
+            from oracle.sac_eo_oracle import mlp, normalize
+            sa = torch.cat([normalize(b["s"], T["m_s_mean"], T["m_s_std"]), normalize(b["a"], T["m_a_mean"], T["m_a_std"])], -1)
+            e = normalize(b["sp"] - b["s"], T["m_d_mean"], T["m_d_std"]) - mlp(th, sa, cfg.model_acts)[:, :-1]
+            sc = (torch.exp(ls) ** 2).mean() if scale else 1.0
+            ref = sc * (1.0 - e ** 2 * torch.exp(-2 * ls)).mean(0, keepdim=True)
+        assert float((g - ref).abs().max()) < 1e-12
