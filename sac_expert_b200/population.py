@@ -43,12 +43,12 @@ class PopulationSpec:
     replay_capacity: int = 100_000
     fvp_rows: int = 0
     std_mult: float = 1.0
-    gemm_mode: int = _l.GEMM_FP32_SIMT
+    gemm_mode: int = _l.GEMM_TCGEN05_BF16X3   # GEMM_FP32_SIMT: exact-fp32 CUDA-core engine (debugging / bit-faithful parity)
     tc_variant: int = 0            # tcgen05 tile variant (0: 128x256 1 CTA/SM, 1: 128x128 2 CTAs/SM)
     fuse_forward: bool = True      # fused 3-layer tcgen05 forward (activations resident in TMEM)
     fuse_backward: bool = True     # fused tcgen05 gradient chain dOut -> dH2 -> dH1 -> dXa
     fuse_model: bool = True        # fused expert-observation term (model forward + MSE + backward to action)
-    use_graph: bool = False
+    use_graph: bool = True         # one update = one CUDA-graph replay
     device: int = 0
 
     def to_config(self) -> _l.Config:

@@ -14,6 +14,10 @@ def rel(a, b):
 
 
 def spec_from_cfg(cfg: NetCfg, n_agents, B, E, N, **kw) -> PopulationSpec:
+    # tests default to the exact-fp32 engine launched kernel by kernel; the tensor-core engine / graphs are opted into
+    from sac_expert_b200 import lib as _lib
+    kw.setdefault("gemm_mode", _lib.GEMM_FP32_SIMT)
+    kw.setdefault("use_graph", False)
     return PopulationSpec(n_agents=n_agents, S=cfg.S, A=cfg.A, actor_hidden=cfg.actor_hidden,
                           critic_hidden=cfg.critic_hidden, model_hidden=cfg.model_hidden,
                           actor_acts=cfg.actor_acts, critic_acts=cfg.critic_acts, model_acts=cfg.model_acts,
