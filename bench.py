@@ -30,7 +30,7 @@ def parse():
     p.add_argument("--agents", type=int, default=256, help="agents per GPU")
     p.add_argument("--replay-rows", type=int, default=100_000)
     p.add_argument("--plain-sac", action="store_true", help="no expert term (BASELINE configs[1])")
-    p.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 bf16x3 (default: best available)")
+    p.add_argument("--gemm-mode", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 hi/lo x3 (default)")
     p.add_argument("--tc-variant", type=int, default=0)
     p.add_argument("--no-fuse-forward", action="store_true")
     p.add_argument("--no-fuse-backward", action="store_true")
@@ -271,7 +271,7 @@ def run_b200(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "agents_per_gpu": a.agents, "batch": B,
-                   "gemm_engine": "tcgen05 bf16x3 (fp32 accum in TMEM), fused 3-layer forward/backward kernels" if gemm_mode == 1 else "fp32 SIMT",
+                   "gemm_engine": "tcgen05 16-bit hi/lo x3 (fp16 planes forward, bf16 planes backward; fp32 accum in TMEM), fused 3-layer forward/backward kernels" if gemm_mode == 1 else "fp32 SIMT",
                    "cuda_graph": not a.no_graph, "rng": "in-kernel Philox4x32-10",
                    "l2_note": f"population state {bytes_step / 1e9:.2f} GB/step >> 126 MB L2; no explicit flush"},
         "clocks": clocks,

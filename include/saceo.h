@@ -54,7 +54,8 @@ enum { SACEO_ACT_RELU = 0, SACEO_ACT_TANH = 1, SACEO_ACT_ELU = 2 };
 /* GEMM engine for the hidden x hidden per-agent contractions. */
 enum {
   SACEO_GEMM_FP32_SIMT = 0,   /* CUDA-core fp32 FMA (exact fp32 products) */
-  SACEO_GEMM_TCGEN05_BF16X3 = 1 /* tcgen05.mma kind::f16, bf16 hi/lo split, 3 MMAs, fp32 accum in TMEM */
+  SACEO_GEMM_TCGEN05_BF16X3 = 1 /* tcgen05.mma kind::f16 on 16-bit hi/lo operand planes (fp16 planes in forward passes,
+                                   bf16 planes for gradients), 3 MMAs per product, fp32 accumulation in TMEM */
 };
 
 /* Static dimensions - what the reference passes through its kwargs dicts
