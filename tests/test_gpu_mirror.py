@@ -273,3 +273,56 @@ def test_bc_alg_update_matches_oracle_with_reference_rng_order():
     for a_, b_ in zip(q_before, alg.q_critics[0].get_weights()):
         assert np.array_equal(a_, b_)
     assert alg.logger.train_dict["BC_MSE_loss"] == [alg.last_losses["BC_MSE_loss"]] or len(alg.logger.train_dict["BC_MSE_loss"]) == 1
+
+
+@pytest.mark.parametrize("use_expert_actions", [True, False])
+def test_adaptive_expert_weight_matches_oracle(use_expert_actions):
+    """MSE bookkeeping on the expert transitions (SAC_expert.py:579-608) and the adaptive weight of
+    _expert_preprocess (:381-418, scale_epsilon_by_true_MSE with min_mult and exp_mult) through the device forwards,
+    against the oracle's model_mse_on_expert / adaptive_epsilon with the same NumPy draw."""
+    from oracle.sac_eo_oracle import adaptive_epsilon, model_mse_on_expert
+    S, A, B, E = 11, 3, 32, 8
+    alg, rng = build_alg("sac_imit", S, A, B, E)
+    alg.scale_epsilon_by_true_MSE, alg.use_expert_actions = True, use_expert_actions
+    alg.min_mult, alg.exp_mult, alg.mult_coeff = True, True, 0.7
+    alg.epsilon, alg.current_reward, alg.expert_reward = 0.5, 40.0, 100.0
+    sE, aE = rng.standard_normal((E, S)).astype(np.float32), rng.uniform(-1, 1, (E, A)).astype(np.float32)
+    spE = rng.standard_normal((E, S)).astype(np.float32)
+    alg.expert_data.add(sE, aE, rng.standard_normal(E).astype(np.float32), spE, np.zeros(E, bool))
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48))
+    st = to_torch_state(snapshot(alg, cfg))
+    np.random.seed(9)
+    on_exp, cf = alg._expert_mse_bookkeeping()
+    np.random.seed(9)
+    u = None if use_expert_actions else np.random.normal(size=(E, A))
+    ref_on = float(model_mse_on_expert(cfg, st, sE, aE, spE, use_expert_actions=True))
+    ref_cf = ref_on if use_expert_actions else float(model_mse_on_expert(cfg, st, sE, aE, spE, u=u))
+    assert on_exp == pytest.approx(ref_on, rel=1e-4) and cf == pytest.approx(ref_cf, rel=1e-4)
+    eps = alg._expert_preprocess()[3]
+    ref_eps = adaptive_epsilon(0.5, scale_by_true_mse=True, mse_cf=ref_cf, j_cur=40.0, j_exp=100.0, min_mult=True,
+                               exp_mult=True, mult_coeff=0.7)
+    assert eps == pytest.approx(ref_eps, rel=1e-4)
+
+
+def test_model_disagreement_weight_matches_oracle():
+    """_calc_disc (SAC_expert.py:427-460) + the scale_max/median/total_disc branches of _expert_preprocess."""
+    from oracle.sac_eo_oracle import adaptive_epsilon, model_sample
+    S, A, B, E = 11, 3, 32, 8
+    alg, rng = build_alg("sac_imit", S, A, B, E)
+    alg.use_expert_actions = True
+    sE, aE = rng.standard_normal((E, S)).astype(np.float32), rng.uniform(-1, 1, (E, A)).astype(np.float32)
+    alg.expert_data.add(sE, aE, rng.standard_normal(E).astype(np.float32), rng.standard_normal((E, S)).astype(np.float32),
+                        np.zeros(E, bool))
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48))
+    st = to_torch_state(snapshot(alg, cfg))
+    p0 = model_sample(cfg, st["m1"], torch.as_tensor(sE), torch.as_tensor(aE), st).numpy()
+    p1 = model_sample(cfg, st["m2"], torch.as_tensor(sE), torch.as_tensor(aE), st).numpy()
+    disc = np.linalg.norm(p0 - p1, axis=1)
+    ratio, mx, med, tot = alg._calc_disc(sE, aE, None)
+    assert mx == pytest.approx(float(disc.max()), rel=1e-4) and med == pytest.approx(float(np.median(disc)), rel=1e-4)
+    assert tot == pytest.approx(float(disc.sum()), rel=1e-4) and np.allclose(ratio, disc / disc.sum(), rtol=1e-4)
+    alg.epsilon = 2.0
+    for flag, mode in (("scale_max_disc", "max"), ("scale_median_disc", "median"), ("scale_total_disc", "total")):
+        alg.scale_max_disc = alg.scale_median_disc = alg.scale_total_disc = False
+        setattr(alg, flag, True)
+        assert alg._expert_preprocess()[3] == pytest.approx(adaptive_epsilon(2.0, disc_mode=mode, disc=disc), rel=1e-4)
