@@ -733,13 +733,30 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tmem, uint32_t patch_b
   for (int c0 = 0; c0 < 64; c0 += 32) {
     const int col = grp * 64 + c0;
     float aux[32];
-    if (!BWD || grow_own < rows) {
-      const float4* ap = reinterpret_cast<const float4*>(BWD ? auxp + (long long)grow_own * FW_H + col : auxp + col);
+    if (!BWD) {
+      const float4* ap = reinterpret_cast<const float4*>(auxp + col);          // bias: the same 32 values for every row
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float4 t4 = __ldg(ap + j); aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w; }
     } else {
+      // saved activations [32 rows x 32 cols] of this warp: read row-wise (8 lanes = one 128-byte row segment, whole
+      // lines per request) into the warp's patch, then every lane picks up ITS row - a lane-per-row global read would
+      // touch 32 different lines per request
+      const int lr = lane >> 3, lc = (lane & 7) * 4;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) aux[j] = 0.f;
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int r = rr + lr;
+        const int grow = row0 + q * 32 + r;
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < rows) t4 = __ldg(reinterpret_cast<const float4*>(auxp + (long long)grow * FW_H + col + lc));
+        sts128(patch + (uint32_t)(r * PSTR + lc) * 4, make_uint4(__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w)));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t4 = lds128(patch + (uint32_t)(lane * PSTR + 4 * j) * 4);
+        aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w;
+      }
+      __syncwarp();                                                             // the patch is reused for the output tile below
     }
     uint32_t v[32];
     if (outer_w) {
