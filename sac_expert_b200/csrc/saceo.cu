@@ -924,7 +924,7 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
     return fail(SACEO_E_INVALID, "a required fit table pointer is NULL");
   const int nls = (t->model_logstd != nullptr) + (t->model_logstd_m != nullptr) + (t->model_logstd_v != nullptr);
   if (nls != 0 && nls != 3) return fail(SACEO_E_INVALID, "model_logstd, model_logstd_m and model_logstd_v must be given together");
-  if (nls && x->cfg.S > 512) return fail(SACEO_E_INVALID, "Gaussian model loss supports S <= 512");
+  if (x->cfg.S > 512) return fail(SACEO_E_INVALID, "model fitting supports S <= 512 (per-column weights of the loss kernel live in shared memory)");
   CU(cudaSetDevice(x->cfg.device));
   if (x->fit_ws) { CU(cudaDeviceSynchronize()); cudaFree(x->fit_ws); x->fit_ws = nullptr; x->fit_bound = false; }
   const saceo_config& c = x->cfg;
