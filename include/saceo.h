@@ -258,6 +258,29 @@ int saceo_fvp(saceo_ctx *ctx, const float *x, float damp, float *Fx, void *strea
 int saceo_cg_solve(saceo_ctx *ctx, const float *b, int32_t iters, float tol, float damp,
                    float *x_out, float *vFv_out, void *stream);
 
+/* TRPO.update surrogate gradient (algs/model_free/trpo.py:36-63) on the rows bound as fvp_states (all fvp_rows of
+ * them), GaussianActor parameterisation (actors/continuous_actors.py:74-100,137-148):
+ *   loss = mean(-exp(nlp_old - neglogp(s,a)) adv) - alpha (mean entropy(s) - ent_targ)
+ * act [n,N,A], adv [n,N] (already centred / scaled by the caller, trpo.py:41-48), nlp_old [n,N] or NULL (= current
+ * neglogp, ratio 1), alpha [n] or NULL (0); grad_out [n, na_stride] = d loss / d theta ("neg_pg", flat layout);
+ * stats_out [n,8] or NULL = {mean(ratio adv), 0, 0.5 mean|ratio-1|, mean entropy, 0...}.  The temperature gradient
+ * is -(stats[3] - ent_targ) (host scalar).  All device pointers. */
+int saceo_trpo_grad(saceo_ctx *ctx, const float *act, const float *adv, const float *nlp_old, const float *alpha,
+                    float *grad_out, float *stats_out, void *stream);
+
+/* Quantities of the back-tracking line search TRPO._backtrack (trpo.py:229-317) at the CURRENT actor parameters:
+ * nlp_out [n,N] = actor.neglogp(s,a) (:137-143); kl_info_out [n,N,A,2] = actor.get_kl_info(s) (:186-192);
+ * stats_out [n,8] = {surr = mean(ratio adv), mean actor.kl(s, kl_ref) (forward, :165-184; 0 if kl_ref NULL),
+ * tv = 0.5 mean|ratio-1|, mean actor.entropy(s) (:145-148), 0...}; ratio = exp(nlp_old - neglogp), 1 if nlp_old NULL.
+ * Any of act, adv, nlp_old, kl_ref and the outputs may be NULL. */
+int saceo_trpo_eval(saceo_ctx *ctx, const float *act, const float *adv, const float *nlp_old, const float *kl_ref,
+                    float *nlp_out, float *kl_info_out, float *stats_out, void *stream);
+
+/* actor.set_weights(theta_ref); actor.set_weights(scale * dir, from_flat=True, increment=True)
+ * (continuous_actors.py:211-233, incl. the log(1e-3) floor of the state-independent logstd variable):
+ * tables.actor[agent] = theta_ref[agent] + scale[agent] * dir[agent]; theta_ref, dir [n, na_stride], scale [n]. */
+int saceo_actor_step(saceo_ctx *ctx, const float *theta_ref, const float *dir, const float *scale, void *stream);
+
 /* Test / inspection surface: device pointer of a named workspace buffer (e.g. "g_q", "g_actor",
  * "y", "losses", "idx", "noise") and its size in bytes; NULL if unknown. */
 void *saceo_debug_ptr(saceo_ctx *ctx, const char *name, int64_t *bytes_out);

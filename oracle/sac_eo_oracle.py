@@ -616,6 +616,120 @@ def trpo_step(f_Ax, b: Tensor, delta: float, cg_iters: int = 20):
     return v, vFv, eta * v
 
 
+def gaussian_neglogp(mean, logstd, a_):
+    """``GaussianActor.neglogp`` (continuous_actors.py:137-143)."""
+    vec = ((a_ - mean) / torch.exp(logstd)) ** 2 + 2 * logstd + math.log(2 * math.pi)
+    return 0.5 * vec.sum(-1)
+
+
+def gaussian_entropy(logstd):
+    """``GaussianActor.entropy`` (continuous_actors.py:145-148)."""
+    return 0.5 * (2 * logstd + math.log(2 * math.pi) + 1).sum(-1)
+
+
+def trpo_normalise_adv(adv: np.ndarray, adv_center: bool = True, adv_scale: bool = True) -> np.ndarray:
+    """trpo.py:41-48 (and again :243-249): NumPy mean / std (+1e-8) of the advantages."""
+    adv = np.asarray(adv)
+    mean, std = np.mean(adv), np.std(adv) + 1e-8
+    if adv_center:
+        adv = adv - mean
+    if adv_scale:
+        adv = adv / std
+    return adv
+
+
+def trpo_surrogate_grad(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, nlp_old, alpha: float,
+                        ent_targ: float, st: Dict):
+    """Surrogate tape of ``TRPO.update`` (trpo.py:52-63; identical in the expert branches :79-89, :121-131):
+    ``pg_loss = mean(-ratio adv) - alpha (mean entropy - ent_targ)``; returns (neg_pg list, alpha_grad, pg_loss)."""
+    dt = theta[0].dtype
+    s_, a_ = torch.as_tensor(s_all).to(dt), torch.as_tensor(a_all).to(dt)
+    adv, old = torch.as_tensor(adv_all).to(dt), torch.as_tensor(nlp_old).to(dt)
+    th = _req(theta)
+    al = torch.tensor(float(alpha), dtype=dt, requires_grad=True)
+    mean, logstd = gaussian_forward(cfg, th, s_, st)
+    ratio = torch.exp(old - gaussian_neglogp(mean, logstd, a_))
+    pg_loss = (ratio * adv * -1).mean()
+    ent_loss = gaussian_entropy(logstd).mean()
+    pg_loss = pg_loss - al * (ent_loss - ent_targ)
+    grads = torch.autograd.grad(pg_loss, th + [al], allow_unused=True)
+    neg_pg = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads[:-1], th)]
+    return [g.detach() for g in neg_pg], grads[-1].detach(), pg_loss.detach()
+
+
+def trpo_eval(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, nlp_old, kl_info_ref, st: Dict) -> Dict:
+    """Quantities ``TRPO._backtrack`` recomputes after every trial step (trpo.py:251-263, :283-288)."""
+    dt = theta[0].dtype
+    s_, a_ = torch.as_tensor(s_all).to(dt), torch.as_tensor(a_all).to(dt)
+    adv, old = torch.as_tensor(adv_all).to(dt), torch.as_tensor(nlp_old).to(dt)
+    with torch.no_grad():
+        mean, logstd = gaussian_forward(cfg, theta, s_, st)
+        nlp = gaussian_neglogp(mean, logstd, a_)
+        ratio = torch.exp(old - nlp)
+        res = {"nlp": nlp, "surr": (ratio * adv).mean(), "tv": 0.5 * (ratio - 1.).abs().mean(),
+               "ent": gaussian_entropy(logstd).mean(), "kl_info": torch.stack((mean, logstd), -1)}
+        if kl_info_ref is not None:
+            ref = torch.as_tensor(kl_info_ref).to(dt)
+            res["kl"] = kl_forward(mean, logstd, ref[..., 0], ref[..., 1]).mean()
+    return res
+
+
+def actor_increment(cfg: NetCfg, theta: Sequence[Tensor], step_flat: Tensor) -> List[Tensor]:
+    """``set_weights(step, from_flat=True, increment=True)`` (continuous_actors.py:211-233): add, then floor the
+    state-independent logstd variable at log(1e-3)."""
+    new = [t + d for t, d in zip(theta, unflat(theta, step_flat.to(theta[0].dtype)))]
+    if not cfg.per_state_std:
+        new[-1] = torch.maximum(new[-1], torch.as_tensor(math.log(1e-3), dtype=new[-1].dtype))
+    return new
+
+
+def trpo_update(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, st: Dict, *, delta: float = 0.01,
+                cg_iters: int = 20, trust_sub: int = 1, trust_damp: float = 0.01, kl_maxfactor: float = 1.5,
+                alpha: float = 0.0, ent_targ: float = 0.0, adv_center: bool = True, adv_scale: bool = True):
+    """``TRPO.update`` (trpo.py:36-198) on the epsilon = 0 slice of the gradient blend (``grad_final = neg_pg``; the
+    reference only defines ``grad_final`` inside its expert branches, :107-111, :154-158) followed by
+    ``TRPO._backtrack`` (:229-317).  Returns (new theta, log dict, pg_vec, eta_v_flat)."""
+    with torch.no_grad():
+        m0, l0 = gaussian_forward(cfg, theta, torch.as_tensor(s_all).to(theta[0].dtype), st)
+        nlp_old = gaussian_neglogp(m0, l0, torch.as_tensor(a_all).to(theta[0].dtype))
+    adv = trpo_normalise_adv(adv_all, adv_center, adv_scale)
+    neg_pg, _, _ = trpo_surrogate_grad(cfg, theta, s_all, a_all, adv, nlp_old, alpha, ent_targ, st)
+    pg_vec = flat(neg_pg) * -1                                                     # :176
+    if np.allclose(pg_vec.numpy(), 0) or delta == 0.0:                             # :179-180
+        eta_v = torch.zeros_like(pg_vec)
+    else:
+        F = make_F(cfg, theta, s_all, st, trust_damp, trust_sub)                   # :182
+        _, _, eta_v = trpo_step(F, pg_vec, delta, cg_iters)                        # :183-187
+    # _backtrack (adv is normalised a second time there, :243-249)
+    adv2 = trpo_normalise_adv(adv, adv_center, adv_scale)
+    before = trpo_eval(cfg, theta, s_all, a_all, adv2, nlp_old, None, st)
+    kl_ref, surr_before, ent = before["kl_info"], before["surr"], before["ent"]
+
+    def trial(step):
+        th = actor_increment(cfg, theta, step)
+        e = trpo_eval(cfg, th, s_all, a_all, adv2, nlp_old, kl_ref, st)
+        return th, e, e["surr"] - surr_before
+
+    th, e, improve = trial(eta_v)
+    tv_pre, kl_pre = float(e["tv"]), float(e["kl"])
+    adj = 1.0
+    for _ in range(10):                                                            # :267-291
+        if float(e["kl"]) > kl_maxfactor * delta or float(improve) < 0:
+            adj = adj / math.sqrt(2)
+            eta_v = eta_v / math.sqrt(2)
+            th, e, improve = trial(eta_v)
+        else:
+            break
+    else:                                                                          # :292-301 no policy update
+        adj = 0
+        th = [t.clone() for t in theta]
+        e = trpo_eval(cfg, th, s_all, a_all, adv2, nlp_old, kl_ref, st)
+        improve = e["surr"] - surr_before
+    log = {"ent": float(ent), "tv_pre": tv_pre, "kl_pre": kl_pre, "tv": float(e["tv"]), "kl": float(e["kl"]),
+           "adj": adj, "improve": float(improve)}
+    return th, log, pg_vec, eta_v
+
+
 # --------------------------------------------------------------------------------------
 # synthetic problem builders (shared by tests, smoke and the CPU baseline)
 # --------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 #include "gemm_skinny.cuh"
 #include "elem.cuh"
 #include "fvp.cuh"
+#include "trpo.cuh"
 #include "tc_gemm.cuh"
 #include "model_term.cuh"
 #include "model_fit.cuh"
@@ -1061,6 +1062,52 @@ extern "C" int saceo_cg_solve(saceo_ctx* x, const float* b, int32_t iters, float
     rc = fvp_apply(x, f.x, damp, f.z, st); if (rc) return rc;         // vFv = x . F(x)   (trpo.py:185)
     LAUNCH(x, k_cg_vfv, dim3(n), 256, 0, st, k, f, vFv_out);
   }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// TRPO surrogate gradient and line-search statistics (trpo.py:36-63, :229-317) on the fvp_states rows
+// ------------------------------------------------------------------------------------------
+static int trpo_check(saceo_ctx* x) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  if (!x->bound || !x->k.T.fvp_states || x->f.N < 1) return fail(SACEO_E_UNBOUND, "fvp_states not bound / fvp_rows == 0");
+  return 0;
+}
+
+extern "C" int saceo_trpo_grad(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* alpha,
+                               float* grad_out, float* stats_out, void* stream) {
+  int rc = trpo_check(x); if (rc) return rc;
+  if (!act || !adv || !grad_out) return fail(SACEO_E_INVALID, "act, adv and grad_out are required");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
+  NetD an = actor_net(x);
+  rc = fvp_prepare(x, st); if (rc) return rc;
+  LAUNCH(x, k_trpo_rows, dim3(cdiv(N, 128), n), 128, 0, st, k, f, act, adv, nlp_old, (const float*)nullptr, alpha,
+         x->cfg.std_mult, 1, (float*)nullptr, (float*)nullptr);
+  if (stats_out) LAUNCH(x, k_trpo_reduce, dim3(n), 256, 0, st, f, stats_out);
+  rc = mlp_backward(x, an, f.X, k.S, (long long)N * k.S, 0, N, f.H1, f.H2, N, f.G, k.Ao, (long long)N * k.Ao, 0, k.Ao,
+                    f.dH2, f.dH1, grad_out, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st); if (rc) return rc;
+  // logstd-variable entries = fixed-order column sums of the per-row terms (damp 0: the x operand is only a finite filler)
+  LAUNCH(x, k_fvp_finish, dim3(cdiv(x->L.na, 256), n), 256, 0, st, k, f, (const float*)k.T.actor, 0.f, grad_out);
+  return check_launch();
+}
+
+extern "C" int saceo_trpo_eval(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* kl_ref,
+                               float* nlp_out, float* kl_info_out, float* stats_out, void* stream) {
+  int rc = trpo_check(x); if (rc) return rc;
+  if ((nlp_out || nlp_old) && !act) return fail(SACEO_E_INVALID, "act is required for neglogp / the ratio");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
+  rc = fvp_prepare(x, st); if (rc) return rc;
+  LAUNCH(x, k_trpo_rows, dim3(cdiv(N, 128), n), 128, 0, st, k, f, act, adv, nlp_old, kl_ref, (const float*)nullptr,
+         x->cfg.std_mult, 0, nlp_out, kl_info_out);
+  if (stats_out) LAUNCH(x, k_trpo_reduce, dim3(n), 256, 0, st, f, stats_out);
+  return check_launch();
+}
+
+extern "C" int saceo_actor_step(saceo_ctx* x, const float* theta_ref, const float* dir, const float* scale, void* stream) {
+  if (!x || !theta_ref || !dir || !scale) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  LAUNCH(x, k_actor_step, dim3(cdiv(x->L.na, 256), k.n_agents), 256, 0, st, k, theta_ref, dir, scale);
   return check_launch();
 }
 

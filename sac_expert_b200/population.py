@@ -522,3 +522,120 @@ class Population:
         _l.check(self.lib.saceo_cg_solve(self.ctx, b.data_ptr(), iters, tol, damp, x.data_ptr(), vfv.data_ptr(), st))
         self._exit()
         return x, vfv
+
+    # ------------------------------------------------------------------ TRPO surrogate / line search
+    def _opt(self, x, *shape):
+        if x is None:
+            return None
+        return torch.as_tensor(x).to(self.dev, torch.float32).contiguous().view(*shape)
+
+    def trpo_grad(self, act, adv, nlp_old=None, alpha=None):
+        """Surrogate tape of ``TRPO.update`` (trpo.py:52-63) on the bound ``fvp_states``: returns
+        (neg_pg [n, na_stride] flat gradients, stats [n, 8] = {mean(ratio adv), 0, tv, mean entropy, ...})."""
+        n, N, A = self.spec.n_agents, self.spec.fvp_rows, self.spec.A
+        act, adv = self._opt(act, n, N, A), self._opt(adv, n, N)
+        nlp_old, alpha = self._opt(nlp_old, n, N), self._opt(alpha, n)
+        grad = torch.zeros(n, self.L.na_stride, device=self.dev)
+        stats = torch.zeros(n, 8, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_trpo_grad(self.ctx, act.data_ptr(), adv.data_ptr(),
+                                          None if nlp_old is None else nlp_old.data_ptr(),
+                                          None if alpha is None else alpha.data_ptr(), grad.data_ptr(), stats.data_ptr(), st))
+        self._exit()
+        return grad, stats
+
+    def trpo_eval(self, act=None, adv=None, nlp_old=None, kl_ref=None, want_nlp=False, want_kl_info=False,
+                  want_rows=False):
+        """Line-search quantities of ``TRPO._backtrack`` (trpo.py:251-263) at the current actor parameters: dict with
+        ``stats`` [n, 8] = {surr, kl, tv, ent, ...} and optionally ``nlp`` [n, N], ``kl_info`` [n, N, A, 2], ``rows``
+        [n, N, 4] (per-row ratio adv, kl, |ratio - 1|, entropy)."""
+        n, N, A = self.spec.n_agents, self.spec.fvp_rows, self.spec.A
+        act, adv, nlp_old = self._opt(act, n, N, A), self._opt(adv, n, N), self._opt(nlp_old, n, N)
+        kl_ref = self._opt(kl_ref, n, N, A, 2)
+        res = {"stats": torch.zeros(n, 8, device=self.dev)}
+        if want_nlp:
+            res["nlp"] = torch.zeros(n, N, device=self.dev)
+        if want_kl_info:
+            res["kl_info"] = torch.zeros(n, N, A, 2, device=self.dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        st = self._enter()
+        _l.check(self.lib.saceo_trpo_eval(self.ctx, ptr(act), ptr(adv), ptr(nlp_old), ptr(kl_ref), ptr(res.get("nlp")),
+                                          ptr(res.get("kl_info")), res["stats"].data_ptr(), st))
+        self._exit()
+        if want_rows:      # per-row {ratio adv, kl, |ratio - 1|, entropy} as the kernel left them in the workspace
+            res["rows"] = self.debug("fTmp")[:n * N * 4].view(n, N, 4).clone()
+        return res
+
+    def actor_step(self, theta_ref: torch.Tensor, direction: torch.Tensor, scale):
+        """``actor = theta_ref + scale[agent] * direction`` (``set_weights(..., increment=True)``,
+        continuous_actors.py:211-233)."""
+        n = self.spec.n_agents
+        theta_ref, direction = self._opt(theta_ref, n, self.L.na_stride), self._opt(direction, n, self.L.na_stride)
+        scale = self._opt(np.asarray(scale, np.float32) if not torch.is_tensor(scale) else scale, n)
+        st = self._enter()
+        _l.check(self.lib.saceo_actor_step(self.ctx, theta_ref.data_ptr(), direction.data_ptr(), scale.data_ptr(), st))
+        self._exit()
+
+    def trpo_update(self, act, adv, *, delta=0.01, cg_iters=20, trust_damp=0.01, kl_maxfactor=1.5, alpha=None,
+                    adv_center=True, adv_scale=True, residual_tol=1e-10):
+        """``TRPO.update`` (trpo.py:36-198) + ``TRPO._backtrack`` (:229-317) for every agent of the population on its
+        bound ``fvp_states`` (trust_sub = 1): surrogate gradient, CG solve with the Fisher-vector product, step length
+        ``sqrt(2 delta / vFv)`` and the back-tracking line search, each agent with its own accept / shrink decisions.
+        ``adv`` [n, N] raw advantages (host); centred / scaled per agent with NumPy like the reference (:41-48, and a
+        second time inside ``_backtrack`` :243-249).  The gradient blend is its epsilon = 0 slice (``grad_final =
+        neg_pg``).  Returns one log dict per agent (``ent, tv_pre, kl_pre, tv, kl, adj, improve``)."""
+        n, N = self.spec.n_agents, self.spec.fvp_rows
+        adv = np.asarray(adv, np.float32).reshape(n, N)
+
+        def norm(a):
+            out = np.empty_like(a)
+            for i in range(n):
+                x = a[i]
+                mean, std = np.mean(x), np.std(x) + 1e-8
+                x = x - mean if adv_center else x
+                out[i] = x / std if adv_scale else x
+            return out
+
+        adv1 = norm(adv)
+        act = self._opt(act, n, N, self.spec.A)
+        first = self.trpo_eval(act=act, want_nlp=True, want_kl_info=True)
+        nlp_old, kl_ref = first["nlp"], first["kl_info"]
+        ent = first["stats"][:, 3].cpu().numpy()
+        neg_pg, _ = self.trpo_grad(act, adv1, nlp_old, alpha)
+        pg = -neg_pg
+        theta_ref = self.t["actor"].clone()
+        if delta == 0.0:
+            eta = np.zeros(n, np.float32)
+            v = torch.zeros_like(pg)
+        else:
+            v, vfv = self.cg_solve(pg, iters=cg_iters, tol=residual_tol, damp=trust_damp)
+            vfv = vfv.cpu().numpy().astype(np.float64)
+            zero = np.array([np.allclose(pg[i, :self.L.na].cpu().numpy(), 0) for i in range(n)])
+            skip = zero | ~(vfv > 0)                          # pg_vec == 0 (:179-180): no step; CG of a zero vector is 0/0
+            eta = np.where(skip, 0.0, np.sqrt(2 * delta / np.where(skip, 1.0, vfv))).astype(np.float32)
+            v[torch.from_numpy(skip).to(self.dev)] = 0.0
+        adv2 = self._opt(norm(adv1), n, N)
+        surr_before = self.trpo_eval(act, adv2, nlp_old)["stats"][:, 0].cpu().numpy()
+
+        def trial(scale):
+            self.actor_step(theta_ref, v, scale)
+            s = self.trpo_eval(act, adv2, nlp_old, kl_ref)["stats"].cpu().numpy()
+            return s, s[:, 0] - surr_before
+
+        adj = np.ones(n)
+        stats, improve = trial(eta * adj)
+        tv_pre, kl_pre = stats[:, 2].copy(), stats[:, 1].copy()
+        done = np.zeros(n, bool)
+        for _ in range(10):
+            bad = ~done & ((stats[:, 1] > kl_maxfactor * delta) | (improve < 0))
+            done |= ~bad
+            if not bad.any():
+                break
+            adj = np.where(bad, adj / np.sqrt(2), adj)
+            stats, improve = trial(eta * adj)
+        else:
+            adj = np.where(done, adj, 0.0)                    # no policy update for the agents still failing
+            stats, improve = trial(eta * adj)
+        return [dict(ent=float(ent[i]), tv_pre=float(tv_pre[i]), kl_pre=float(kl_pre[i]), tv=float(stats[i, 2]),
+                     kl=float(stats[i, 1]), adj=float(adj[i]), improve=float(improve[i])) for i in range(n)]
+

@@ -86,3 +86,29 @@ class SquashedGaussianActor(DeviceNet):
 
     def tf_clip(self, a):
         return torch.clamp(torch.as_tensor(a), torch.as_tensor(self.act_low), torch.as_tensor(self.act_high))
+
+    # ---- GaussianActor interface used by the trust-region update (continuous_actors.py:137-192) ----------------
+    # _forward parameterisation (softplus std + logstd_init, floor log 1e-3), NOT the clipped one of evaluate/sample.
+    def _gauss(self, s, **kw):
+        from ..common.update_utils import make_F
+        F = make_F(self, self._as_rows(s, self.s_dim))
+        try:
+            return F.pop.trpo_eval(**kw)
+        finally:
+            F.pop.close()
+
+    def neglogp(self, s, a):
+        a = np.asarray(a, np.float32).reshape(1, -1, self.a_dim)
+        return self._host(self._gauss(s, act=a, want_nlp=True)["nlp"][0])
+
+    def entropy(self, s):
+        return self._host(self._gauss(s, want_rows=True)["rows"][0, :, 3])
+
+    def get_kl_info(self, s):
+        return self._host(self._gauss(s, want_kl_info=True)["kl_info"][0]).numpy()
+
+    def kl(self, s, kl_info_ref, direction='forward'):
+        if direction != 'forward':
+            raise ValueError("only the forward KL is on the device path (the reverse branch reads self.logstd, :180-182)")
+        ref = np.asarray(kl_info_ref, np.float32)[None]
+        return self._host(self._gauss(s, kl_ref=ref, want_rows=True)["rows"][0, :, 1])

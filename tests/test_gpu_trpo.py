@@ -1,0 +1,168 @@
+"""GPU: TRPO surrogate gradient, line-search statistics, parameter step and the whole TRPO.update against the oracle
+(trpo.py:36-198, :229-317; GaussianActor interface continuous_actors.py:74-100,137-192).  All through the C ABI."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sac_eo_oracle as O
+from sac_expert_b200 import lib
+from sac_expert_b200.population import Population
+from tests.helpers import rel, spec_from_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(per_state_std, acts, n=2, N=96, gemm_mode=lib.GEMM_FP32_SIMT, hidden=(64, 48), S=9, A=3, seed=20, perturb=0.2):
+    cfg = O.NetCfg(S=S, A=A, actor_hidden=hidden, critic_hidden=(16, 16), num_models=0, per_state_std=per_state_std,
+                   actor_acts=acts, std_mult=0.7)
+    pop = Population(spec_from_cfg(cfg, n, 8, 0, 16, fvp_rows=N, gemm_mode=gemm_mode))
+    probs = []
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        st, replay, _, hyper = O.make_problem(cfg, 8, 2, 300, seed=seed + i, perturb=perturb)
+        pop.load_agent(i, st, hyper)
+        s = replay["s"][:N]
+        th = O.to_torch_state(st, torch.float64)
+        with torch.no_grad():       # rollout actions come from the policy itself (ratios near 1, as in TRPO's use)
+            mean, ls = O.gaussian_forward(cfg, th["actor"], torch.as_tensor(s, dtype=torch.float64), th)
+        a = (mean + torch.exp(ls) * torch.from_numpy(rng.standard_normal((N, A)))).numpy().astype(np.float32)
+        pop.t["fvp_states"][i].copy_(torch.from_numpy(s))
+        probs.append((st, s, a, rng.standard_normal(N).astype(np.float32) * (1 + i)))
+    return cfg, pop, probs
+
+
+@pytest.mark.parametrize("per_state_std,acts,mode", [
+    (True, ("relu", "relu"), lib.GEMM_FP32_SIMT), (False, ("tanh", "tanh"), lib.GEMM_FP32_SIMT),
+    (True, ("elu", "tanh"), lib.GEMM_FP32_SIMT), (True, ("tanh", "tanh"), lib.GEMM_TCGEN05_BF16X3)])
+def test_surrogate_gradient_and_eval(per_state_std, acts, mode):
+    # reference sizes on the tensor-core engine.  perturb stays small there: with 256-wide layers a 0.2 perturbation drives
+    # many softplus stds to the 1e-3 floor, and the gradient's 1/std^2 weights then amplify the last-bit error of the
+    # forward means by ~1e3 on ANY fp32 engine (measured: 1.2e-3 on the fp32 SIMT engine, 3.9e-3 on tcgen05, while the
+    # Fisher-vector product on the same activations is at 1.5e-6 / 1.0e-5; tools/trpo_tc_check.py)
+    big = dict(hidden=(256, 256), S=27, A=8, N=256, perturb=0.02) if mode == lib.GEMM_TCGEN05_BF16X3 else {}
+    cfg, pop, probs = _setup(per_state_std, acts, gemm_mode=mode, **big)
+    n, N, A, L = len(probs), len(probs[0][1]), cfg.A, pop.L
+    rng = np.random.default_rng(5)
+    act = np.stack([p[2] for p in probs]); adv = np.stack([O.trpo_normalise_adv(p[3]) for p in probs]).astype(np.float32)
+    alpha = np.array([0.3, 0.0], np.float32)
+    refs = []
+    nlp_old = np.zeros((n, N), np.float32); kl_ref = np.zeros((n, N, A, 2), np.float32)
+    for i, (st, s, a, _) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        e0 = O.trpo_eval(cfg, th["actor"], s, a, adv[i], np.zeros(N), None, th)
+        nlp_old[i] = (e0["nlp"].numpy() + rng.normal(size=N) * 0.1).astype(np.float32)
+        info = e0["kl_info"].numpy().copy()
+        info[..., 0] += rng.normal(size=(N, A)) * 0.05; info[..., 1] += rng.normal(size=(N, A)) * 0.05
+        kl_ref[i] = info.astype(np.float32)
+        g, ag, _ = O.trpo_surrogate_grad(cfg, th["actor"], s, a, adv[i], nlp_old[i].astype(np.float64), float(alpha[i]), 0.0, th)
+        e = O.trpo_eval(cfg, th["actor"], s, a, adv[i], nlp_old[i].astype(np.float64), kl_ref[i].astype(np.float64), th)
+        refs.append((O.flat(g).numpy(), e, e0))
+    grad, gstats = pop.trpo_grad(act, adv, nlp_old, alpha)
+    ev = pop.trpo_eval(act, adv, nlp_old, kl_ref, want_nlp=True, want_kl_info=True, want_rows=True)
+    grad, gstats = grad.cpu().numpy(), gstats.cpu().numpy()
+    stats = ev["stats"].cpu().numpy()
+    tol = 1e-3
+    for i in range(n):
+        g_ref, e, e0 = refs[i]
+        assert rel(grad[i, :L.na], g_ref) < tol
+        assert np.all(grad[i, L.na:] == 0)
+        assert rel(ev["nlp"][i].cpu().numpy(), e["nlp"].numpy()) < tol
+        assert rel(ev["kl_info"][i].cpu().numpy(), e0["kl_info"].numpy()) < tol
+        for k, key in enumerate(("surr", "kl", "tv", "ent")):
+            assert abs(stats[i, k] - float(e[key])) <= tol * max(abs(float(e[key])), 1e-2), key
+        assert abs(gstats[i, 0] - float(e["surr"])) <= tol * max(abs(float(e["surr"])), 1e-2)
+        assert abs(gstats[i, 3] - float(e["ent"])) <= tol * abs(float(e["ent"]))
+        rows = ev["rows"][i].cpu().numpy()
+        assert abs(rows[:, 3].mean() - float(e["ent"])) <= tol * abs(float(e["ent"]))
+    # nlp_old = NULL means ratio 1: the gradient at the reference policy itself
+    g1, _ = pop.trpo_grad(act, adv, None, None)
+    for i, (st, s, a, _) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        e0 = O.trpo_eval(cfg, th["actor"], s, a, adv[i], np.zeros(N), None, th)
+        g, _, _ = O.trpo_surrogate_grad(cfg, th["actor"], s, a, adv[i], e0["nlp"], 0.0, 0.0, th)
+        assert rel(g1[i, :L.na].cpu().numpy(), O.flat(g).numpy()) < tol
+    pop.close()
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_actor_step_is_exact_and_floors_the_logstd_variable(per_state_std):
+    cfg, pop, probs = _setup(per_state_std, ("tanh", "tanh"))
+    L, n = pop.L, len(probs)
+    rng = np.random.default_rng(2)
+    ref = pop.t["actor"].clone()
+    d = torch.from_numpy(rng.standard_normal((n, L.na_stride)).astype(np.float32)).cuda()
+    if not per_state_std:
+        d[:, L.na - cfg.A] = -1e4
+    scale = np.array([0.25, -1.5], np.float32)
+    pop.actor_step(ref, d, scale)
+    want = ref.cpu().numpy() + scale[:, None] * d.cpu().numpy()          # fp32: one product, one sum
+    if not per_state_std:
+        want[:, L.na - cfg.A:L.na] = np.maximum(want[:, L.na - cfg.A:L.na], np.float32(math.log(1e-3)))
+    got = pop.t["actor"].cpu().numpy()
+    assert got[:, :L.na].tobytes() == want[:, :L.na].astype(np.float32).tobytes()
+    assert np.array_equal(got[:, L.na:], ref.cpu().numpy()[:, L.na:])    # padding untouched
+    pop.close()
+
+
+@pytest.mark.parametrize("per_state_std,acts,kl_maxfactor", [(True, ("tanh", "tanh"), 1.5), (False, ("relu", "tanh"), 1.5),
+                                                              (True, ("tanh", "tanh"), 0.6), (True, ("tanh", "tanh"), 1e-9)])
+def test_trpo_update_matches_the_oracle(per_state_std, acts, kl_maxfactor):
+    cfg, pop, probs = _setup(per_state_std, acts, n=3, N=128)
+    L = pop.L
+    act = np.stack([p[2] for p in probs]); adv = np.stack([p[3] for p in probs])
+    before = pop.t["actor"].cpu().numpy().copy()
+    logs = pop.trpo_update(act, adv, delta=0.02, cg_iters=5, trust_damp=0.01, kl_maxfactor=kl_maxfactor)
+    after = pop.t["actor"].cpu().numpy()
+    for i, (st, s, a, ad) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        new, log, _, _ = O.trpo_update(cfg, th["actor"], s, a, ad, th, delta=0.02, cg_iters=5, trust_damp=0.01,
+                                       kl_maxfactor=kl_maxfactor)
+        assert abs(logs[i]["adj"] - log["adj"]) < 1e-6, (logs[i], log)
+        step_ref = (O.flat(new) - O.flat(th["actor"])).numpy()
+        if log["adj"] == 0:
+            assert np.array_equal(after[i], before[i])
+        else:
+            assert rel(after[i, :L.na] - before[i, :L.na], step_ref) < 1e-2        # 5 fp32 CG iterations vs fp64
+        for key in ("ent", "tv_pre", "kl_pre", "tv", "kl", "improve"):
+            assert abs(logs[i][key] - log[key]) <= 2e-2 * max(abs(log[key]), 1e-3), (key, logs[i], log)
+    pop.close()
+
+
+def test_trpo_class_interface():
+    """``TRPO(actor, update_kwargs).update(rollout_data)`` and the GaussianActor accessors through the mirror classes."""
+    from sac_expert_b200.sac_eo.actors.init_actor import init_actor
+    from sac_expert_b200.sac_eo.algs.model_free.trpo import TRPO
+    from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
+    np.random.seed(0)
+    env = SyntheticEnv(7, 2)
+    actor = init_actor(env, [32, 32], ["tanh"], 0.01, 1.0, "orthogonal", False, None, actor_per_state_std=False,
+                       actor_squash=True)
+    rng = np.random.default_rng(1)
+    N = 80
+    s = rng.standard_normal((N, 7)).astype(np.float32); a = rng.standard_normal((N, 2)).astype(np.float32)
+    adv = rng.standard_normal(N).astype(np.float32)
+    cfg = O.NetCfg(S=7, A=2, actor_hidden=(32, 32), critic_hidden=(8, 8), num_models=0, per_state_std=False,
+                   actor_acts=("tanh", "tanh"), std_mult=1.0)
+    w0 = actor.get_weights()
+    st = {"actor": [torch.from_numpy(w.astype(np.float64)) for w in w0], "s_mean": torch.zeros(7, dtype=torch.float64),
+          "s_std": torch.ones(7, dtype=torch.float64)}
+    e = O.trpo_eval(cfg, st["actor"], s, a, adv, np.zeros(N), None, st)
+    assert rel(actor.neglogp(s, a).numpy(), e["nlp"].numpy()) < 1e-4
+    assert rel(actor.get_kl_info(s), e["kl_info"].numpy()) < 1e-4
+    assert abs(float(actor.entropy(s).mean()) - float(e["ent"])) < 1e-4 * abs(float(e["ent"]))
+    assert float(actor.kl(s, actor.get_kl_info(s)).abs().max()) < 1e-6
+    kw = dict(adv_center=True, adv_scale=True, delta_trpo=0.02, cg_it=5, trust_sub=1, trust_damp=0.01, kl_maxfactor=1.5,
+              ent_reg=True, ent_targ=0.0, alpha_lr=0.01)
+    alg = TRPO(actor, kw)
+    log = alg.update((s, a, adv, None, None, None))
+    new, ref, _, _ = O.trpo_update(cfg, st["actor"], s, a, adv, st, delta=0.02, cg_iters=5)
+    assert abs(log["adj"] - ref["adj"]) < 1e-6
+    w1 = actor.get_weights()
+    assert rel(np.concatenate([x.ravel() for x in w1]) - np.concatenate([x.ravel() for x in w0]),
+               (O.flat(new) - O.flat(st["actor"])).numpy()) < 1e-2
+    # entropy above the target of 0 pushes the temperature down; it is clamped at 0 (:169-172)
+    assert log["alpha"] == 0.0 and log["epsilon"] == 0.0
+    with pytest.raises(NotImplementedError):
+        alg.update((s, a, adv, None, None, None), expert_reg=(s, a, s, 0.5, [], False, None))

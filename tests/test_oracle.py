@@ -302,3 +302,73 @@ def test_gaussian_model_loss_gradients():
             sc = (torch.exp(ls) ** 2).mean() if scale else 1.0
             ref = sc * (1.0 - e ** 2 * torch.exp(-2 * ls)).mean(0, keepdim=True)
         assert float((g - ref).abs().max()) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------
+# TRPO surrogate / line search restatement (trpo.py:36-198, :229-317)
+# ----------------------------------------------------------------------------------------------------------
+def _trpo_problem(per_state_std, acts=("tanh", "tanh"), N=64, seed=3, std_mult=0.8):
+    cfg = O.NetCfg(S=6, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), num_models=0, per_state_std=per_state_std,
+                   actor_acts=acts, std_mult=std_mult)
+    st, replay, _, _ = O.make_problem(cfg, 8, 2, 200, seed=seed, perturb=0.2)
+    rng = np.random.default_rng(seed)
+    return cfg, st, replay["s"][:N], replay["a"][:N], rng.standard_normal(N).astype(np.float32)
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_trpo_surrogate_gradient_matches_the_closed_form_output_cotangent(per_state_std):
+    """The CUDA head (csrc/trpo.cuh::k_trpo_rows) uses d/dmean = -adv ratio q / std / N and
+    d/dlogstd = (adv ratio (1 - q^2) - alpha) / N; check them against autograd of the restated tape in fp64."""
+    cfg, st, s, a, adv = _trpo_problem(per_state_std)
+    th = O.to_torch_state(st, torch.float64)
+    theta = th["actor"]
+    N, A = len(s), cfg.A
+    adv_n = O.trpo_normalise_adv(adv)
+    rng = np.random.default_rng(0)
+    with torch.no_grad():
+        m0, l0 = O.gaussian_forward(cfg, theta, torch.as_tensor(s, dtype=torch.float64), th)
+        nlp_old = O.gaussian_neglogp(m0, l0, torch.as_tensor(a, dtype=torch.float64)) + torch.as_tensor(rng.normal(size=N) * 0.1)
+    alpha = 0.37
+    neg_pg, alpha_grad, _ = O.trpo_surrogate_grad(cfg, theta, s, a, adv_n, nlp_old, alpha, -1.5, th)
+    # closed form through the (mean, logstd) outputs
+    tt = [t.clone().requires_grad_(True) for t in theta]
+    mean, ls = O.gaussian_forward(cfg, tt, torch.as_tensor(s, dtype=torch.float64), th)
+    with torch.no_grad():
+        sd = torch.exp(ls)
+        q = (torch.as_tensor(a, dtype=torch.float64) - mean) / sd
+        ratio = torch.exp(nlp_old - O.gaussian_neglogp(mean, ls, torch.as_tensor(a, dtype=torch.float64)))
+        w = (torch.as_tensor(adv_n, dtype=torch.float64) * ratio / N)[:, None]
+        g_mean = -w * q / sd
+        g_ls = w * (1 - q * q) - alpha / N
+    res = torch.autograd.grad([mean, ls], tt, grad_outputs=[g_mean, g_ls * torch.ones_like(ls)], allow_unused=True)
+    res = [r if r is not None else torch.zeros_like(p) for r, p in zip(res, tt)]
+    assert rel(O.flat(res), O.flat(neg_pg)) < 1e-12
+    ent = float(O.gaussian_entropy(ls.detach()).mean())
+    assert abs(float(alpha_grad) + (ent - (-1.5))) < 1e-12
+
+
+def test_trpo_update_line_search_semantics():
+    cfg, st, s, a, adv = _trpo_problem(True, ("relu", "tanh"))
+    th64 = O.to_torch_state(st, torch.float64)
+    new, log, pg, eta_v = O.trpo_update(cfg, th64["actor"], s, a, adv, th64, delta=0.02, cg_iters=5)
+    assert log["adj"] in [2 ** (-k / 2) for k in range(11)] or log["adj"] == 0
+    assert log["kl"] <= 1.5 * 0.02 + 1e-12 and log["improve"] >= 0
+    # the accepted step is adj * eta * v
+    assert rel(O.flat(new) - O.flat(th64["actor"]), eta_v) < 1e-12
+    # a trust region no step can satisfy: ten shrinks, then the parameters are restored and adj = 0 (:292-301)
+    new0, log0, _, _ = O.trpo_update(cfg, th64["actor"], s, a, adv, th64, delta=0.02, cg_iters=5, kl_maxfactor=1e-9)
+    assert log0["adj"] == 0 and abs(log0["kl"]) < 1e-15 and rel(O.flat(new0), O.flat(th64["actor"])) == 0
+    # fp32 twin of the same update agrees with fp64
+    th32 = O.to_torch_state(st, torch.float32)
+    new32, log32, _, _ = O.trpo_update(cfg, th32["actor"], s, a, adv, th32, delta=0.02, cg_iters=5)
+    assert log32["adj"] == log["adj"]
+    assert rel(O.flat(new32) - O.flat(th32["actor"]), O.flat(new) - O.flat(th64["actor"])) < 1e-2
+
+
+def test_trpo_state_independent_logstd_floor_on_increment():
+    cfg, st, s, a, adv = _trpo_problem(False)
+    th = O.to_torch_state(st, torch.float64)["actor"]
+    step = torch.zeros(sum(t.numel() for t in th), dtype=torch.float64)
+    step[-cfg.A:] = -100.0
+    new = O.actor_increment(cfg, th, step)
+    assert torch.all(new[-1] == math.log(1e-3)) and rel(O.flat(new[:-1]), O.flat(th[:-1])) == 0
