@@ -268,6 +268,19 @@ int saceo_cg_solve(saceo_ctx *ctx, const float *b, int32_t iters, float tol, flo
 int saceo_trpo_grad(saceo_ctx *ctx, const float *act, const float *adv, const float *nlp_old, const float *alpha,
                     float *grad_out, float *stats_out, void *stream);
 
+/* PPO._apply_actor_grad gradient (algs/model_free/ppo.py:132-147, expert_reg = None) on the rows bound as fvp_states:
+ *   loss = mean(max(-ratio adv, -clip(ratio, 1-eps_clip, 1+eps_clip) adv)) - alpha (mean entropy - ent_targ)
+ * followed by tf.clip_by_global_norm(neg_pg, max_grad_norm) (:226-231; max_grad_norm <= 0: no clipping).
+ * Arguments as saceo_trpo_grad (nlp_old required); stats_out [n,8] additionally carries [4] = global norm before and
+ * [5] = after clipping. */
+int saceo_ppo_grad(saceo_ctx *ctx, const float *act, const float *adv, const float *nlp_old, const float *alpha,
+                   float eps_clip, float max_grad_norm, float *grad_out, float *stats_out, void *stream);
+
+/* actor_optimizer.apply_gradients(zip(neg_pg, actor.trainable)) (ppo.py:234): one Keras-Adam step of the ACTOR
+ * optimiser (tables.actor / actor_m / actor_v, adam_t[.,2], learning rate hyper[3]) with grad [n, na_stride]
+ * (device, 16-byte aligned).  No other optimiser advances. */
+int saceo_actor_adam(saceo_ctx *ctx, const float *grad, void *stream);
+
 /* Quantities of the back-tracking line search TRPO._backtrack (trpo.py:229-317) at the CURRENT actor parameters:
  * nlp_out [n,N] = actor.neglogp(s,a) (:137-143); kl_info_out [n,N,A,2] = actor.get_kl_info(s) (:186-192);
  * stats_out [n,8] = {surr = mean(ratio adv), mean actor.kl(s, kl_ref) (forward, :165-184; 0 if kl_ref NULL),

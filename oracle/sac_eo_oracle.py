@@ -730,6 +730,72 @@ def trpo_update(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, st:
     return th, log, pg_vec, eta_v
 
 
+def ppo_actor_grad(cfg: NetCfg, theta: Sequence[Tensor], s_act, a_act, adv_act, nlp_old_act, alpha: float,
+                   ent_targ: float, eps_ppo: float, max_grad_norm: Optional[float], st: Dict):
+    """Gradient part of ``PPO._apply_actor_grad`` (ppo.py:132-147 tape, :226-231 global-norm clip), expert_reg = None.
+    Returns (neg_pg list after clipping, alpha_grad, grad_norm_pre, grad_norm_post)."""
+    dt = theta[0].dtype
+    s_, a_ = torch.as_tensor(s_act).to(dt), torch.as_tensor(a_act).to(dt)
+    adv, old = torch.as_tensor(adv_act).to(dt), torch.as_tensor(nlp_old_act).to(dt)
+    th = _req(theta)
+    al = torch.tensor(float(alpha), dtype=dt, requires_grad=True)
+    mean, logstd = gaussian_forward(cfg, th, s_, st)
+    ratio = torch.exp(old - gaussian_neglogp(mean, logstd, a_))
+    ratio_clip = torch.clamp(ratio, 1. - eps_ppo, 1. + eps_ppo)
+    surr, clip = ratio * adv * -1, ratio_clip * adv * -1
+    # tf.maximum routes the gradient to its first argument where it is >= the second (torch.maximum would split ties)
+    pg_loss = torch.where(surr >= clip, surr, clip).mean()
+    pg_loss = pg_loss - al * (gaussian_entropy(logstd).mean() - ent_targ)
+    grads = torch.autograd.grad(pg_loss, th + [al], allow_unused=True)
+    neg_pg = [(g if g is not None else torch.zeros_like(p)).detach() for g, p in zip(grads[:-1], th)]
+    norm_pre = torch.sqrt(sum((g ** 2).sum() for g in neg_pg))
+    if max_grad_norm is not None:                                       # tf.clip_by_global_norm
+        neg_pg = [g * (max_grad_norm / torch.maximum(norm_pre, torch.as_tensor(float(max_grad_norm), dtype=dt))) for g in neg_pg]
+    norm_post = torch.sqrt(sum((g ** 2).sum() for g in neg_pg))
+    return neg_pg, grads[-1].detach(), float(norm_pre), float(norm_post)
+
+
+def ppo_update(cfg: NetCfg, theta: Sequence[Tensor], adam: Dict, s_all, a_all, adv_all, st: Dict, *, actor_lr: float = 3e-4,
+               actor_update_it: int = 2, actor_nminibatch: int = 4, eps_ppo: float = 0.2,
+               max_grad_norm: Optional[float] = 0.5, alpha: float = 0.0, ent_targ: float = 0.0,
+               adv_center: bool = True, adv_scale: bool = True, np_rng=np.random):
+    """``PPO.update`` (ppo.py:41-119) with expert_reg = None and ent_reg off: epochs x shuffled minibatches
+    (``np.random.shuffle`` of the global RNG, ragged tail dropped), per-minibatch advantage normalisation, the clipped
+    surrogate step and Keras-Adam on the actor.  ``adam`` = {"m": [...], "v": [...], "t": int} is updated in place.
+    Returns (theta, log)."""
+    dt = theta[0].dtype
+    s_all, a_all, adv_all = np.asarray(s_all), np.asarray(a_all), np.asarray(adv_all)
+    with torch.no_grad():
+        m0, l0 = gaussian_forward(cfg, theta, torch.as_tensor(s_all).to(dt), st)
+        nlp_old = gaussian_neglogp(m0, l0, torch.as_tensor(a_all).to(dt)).numpy()
+        kl_ref = torch.stack((m0, l0), -1)
+        ent = float(gaussian_entropy(l0).mean())
+    n_samples = s_all.shape[0]
+    n_batch = int(n_samples / actor_nminibatch)
+    pre_all = post_all = 0.0
+    theta = [t.clone() for t in theta]
+    for _ in range(actor_update_it):
+        idx = np.arange(n_samples)
+        np_rng.shuffle(idx)
+        sections = np.arange(0, n_samples, n_batch)[1:]
+        batches = np.array_split(idx, sections)
+        if n_samples % n_batch != 0:
+            batches = batches[:-1]
+        for b in batches:
+            adv_b = trpo_normalise_adv(adv_all[b], adv_center, adv_scale)
+            g, _, pre, post = ppo_actor_grad(cfg, theta, s_all[b], a_all[b], adv_b, nlp_old[b], alpha, ent_targ, eps_ppo,
+                                             max_grad_norm, st)
+            pre_all += pre; post_all += post
+            theta, adam["m"], adam["v"], adam["t"] = keras_adam(theta, g, adam["m"], adam["v"], adam["t"], actor_lr)
+    e = trpo_eval(cfg, theta, s_all, a_all, np.zeros(n_samples), nlp_old, kl_ref, st)
+    with torch.no_grad():
+        ratio_diff = (torch.exp(torch.as_tensor(nlp_old).to(dt) - e["nlp"]) - 1.).abs()
+    nb = actor_update_it * len(batches)
+    log = {"ent": ent, "tv": float(e["tv"]), "kl": float(e["kl"]), "outside_clip": float((ratio_diff > eps_ppo).double().mean()),
+           "actor_grad_norm_pre": pre_all / nb, "actor_grad_norm": post_all / nb}
+    return theta, log
+
+
 # --------------------------------------------------------------------------------------
 # synthetic problem builders (shared by tests, smoke and the CPU baseline)
 # --------------------------------------------------------------------------------------

@@ -1074,20 +1074,47 @@ static int trpo_check(saceo_ctx* x) {
   return 0;
 }
 
-extern "C" int saceo_trpo_grad(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* alpha,
-                               float* grad_out, float* stats_out, void* stream) {
+static int surrogate_grad(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* alpha,
+                          float clip_eps, float max_grad_norm, bool want_norm, float* grad_out, float* stats_out,
+                          cudaStream_t st) {
   int rc = trpo_check(x); if (rc) return rc;
   if (!act || !adv || !grad_out) return fail(SACEO_E_INVALID, "act, adv and grad_out are required");
-  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
+  const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
   NetD an = actor_net(x);
   rc = fvp_prepare(x, st); if (rc) return rc;
   LAUNCH(x, k_trpo_rows, dim3(cdiv(N, 128), n), 128, 0, st, k, f, act, adv, nlp_old, (const float*)nullptr, alpha,
-         x->cfg.std_mult, 1, (float*)nullptr, (float*)nullptr);
+         x->cfg.std_mult, 1, clip_eps, (float*)nullptr, (float*)nullptr);
   if (stats_out) LAUNCH(x, k_trpo_reduce, dim3(n), 256, 0, st, f, stats_out);
   rc = mlp_backward(x, an, f.X, k.S, (long long)N * k.S, 0, N, f.H1, f.H2, N, f.G, k.Ao, (long long)N * k.Ao, 0, k.Ao,
                     f.dH2, f.dH1, grad_out, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st); if (rc) return rc;
   // logstd-variable entries = fixed-order column sums of the per-row terms (damp 0: the x operand is only a finite filler)
   LAUNCH(x, k_fvp_finish, dim3(cdiv(x->L.na, 256), n), 256, 0, st, k, f, (const float*)k.T.actor, 0.f, grad_out);
+  if (want_norm) LAUNCH(x, k_grad_clip, dim3(n), 256, 0, st, k, grad_out, max_grad_norm, stats_out);
+  return check_launch();
+}
+
+extern "C" int saceo_trpo_grad(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* alpha,
+                               float* grad_out, float* stats_out, void* stream) {
+  return surrogate_grad(x, act, adv, nlp_old, alpha, -1.f, 0.f, false, grad_out, stats_out, (cudaStream_t)stream);
+}
+
+extern "C" int saceo_ppo_grad(saceo_ctx* x, const float* act, const float* adv, const float* nlp_old, const float* alpha,
+                              float eps_clip, float max_grad_norm, float* grad_out, float* stats_out, void* stream) {
+  if (!(eps_clip >= 0.f)) return fail(SACEO_E_INVALID, "eps_clip must be >= 0");
+  if (!nlp_old) return fail(SACEO_E_INVALID, "nlp_old is required");
+  return surrogate_grad(x, act, adv, nlp_old, alpha, eps_clip, max_grad_norm, true, grad_out, stats_out, (cudaStream_t)stream);
+}
+
+// One Keras-Adam step of the actor optimiser with a caller-supplied gradient (ppo.py:234): only the actor's step
+// counter advances; the learning rate is hyper[3] (actor_lr), read at launch time.
+extern "C" int saceo_actor_adam(saceo_ctx* x, const float* grad, void* stream) {
+  if (!x || !grad) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  if (reinterpret_cast<uintptr_t>(grad) & 15) return fail(SACEO_E_INVALID, "grad must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  LAUNCH(x, k_bc_begin, dim3(cdiv(k.n_agents, 128)), 128, 0, st, k, 0);
+  LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.na, 4), 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
+         grad, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0);
   return check_launch();
 }
 
@@ -1098,7 +1125,7 @@ extern "C" int saceo_trpo_eval(saceo_ctx* x, const float* act, const float* adv,
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
   rc = fvp_prepare(x, st); if (rc) return rc;
   LAUNCH(x, k_trpo_rows, dim3(cdiv(N, 128), n), 128, 0, st, k, f, act, adv, nlp_old, kl_ref, (const float*)nullptr,
-         x->cfg.std_mult, 0, nlp_out, kl_info_out);
+         x->cfg.std_mult, 0, -1.f, nlp_out, kl_info_out);
   if (stats_out) LAUNCH(x, k_trpo_reduce, dim3(n), 256, 0, st, f, stats_out);
   return check_launch();
 }

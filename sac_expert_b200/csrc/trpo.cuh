@@ -31,11 +31,12 @@ __device__ __forceinline__ GaussRow gauss_row(const KCtx& c, const float* out, c
 //   nlp  = 0.5 sum_j(((a-mean)/exp(ls))^2 + 2 ls + log 2pi)         ent = 0.5 sum_j(2 ls + log 2pi + 1)
 //   kl   = 0.5 sum_j(((mean-mean_ref)^2 + exp(2 ls_ref)) / exp(2 ls) + 2 ls - 2 ls_ref - 1)      (forward KL)
 //   ratio = exp(nlp_old - nlp)      row statistics (f.Tmp[row*4..]) = { ratio adv, kl, |ratio - 1|, ent }
-//   want_grad: G = d/d(raw outputs) of  mean(-ratio adv) - alpha (mean ent - ent_targ):
+//   want_grad: G = d/d(raw outputs) of  mean(-ratio adv) - alpha (mean ent - ent_targ)   (clip_eps >= 0: PPO's clipped
+//   surrogate instead of -ratio adv):
 //     d/dmean_j = -adv ratio q_j / std_j / N,  d/dls_j = (adv ratio (1 - q_j^2) - alpha) / N,  q = (a-mean)/std
 __global__ void k_trpo_rows(KCtx c, FvpWs f, const float* __restrict__ act, const float* __restrict__ adv,
                             const float* __restrict__ nlp_old, const float* __restrict__ kl_ref,
-                            const float* __restrict__ alpha, float std_mult, int want_grad,
+                            const float* __restrict__ alpha, float std_mult, int want_grad, float clip_eps,
                             float* __restrict__ nlp_out, float* __restrict__ kl_info_out) {
   const int agent = blockIdx.y;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +68,13 @@ __global__ void k_trpo_rows(KCtx c, FvpWs f, const float* __restrict__ act, cons
   rs[0] = ratio * av; rs[1] = kl; rs[2] = fabsf(ratio - 1.f); rs[3] = ent;
   if (!want_grad) return;
   const float invN = 1.f / (float)f.N;
-  const float w = av * ratio * invN;
+  float w = av * ratio * invN;
+  if (clip_eps >= 0.f) {
+    // PPO (ppo.py:135-141): mean(max(-ratio adv, -clip(ratio, 1-eps, 1+eps) adv)); tf.maximum sends the gradient to its
+    // first argument when it is >= the second, and the clipped branch has zero gradient outside [1-eps, 1+eps]
+    const float rc = fminf(fmaxf(ratio, 1.f - clip_eps), 1.f + clip_eps);
+    if (!(-ratio * av >= -rc * av)) w = 0.f;
+  }
   const float al = alpha ? alpha[agent] * invN : 0.f;
   float* g_out = f.G + r * c.Ao;
   for (int j = 0; j < A; ++j) {
@@ -111,6 +118,25 @@ __global__ void k_actor_step(KCtx c, const float* __restrict__ theta_ref, const 
   float v = __fadd_rn(theta_ref[o], __fmul_rn(scale[agent], dir[o]));
   if (!c.per_state_std && i >= c.L.na - c.A) v = fmaxf(v, logf(1e-3f));
   c.T.actor[o] = v;
+}
+
+// tf.clip_by_global_norm over the actor's trainable tensors (ppo.py:226-231): norm = sqrt(sum g^2) (fixed order),
+// g *= max_norm / max(norm, max_norm); max_norm <= 0: norm only.  stats[agent*8 + {4: norm before, 5: norm after}].
+// grid: (n_agents), block 256
+__global__ void k_grad_clip(KCtx c, float* __restrict__ g, float max_norm, float* __restrict__ stats) {
+  __shared__ float sh[32];
+  const int agent = blockIdx.x;
+  float* ga = g + (long long)agent * c.L.na_stride;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < c.L.na; i += blockDim.x) acc += ga[i] * ga[i];
+  const float norm = sqrtf(block_sum(acc, sh));
+  float post = norm;
+  if (max_norm > 0.f) {
+    const float scale = max_norm / fmaxf(norm, max_norm);
+    for (long long i = threadIdx.x; i < c.L.na; i += blockDim.x) ga[i] *= scale;
+    post = norm * scale;
+  }
+  if (threadIdx.x == 0 && stats) { stats[agent * 8 + 4] = norm; stats[agent * 8 + 5] = post; }
 }
 
 }  // namespace saceo

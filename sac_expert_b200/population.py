@@ -544,6 +544,31 @@ class Population:
         self._exit()
         return grad, stats
 
+    def ppo_grad(self, act, adv, nlp_old, alpha=None, eps_clip=0.2, max_grad_norm=None):
+        """Gradient of ``PPO._apply_actor_grad`` (ppo.py:132-147, :226-231) on the bound ``fvp_states``: clipped surrogate
+        + entropy regulariser, then ``clip_by_global_norm``.  Returns (neg_pg [n, na_stride], stats [n, 8] with
+        [4] / [5] = global norm before / after clipping)."""
+        n, N, A = self.spec.n_agents, self.spec.fvp_rows, self.spec.A
+        act, adv, nlp_old = self._opt(act, n, N, A), self._opt(adv, n, N), self._opt(nlp_old, n, N)
+        alpha = self._opt(alpha, n)
+        grad = torch.zeros(n, self.L.na_stride, device=self.dev)
+        stats = torch.zeros(n, 8, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_ppo_grad(self.ctx, act.data_ptr(), adv.data_ptr(), nlp_old.data_ptr(),
+                                         None if alpha is None else alpha.data_ptr(), float(eps_clip),
+                                         float(max_grad_norm) if max_grad_norm is not None else 0.0,
+                                         grad.data_ptr(), stats.data_ptr(), st))
+        self._exit()
+        return grad, stats
+
+    def actor_adam(self, grad: torch.Tensor):
+        """``actor_optimizer.apply_gradients`` (ppo.py:234): one Keras-Adam step of the actor optimiser with ``grad``
+        [n, na_stride]; the learning rate is the per-agent ``actor_lr`` hyper-parameter."""
+        grad = self._opt(grad, self.spec.n_agents, self.L.na_stride)
+        st = self._enter()
+        _l.check(self.lib.saceo_actor_adam(self.ctx, grad.data_ptr(), st))
+        self._exit()
+
     def trpo_eval(self, act=None, adv=None, nlp_old=None, kl_ref=None, want_nlp=False, want_kl_info=False,
                   want_rows=False):
         """Line-search quantities of ``TRPO._backtrack`` (trpo.py:251-263) at the current actor parameters: dict with

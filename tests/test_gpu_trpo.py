@@ -166,3 +166,89 @@ def test_trpo_class_interface():
     assert log["alpha"] == 0.0 and log["epsilon"] == 0.0
     with pytest.raises(NotImplementedError):
         alg.update((s, a, adv, None, None, None), expert_reg=(s, a, s, 0.5, [], False, None))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# PPO (ppo.py:41-119, :122-237)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("per_state_std,max_norm", [(True, None), (False, 0.05)])
+def test_ppo_gradient_clip_and_actor_adam(per_state_std, max_norm):
+    cfg, pop, probs = _setup(per_state_std, ("tanh", "tanh"), n=2, N=128)
+    n, N, L = len(probs), 128, pop.L
+    rng = np.random.default_rng(8)
+    act = np.stack([p[2] for p in probs]); adv = np.stack([O.trpo_normalise_adv(p[3]) for p in probs]).astype(np.float32)
+    alpha = np.array([0.1, 0.0], np.float32)
+    nlp_old = np.zeros((n, N), np.float32)
+    refs = []
+    for i, (st, s, a, _) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        e0 = O.trpo_eval(cfg, th["actor"], s, a, adv[i], np.zeros(N), None, th)
+        nlp_old[i] = (e0["nlp"].numpy() + rng.normal(size=N) * 0.3).astype(np.float32)       # many rows outside the clip
+        g, _, pre, post = O.ppo_actor_grad(cfg, th["actor"], s, a, adv[i], nlp_old[i].astype(np.float64), float(alpha[i]),
+                                           0.0, 0.2, max_norm, th)
+        ad = st["adam_actor"]                               # the problems start from a non-trivial optimiser state (t = 7)
+        new, m, v, _ = O.keras_adam(th["actor"], g, [torch.from_numpy(x.astype(np.float64)) for x in ad["m"]],
+                                    [torch.from_numpy(x.astype(np.float64)) for x in ad["v"]], int(ad["t"]), 1e-3)
+        refs.append((O.flat(g).numpy(), pre, post, O.flat(new).numpy(), O.flat(m).numpy(), O.flat(v).numpy(),
+                     O.flat(th["actor"]).numpy()))
+        pop.set_hyper(i, lr_pi=1e-3)
+    before_t = pop.t["adam_t"].cpu().numpy().copy()
+    grad, stats = pop.ppo_grad(act, adv, nlp_old, alpha, 0.2, max_norm)
+    pop.actor_adam(grad)
+    grad, stats = grad.cpu().numpy(), stats.cpu().numpy()
+    after_t = pop.t["adam_t"].cpu().numpy()
+    assert np.array_equal(after_t[:, 2], before_t[:, 2] + 1) and np.array_equal(after_t[:, [0, 1, 3]], before_t[:, [0, 1, 3]])
+    for i in range(n):
+        g_ref, pre, post, new, m, v, old = refs[i]
+        assert rel(grad[i, :L.na], g_ref) < 1e-3
+        assert abs(stats[i, 4] - pre) < 1e-3 * pre and abs(stats[i, 5] - post) < 1e-3 * post
+        if max_norm is not None:
+            assert pre > max_norm and abs(stats[i, 5] - max_norm) < 1e-5 * max_norm
+        assert rel(pop.t["actor_m"][i, :L.na].cpu().numpy(), m) < 1e-3
+        assert rel(pop.t["actor_v"][i, :L.na].cpu().numpy(), v) < 2e-3
+        assert rel(pop.t["actor"][i, :L.na].cpu().numpy() - old.astype(np.float32), new - old) < 2e-3
+    pop.close()
+
+
+def test_ppo_class_interface():
+    from sac_expert_b200.sac_eo.actors.init_actor import init_actor
+    from sac_expert_b200.sac_eo.algs.model_free.ppo import PPO
+    from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
+    np.random.seed(0)
+    env = SyntheticEnv(7, 2)
+    actor = init_actor(env, [32, 32], ["tanh"], 0.01, 1.0, "orthogonal", False, None, actor_per_state_std=True,
+                       actor_squash=True)
+    cfg = O.NetCfg(S=7, A=2, actor_hidden=(32, 32), critic_hidden=(8, 8), num_models=0, per_state_std=True,
+                   actor_acts=("tanh", "tanh"), std_mult=1.0)
+    rng = np.random.default_rng(1)
+    N = 200                                             # 3 minibatches of 66, ragged tail of 2 dropped (:61-62)
+    s = rng.standard_normal((N, 7)).astype(np.float32)
+    w0 = actor.get_weights()
+    st = {"actor": [torch.from_numpy(w.astype(np.float64)) for w in w0], "s_mean": torch.zeros(7, dtype=torch.float64),
+          "s_std": torch.ones(7, dtype=torch.float64)}
+    with torch.no_grad():
+        mean, ls = O.gaussian_forward(cfg, st["actor"], torch.as_tensor(s, dtype=torch.float64), st)
+    a = (mean + torch.exp(ls) * torch.from_numpy(rng.standard_normal((N, 2)))).numpy().astype(np.float32)
+    adv = rng.standard_normal(N).astype(np.float32)
+    kw = dict(actor_lr=3e-4, actor_update_it=2, actor_nminibatch=3, adv_center=True, adv_scale=True, eps_ppo=0.2,
+              max_grad_norm=0.5, adaptlr=True, adapt_factor=0.03, adapt_minthresh=0.0, adapt_maxthresh=1e-6,
+              ent_reg=False, ent_targ=0.0, alpha_lr=0.01)
+    alg = PPO(actor, kw)
+    np.random.seed(11)
+    log = alg.update((s, a, adv, None, None, None))
+    after_rng = np.random.randint(1 << 30)
+    adam = {"m": [torch.zeros_like(t) for t in st["actor"]], "v": [torch.zeros_like(t) for t in st["actor"]], "t": 0}
+    np.random.seed(11)
+    new, ref = O.ppo_update(cfg, st["actor"], adam, s, a, adv, st, actor_lr=3e-4, actor_update_it=2, actor_nminibatch=3,
+                            eps_ppo=0.2, max_grad_norm=0.5)
+    assert after_rng == np.random.randint(1 << 30)       # same consumption of the global NumPy RNG
+    w1 = actor.get_weights()
+    step = np.concatenate([x.ravel() for x in w1]) - np.concatenate([x.ravel() for x in w0])
+    assert rel(step, (O.flat(new) - O.flat(st["actor"])).numpy()) < 5e-3
+    for k in ("ent", "tv", "kl", "outside_clip", "actor_grad_norm_pre", "actor_grad_norm"):
+        assert abs(log[k] - ref[k]) <= 1e-2 * max(abs(ref[k]), 1e-4), (k, log, ref)
+    assert alg._t == 6 and log["actor_lr"] == pytest.approx(3e-4)
+    assert alg.actor_lr == pytest.approx(3e-4 / 1.03)    # tv above the (tiny) upper threshold: learning rate shrinks (:107-111)
+    # optimiser slots persist into the next update, as the Keras optimiser's do
+    alg.update((s, a, adv, None, None, None))
+    assert alg._t == 12

@@ -372,3 +372,45 @@ def test_trpo_state_independent_logstd_floor_on_increment():
     step[-cfg.A:] = -100.0
     new = O.actor_increment(cfg, th, step)
     assert torch.all(new[-1] == math.log(1e-3)) and rel(O.flat(new[:-1]), O.flat(th[:-1])) == 0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# PPO restatement (ppo.py:41-119, :122-237)
+# ----------------------------------------------------------------------------------------------------------
+def test_ppo_gradient_is_the_surrogate_gradient_with_clipped_rows_masked():
+    """csrc/trpo.cuh::k_trpo_rows (clip_eps >= 0) zeroes the row weight where the clipped branch is selected."""
+    cfg, st, s, a, adv = _trpo_problem(True)
+    th = O.to_torch_state(st, torch.float64)
+    theta = th["actor"]
+    N = len(s)
+    adv_n = O.trpo_normalise_adv(adv)
+    rng = np.random.default_rng(4)
+    with torch.no_grad():
+        m0, l0 = O.gaussian_forward(cfg, theta, torch.as_tensor(s, dtype=torch.float64), th)
+        cur = O.gaussian_neglogp(m0, l0, torch.as_tensor(a, dtype=torch.float64))
+        nlp_old = cur + torch.as_tensor(rng.normal(size=N) * 0.3)
+        ratio = torch.exp(nlp_old - cur)
+        rc = torch.clamp(ratio, 0.8, 1.2)
+        advt = torch.as_tensor(adv_n, dtype=torch.float64)
+        keep = (-ratio * advt >= -rc * advt)
+    assert 0 < int(keep.sum()) < N                       # both branches occur
+    g, _, pre, post = O.ppo_actor_grad(cfg, theta, s, a, adv_n, nlp_old, 0.2, 0.0, 0.2, None, th)
+    g_ref, _, _ = O.trpo_surrogate_grad(cfg, theta, s, a, adv_n * keep.numpy(), nlp_old, 0.2, 0.0, th)
+    assert rel(O.flat(g), O.flat(g_ref)) < 1e-12 and pre == post
+    gc, _, pre2, post2 = O.ppo_actor_grad(cfg, theta, s, a, adv_n, nlp_old, 0.2, 0.0, 0.2, 0.5 * pre, th)
+    assert abs(pre2 - pre) < 1e-12 and abs(post2 - 0.5 * pre) < 1e-12 and rel(O.flat(gc), 0.5 * O.flat(g)) < 1e-12
+
+
+def test_ppo_update_fp32_vs_fp64_and_rng_consumption():
+    cfg, st, s, a, adv = _trpo_problem(False, N=96)
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        th = O.to_torch_state(st, dt)
+        adam = {"m": [torch.zeros_like(t) for t in th["actor"]], "v": [torch.zeros_like(t) for t in th["actor"]], "t": 0}
+        np.random.seed(7)
+        new, log = O.ppo_update(cfg, th["actor"], adam, s, a, adv, th, actor_update_it=2, actor_nminibatch=3)
+        out[dt] = (O.flat(new) - O.flat(th["actor"]), log, adam["t"], np.random.randint(1 << 30))
+    assert out[torch.float64][2] == 6 and out[torch.float64][3] == out[torch.float32][3]
+    assert rel(out[torch.float32][0], out[torch.float64][0]) < 2e-3
+    for k, v in out[torch.float64][1].items():
+        assert abs(out[torch.float32][1][k] - v) <= 1e-3 * max(abs(v), 1e-3), k
