@@ -635,7 +635,7 @@ class Population:
         else:
             v, vfv = self.cg_solve(pg, iters=cg_iters, tol=residual_tol, damp=trust_damp)
             vfv = vfv.cpu().numpy().astype(np.float64)
-            zero = np.array([np.allclose(pg[i, :self.L.na].cpu().numpy(), 0) for i in range(n)])
+            zero = (pg[:, :self.L.na].abs().amax(dim=1) <= 1e-8).cpu().numpy()      # np.allclose(pg_vec, 0) per agent (:179)
             skip = zero | ~(vfv > 0)                          # pg_vec == 0 (:179-180): no step; CG of a zero vector is 0/0
             eta = np.where(skip, 0.0, np.sqrt(2 * delta / np.where(skip, 1.0, vfv))).astype(np.float32)
             v[torch.from_numpy(skip).to(self.dev)] = 0.0
