@@ -14,6 +14,9 @@ that follows the reference's operation order line by line, citing each source lo
 It is pinned only by its own cross-checks (tests/test_oracle.py): fp32 vs fp64 twin,
 autograd vs hand-derived analytic backward (``analytic_update``), Fisher-vector product
 in double-backprop form vs J^T M J form, and one unit test per reference quirk.
+Exception: the GaussianActor entropy / logstd parameterisation and the TRPO line-search control
+flow (``backtrack``) ARE checked against outputs of the reference itself - the TRPO log it
+recorded in sac_eo/logs/TEMPLOG_0 (tests/golden/templog0_trpo_log.json).
 
 All citations are relative to /root/reference/ (read-only, absent on the GPU box).
 
@@ -683,6 +686,29 @@ def actor_increment(cfg: NetCfg, theta: Sequence[Tensor], step_flat: Tensor) -> 
     return new
 
 
+def backtrack(trial, eta_v, kl_maxfactor: float, delta: float):
+    """Control flow of ``TRPO._backtrack`` (trpo.py:251-301).  ``trial(step) -> (theta, stats, improve)`` applies
+    ``theta_k + step`` and evaluates it (``stats`` needs "kl", "tv").  Returns (theta, stats, improve, adj, step, tv_pre,
+    kl_pre); ``adj == 0`` means ten shrinks did not help and the caller restores the old parameters (:292-301)."""
+    th, e, improve = trial(eta_v)
+    tv_pre, kl_pre = float(e["tv"]), float(e["kl"])
+    adj = 1
+    for _ in range(10):                                                            # :267-291
+        if float(e["kl"]) > kl_maxfactor * delta:
+            pass
+        elif float(improve) < 0:
+            pass
+        else:
+            break
+        factor = np.sqrt(2)
+        adj = adj / factor
+        eta_v = eta_v / factor
+        th, e, improve = trial(eta_v)
+    else:
+        adj = 0
+    return th, e, improve, adj, eta_v, tv_pre, kl_pre
+
+
 def trpo_update(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, st: Dict, *, delta: float = 0.01,
                 cg_iters: int = 20, trust_sub: int = 1, trust_damp: float = 0.01, kl_maxfactor: float = 1.5,
                 alpha: float = 0.0, ent_targ: float = 0.0, adv_center: bool = True, adv_scale: bool = True):
@@ -710,18 +736,8 @@ def trpo_update(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, st:
         e = trpo_eval(cfg, th, s_all, a_all, adv2, nlp_old, kl_ref, st)
         return th, e, e["surr"] - surr_before
 
-    th, e, improve = trial(eta_v)
-    tv_pre, kl_pre = float(e["tv"]), float(e["kl"])
-    adj = 1.0
-    for _ in range(10):                                                            # :267-291
-        if float(e["kl"]) > kl_maxfactor * delta or float(improve) < 0:
-            adj = adj / math.sqrt(2)
-            eta_v = eta_v / math.sqrt(2)
-            th, e, improve = trial(eta_v)
-        else:
-            break
-    else:                                                                          # :292-301 no policy update
-        adj = 0
+    th, e, improve, adj, eta_v, tv_pre, kl_pre = backtrack(trial, eta_v, kl_maxfactor, delta)
+    if adj == 0:                                                                   # :292-301 no policy update
         th = [t.clone() for t in theta]
         e = trpo_eval(cfg, th, s_all, a_all, adv2, nlp_old, kl_ref, st)
         improve = e["surr"] - surr_before

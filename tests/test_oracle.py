@@ -414,3 +414,68 @@ def test_ppo_update_fp32_vs_fp64_and_rng_consumption():
     assert rel(out[torch.float32][0], out[torch.float64][0]) < 2e-3
     for k, v in out[torch.float64][1].items():
         assert abs(out[torch.float32][1][k] - v) <= 1e-3 * max(abs(v), 1e-3), k
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Pinned against OUTPUTS OF THE REFERENCE: the TRPO log the reference recorded in sac_eo/logs/TEMPLOG_0
+# (tests/golden/templog0_trpo_log.json, extracted by tests/golden/make_golden_trpo_log.py)
+# ----------------------------------------------------------------------------------------------------------
+def _ref_trpo_log():
+    import json
+    return json.load(open(os.path.join(GOLD, "templog0_trpo_log.json")))
+
+
+def test_reference_log_pins_the_gaussian_entropy_and_logstd_parameterisation():
+    """Update 0 of the reference run starts from the freshly initialised state-independent-std actor (logstd variable
+    0, continuous_actors.py:56-57; logstd_init = log(std_mult) = 0): its logged mean entropy must be what the restated
+    ``gaussian_forward`` + ``gaussian_entropy`` give for those weights, and the final logstd the run saved must be
+    consistent with the entropy / KL it logged on the way."""
+    ref = _ref_trpo_log()
+    A = ref["actor"]["a_dim"]
+    assert not ref["actor"]["per_state_std"] and A == 1
+    cfg = O.NetCfg(S=3, A=A, actor_hidden=(64, 64), critic_hidden=(8, 8), num_models=0, per_state_std=False,
+                   actor_acts=("tanh", "tanh"), std_mult=ref["actor"]["std_mult"])
+    gold = np.load(os.path.join(GOLD, "pendulum_templog0.npz"))
+    theta = [torch.from_numpy(gold[f"actor_{i}"]) for i in range(7)]
+    st = {"s_mean": torch.from_numpy(gold["s_mean"]), "s_std": torch.from_numpy(gold["s_std"])}
+    s = torch.from_numpy(np.random.default_rng(0).standard_normal((50, 3)).astype(np.float32))
+    theta0 = theta[:6] + [torch.zeros(1, A)]                                   # the initial logstd variable
+    _, ls0 = O.gaussian_forward(cfg, theta0, s, st)
+    assert abs(float(O.gaussian_entropy(ls0).mean()) - ref["ent"][0]) < 5e-7   # reference: 1.4189382 (fp32)
+    # entropy is affine in the logstd variable (A = 1): the logged entropies give the variable before update 1
+    ls_before_last = ref["ent"][1] - ref["ent"][0]
+    _, ls_fin = O.gaussian_forward(cfg, theta, s, st)
+    assert abs(float(ls_fin[0, 0]) - ref["actor"]["final_logstd"][0]) < 1e-7
+    # the last update moved the logstd variable from ls_before_last to final_logstd; the KL it logged for that step
+    # (forward KL to the old policy) can be no smaller than its logstd-only part (mean shift = 0)
+    ref_info_ls = torch.full((1, A), ls_before_last)
+    kl_floor = float(O.kl_forward(torch.zeros(1, A), ls_fin[:1], torch.zeros(1, A), ref_info_ls))
+    assert 0 < kl_floor < ref["kl"][1]
+    # and the accepted step is the shrunk one: the full step would have moved logstd 1/adj times as far
+    assert ref["adj"][1] < 1 and ref["actor"]["final_logstd"][0] < ls_before_last < 0
+
+
+def test_reference_log_pins_the_line_search_rule():
+    """Replays the reference's own (kl, improve) trajectory through the restated control flow: it must take the same
+    decisions - accept at once in update 0 (adj 1, tv/kl == tv_pre/kl_pre), shrink exactly once by sqrt(2) in update 1
+    (kl_pre 0.0553 > kl_maxfactor * delta = 0.03, then 0.0203 <= 0.03) - and report the same adj to the last bit."""
+    ref = _ref_trpo_log()
+    hp = ref["hyper"]
+    for u in range(2):
+        seq = [dict(kl=ref["kl_pre"][u], tv=ref["tv_pre"][u])]
+        if ref["adj"][u] != 1.0:
+            seq.append(dict(kl=ref["kl"][u], tv=ref["tv"][u]))
+        calls = []
+
+        def trial(step):
+            calls.append(float(step))
+            e = seq[min(len(calls) - 1, len(seq) - 1)]
+            return None, e, ref["improve"][u]
+
+        _, e, improve, adj, step, tv_pre, kl_pre = O.backtrack(trial, 1.0, hp["kl_maxfactor"], hp["delta_trpo"])
+        assert adj == ref["adj"][u]                                              # bit-identical (1.0, 0.7071067811865475)
+        assert len(calls) == len(seq) and step == calls[-1] == ref["adj"][u]
+        assert (tv_pre, kl_pre) == (ref["tv_pre"][u], ref["kl_pre"][u]) and (e["tv"], e["kl"]) == (ref["tv"][u], ref["kl"][u])
+        assert e["kl"] <= hp["kl_maxfactor"] * hp["delta_trpo"] and improve >= 0
+    assert ref["kl_pre"][1] > hp["kl_maxfactor"] * hp["delta_trpo"]             # why the reference shrank
+    assert all(a == 0.0 for a in ref["alpha"]) and not hp["ent_reg"]             # temperature untouched without ent_reg
