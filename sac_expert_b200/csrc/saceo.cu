@@ -233,6 +233,9 @@ extern "C" int saceo_query_layout(const saceo_config* cfg, saceo_layout* out) {
 extern "C" int saceo_abi_version(void) { return SACEO_ABI_VERSION; }
 extern "C" const char* saceo_last_error(void) { return g_err; }
 
+static int create_fill(saceo_ctx* x, const saceo_config* cfg);
+extern "C" int saceo_destroy(saceo_ctx* x);
+
 extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   int rc = validate(cfg); if (rc) return rc;
   if (!out) return fail(SACEO_E_INVALID, "null out");
@@ -247,14 +250,21 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   if (prop.major != 10) return fail(SACEO_E_NODEVICE, "device %d is sm_%d%d; libsaceo is built for sm_100a only", cfg->device, prop.major, prop.minor);
   CU(cudaSetDevice(cfg->device));
   saceo_ctx* x = new saceo_ctx();
+  rc = create_fill(x, cfg);
+  if (rc) { saceo_destroy(x); return rc; }     // nothing of a half-built context leaks
+  *out = x;
+  return 0;
+}
+
+static int create_fill(saceo_ctx* x, const saceo_config* cfg) {
   x->cfg = *cfg;
   fill_layout(cfg, &x->L);
   memset(&x->k, 0, sizeof(KCtx)); memset(&x->f, 0, sizeof(FvpWs)); memset(&x->fit, 0, sizeof(FitCtx));
   carve(x, nullptr);
   x->L.workspace_bytes = x->ws_bytes;
   if (cudaMalloc(&x->ws, (size_t)x->ws_bytes) != cudaSuccess) {
-    cudaGetLastError(); long long wb = x->ws_bytes; delete x;
-    return fail(SACEO_E_NOMEM, "cudaMalloc of %lld workspace bytes failed", wb);
+    cudaGetLastError(); x->ws = nullptr;
+    return fail(SACEO_E_NOMEM, "cudaMalloc of %lld workspace bytes failed", (long long)x->ws_bytes);
   }
   CU(cudaMemset(x->ws, 0, (size_t)x->ws_bytes));
   carve(x, (char*)x->ws);
@@ -279,7 +289,6 @@ extern "C" int saceo_create(const saceo_config* cfg, saceo_ctx** out) {
   CU(tc_gemm_init());
   CU(mlp_fwd_tc_init());
   CU(model_term_init());
-  *out = x;
   return 0;
 }
 
