@@ -686,6 +686,40 @@ def actor_increment(cfg: NetCfg, theta: Sequence[Tensor], step_flat: Tensor) -> 
     return new
 
 
+def gaussian_sample(cfg: NetCfg, theta: Sequence[Tensor], s_: Tensor, u: Optional[Tensor], st: Dict) -> Tensor:
+    """``GaussianActor.sample`` (continuous_actors.py:103-123): ``_forward`` parameterisation, ``a = mean +
+    exp(logstd) u`` with u ~ np.random.normal (None: deterministic), NO squash and NO clipping."""
+    mean, logstd = gaussian_forward(cfg, theta, s_, st)
+    return mean if u is None else mean + torch.exp(logstd) * torch.as_tensor(u).to(mean.dtype)
+
+
+def trpo_expert_blend(cfg: NetCfg, theta: Sequence[Tensor], neg_pg: Sequence[Tensor], batch: Dict, eps: float, st: Dict):
+    """Two-model expert branch of ``TRPO.update`` (trpo.py:113-165): the expert rows are shuffled with the algorithm's
+    own generator and split in two (``batch["I1"], batch["I2"]``, :115-117), each half goes through
+    ``actor.sample`` (fresh noise ``u3``, ``u4``) and its own model, ``MSE = mean(0.5 (sum (s'E1 - p1)^2 + sum (s'E2 -
+    p2)^2))`` (equal halves required), ``grad_final = (1 - eps) neg_pg + eps MSE_grads``; the temperature gradient is
+    NOT blended (:165 is commented out).  Returns (grad_final, mse, norm_pg, norm_MSE) with the norms as the reference
+    logs them: sums of per-tensor L2 norms (:160-163).
+    The single-model branch (:77-111) is not restated: ``tape.gradient(MSE_loss, [..., self.alpha])`` yields None for
+    the temperature and ``(1 - epsilon) * alpha_grad + epsilon * None`` (:111) raises TypeError in the reference."""
+    dt = theta[0].dtype
+    sE, spE = torch.as_tensor(batch["sE"]).to(dt), torch.as_tensor(batch["spE"]).to(dt)
+    I1 = torch.as_tensor(np.asarray(batch["I1"]), dtype=torch.long)
+    I2 = torch.as_tensor(np.asarray(batch["I2"]), dtype=torch.long)
+    th = _req(theta)
+    c1 = gaussian_sample(cfg, th, sE[I1], batch["u3"], st)
+    c2 = gaussian_sample(cfg, th, sE[I2], batch["u4"], st)
+    p1 = model_sample(cfg, st["m1"], sE[I1], c1, st)
+    p2 = model_sample(cfg, st["m2"], sE[I2], c2, st)
+    mse = (0.5 * (((spE[I1] - p1) ** 2).sum(-1) + ((spE[I2] - p2) ** 2).sum(-1))).mean()
+    g = torch.autograd.grad(mse, th, allow_unused=True)
+    g = [x if x is not None else torch.zeros_like(p) for x, p in zip(g, th)]
+    final = [(1 - eps) * a + eps * b for a, b in zip(neg_pg, g)]
+    norm_pg = sum(float(torch.linalg.norm(a)) for a in neg_pg)
+    norm_mse = sum(float(torch.linalg.norm(b)) for b in g)
+    return [f.detach() for f in final], mse.detach(), norm_pg, norm_mse
+
+
 def backtrack(trial, eta_v, kl_maxfactor: float, delta: float):
     """Control flow of ``TRPO._backtrack`` (trpo.py:251-301).  ``trial(step) -> (theta, stats, improve)`` applies
     ``theta_k + step`` and evaluates it (``stats`` needs "kl", "tv").  Returns (theta, stats, improve, adj, step, tv_pre,
@@ -711,15 +745,20 @@ def backtrack(trial, eta_v, kl_maxfactor: float, delta: float):
 
 def trpo_update(cfg: NetCfg, theta: Sequence[Tensor], s_all, a_all, adv_all, st: Dict, *, delta: float = 0.01,
                 cg_iters: int = 20, trust_sub: int = 1, trust_damp: float = 0.01, kl_maxfactor: float = 1.5,
-                alpha: float = 0.0, ent_targ: float = 0.0, adv_center: bool = True, adv_scale: bool = True):
-    """``TRPO.update`` (trpo.py:36-198) on the epsilon = 0 slice of the gradient blend (``grad_final = neg_pg``; the
-    reference only defines ``grad_final`` inside its expert branches, :107-111, :154-158) followed by
+                alpha: float = 0.0, ent_targ: float = 0.0, adv_center: bool = True, adv_scale: bool = True,
+                expert: Optional[Dict] = None, eps: float = 0.0):
+    """``TRPO.update`` (trpo.py:36-198): with ``expert`` (a dict like ``draw_batch``'s: sE, spE, I1, I2, u3, u4) the
+    two-model gradient blend ``grad_final = (1 - eps) neg_pg + eps MSE_grads``; without it the epsilon = 0 slice
+    (``grad_final = neg_pg``; the reference only defines ``grad_final`` inside its expert branches, :107-111,
+    :154-158); followed by
     ``TRPO._backtrack`` (:229-317).  Returns (new theta, log dict, pg_vec, eta_v_flat)."""
     with torch.no_grad():
         m0, l0 = gaussian_forward(cfg, theta, torch.as_tensor(s_all).to(theta[0].dtype), st)
         nlp_old = gaussian_neglogp(m0, l0, torch.as_tensor(a_all).to(theta[0].dtype))
     adv = trpo_normalise_adv(adv_all, adv_center, adv_scale)
     neg_pg, _, _ = trpo_surrogate_grad(cfg, theta, s_all, a_all, adv, nlp_old, alpha, ent_targ, st)
+    if expert is not None:                                                         # :113-165, two-model branch
+        neg_pg, _, _, _ = trpo_expert_blend(cfg, theta, neg_pg, expert, eps, st)
     pg_vec = flat(neg_pg) * -1                                                     # :176
     if np.allclose(pg_vec.numpy(), 0) or delta == 0.0:                             # :179-180
         eta_v = torch.zeros_like(pg_vec)

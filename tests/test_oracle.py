@@ -479,3 +479,60 @@ def test_reference_log_pins_the_line_search_rule():
         assert e["kl"] <= hp["kl_maxfactor"] * hp["delta_trpo"] and improve >= 0
     assert ref["kl_pre"][1] > hp["kl_maxfactor"] * hp["delta_trpo"]             # why the reference shrank
     assert all(a == 0.0 for a in ref["alpha"]) and not hp["ent_reg"]             # temperature untouched without ent_reg
+
+
+# ----------------------------------------------------------------------------------------------------------
+# TRPO two-model expert blend (trpo.py:113-165) - checker for the device path of a later round
+# ----------------------------------------------------------------------------------------------------------
+def _blend_problem(per_state_std):
+    cfg = O.NetCfg(S=6, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(40, 40), num_models=2,
+                   per_state_std=per_state_std, actor_acts=("tanh", "tanh"), std_mult=0.8)
+    st, replay, expert, _ = O.make_problem(cfg, 8, 10, 200, seed=5, perturb=0.1)
+    batch = O.draw_batch(cfg, replay, expert, 8, seed=6)
+    rng = np.random.default_rng(5)
+    return cfg, st, replay["s"][:64], replay["a"][:64], rng.standard_normal(64).astype(np.float32), batch
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_trpo_expert_blend_gradient_and_norm_bookkeeping(per_state_std):
+    cfg, st, s, a, adv, batch = _blend_problem(per_state_std)
+    th = O.to_torch_state(st, torch.float64)
+    theta = th["actor"]
+    neg_pg = [torch.randn_like(t) * 0.1 for t in theta]
+    g0, mse, n_pg, n_mse = O.trpo_expert_blend(cfg, theta, neg_pg, batch, 0.0, th)
+    g1, _, _, _ = O.trpo_expert_blend(cfg, theta, neg_pg, batch, 1.0, th)
+    gh, _, _, _ = O.trpo_expert_blend(cfg, theta, neg_pg, batch, 0.3, th)
+    assert rel(O.flat(g0), O.flat(neg_pg)) == 0                                   # epsilon = 0: the plain gradient
+    assert rel(O.flat(gh), 0.7 * O.flat(neg_pg) + 0.3 * O.flat(g1)) < 1e-14       # linear in epsilon
+    assert abs(n_pg - sum(float(t.norm()) for t in neg_pg)) < 1e-12               # sum of per-tensor norms, not the global norm
+    assert abs(n_mse - sum(float(t.norm()) for t in g1)) < 1e-12 and float(mse) > 0
+    # closed form of the unsquashed sample head: dL/dmean = dL/da, dL/dlogstd = dL/da * std * u (floor mask on logstd)
+    tt = [t.clone().requires_grad_(True) for t in theta]
+    dt = torch.float64
+    sE, spE = torch.as_tensor(batch["sE"]).to(dt), torch.as_tensor(batch["spE"]).to(dt)
+    res = [torch.zeros_like(t) for t in theta]
+    for I, u, mk in ((batch["I1"], batch["u3"], "m1"), (batch["I2"], batch["u4"], "m2")):
+        I = torch.as_tensor(np.asarray(I), dtype=torch.long)
+        mean, ls = O.gaussian_forward(cfg, tt, sE[I], th)
+        act = (mean + torch.exp(ls) * torch.as_tensor(u).to(dt)).detach().requires_grad_(True)
+        pred = O.model_sample(cfg, th[mk], sE[I], act, th)
+        loss = (0.5 * ((spE[I] - pred) ** 2).sum(-1)).sum() / len(I)
+        (dLda,) = torch.autograd.grad(loss, act)
+        g_ls = dLda * torch.exp(ls.detach()) * torch.as_tensor(u).to(dt)
+        part = torch.autograd.grad([mean, ls], tt, grad_outputs=[dLda, g_ls], allow_unused=True)
+        res = [r + (p if p is not None else 0) for r, p in zip(res, part)]
+    assert rel(O.flat(res), O.flat(g1)) < 1e-12
+
+
+def test_trpo_update_with_expert_blend_runs_the_line_search():
+    cfg, st, s, a, adv, batch = _blend_problem(True)
+    th = O.to_torch_state(st, torch.float64)
+    plain, log_p, pg_p, _ = O.trpo_update(cfg, th["actor"], s, a, adv, th, delta=0.02, cg_iters=5)
+    same, log_s, pg_s, _ = O.trpo_update(cfg, th["actor"], s, a, adv, th, delta=0.02, cg_iters=5, expert=batch, eps=0.0)
+    assert rel(pg_s, pg_p) == 0 and log_s == log_p
+    mixed, log_m, pg_m, _ = O.trpo_update(cfg, th["actor"], s, a, adv, th, delta=0.02, cg_iters=5, expert=batch, eps=0.5)
+    assert rel(pg_m, pg_p) > 1e-3 and log_m["kl"] <= 1.5 * 0.02 + 1e-12
+    # odd expert count: the two halves differ in length and the row-wise sum of their losses (:147-150) cannot be formed
+    odd = dict(batch); odd["I2"] = batch["I2"][:-1]; odd["u4"] = batch["u4"][:-1]
+    with pytest.raises(RuntimeError):
+        O.trpo_expert_blend(cfg, th["actor"], [torch.zeros_like(t) for t in th["actor"]], odd, 0.5, th)
