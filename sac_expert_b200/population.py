@@ -104,6 +104,30 @@ def unpack_flat(vec: np.ndarray, shapes: Sequence[Tuple[int, ...]]) -> List[np.n
     return out
 
 
+def backtrack_population(trial, n: int, kl_maxfactor: float, delta: float):
+    """Control flow of ``TRPO._backtrack`` (trpo.py:251-301) for ``n`` agents at once, each with its own accept /
+    shrink decisions.  ``trial(adj[n]) -> (stats[n, >=3], improve[n])`` applies ``theta_k + adj * eta * v`` for every
+    agent and evaluates it (``stats[:, 1]`` = kl, ``stats[:, 2]`` = tv).  An agent accepts the first trial whose
+    ``kl <= kl_maxfactor * delta`` and ``improve >= 0`` and keeps that ``adj`` from then on; otherwise its ``adj`` is
+    divided by sqrt(2), at most ten times; an agent that has not accepted after the tenth shrink gets ``adj = 0`` (its
+    old parameters).  Returns (adj, stats, improve, tv_pre, kl_pre) at the final parameters.  Pure host logic."""
+    adj = np.ones(n)
+    stats, improve = trial(adj)
+    tv_pre, kl_pre = stats[:, 2].copy(), stats[:, 1].copy()
+    done = np.zeros(n, bool)
+    for _ in range(10):
+        bad = ~done & ((stats[:, 1] > kl_maxfactor * delta) | (improve < 0))
+        done |= ~bad
+        if not bad.any():
+            break
+        adj = np.where(bad, adj / np.sqrt(2), adj)
+        stats, improve = trial(adj)
+    else:
+        adj = np.where(done, adj, 0.0)                        # no policy update for the agents still failing
+        stats, improve = trial(adj)
+    return adj, stats, improve, tv_pre, kl_pre
+
+
 class _DevBuf:
     """Zero-copy view of a library-owned device buffer through ``__cuda_array_interface__``."""
 
@@ -647,20 +671,7 @@ class Population:
             s = self.trpo_eval(act, adv2, nlp_old, kl_ref)["stats"].cpu().numpy()
             return s, s[:, 0] - surr_before
 
-        adj = np.ones(n)
-        stats, improve = trial(eta * adj)
-        tv_pre, kl_pre = stats[:, 2].copy(), stats[:, 1].copy()
-        done = np.zeros(n, bool)
-        for _ in range(10):
-            bad = ~done & ((stats[:, 1] > kl_maxfactor * delta) | (improve < 0))
-            done |= ~bad
-            if not bad.any():
-                break
-            adj = np.where(bad, adj / np.sqrt(2), adj)
-            stats, improve = trial(eta * adj)
-        else:
-            adj = np.where(done, adj, 0.0)                    # no policy update for the agents still failing
-            stats, improve = trial(eta * adj)
+        adj, stats, improve, tv_pre, kl_pre = backtrack_population(lambda a: trial(eta * a), n, kl_maxfactor, delta)
         return [dict(ent=float(ent[i]), tv_pre=float(tv_pre[i]), kl_pre=float(kl_pre[i]), tv=float(stats[i, 2]),
                      kl=float(stats[i, 1]), adj=float(adj[i]), improve=float(improve[i])) for i in range(n)]
 

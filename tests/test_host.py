@@ -102,3 +102,60 @@ def test_dp_gradient_average_equals_global_batch_gloo():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert err < 1e-12
+
+
+def test_population_line_search_equals_the_per_agent_reference_flow():
+    """``backtrack_population`` (vectorised accept / shrink decisions of Population.trpo_update) against the restated
+    single-agent ``TRPO._backtrack`` control flow (oracle.backtrack, itself pinned on the reference's logged
+    trajectory) on synthetic per-agent (kl, improve) tables: accept at any level, never accept, mixed populations."""
+    import json
+    import os
+    from oracle import sac_eo_oracle as O
+    from sac_expert_b200.population import backtrack_population
+    rng = np.random.default_rng(0)
+    delta, klf = 0.02, 1.5
+    for rep in range(30):
+        n = int(rng.integers(1, 9))
+        # level k = number of sqrt(2) shrinks (0..10); level 11 = restored parameters (adj 0)
+        kl = rng.uniform(0.0, 0.09, size=(n, 12)) * (0.75 ** np.arange(12))[None]
+        imp = rng.normal(0.01, 0.02, size=(n, 12))
+        tv = rng.uniform(0, 0.2, size=(n, 12))
+        if rep % 3 == 0:
+            kl[0] = 1.0                                    # an agent no shrink can save
+        kl[:, 11] = 0.0; imp[:, 11] = 0.0; tv[:, 11] = 0.0
+        level = lambda a: 11 if a == 0 else int(round(-2 * np.log2(a)))
+        calls = []
+
+        def trial(adj):
+            calls.append(adj.copy())
+            k = [level(a) for a in adj]
+            st = np.stack([[0.0, kl[i, k[i]], tv[i, k[i]]] for i in range(n)])
+            return st, np.array([imp[i, k[i]] for i in range(n)])
+
+        adj, stats, improve, tv_pre, kl_pre = backtrack_population(trial, n, klf, delta)
+        for i in range(n):
+            def trial_i(step, i=i):
+                k = level(step)
+                return None, dict(kl=kl[i, k], tv=tv[i, k]), imp[i, k]
+            _, e, im, adj_i, step, tvp, klp = O.backtrack(trial_i, 1.0, klf, delta)
+            assert adj[i] == adj_i, (rep, i, adj, adj_i)
+            assert (tv_pre[i], kl_pre[i]) == (tvp, klp)
+            k = level(adj[i])
+            assert stats[i, 1] == kl[i, k] and stats[i, 2] == tv[i, k] and improve[i] == imp[i, k]
+            if adj_i != 0:
+                assert stats[i, 1] == e["kl"] and improve[i] == im and step == adj_i
+        assert len(calls) <= 12
+    # the reference's own logged trajectory (tests/golden/templog0_trpo_log.json), both updates as a 2-agent population
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "templog0_trpo_log.json")))
+
+    def trial_ref(adj):
+        st = np.zeros((2, 3)); im = np.array(ref["improve"])
+        for u in range(2):
+            first = adj[u] == 1.0
+            st[u, 1] = ref["kl_pre"][u] if first else ref["kl"][u]
+            st[u, 2] = ref["tv_pre"][u] if first else ref["tv"][u]
+        return st, im
+
+    adj, stats, _, tv_pre, kl_pre = backtrack_population(trial_ref, 2, ref["hyper"]["kl_maxfactor"], ref["hyper"]["delta_trpo"])
+    assert list(adj) == ref["adj"] and list(stats[:, 1]) == ref["kl"] and list(stats[:, 2]) == ref["tv"]
+    assert list(kl_pre) == ref["kl_pre"] and list(tv_pre) == ref["tv_pre"]
