@@ -1080,6 +1080,8 @@ extern "C" int saceo_cg_solve(saceo_ctx* x, const float* b, int32_t iters, float
 static int trpo_check(saceo_ctx* x) {
   if (!x) return fail(SACEO_E_INVALID, "null ctx");
   if (!x->bound || !x->k.T.fvp_states || x->f.N < 1) return fail(SACEO_E_UNBOUND, "fvp_states not bound / fvp_rows == 0");
+  // the four per-row statistics live in the [N, max(h2, Ao)] scratch of the Fisher-vector workspace
+  if (x->cfg.actor_hidden[1] < 4 && x->L.Ao < 4) return fail(SACEO_E_INVALID, "TRPO / PPO entry points need actor_hidden[1] >= 4");
   return 0;
 }
 

@@ -159,3 +159,25 @@ def test_population_line_search_equals_the_per_agent_reference_flow():
     adj, stats, _, tv_pre, kl_pre = backtrack_population(trial_ref, 2, ref["hyper"]["kl_maxfactor"], ref["hyper"]["delta_trpo"])
     assert list(adj) == ref["adj"] and list(stats[:, 1]) == ref["kl"] and list(stats[:, 2]) == ref["tv"]
     assert list(kl_pre) == ref["kl_pre"] and list(tv_pre) == ref["tv_pre"]
+
+
+@pytest.mark.parametrize("which", ["trpo", "ppo"])
+def test_on_policy_temperature_step_is_keras_adam_with_the_zero_floor(which):
+    """``alpha_optimizer.apply_gradients([alpha_grad * -1])`` + ``alpha = max(alpha, 0)`` (trpo.py:169-172,
+    ppo.py:221-224): the host scalar step of the mirror classes against the oracle's Keras-Adam restatement."""
+    from oracle.sac_eo_oracle import keras_adam
+    from sac_expert_b200.sac_eo.algs.model_free.ppo import PPO
+    from sac_expert_b200.sac_eo.algs.model_free.trpo import TRPO
+    kw = dict(adv_center=True, adv_scale=True, delta_trpo=0.02, cg_it=5, trust_sub=1, trust_damp=0.01, kl_maxfactor=1.5,
+              ent_reg=True, ent_targ=-1.0, alpha_lr=0.01, actor_lr=3e-4, actor_update_it=2, actor_nminibatch=3,
+              eps_ppo=0.2, max_grad_norm=0.5, adaptlr=True, adapt_factor=0.03, adapt_minthresh=0.0, adapt_maxthresh=1.0)
+    alg = (TRPO if which == "trpo" else PPO)(None, kw)          # constructing the update object needs no device
+    a, m, v, t = [torch.zeros((), dtype=torch.float64)], [torch.zeros((), dtype=torch.float64)], \
+        [torch.zeros((), dtype=torch.float64)], 0
+    grads = [-0.8, -1.1, -0.3, 0.5, 2.0, 2.5, -0.1]             # first pushes alpha up, later ones drive it into the floor
+    for g in grads:
+        alg._alpha_step(g)
+        a, m, v, t = keras_adam(a, [torch.tensor(g, dtype=torch.float64)], m, v, t, 0.01)
+        a = [torch.clamp(a[0], min=0.0)]
+        assert abs(float(alg.alpha) - float(a[0])) < 2e-6, (g, alg.alpha, a)
+    assert alg._alpha_t == len(grads) and float(alg.alpha) >= 0.0
