@@ -36,7 +36,7 @@ def parse():
     p.add_argument("--no-fuse-backward", action="store_true")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--cpu-seconds", type=float, default=16.0)
     return p.parse_args()
 
 
@@ -133,21 +133,73 @@ def cpu_update_rate(a, seconds, threads=None):
     return (n - n0) / dt, cores, n - n0
 
 
+def _pool_worker(shape, plain_sac, seconds, q):
+    """One single-threaded process = one independent agent, the reference's own parallel model (one process per seed
+    through multiprocessing.Pool, train.py:130-152)."""
+    import argparse
+    try:
+        rate, _, n = cpu_update_rate(argparse.Namespace(shape=shape, plain_sac=plain_sac), seconds, threads=1)
+        q.put((rate, n))
+    except Exception as e:          # a dead worker must not hang the parent
+        q.put((0.0, 0))
+        raise e
+
+
+def cpu_pool_rate(a, seconds, procs=None):
+    """Aggregate agent-updates/s of `procs` single-threaded worker processes, each updating its own agent for `seconds`
+    (spawned, so that a CUDA context in the parent is not inherited)."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_pool_worker, args=(a.shape, a.plain_sac, seconds, q)) for _ in range(procs)]
+    for p in ps:
+        p.start()
+    res = []
+    try:
+        for _ in ps:
+            res.append(q.get(timeout=seconds + 150))
+    finally:
+        for p in ps:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    return sum(r for r, _ in res), procs, sum(n for _, n in res)
+
+
+def cpu_baseline(a, seconds):
+    """The reference's CPU update step on all host cores, both ways the reference can use them: (1) one agent, all cores
+    as intra-op threads; (2) its multiprocessing model - one single-threaded process per core, independent agents.  The
+    better aggregate is reported as the value; both are described."""
+    r1, cores, n1 = cpu_update_rate(a, seconds / 2)
+    try:
+        r2, procs, n2 = cpu_pool_rate(a, seconds / 2, cores)
+    except Exception as e:          # e.g. a sandbox without process spawning: keep the single-process figure
+        r2, procs, n2 = 0.0, 0, 0
+        print(f"# cpu pool baseline unavailable: {e}", file=sys.stderr)
+    rate = max(r1, r2)
+    sample = (f"oracle/sac_eo_oracle.py (torch-CPU eager restatement of SAC_exp._update; TensorFlow not installable), "
+              f"single-agent updates of the same shape: (1) one process, {cores} intra-op threads: {n1} updates in "
+              f"{seconds / 2:.0f} s = {r1:.1f}/s; (2) {procs} single-threaded processes x independent agents (the "
+              f"reference's mp.Pool model, train.py:130-152): {n2} updates in {seconds / 2:.0f} s = {r2:.1f}/s")
+    return {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port", "sample": sample,
+            "single_process": r1, "process_pool": r2}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # K "steps", each a bounded sample (a fixed number of single-agent updates) of the population step
-    per_step_budget = max(0.5, min(6.0, 120.0 / max(1, a.steps + a.warmup)))
-    rate, cores, n = cpu_update_rate(a, per_step_budget * (a.steps + a.warmup))
+    per_step_budget = max(0.5, min(6.0, 80.0 / max(1, a.steps + a.warmup)))
+    cb = cpu_baseline(a, per_step_budget * (a.steps + a.warmup))
+    rate, cores = cb["value"], cb["cores"]
     line = {
         "impl": "reference", "metric": "agent-updates/sec", "value": rate, "unit": "agent-updates/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 / rate,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a)},
-        "cpu_baseline": {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} consecutive single-agent updates of the same shape (oracle/sac_eo_oracle.py, "
-                                   f"torch-CPU eager restatement of SAC_exp._update; TensorFlow not installable)"},
+        "cpu_baseline": cb,
         "e2e": {"value": rate, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -303,11 +355,8 @@ def run_b200(a):
                                         "launch on the launching stream, mean of 3; launch gaps are charged to the following kernel; "
                                         f"un-graphed step total {tot_us / 1e3:.2f} ms; k_adam reads the gradients the preceding GEMMs just wrote (partly L2 hits), "
                                         "so its algorithmic-bytes rate can exceed the DRAM copy peak")
-    if not a.no_cpu_baseline:
-        rate, cores, nupd = cpu_update_rate(a, a.cpu_seconds)
-        line["cpu_baseline"] = {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port",
-                                "sample": f"{nupd} consecutive single-agent updates of the same shape in {a.cpu_seconds:.0f} s "
-                                          "(oracle/sac_eo_oracle.py, torch-CPU eager restatement of SAC_exp._update)"}
+    if not a.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N = 1 only
+        line["cpu_baseline"] = cpu_baseline(a, a.cpu_seconds)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
