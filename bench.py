@@ -137,6 +137,10 @@ def _pool_worker(shape, plain_sac, seconds, q):
     """One single-threaded process = one independent agent, the reference's own parallel model (one process per seed
     through multiprocessing.Pool, train.py:130-152)."""
     import argparse
+    # one thread per process, BLAS pools included (NumPy's QR in the problem builder would otherwise start one
+    # OpenBLAS pool per process and the oversubscribed start-up takes half a minute)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
     try:
         rate, _, n = cpu_update_rate(argparse.Namespace(shape=shape, plain_sac=plain_sac), seconds, threads=1)
         q.put((rate, n))
@@ -153,18 +157,37 @@ def cpu_pool_rate(a, seconds, procs=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     ps = [ctx.Process(target=_pool_worker, args=(a.shape, a.plain_sac, seconds, q)) for _ in range(procs)]
-    for p in ps:
-        p.start()
-    res = []
+    saved = {v: os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for v in saved:
+        os.environ[v] = "1"                     # inherited by the spawned interpreters before they import NumPy / torch
     try:
-        for _ in ps:
-            res.append(q.get(timeout=seconds + 150))
+        for p in ps:
+            p.start()
+    finally:
+        for v, old in saved.items():
+            if old is None:
+                os.environ.pop(v, None)
+            else:
+                os.environ[v] = old
+    import queue
+    res = []
+    deadline = time.perf_counter() + seconds + 150
+    try:
+        while len(res) < procs and time.perf_counter() < deadline:
+            try:
+                res.append(q.get(timeout=1.0))
+            except queue.Empty:
+                if not any(p.is_alive() for p in ps) and q.empty():
+                    break                       # workers died without reporting: do not wait for the deadline
     finally:
         for p in ps:
-            p.join(timeout=30)
+            p.join(timeout=10)
             if p.is_alive():
                 p.kill()
-    return sum(r for r, _ in res), procs, sum(n for _, n in res)
+    res = [r for r in res if r[1] > 0]
+    if not res:
+        raise RuntimeError("no worker process reported a rate")
+    return sum(r for r, _ in res), len(res), sum(n for _, n in res)
 
 
 def cpu_baseline(a, seconds):
@@ -183,7 +206,8 @@ def cpu_baseline(a, seconds):
               f"{seconds / 2:.0f} s = {r1:.1f}/s; (2) {procs} single-threaded processes x independent agents (the "
               f"reference's mp.Pool model, train.py:130-152): {n2} updates in {seconds / 2:.0f} s = {r2:.1f}/s")
     return {"value": rate, "unit": "agent-updates/s", "cores": cores, "kind": "port", "sample": sample,
-            "single_process": r1, "process_pool": r2}
+            "single_process": r1, "process_pool": r2, "one_thread_process": (r2 / procs if procs else None),
+            "os_cpu_count": os.cpu_count()}
 
 
 def run_reference(a):
