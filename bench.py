@@ -216,7 +216,8 @@ def run_reference(a):
         return
     # K "steps", each a bounded sample (a fixed number of single-agent updates) of the population step
     per_step_budget = max(0.5, min(6.0, 80.0 / max(1, a.steps + a.warmup)))
-    cb = cpu_baseline(a, per_step_budget * (a.steps + a.warmup))
+    budget = float(os.environ.get("SACEO_REF_SECONDS", per_step_budget * (a.steps + a.warmup)))   # env: contract test only
+    cb = cpu_baseline(a, budget)
     rate, cores = cb["value"], cb["cores"]
     line = {
         "impl": "reference", "metric": "agent-updates/sec", "value": rate, "unit": "agent-updates/s",
