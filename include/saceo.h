@@ -126,7 +126,7 @@ typedef struct saceo_tables {
   const float *replay;                       /* [n_agents, replay_capacity, row_words] */
   const int32_t *replay_size;                /* [n_agents] rows currently valid */
   const int32_t *replay_start;               /* [n_agents] physical row of logical index 0 (ring), may be NULL */
-  const float *expert_s, *expert_sp;         /* [n_agents, E, S] */
+  float *expert_s, *expert_sp;               /* [n_agents, E, S]; saceo_update_host* overwrite them with expert_host */
   const float *fvp_states;                   /* [n_agents, fvp_rows, S] or NULL */
 } saceo_tables;
 
@@ -168,7 +168,8 @@ int saceo_update(saceo_ctx *ctx, int32_t n_steps, int64_t num_timesteps, int32_t
 
 /* Same, through HOST buffers (the call the Python `_update` makes per step): copies idx_host
  * [n,B] int64 (may be NULL => device RNG) and expert_host [2, n, E, S] f32 (all sE rows, then all s'E rows; may be
- * NULL => keep bound tables) host->device, runs one update, copies losses [n, n_losses] back into
+ * NULL => keep the bound tables; otherwise the rows are copied INTO the bound expert_s / expert_sp tables, exactly as if
+ * the caller had refreshed them before the update) host->device, runs one update, copies losses [n, n_losses] back into
  * losses_host and synchronises the stream. */
 int saceo_update_host(saceo_ctx *ctx, int64_t num_timesteps, uint64_t seed, const int64_t *idx_host,
                       const float *expert_host, float *losses_host, void *stream);

@@ -228,7 +228,9 @@ static inline bool model_term_eligible(const KCtx& c) {
          model_term_smem(c, model_term_ms(c)) <= 200 * 1024;
 }
 static inline cudaError_t model_term_init() {
-  static bool done = false;
+  static bool done_dev[64] = {};
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& done = done_dev[dev_ & 63];       // cudaFuncSetAttribute is per device
   if (done) return cudaSuccess;
   cudaError_t e;
 #define MT_ATTR(MSV) e = cudaFuncSetAttribute(k_model_term<MSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e;

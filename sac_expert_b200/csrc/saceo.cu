@@ -59,9 +59,9 @@ struct saceo_ctx {
   void* ws = nullptr;
   long long ws_bytes = 0;
   std::map<std::string, std::pair<void*, long long>> names;
-  float *exp_stage = nullptr;          // [n, 2, E, S] host-staged expert rows
   long long* idx_stage = nullptr;
   float* dbpart = nullptr;             // per-tile bias-gradient partials of the fused backward kernel
+  long long dbpart_cap = 0;            // floats; a launch that needs more falls back to the ones-row bias path
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -195,9 +195,13 @@ static void carve(saceo_ctx* x, char* base) {
   k.lrt = b.get<float>("lrt", n * 4);
   k.losses = b.get<float>("losses", n * L.n_losses);
   k.mse_part = b.get<float>("mse_part", n * 2);
-  x->dbpart = b.get<float>("dbpart", n * 2 * cdiv(R > B ? R : B, TC_BM) * 2 * FW_H);
+  {   // sized for the largest fused-backward caller: the update (R rows) and the Fisher-vector / TRPO / PPO paths (fvp_rows)
+    long long rmax = R > B ? R : B;
+    if (c.fvp_rows > rmax) rmax = c.fvp_rows;
+    x->dbpart_cap = n * 2 * cdiv(rmax, TC_BM) * 2 * FW_H;
+    x->dbpart = b.get<float>("dbpart", x->dbpart_cap);
+  }
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
-  x->exp_stage = b.get<float>("exp_stage", n * 2 * e1 * S);
   x->idx_stage = b.get<long long>("idx_stage", n * B);
   // Fisher-vector / CG workspace
   FvpWs& f = x->f;
@@ -451,8 +455,11 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     f.dH2 = grads ? dH2 : nullptr; f.dH1 = grads ? dH1 : nullptr;
     f.dXa = dXa; f.s_cols = S_cols; f.a_cols = A_cols; f.sXa = sXaA; f.sXn = sXaN;
     f.rows = rows; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
-    f.dbpart = (grads && x->dbpart && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
     dim3 grid((rows + TC_BM - 1) / TC_BM, na * n.nnet);
+    // the kernel indexes dbpart as [agent*nnet+net][tile][2][256]: callers with more row tiles than the workspace was
+    // sized for (e.g. model fitting with 256-wide models and a large minibatch) take the ones-row bias path instead
+    const bool db_fits = (long long)na * n.nnet * grid.x * 2 * FW_H <= x->dbpart_cap;
+    f.dbpart = (grads && x->dbpart && db_fits && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
     k_mlp_bwd_tc<<<grid, FW_NT, FW_BYTES, st>>>(f);
     count_launch(x, "k_mlp_bwd_tc", st);
     fused = true;
@@ -801,13 +808,10 @@ static int update_host_impl(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, 
   cudaStream_t st = (cudaStream_t)stream; KCtx& k = x->k;
   if (expert_host && k.E > 0) {
     const long long ne = (long long)k.n_agents * k.E * k.S;
-    // host layout [2, n, E, S] (all sE rows, then all s'E rows): one contiguous copy, two device planes
-    CU(cudaMemcpyAsync(x->exp_stage, expert_host, sizeof(float) * 2 * ne, cudaMemcpyHostToDevice, st));
-    if (k.expert_s != x->exp_stage) {
-      k.expert_s = x->exp_stage; k.expert_sp = x->exp_stage + ne;
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j)
-        if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
-    }
+    // host layout [2, n, E, S] (all sE rows, then all s'E rows) -> the BOUND expert tables (like Population.set_expert
+    // followed by an update): the kernels and the captured graphs keep reading the tables saceo_bind() gave them
+    CU(cudaMemcpyAsync(k.T.expert_s, expert_host, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(k.T.expert_sp, expert_host + ne, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
   }
   int rc;
   if (idx_host) {

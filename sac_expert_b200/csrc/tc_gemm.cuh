@@ -560,7 +560,9 @@ __global__ void __launch_bounds__(TS_NT, 1) k_gemm_tc_stream(TcP q) {
 //              load / MMA / epilogue phases; each SM keeps more bytes in flight)
 #define TC_FOR_ALL(X) X(256, 2, 512, 1) X(128, 3, 512, 1) X(64, 4, 512, 1) X(128, 1, 256, 2) X(64, 1, 256, 2)
 static inline cudaError_t tc_gemm_init() {
-  static bool done = false;
+  static bool done_dev[64] = {};
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& done = done_dev[dev_ & 63];       // cudaFuncSetAttribute is per device
   if (done) return cudaSuccess;
   cudaError_t e;
 #define TC_ATTR(BN_, NS_, NT_, MB_) \
@@ -1207,7 +1209,9 @@ static inline bool mlp_fwd_tc_eligible(int h1, int h2, int nout, int rows, const
          ((reinterpret_cast<uintptr_t>(theta) & 15) == 0) && ((sTa & 3) == 0) && ((sTn & 3) == 0);
 }
 static inline cudaError_t mlp_fwd_tc_init() {
-  static bool done = false;
+  static bool done_dev[64] = {};
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& done = done_dev[dev_ & 63];       // cudaFuncSetAttribute is per device
   if (done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(k_mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_BYTES);
   if (e != cudaSuccess) return e;

@@ -43,6 +43,7 @@ class SquashedGaussianActor(DeviceNet):
         self._rms = normalizer.get_rms()
         self.s_rms = self._rms[0]
         self._push_rms()
+        self._rms_pushed = self._rms_versions()
 
     def _push_rms(self):
         if self._pop is not None:
@@ -59,6 +60,7 @@ class SquashedGaussianActor(DeviceNet):
 
     def _run(self, s, noise, want_nlp):
         pop = self._need_device()
+        self._sync_rms()
         if pop.spec.n_agents != 1:
             raise ValueError("the class interface drives a single-agent population; use Population for many agents")
         x = self._as_rows(s, self.s_dim)

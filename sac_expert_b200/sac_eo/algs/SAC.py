@@ -139,7 +139,14 @@ class SAC:
         noise = np.concatenate([u1, u2] + u_exp + [u5], 0).astype(np.float32)
         return idx.astype(np.int64), noise, perm
 
+    def _sync_rms(self):
+        """Re-pushes normaliser statistics that changed since the last push (``update_rms`` / ``set_rms_stats``): the
+        reference's networks see them live (SAC_expert.py:135-153, normalizer.py:126-190)."""
+        for net in [self.actor] + list(self.q_critics) + list(self.q_targets) + list(self.models[: self._n_models()]):
+            net._sync_rms()
+
     def _device_update(self, num_timesteps, expert_reg=None):
+        self._sync_rms()
         idx, noise, perm = self._draw(expert_reg)
         self.last_idx = idx
         self.pop.set_draws(idx[None], noise[None], None if perm is None else perm[None].astype(np.int32))

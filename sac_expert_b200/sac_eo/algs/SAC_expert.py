@@ -48,11 +48,12 @@ class SAC_exp(SAC):
         s_expert, sp_expert = np.asarray(s_expert, np.float32), np.asarray(sp_expert, np.float32)
         if len(s_expert) != self.pop.spec.E:
             raise ValueError(f"expert_reg carries {len(s_expert)} rows, the device population was built for {self.pop.spec.E}")
-        key = (id(expert_reg[0]), id(expert_reg[2]), float(epsilon))
-        if key != self._last_expert:          # expert_reg only changes once per episode (:774)
-            self.pop.set_expert(0, s_expert, sp_expert)
+        # E*S floats: uploaded on every call (an identity / id() cache can go stale when the arrays are edited in
+        # place or a freed array's id is reused by the next per-episode resample, :421-422)
+        self.pop.set_expert(0, s_expert, sp_expert)
+        if float(epsilon) != self._last_expert:
             self.pop.set_hyper(0, eps=float(epsilon))
-            self._last_expert = key
+            self._last_expert = float(epsilon)
         self.last_losses = out = self._device_update(num_timesteps, expert_reg)
         self.logger.log_train({"alpha_loss": out["alpha_loss"], "p_loss": out["p_loss"], "epsilon": epsilon})   # :351-356
 
@@ -107,6 +108,7 @@ class SAC_exp(SAC):
         reset, then the expert-data MSE bookkeeping.  All gradient steps of the call run back to back on the device."""
         if not getattr(self, "_fit_ready", False):
             self._setup_model_fit()
+        self._sync_rms()
         self._push_fit_hyper()
 
         def shuffled(n):                       # one np.random.shuffle of arange(n): the reference's only RNG use here

@@ -21,6 +21,7 @@ class DeviceNet:
         self._pop, self._agent, self._table = pop, agent, table
         pop.set_net(agent, table, self._host_weights)
         self._push_rms()
+        self._rms_pushed = self._rms_versions()
 
     def _need_device(self):
         if self._pop is None:
@@ -30,6 +31,18 @@ class DeviceNet:
 
     def _push_rms(self):
         pass
+
+    def _rms_versions(self):
+        return None if self._rms is None else tuple(getattr(r, "version", 0) for r in self._rms)
+
+    def _sync_rms(self):
+        """The reference's networks hold live references to the RunningNormalizer objects, so ``update_rms`` takes
+        effect on the very next forward / update (normalizer.py:60-110).  Here the statistics live in the device
+        normaliser record: re-push them whenever a bound normaliser changed since the last push."""
+        v = self._rms_versions()
+        if self._pop is not None and v != getattr(self, "_rms_pushed", None):
+            self._push_rms()
+            self._rms_pushed = v
 
     # ---- weights (Keras get_weights()/set_weights() order) -------------------------------
     def _shapes(self):

@@ -8,9 +8,11 @@ import numpy as np
 class RunningNormalizer:
     def __init__(self, dim):
         self.dim = dim
+        self.version = 0          # bumped by every change of the statistics: bound networks re-push them to the device
         self.reset()
 
     def reset(self):
+        self.version += 1
         self.t_last = 0
         if self.dim == 1:                     # scalars stay Python floats (normalizer.py:17-24)
             self.mean, self.var, self.std = 0.0, 0.0, 1.0
@@ -43,8 +45,10 @@ class RunningNormalizer:
         self.var = var.astype(np.float32) if self.dim != 1 else np.float32(var)
         self.std = np.ones_like(self.var) if n == 1 else np.sqrt(self.var)
         self.t_last = n
+        self.version += 1
 
     def instantiate(self, t, mean, var, ignore=None):
+        self.version += 1
         self.t_last, self.mean, self.var = t, mean, var
         if t == 0:
             self.reset()

@@ -22,6 +22,7 @@ class QCritic(DeviceNet):
         self._rms = normalizer.get_rms()
         self.s_rms, self.a_rms, _, _, self.ret_rms = self._rms
         self._push_rms()
+        self._rms_pushed = self._rms_versions()
 
     def _push_rms(self):
         if self._pop is not None and self._rms is not None:
@@ -30,6 +31,7 @@ class QCritic(DeviceNet):
 
     def _q(self, s, a, scale):
         pop = self._need_device()
+        self._sync_rms()
         target = self._table.startswith("t")
         net = int(self._table[1]) - 1
         s_, a_ = self._as_rows(s, self.s_dim), self._as_rows(np.asarray(a), self.a_dim)

@@ -38,6 +38,7 @@ class MSEModel(DeviceNet):
         self._rms = normalizer.get_rms()
         self.s_rms, self.a_rms, self.r_rms, self.delta_rms, _ = self._rms
         self._push_rms()
+        self._rms_pushed = self._rms_versions()
 
     def _push_rms(self):
         if self._pop is not None and self._rms is not None:
@@ -79,6 +80,7 @@ class MSEModel(DeviceNet):
         if self.gaussian and not deterministic:
             raise NotImplementedError("stochastic GaussianModel rollouts are not on the SAC-EO update path")
         pop = self._need_device()
+        self._sync_rms()
         net = int(self._table[1]) - 1
         s_, a_ = self._as_rows(s, self.s_dim), self._as_rows(np.asarray(a), self.a_dim)
         sp = pop.model_eval(torch.from_numpy(s_)[None], torch.from_numpy(a_)[None])

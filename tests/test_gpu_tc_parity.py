@@ -1,0 +1,156 @@
+"""GPU: parity of the tcgen05 engine (the one bench.py measures) at the BENCHMARKED sizes - round-1 VERDICT item 1.
+
+(i)   Fisher-vector product + CG solve, Humanoid-shaped (S=376, A=17, 2x256 actor, N=1024 states, 20 iterations + vFv)
+      vs the fp64 oracle (/root/reference/sac_eo/common/update_utils.py:4-24, algs/model_free/trpo.py:179-187,200-227),
+      per-state and state-independent std.  Also covers the bias-partial workspace sizing of the fused backward kernel
+      (8 row tiles per agent - ADVICE r1 high).
+(ii)  one injected-draw SAC-EO update of a 256-AGENT population with the CUDA graph on (multi-wave grids,
+      blockIdx = agent * nnet + net): oracle check of agents {0, 73, 147, 148, 255} and bit-identity of every other
+      agent with the representative that carries the same problem.
+(iii) HalfCheetah-shaped plain SAC, 2x256 relu (BASELINE configs[1]).
+(iv)  the data-parallel mode on 2 GPUs at 2x256 (skipped with fewer than 2 devices).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac_eo_oracle import NetCfg, cg, draw_batch, make_F, make_problem, to_torch_state
+from sac_expert_b200 import lib as L
+from sac_expert_b200.population import Population
+from tests.helpers import build, compare_update, inject, oracle_update, rel, spec_from_cfg
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_cg_humanoid_shaped_tcgen05(per_state_std):
+    cfg = NetCfg(S=376, A=17, actor_hidden=(256, 256), critic_hidden=(256, 256), num_models=0,
+                 per_state_std=per_state_std, std_mult=0.8)
+    n, N, iters, damp = 2, 1024, 20, 0.01
+    pop = Population(spec_from_cfg(cfg, n, 128, 0, 16, fvp_rows=N, gemm_mode=L.GEMM_TCGEN05_BF16X3))
+    Lo = pop.L
+    rng = np.random.default_rng(5)
+    xd = torch.zeros(n, Lo.na_stride)
+    bd = torch.zeros(n, Lo.na_stride)
+    refs = []
+    for i in range(n):
+        st, replay, _, hyper = make_problem(cfg, 128, 2, N + 8, seed=60 + i, perturb=0.1)
+        pop.load_agent(i, st, hyper)
+        states = replay["s"][:N]
+        pop.t["fvp_states"][i].copy_(torch.from_numpy(states))
+        x = rng.standard_normal(Lo.na)
+        b = rng.standard_normal(Lo.na) * 0.1
+        xd[i, :Lo.na] = torch.from_numpy(x).float()
+        bd[i, :Lo.na] = torch.from_numpy(b).float()
+        th64, th32 = to_torch_state(st, torch.float64), to_torch_state(st, torch.float32)
+        F64 = make_F(cfg, th64["actor"], states, th64, damp=damp)
+        F32 = make_F(cfg, th32["actor"], states.astype(np.float32), th32, damp=damp)
+        sol64 = cg(F64, torch.from_numpy(b), cg_iters=iters)
+        sol32 = cg(F32, torch.from_numpy(b).float(), cg_iters=iters)          # the reference's own precision
+        refs.append(dict(Fx=F64(torch.from_numpy(x)).numpy(), sol=sol64.numpy(), vfv=float(sol64.dot(F64(sol64))),
+                         sol32_dev=rel(sol32.numpy(), sol64.numpy())))
+    Fx = pop.fvp(xd, damp).cpu().numpy()
+    sol, vfv = pop.cg_solve(bd, iters=iters, tol=1e-10, damp=damp)
+    sol, vfv = sol.cpu().numpy(), vfv.cpu().numpy()
+    pop.close()
+    for i, r in enumerate(refs):
+        assert rel(Fx[i, :Lo.na], r["Fx"]) < TOL, ("Fx", i, rel(Fx[i, :Lo.na], r["Fx"]))
+        # 20 fp32 CG iterations drift from the fp64 solve by themselves (sol32_dev: the fp32 ORACLE's own deviation);
+        # the device must stay within 1e-3 of the fp64 solution or within 3x of what fp32 arithmetic costs anyway
+        bound = max(TOL, 3.0 * r["sol32_dev"])
+        assert rel(sol[i, :Lo.na], r["sol"]) < bound, ("cg", i, rel(sol[i, :Lo.na], r["sol"]), r["sol32_dev"])
+        assert abs(vfv[i] - r["vfv"]) / abs(r["vfv"]) < 2 * bound, ("vFv", i, vfv[i], r["vfv"])
+
+
+def test_population_256_graph_multiwave():
+    cfg = NetCfg(S=27, A=8)          # the bench configuration: Ant-shaped, 2x256 relu, 2 MSEModels 2x512, B=256, E=20
+    n, B, E, N = 256, 256, 20, 600
+    reps = [0, 73, 147, 148, 255]    # first / last CTA of the waves of a 148-SM part
+    pop = Population(spec_from_cfg(cfg, n, B, E, N, gemm_mode=L.GEMM_TCGEN05_BF16X3, use_graph=True))
+    base = []
+    for j, a in enumerate(reps):
+        st, replay, expert, hyper = make_problem(cfg, B, E, N, seed=900 + 17 * j, perturb=0.05)
+        hyper["eps"] = 0.3
+        hyper["gamma"] = 0.995 - 0.01 * j
+        base.append((st, replay, expert, hyper, draw_batch(cfg, replay, expert, B, seed=1900 + j)))
+    owner = [reps.index(a) if a in reps else a % len(reps) for a in range(n)]
+    probs = [base[owner[a]] for a in range(n)]
+    rows = [pop.pack_rows(p[1]["s"], p[1]["a"], p[1]["r"], p[1]["sp"], p[1]["d"]) for p in base]
+    for j, a in enumerate(reps):     # representatives through the regular loaders ...
+        st, replay, expert, hyper, _ = base[j]
+        pop.load_agent(a, st, hyper)
+        pop.append_rows(a, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+        pop.set_expert(a, expert["sE"], expert["spE"])
+    for a in range(n):               # ... every other agent is a device-side copy of its representative
+        src = reps[owner[a]]
+        if a == src:
+            continue
+        for k, t in pop.t.items():
+            if k in ("fvp_states",):
+                continue
+            t[a].copy_(t[src])
+        pop._host_size[a], pop._host_start[a] = pop._host_size[src], pop._host_start[src]
+    inject(pop, cfg, probs)
+    pop.update(1, num_timesteps=0, use_device_rng=False)
+    torch.cuda.synchronize()
+    # (a) oracle parity of the representatives
+    Lo = pop.L
+    g_q = pop.debug("g_q").cpu().numpy().reshape(n, 2, Lo.nc_stride)
+    g_a = pop.debug("g_actor").cpu().numpy().reshape(n, Lo.na_stride)
+    losses = pop.losses.cpu().numpy()
+    for j, a in enumerate(reps):
+        o = oracle_update(cfg, base[j])
+        for net, key in ((0, "g_q1"), (1, "g_q2")):
+            ref = np.concatenate([g.numpy().ravel() for g in o[key]])
+            assert rel(g_q[a, net, :ref.size], ref) < TOL, (a, key)
+        ref = np.concatenate([g.numpy().ravel() for g in o["g_actor"]])
+        assert rel(g_a[a, :ref.size], ref) < TOL, (a, "g_actor")
+        for jj, k in enumerate(("L_q1", "L_q2", "L_pi", "mse", "p_loss", "alpha_loss")):
+            assert abs(losses[a, jj] - float(o[k])) <= TOL * max(abs(float(o[k])), 1e-6), (a, k)
+        for name in ("q1", "q2", "t1", "t2", "actor"):      # parameter change of the whole net (all tensors concatenated)
+            got = np.concatenate([np.asarray(w).ravel() for w in pop.get_net(a, name)])
+            new = np.concatenate([w.numpy().ravel() for w in o["new"][name]])
+            old = np.concatenate([np.asarray(w).ravel() for w in base[j][0][name]])
+            assert rel(got, new) < 1e-5, (a, name)
+            assert rel(got - old, new - old) < TOL, (a, name, rel(got - old, new - old))
+    # (b) every agent equals the representative that carries the same problem, bit for bit (same arithmetic in every
+    #     CTA of every wave, no cross-agent interference)
+    for k in ("actor", "q", "qt", "actor_m", "actor_v", "q_m", "q_v", "alpha"):
+        t = pop.t[k].cpu().numpy()
+        for a in range(n):
+            assert np.array_equal(t[a], t[reps[owner[a]]]), (k, a)
+    assert np.array_equal(losses, losses[[reps[o] for o in owner]])
+    pop.close()
+
+
+def test_halfcheetah_plain_sac_relu_tcgen05():
+    cfg = NetCfg(S=17, A=6, num_models=0)        # BASELINE configs[1]: plain SAC, 2x256 relu
+    pop, probs = build(cfg, n_agents=3, B=256, E=0, N=1500, seed=52, gemm_mode=L.GEMM_TCGEN05_BF16X3, use_graph=True)
+    w = compare_update(pop, cfg, probs)
+    pop.close()
+    bad = {k: v for k, v in w.items() if v > TOL and not k.startswith("oracle32") and k not in ("mse",)}
+    assert not bad, bad
+
+
+def test_hopper_saceo_tcgen05_graph():
+    cfg = NetCfg(S=11, A=3)                       # BASELINE configs[0] shape on the benchmarked engine
+    pop, probs = build(cfg, n_agents=3, B=256, E=20, N=1500, seed=77, gemm_mode=L.GEMM_TCGEN05_BF16X3, use_graph=True)
+    w = compare_update(pop, cfg, probs)
+    pop.close()
+    bad = {k: v for k, v in w.items() if v > TOL and not k.startswith("oracle32")}
+    assert not bad, bad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="data-parallel mode needs 2 GPUs")
+def test_data_parallel_two_gpus_2x256():
+    env = dict(os.environ, SACEO_DP_WIDE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "dp_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

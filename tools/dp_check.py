@@ -14,12 +14,19 @@ from tests.helpers import rel, spec_from_cfg
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-cfg = NetCfg(S=11, A=3, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(64, 64))
-B, E, N = 64, 8, 400
+WIDE = os.environ.get("SACEO_DP_WIDE") == "1"     # reference sizes on the tcgen05 engine (tests/test_gpu_tc_parity.py)
+if WIDE:
+    cfg = NetCfg(S=27, A=8)
+    B, E, N = 256, 20, 1200
+else:
+    cfg = NetCfg(S=11, A=3, actor_hidden=(64, 64), critic_hidden=(64, 64), model_hidden=(64, 64))
+    B, E, N = 64, 8, 400
 st, replay, expert, hyper = make_problem(cfg, B, E, N, seed=21, perturb=0.05)
 hyper["eps"] = 0.25
 full = draw_batch(cfg, replay, expert, B, seed=22)
-pop = Population(spec_from_cfg(cfg, 1, B // world, E, N, device=local))
+from sac_expert_b200 import lib as _lib
+pop = Population(spec_from_cfg(cfg, 1, B // world, E, N, device=local,
+                               gemm_mode=_lib.GEMM_TCGEN05_BF16X3 if WIDE else _lib.GEMM_FP32_SIMT))
 pop.load_agent(0, st, hyper)
 pop.append_rows(0, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
 pop.set_expert(0, expert["sE"], expert["spE"])
