@@ -85,7 +85,9 @@ typedef struct saceo_config {
   int32_t reserved[8];        /* tuning switches, 0 = default: [0] tcgen05 tile variant (0: 128x256 tile, 1: 128x128 2 CTAs/SM,
                                  2: force the register-staged kernel); [1] != 0 disables the fused 3-layer forward kernel;
                                  [2] != 0 disables the fused backward-chain kernel; [3] != 0 disables the fused model-term kernel;
-                                 [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path */
+                                 [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path;
+                                 [5] != 0 disables the warp-specialised TMA-fed fused kernels and their weight planes
+                                 (round-1 fused kernels are used instead) */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */
@@ -140,6 +142,13 @@ int saceo_query_layout(const saceo_config *cfg, saceo_layout *out);
 int saceo_create(const saceo_config *cfg, saceo_ctx **out);
 int saceo_destroy(saceo_ctx *ctx);
 int saceo_bind(saceo_ctx *ctx, const saceo_tables *tables);
+
+/* The tcgen05 engine keeps fp16 hi/lo operand images ("weight planes") of the actor / q / qt tables in its workspace;
+ * every kernel of the library that updates a parameter (Adam, Polyak, the trust-region step) keeps them current.  A
+ * caller that writes into those tables itself (set_weights, checkpoint restore, torch ops on the tensors) must call
+ * this afterwards; the images are rebuilt before the next use.  saceo_bind() implies it.  Replaces nothing in the
+ * reference (tf.Variable.assign has no such side state); it is the cost of never converting a weight inside a pass. */
+int saceo_weights_changed(saceo_ctx *ctx);
 
 /* TrajectoryBuffer.get_offmodel_info / get_model_info (common/buffers.py:107-144): for the SAME
  * int64 indices (device, [n_agents, B], logical row numbers) writes exact copies of the rows:

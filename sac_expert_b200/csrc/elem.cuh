@@ -8,6 +8,7 @@
 #include "../../include/saceo.h"
 #include "gemm_simt.cuh"
 #include "rng.cuh"
+#include "planes.cuh"
 
 namespace saceo {
 
@@ -473,7 +474,10 @@ __global__ void k_lsv_reduce(KCtx c, int nrows) {
 __global__ void k_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                        const float* __restrict__ g, float* __restrict__ target,
                        const float* __restrict__ lrt, const float* __restrict__ hyper, int hyper_stride,
-                       int opt0, long long n, long long stride, int nnet, int do_polyak) {
+                       int opt0, long long n, long long stride, int nnet, int do_polyak,
+                       uint8_t* __restrict__ planes, uint8_t* __restrict__ tplanes, int K0) {
+  // planes / tplanes (nullable): fp16 hi/lo weight-plane images of theta / target (planes.cuh), one image per
+  // (agent, net), kept current here so that no forward / backward pass ever converts a weight again
   // one float4 (4 consecutive parameters) per thread: every table row is 128-byte aligned (strides are multiples of 32)
   const int agent = blockIdx.z, net = blockIdx.y;
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -504,6 +508,11 @@ __global__ void k_adam(float* __restrict__ theta, float* __restrict__ m, float* 
   *reinterpret_cast<float4*>(v + o) = make_float4(vi[0], vi[1], vi[2], vi[3]);
   *reinterpret_cast<float4*>(theta + o) = make_float4(th[0], th[1], th[2], th[3]);
   if (do_polyak) *reinterpret_cast<float4*>(target + o) = make_float4(tg[0], tg[1], tg[2], tg[3]);
+  if (planes) {
+    const long long ib = ((long long)agent * nnet + net) * ws_image_bytes(K0);
+    ws_planes_store4(planes + ib, K0, i4, th);
+    if (do_polyak && tplanes) ws_planes_store4(tplanes + ib, K0, i4, tg);
+  }
 }
 
 // temperature step + loss bookkeeping (SAC_expert.py:341-356).  grid: (n_agents), block 256

@@ -16,6 +16,7 @@
 #include "fvp.cuh"
 #include "trpo.cuh"
 #include "tc_gemm.cuh"
+#include "mlp_ws.cuh"
 #include "model_term.cuh"
 #include "model_fit.cuh"
 #include "pair_gemm.cuh"
@@ -42,6 +43,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 struct NetD {            // one (population of) MLP(s) in the flat Keras layout
   const float* theta; long long sa, sn; int nnet;
   int in, h1, h2, out, act0, act1;
+  const uint8_t* planes = nullptr; long long pa = 0, pn = 0;   // fp16 hi/lo weight-plane images (mlp_ws.cuh), bytes per agent / net
   long long oW0() const { return 0; }
   long long ob0() const { return (long long)in * h1; }
   long long oW1() const { return ob0() + h1; }
@@ -62,6 +64,9 @@ struct saceo_ctx {
   long long* idx_stage = nullptr;
   float* dbpart = nullptr;             // per-tile bias-gradient partials of the fused backward kernel
   long long dbpart_cap = 0;            // floats; a launch that needs more falls back to the ones-row bias path
+  // weight-plane images maintained by k_adam / k_planes_build (warp-specialised fused kernels, mlp_ws.cuh)
+  uint8_t *pl_actor = nullptr, *pl_q = nullptr, *pl_qt = nullptr;
+  int planes_dirty = 3;                // bit 0: actor image stale, bit 1: critic / target images stale
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -202,6 +207,15 @@ static void carve(saceo_ctx* x, char* base) {
     x->dbpart = b.get<float>("dbpart", x->dbpart_cap);
   }
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
+  x->pl_actor = x->pl_q = x->pl_qt = nullptr;
+  if (c.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && c.reserved[5] == 0) {
+    if (c.actor_hidden[0] == FW_H && c.actor_hidden[1] == FW_H)
+      x->pl_actor = b.get<uint8_t>("pl_actor", n * ws_image_bytes(S));
+    if (c.critic_hidden[0] == FW_H && c.critic_hidden[1] == FW_H) {
+      x->pl_q = b.get<uint8_t>("pl_q", n * 2 * ws_image_bytes(SA));
+      x->pl_qt = b.get<uint8_t>("pl_qt", n * 2 * ws_image_bytes(SA));
+    }
+  }
   x->idx_stage = b.get<long long>("idx_stage", n * B);
   // Fisher-vector / CG workspace
   FvpWs& f = x->f;
@@ -292,6 +306,7 @@ static int create_fill(saceo_ctx* x, const saceo_config* cfg) {
   }
   CU(tc_gemm_init());
   CU(mlp_fwd_tc_init());
+  CU(mlp_ws_init());
   CU(model_term_init());
   return 0;
 }
@@ -316,6 +331,7 @@ extern "C" int saceo_bind(saceo_ctx* x, const saceo_tables* t) {
   x->k.T = *t;
   x->k.expert_s = t->expert_s; x->k.expert_sp = t->expert_sp;
   x->bound = true;
+  x->planes_dirty = 3;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j)
     if (x->graph[i][j]) { cudaGraphExecDestroy(x->graph[i][j]); x->graph[i][j] = nullptr; }
   return 0;
@@ -329,6 +345,33 @@ extern "C" void* saceo_debug_ptr(saceo_ctx* x, const char* name, int64_t* bytes_
   return it->second.first;
 }
 extern "C" int64_t saceo_launch_count(const saceo_ctx* x) { return x ? x->launches : 0; }
+
+// The fp16 hi/lo weight-plane images follow the fp32 tables: k_adam keeps them current for everything the library
+// itself updates; after a bind or an external write (saceo_weights_changed) they are rebuilt before the next use.
+extern "C" int saceo_weights_changed(saceo_ctx* x) {
+  if (!x) return fail(SACEO_E_INVALID, "null ctx");
+  x->planes_dirty = 3;
+  return 0;
+}
+static int ensure_planes(saceo_ctx* x, cudaStream_t st) {
+  if (!x->planes_dirty || !x->bound) return 0;
+  const saceo_config& c = x->cfg; const int n = c.n_agents;
+  auto items = [](int K0) { return (((K0 + 31) / 32) * 32 + 256) * 32; };
+  if (x->pl_actor && (x->planes_dirty & 1)) {
+    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S), 256), n), 256, 0, st, x->k.T.actor, x->L.na_stride, x->pl_actor, c.S);
+  }
+  if (x->pl_q && (x->planes_dirty & 2)) {
+    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st, x->k.T.q, x->L.nc_stride, x->pl_q, c.S + c.A);
+    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st, x->k.T.qt, x->L.nc_stride, x->pl_qt, c.S + c.A);
+  }
+  x->planes_dirty = 0;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(SACEO_E_CUDA, "plane build failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static unsigned long long* g_ws_dbg = nullptr;
+static int g_ws_sel = 0, g_ws_count = 0;      // test-only: which warp-specialised launch (ordinal since the last set) stamps its phases
 
 // ------------------------------------------------------------------------------------------
 // GEMM dispatch
@@ -406,6 +449,21 @@ static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lon
                        int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
                        long long sOa, long long sOn, cudaStream_t st, bool save_h = true) {
   int row0 = 0;
+  if (n.planes && x->cfg.reserved[1] == 0 && mlp_fwd_ws_eligible(n.h1, n.h2, n.out, n.in, n.theta, n.sa, n.sn)) {
+    // warp-specialised kernel on the TMA-fed weight planes: every row (partial tiles are masked)
+    FwdW f{};
+    f.X = X; f.ldx = ldx; f.sXa = sXa; f.sXn = sXn;
+    f.theta = n.theta; f.sTa = n.sa; f.sTn = n.sn;
+    f.planes = n.planes; f.sPa = n.pa; f.sPn = n.pn;
+    f.H1 = save_h ? H1 : nullptr; f.H2 = save_h ? H2 : nullptr;
+    f.sHa = (long long)n.nnet * rowsAllocH * n.h1; f.sHn = rowsAllocH * n.h1;
+    f.Out = Out; f.ldo = ldo; f.sOa = sOa; f.sOn = sOn;
+    f.rows = rows; f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
+    if (mlp_fwd_ws_launch(f, x->cfg.n_agents, st) != cudaSuccess) return fail(SACEO_E_CUDA, "fused forward launch failed");
+    count_launch(x, "k_mlp_fwd_ws", st);
+    return 0;
+  }
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[1] == 0 &&
       mlp_fwd_tc_eligible(n.h1, n.h2, n.out, rows, n.theta, n.sa, n.sn, n.in)) {
     int tiles = rows / TC_BM;
@@ -445,6 +503,29 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   GemmP p{};
   // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
   bool fused = false, bias_done = false;
+  if (n.planes && x->cfg.reserved[2] == 0 &&
+      mlp_bwd_ws_eligible(n.h1, n.h2, out_cols, n.out, dXa != nullptr, A_cols, n.theta, n.sa, n.sn)) {
+    BwdW f{};
+    f.dOut = dOut; f.ldd = ldd; f.sDa = sDa; f.sDn = sDn; f.kout = out_cols;
+    f.theta = n.theta; f.sTa = n.sa; f.sTn = n.sn; f.K0 = n.in; f.nout = n.out;
+    f.planes = n.planes; f.sPa = n.pa; f.sPn = n.pn;
+    f.H1 = H1; f.H2 = H2; f.sHa = sH1a; f.sHn = sH1n;
+    f.dH2 = grads ? dH2 : nullptr; f.dH1 = grads ? dH1 : nullptr;
+    f.dXa = dXa; f.s_cols = S_cols; f.a_cols = A_cols; f.sXa = sXaA; f.sXn = sXaN;
+    f.rows = rows; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
+    const int tiles = (rows + TC_BM - 1) / TC_BM;
+    const bool db_fits = (long long)na * n.nnet * tiles * 2 * FW_H <= x->dbpart_cap;
+    f.dbpart = (grads && x->dbpart && db_fits && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
+    f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
+    if (mlp_bwd_ws_launch(f, na, st) != cudaSuccess) return fail(SACEO_E_CUDA, "fused backward launch failed");
+    count_launch(x, "k_mlp_bwd_ws", st);
+    fused = true;
+    if (f.dbpart) {
+      k_bias_finish<<<na * n.nnet, 2 * FW_H, 0, st>>>(f.dbpart, tiles, grads, sGa, sGn, n.nnet, n.ob1(), n.ob0());
+      count_launch(x, "k_bias_finish", st);
+      bias_done = true;
+    }
+  } else
   if (x->cfg.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && x->cfg.reserved[2] == 0 && n.h1 == FW_H && n.h2 == FW_H &&
       out_cols >= 1 && out_cols <= 64 && rows >= TC_BM && (rows % TC_BM == 0 || rows % TC_BM >= 16) &&
       (!dXa || A_cols <= 32) && ((reinterpret_cast<uintptr_t>(n.theta) & 15) == 0) && ((n.sa & 3) == 0) && ((n.sn & 3) == 0)) {
@@ -524,13 +605,17 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
 
 static NetD actor_net(const saceo_ctx* x) {
   const saceo_config& c = x->cfg;
-  return NetD{x->k.T.actor, x->L.na_stride, 0, 1, c.S, c.actor_hidden[0], c.actor_hidden[1], x->L.Ao,
-              c.actor_act[0], c.actor_act[1]};
+  NetD d{x->k.T.actor, x->L.na_stride, 0, 1, c.S, c.actor_hidden[0], c.actor_hidden[1], x->L.Ao,
+         c.actor_act[0], c.actor_act[1]};
+  d.planes = x->pl_actor; d.pa = ws_image_bytes(c.S); d.pn = 0;
+  return d;
 }
 static NetD critic_net(const saceo_ctx* x, bool target) {
   const saceo_config& c = x->cfg;
-  return NetD{target ? x->k.T.qt : x->k.T.q, 2 * x->L.nc_stride, x->L.nc_stride, 2, c.S + c.A,
-              c.critic_hidden[0], c.critic_hidden[1], 1, c.critic_act[0], c.critic_act[1]};
+  NetD d{target ? x->k.T.qt : x->k.T.q, 2 * x->L.nc_stride, x->L.nc_stride, 2, c.S + c.A,
+         c.critic_hidden[0], c.critic_hidden[1], 1, c.critic_act[0], c.critic_act[1]};
+  d.planes = target ? x->pl_qt : x->pl_q; d.pn = ws_image_bytes(c.S + c.A); d.pa = 2 * d.pn;
+  return d;
 }
 static NetD model_net(const saceo_ctx* x, int nnet) {
   const saceo_config& c = x->cfg;
@@ -577,7 +662,7 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
 static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
   const KCtx& k = x->k;
   LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.nc, 4), 256), 2, k.n_agents), 256, 0, st, k.T.q, k.T.q_m, k.T.q_v, k.g_q, k.T.qt,
-         k.lrt, k.T.hyper, x->L.hyper_stride, 0, x->L.nc, x->L.nc_stride, 2, do_polyak);
+         k.lrt, k.T.hyper, x->L.hyper_stride, 0, x->L.nc, x->L.nc_stride, 2, do_polyak, x->pl_q, x->pl_qt, k.S + k.A);
   return check_launch();
 }
 
@@ -666,7 +751,8 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
 static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
   const KCtx& k = x->k;
   LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.na, 4), 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
-         k.g_actor, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0);
+         k.g_actor, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0,
+         x->pl_actor, (uint8_t*)nullptr, k.S);
   return check_launch();
 }
 
@@ -716,6 +802,7 @@ extern "C" int saceo_update(saceo_ctx* x, int32_t n_steps, int64_t num_timesteps
   if (n_steps < 1) return fail(SACEO_E_INVALID, "n_steps must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   const int rng = use_device_rng == 2 ? 2 : (use_device_rng ? 1 : 0);   // 2: device noise/permutation, indices already in place
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   if (rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, x->k, (unsigned long long)seed);
   for (int i = 0; i < n_steps; ++i) {
     const int pol = ((num_timesteps + i) % x->cfg.target_update_int) == 0 ? 1 : 0;
@@ -753,6 +840,7 @@ extern "C" int saceo_bc_update(saceo_ctx* x, int32_t n_steps, int32_t use_device
   if (x->cfg.num_models < 1) return fail(SACEO_E_INVALID, "behaviour cloning needs num_models >= 1");
   if (n_steps < 1) return fail(SACEO_E_INVALID, "n_steps must be >= 1");
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   if (use_device_rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, k, (unsigned long long)seed);
   for (int i = 0; i < n_steps; ++i) {
     LAUNCH(x, k_bc_begin, cdiv(k.n_agents, 128), 128, 0, st, k, use_device_rng ? 1 : 0);
@@ -778,6 +866,7 @@ extern "C" int saceo_profile_step(saceo_ctx* x, int64_t num_timesteps, int32_t u
   cudaStream_t st = (cudaStream_t)stream;
   const int rng = use_device_rng == 2 ? 2 : (use_device_rng ? 1 : 0);
   const int pol = (num_timesteps % x->cfg.target_update_int) == 0 ? 1 : 0;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   if (rng) LAUNCH(x, k_set_seed, 1, 1, 0, st, x->k, (unsigned long long)seed);
   cudaEvent_t e0; CU(cudaEventCreate(&e0));
   x->prof = true; x->prof_n = 0;
@@ -840,6 +929,7 @@ extern "C" int saceo_update_phase(saceo_ctx* x, int32_t phase, int64_t num_times
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
   int rc;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   switch (phase) {
     case 0:
       LAUNCH(x, k_step_begin, dim3(cdiv(k.n_agents * 4, 128)), 128, 0, st, k, 0);
@@ -872,6 +962,7 @@ extern "C" int saceo_actor_forward(saceo_ctx* x, const float* obs, int32_t rows,
   if (!x || !obs || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   NetD an = actor_net(x);
   // expert rows would be routed to the model input: use only the first B ("main") rows per chunk
   for (int r0 = 0; r0 < rows; r0 += k.B) {
@@ -891,6 +982,7 @@ extern "C" int saceo_critic_forward(saceo_ctx* x, int32_t which, const float* ob
   if (!x || !obs || !act || !q_out || rows < 1) return fail(SACEO_E_INVALID, "bad argument");
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k; const int n = k.n_agents;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   NetD qn = critic_net(x, which != 0);
   for (int r0 = 0; r0 < rows; r0 += k.B) {
     const int nr = rows - r0 < k.B ? rows - r0 : k.B;
@@ -1007,6 +1099,7 @@ extern "C" int saceo_model_fit(saceo_ctx* x, int32_t n_steps, const int64_t* idx
 // Fisher-vector product and conjugate gradient (trpo.py:200-227, update_utils.py:4-24)
 // ------------------------------------------------------------------------------------------
 static int fvp_prepare(saceo_ctx* x, cudaStream_t st) {
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
   const KCtx& k = x->k; const FvpWs& f = x->f; const int n = k.n_agents, N = f.N;
   NetD an = actor_net(x);
   LAUNCH(x, k_stage_obs, dim3(cdiv((long long)N * k.S, 256), n), 256, 0, st, k, k.T.fvp_states, N, 0, N, f.X, k.S,
@@ -1129,7 +1222,8 @@ extern "C" int saceo_actor_adam(saceo_ctx* x, const float* grad, void* stream) {
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
   LAUNCH(x, k_bc_begin, dim3(cdiv(k.n_agents, 128)), 128, 0, st, k, 0);
   LAUNCH(x, k_adam, dim3(cdiv(cdiv(x->L.na, 4), 256), 1, k.n_agents), 256, 0, st, k.T.actor, k.T.actor_m, k.T.actor_v,
-         grad, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0);
+         grad, (float*)nullptr, k.lrt, k.T.hyper, x->L.hyper_stride, 2, x->L.na, x->L.na_stride, 1, 0,
+         x->pl_actor, (uint8_t*)nullptr, k.S);
   return check_launch();
 }
 
@@ -1150,6 +1244,7 @@ extern "C" int saceo_actor_step(saceo_ctx* x, const float* theta_ref, const floa
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
   LAUNCH(x, k_actor_step, dim3(cdiv(x->L.na, 256), k.n_agents), 256, 0, st, k, theta_ref, dir, scale);
+  x->planes_dirty |= 1;        // theta written outside k_adam: the weight planes are rebuilt before their next use
   return check_launch();
 }
 
@@ -1158,6 +1253,8 @@ extern "C" int saceo_actor_step(saceo_ctx* x, const float* theta_ref, const floa
 // ------------------------------------------------------------------------------------------
 // test-only: per-CTA phase timestamps of the tcgen05 streaming kernel (dbg = device buffer, 8 u64 per CTA)
 extern "C" int saceo_test_set_tc_debug(void* dbg) { g_tc_dbg = (unsigned long long*)dbg; return 0; }
+// test-only: the sel-th warp-specialised fused launch from now on writes 16 phase stamps per CTA into dbg
+extern "C" int saceo_test_set_ws_debug(void* dbg, int32_t sel) { g_ws_dbg = (unsigned long long*)dbg; g_ws_sel = sel; g_ws_count = 0; return 0; }
 
 extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int32_t N, int32_t K, int32_t transA,
                                int32_t transB, const float* A, const float* Bm, float* C, void* stream) {

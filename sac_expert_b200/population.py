@@ -49,6 +49,7 @@ class PopulationSpec:
     fuse_backward: bool = True     # fused tcgen05 gradient chain dOut -> dH2 -> dH1 -> dXa
     fuse_model: bool = True        # fused expert-observation term (model forward + MSE + backward to action)
     use_graph: bool = True         # one update = one CUDA-graph replay
+    ws_kernels: bool = True        # warp-specialised TMA-fed fused kernels on optimiser-maintained weight planes (round 2)
     device: int = 0
 
     def to_config(self) -> _l.Config:
@@ -81,6 +82,7 @@ class PopulationSpec:
         c.reserved[1] = 0 if self.fuse_forward else 1
         c.reserved[2] = 0 if self.fuse_backward else 1
         c.reserved[3] = 0 if self.fuse_model else 1
+        c.reserved[5] = 0 if self.ws_kernels else 1
         return c
 
 
@@ -135,6 +137,31 @@ class _DevBuf:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+class _Tables(dict):
+    """The per-agent device tables by name.  Handing out a weight table (``actor``, ``q``, ``qt``) may be followed by a
+    write the library cannot see (``tensor.copy_``, indexing assignment), so every such access marks the library's
+    fp16 weight-plane images stale; they are rebuilt before the next kernel that reads them (``saceo_weights_changed``).
+    The hot loop never looks the tables up, so it never pays for this."""
+    _WEIGHTS = ("actor", "q", "qt")
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.dirty = True
+
+    def __getitem__(self, key):
+        if key in self._WEIGHTS:
+            self.dirty = True
+        return super().__getitem__(key)
+
+    def items(self):
+        self.dirty = True
+        return super().items()
+
+    def values(self):
+        self.dirty = True
+        return super().values()
+
+
 class Population:
     def __init__(self, spec: PopulationSpec):
         if not torch.cuda.is_available():
@@ -147,7 +174,7 @@ class Population:
         self.stream = torch.cuda.Stream(self.dev)
         n, L = spec.n_agents, self.L
         z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)
-        self.t: Dict[str, torch.Tensor] = dict(
+        self.t: Dict[str, torch.Tensor] = _Tables(
             actor=z(n, L.na_stride), actor_m=z(n, L.na_stride), actor_v=z(n, L.na_stride),
             q=z(n, 2, L.nc_stride), q_m=z(n, 2, L.nc_stride), q_v=z(n, 2, L.nc_stride), qt=z(n, 2, L.nc_stride),
             model=z(n, 2, L.nm_stride),
@@ -201,6 +228,9 @@ class Population:
             pass
 
     def _enter(self):
+        if self.t.dirty:          # a weight table was handed out since the last call: the weight planes may be stale
+            self.lib.saceo_weights_changed(self.ctx)
+            self.t.dirty = False
         self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         return self.stream.cuda_stream
 
