@@ -31,11 +31,12 @@
 
 namespace saceo {
 
-constexpr int WS_NT = 320, WS_NEPI = 256;
-constexpr int WS_NST = 4, WS_RING = WS_NST * WS_STAGE;
-constexpr int WS_AUX = 49152;                 // X planes (fwd layer 0) | fp32 skinny weights | reductions / column sums
-constexpr int WS_PSTR = 36;
-constexpr int WS_PATCH = 8 * 32 * WS_PSTR * 4;
+constexpr int WS_NEW = 16;                    // conversion / epilogue warps: 4 TMEM lane quarters x 4 column groups of 64
+constexpr int WS_NEPI = WS_NEW * 32, WS_NT = WS_NEPI + 64;    // + TMA producer warp + MMA / TMEM-allocator warp
+constexpr int WS_NST = 3, WS_RING = WS_NST * WS_STAGE;
+constexpr int WS_AUX = 49152;                 // [0, WS_RED): X planes (fwd layer 0) | fp32 skinny weights; [WS_RED, ..): reductions / column sums
+constexpr int WS_PATCH1 = 32 * 32 * 4;        // warp-private 32 x 32 float transposition patch, 16-byte chunks XOR (row & 7)
+constexpr int WS_PATCH = WS_NEW * WS_PATCH1;
 constexpr int WS_MAIN = WS_RING + WS_AUX + WS_PATCH;
 constexpr int WS_BYTES = WS_MAIN + 1024 + 256;
 constexpr int WS_RED = 40960;                 // offset inside AUX of the 8 KB reduction / column-sum scratch
@@ -52,7 +53,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps only
 // MN-major SWIZZLE_128B descriptor of a weight-plane stage: LBO = 4096 (next 64-wide n atom), SBO = 1024 (next 8 k rows)
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -90,18 +91,23 @@ __global__ void k_planes_build(const float* __restrict__ theta, long long stride
 // ------------------------------------------------------------------------------------------
 // shared pieces of the epilogues
 // ------------------------------------------------------------------------------------------
+// warp-private patch addressing: row r (0..31), float column c (0..31): chunk (c>>2) XOR (r&7); conflict-free for the
+// lane-per-row float4 accesses, the 8-lanes-per-row float4 accesses and the lane-per-column scalar reads alike
+__device__ __forceinline__ uint32_t ws_pa(uint32_t patch, int r, int c) {
+  return patch + (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
+}
 // v (this lane's row, 32 columns) -> global tile rows through the warp-private patch (whole 128-byte segments per request)
 __device__ __forceinline__ void ws_store_rows(uint32_t patch, const uint32_t (&v)[32], float* __restrict__ G, int rbase,
                                               int rows, int col, int lane) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sts128(patch + (uint32_t)(lane * WS_PSTR + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  for (int j = 0; j < 8; ++j) sts128(ws_pa(patch, lane, 4 * j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
   __syncwarp();
   const int lr = lane >> 3, lc = (lane & 7) * 4;
 #pragma unroll
   for (int rr = 0; rr < 32; rr += 4) {
     const int r = rr + lr, grow = rbase + r;
     if (grow < rows) {
-      const float4 t4 = lds128(patch + (uint32_t)(r * WS_PSTR + lc) * 4);
+      const float4 t4 = lds128(ws_pa(patch, r, lc));
       *reinterpret_cast<float4*>(G + (long long)grow * FW_H + col + lc) = t4;
     }
   }
@@ -111,10 +117,33 @@ __device__ __forceinline__ void ws_colsum(uint32_t patch, uint32_t cs, int q, in
   const int nvalid = rows - rbase;
   float s = 0.f;
 #pragma unroll 8
-  for (int r = 0; r < 32; ++r) { const float t = lds32(patch + (uint32_t)(r * WS_PSTR + lane) * 4); s += r < nvalid ? t : 0.f; }
+  for (int r = 0; r < 32; ++r) { const float t = lds32(ws_pa(patch, r, lane)); s += r < nvalid ? t : 0.f; }
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(cs + (uint32_t)(q * FW_H + col + lane) * 4), "f"(s) : "memory");
 }
-// saved activations [32 rows x 32 cols] of this warp -> aux (this lane's row), read row-wise through the patch
+// saved activations [32 rows x 32 cols] of this warp, two-phase: the global loads are issued early (before a barrier
+// wait / during the previous chunk's math), the transposition through the patch happens when the values are needed
+__device__ __forceinline__ void ws_rows_issue(const float* __restrict__ Hs, int rbase, int rows, int col, int lane, float4 (&t)[8]) {
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int grow = rbase + 4 * i + lr;
+    t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < rows) t[i] = __ldg(reinterpret_cast<const float4*>(Hs + (long long)grow * FW_H + col + lc));
+  }
+}
+__device__ __forceinline__ void ws_rows_commit(uint32_t patch, int lane, const float4 (&t)[8], float (&aux)[32]) {
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    sts128(ws_pa(patch, 4 * i + lr, lc), make_uint4(__float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z), __float_as_uint(t[i].w)));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t4 = lds128(ws_pa(patch, lane, 4 * j));
+    aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w;
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void ws_load_rows(uint32_t patch, const float* __restrict__ Hs, int rbase, int rows, int col, int lane,
                                              float (&aux)[32]) {
   const int lr = lane >> 3, lc = (lane & 7) * 4;
@@ -123,12 +152,12 @@ __device__ __forceinline__ void ws_load_rows(uint32_t patch, const float* __rest
     const int r = rr + lr, grow = rbase + r;
     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grow < rows) t4 = __ldg(reinterpret_cast<const float4*>(Hs + (long long)grow * FW_H + col + lc));
-    sts128(patch + (uint32_t)(r * WS_PSTR + lc) * 4, make_uint4(__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w)));
+    sts128(ws_pa(patch, r, lc), make_uint4(__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w)));
   }
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 t4 = lds128(patch + (uint32_t)(lane * WS_PSTR + 4 * j) * 4);
+    const float4 t4 = lds128(ws_pa(patch, lane, 4 * j));
     aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w;
   }
   __syncwarp();
@@ -167,6 +196,52 @@ __device__ __forceinline__ void ws_store_wrow(uint32_t dst, int j, int np, const
   for (int c4 = 0; c4 < NR / 4; ++c4)
     if (c4 * 4 < np) sts128f(dst + (uint32_t)(j * np + 4 * c4) * 4, w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 32 fp32 values x scale -> fp16 hi/lo A-operand columns [c0, c0+16) hi, [c0+16, c0+32) lo, 16 values at a time (registers)
+__device__ __forceinline__ void ws_split_store(uint32_t taddr, const uint32_t (&v)[32], float scale) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x0 = __uint_as_float(v[16 * h + 2 * j]) * scale, x1 = __uint_as_float(v[16 * h + 2 * j + 1]) * scale;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(x1), "f"(x0));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    }
+    tmem_st8(taddr + 8 * h, hi);
+    tmem_st8(taddr + 16 + 8 * h, lo);
+  }
+}
+// v *= s * act'(h) with h = this lane's row of the saved activations parked in the patch by ws_rows_commit_p
+template <int ACT>
+__device__ __forceinline__ void ws_mul_dact_p(uint32_t (&v)[32], uint32_t patch, int lane, float s) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 h = lds128(ws_pa(patch, lane, 4 * j));
+    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) * s * dact_from_out(ACT, h.x));
+    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) * s * dact_from_out(ACT, h.y));
+    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) * s * dact_from_out(ACT, h.z));
+    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) * s * dact_from_out(ACT, h.w));
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void ws_mul_dact_p_rt(int act, uint32_t (&v)[32], uint32_t patch, int lane, float s) {
+  if (act == ACT_RELU) ws_mul_dact_p<ACT_RELU>(v, patch, lane, s);
+  else if (act == ACT_TANH) ws_mul_dact_p<ACT_TANH>(v, patch, lane, s);
+  else ws_mul_dact_p<ACT_ELU>(v, patch, lane, s);
+}
+// the patch half of ws_rows_commit: rows in flight -> patch (row-wise), nothing kept in registers
+__device__ __forceinline__ void ws_rows_commit_p(uint32_t patch, int lane, const float4 (&t)[8]) {
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    sts128(ws_pa(patch, 4 * i + lr, lc), make_uint4(__float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z), __float_as_uint(t[i].w)));
+  __syncwarp();
+}
 // fp32 x scale -> fp16 hi/lo pairs (A-operand columns)
 __device__ __forceinline__ void ws_split_f16(const uint32_t (&v)[32], float scale, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
@@ -177,18 +252,20 @@ __device__ __forceinline__ void ws_split_f16(const uint32_t (&v)[32], float scal
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
   }
 }
+// bias: shared-memory address of the 32 bias values of this chunk (staged once per CTA: a global load here would sit
+// on the critical path of every chunk)
 template <int ACT>
-__device__ __forceinline__ void ws_bias_act(uint32_t (&v)[32], const float* __restrict__ bias) {
+__device__ __forceinline__ void ws_bias_act(uint32_t (&v)[32], uint32_t bias) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
+    const float4 b = lds128(bias + j * 16);
     v[4 * j] = __float_as_uint(apply_act(ACT, __uint_as_float(v[4 * j]) + b.x));
     v[4 * j + 1] = __float_as_uint(apply_act(ACT, __uint_as_float(v[4 * j + 1]) + b.y));
     v[4 * j + 2] = __float_as_uint(apply_act(ACT, __uint_as_float(v[4 * j + 2]) + b.z));
     v[4 * j + 3] = __float_as_uint(apply_act(ACT, __uint_as_float(v[4 * j + 3]) + b.w));
   }
 }
-__device__ __forceinline__ void ws_bias_act_rt(int act, uint32_t (&v)[32], const float* __restrict__ bias) {
+__device__ __forceinline__ void ws_bias_act_rt(int act, uint32_t (&v)[32], uint32_t bias) {
   if (act == ACT_RELU) ws_bias_act<ACT_RELU>(v, bias);
   else if (act == ACT_TANH) ws_bias_act<ACT_TANH>(v, bias);
   else ws_bias_act<ACT_ELU>(v, bias);
@@ -216,7 +293,9 @@ __device__ __forceinline__ float ws_row_scale(float bound) {
 
 // ==========================================================================================
 // forward:  h1 = act0(X W0 + b0);  h2 = act1(h1 W1 + b1);  out = h2 W2 + b2        (nn_utils.py:101-136)
-// grid (row tiles, agents * nnet), 320 threads.  NG = ceil(nout / 16) accumulator groups of the output layer.
+// grid (row tiles, agents * nnet), 576 threads.  NG = ceil(nout / 16) accumulator groups of the output layer.
+// Epilogue warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31 of the tile), column group cg = w >> 2 (columns
+// 64cg..64cg+63 = the k group cg of the next layer).
 // ==========================================================================================
 struct FwdW {
   const float* X; int ldx; long long sXa, sXn;
@@ -242,12 +321,12 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2 * WS_NST; ++s) mbar_init(bar(s), 1);
-    mbar_init(bar(WB_XFULL), 8); mbar_init(bar(WB_XEMPTY), 1);
+    mbar_init(bar(WB_XFULL), WS_NEW); mbar_init(bar(WB_XEMPTY), 1);
     mbar_init(bar(WB_D0), 1); mbar_init(bar(WB_D1), 1);
     for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == WS_NEW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -257,7 +336,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
   const uint32_t tmem = lds_u32(tslot);
   const uint32_t tP = tmem, tQ = tmem + 256;
 
-  if (warp == 8) {
+  if (warp == WS_NEW) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       const uint8_t* img = f.planes + agent * f.sPa + net * f.sPn;
@@ -270,7 +349,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
       }
       WS_STAMP(11);
     }
-  } else if (warp == 9) {
+  } else if (warp == WS_NEW + 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       int it = 0;
@@ -319,9 +398,9 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
     }
   } else {
     // ------------------------------ conversion + epilogue warps ------------------------------
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cg = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t patch = patch_base + (uint32_t)warp * 32 * WS_PSTR * 4;
+    const uint32_t patch = patch_base + (uint32_t)warp * WS_PATCH1;
     const int rbase = row0 + q * 32, grow = rbase + lane;
     const float* __restrict__ X = f.X + agent * f.sXa + net * f.sXn;
     const float* __restrict__ th = f.theta + agent * f.sTa + net * f.sTn;
@@ -332,8 +411,15 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
     float* Out = f.Out + agent * f.sOa + net * f.sOn;
     if (warp == 0) WS_STAMP(0);
     const int np = (f.nout + 3) & ~3;
-    float w2r[NG * 16];                 // output-layer weight row of hidden unit j = threadIdx.x: in flight during layer 0
-    if (f.nout > 1) ws_load_wrow<NG * 16>(th + oW2, threadIdx.x, f.nout, w2r);
+    // per-CTA constants -> shared memory: b0 | b1 | w2 (single-output nets) | b2
+    const uint32_t cb0 = aux + WS_RED + 2048, cb1 = cb0 + 1024, cw2 = cb1 + 1024, cb2 = cw2 + 1024;
+    if (threadIdx.x < FW_H) {
+      const int t = threadIdx.x;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(cb0 + t * 4), "f"(__ldg(th + ob0 + t)) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(cb1 + t * 4), "f"(__ldg(th + ob1 + t)) : "memory");
+      if (f.nout == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cw2 + t * 4), "f"(__ldg(th + oW2 + t)) : "memory");
+      if (t < f.nout) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cb2 + t * 4), "f"(__ldg(th + ob2 + t)) : "memory");
+    }
     {   // input tile -> fp16 hi/lo K-major planes (A operand of layer 0), one 64-wide k slab at a time
       Slab<TC_BM, WS_NEPI> sx;
       sx.init(X, f.ldx, 1, row0, f.rows);
@@ -346,38 +432,35 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
         if (lane == 0) mbar_arrive(bar(WB_XFULL));
       }
     }
+    epi_bar();                                        // constants visible
     if (warp == 0) WS_STAMP(1);
     // ---- epilogue 0: h1 = act0(D0 + b0) -> fp16 hi/lo in place (A operand of layer 1) [+ saved h1]
     mbar_wait(bar(WB_D0), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) WS_STAMP(2);
 #pragma unroll 1
-    for (int cp = 0; cp < 2; ++cp) {
-      const int col = half * 128 + cp * 64;
-      uint32_t va[32], vb[32], hi[16], lo[16];
-      tmem_ld32_nw(tP + lane_addr + (uint32_t)col, va);
-      tmem_ld32_nw(tP + lane_addr + (uint32_t)(col + 32), vb);
-      tmem_ld_wait();
-      ws_bias_act_rt(f.act0, va, th + ob0 + col);
-      ws_split_f16(va, 1.f, hi, lo);
-      tmem_st16(tP + lane_addr + (uint32_t)col, hi);
-      tmem_st16(tP + lane_addr + (uint32_t)(col + 16), lo);
-      ws_bias_act_rt(f.act0, vb, th + ob0 + col + 32);
-      ws_split_f16(vb, 1.f, hi, lo);
-      tmem_st16(tP + lane_addr + (uint32_t)(col + 32), hi);
-      tmem_st16(tP + lane_addr + (uint32_t)(col + 48), lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(WB_AP + half * 2 + cp));      // the layer-1 MMAs of this 64-wide k group may start
-      if (H1) {
-        ws_store_rows(patch, va, H1, rbase, f.rows, col, lane); __syncwarp();
-        ws_store_rows(patch, vb, H1, rbase, f.rows, col + 32, lane); __syncwarp();
+    for (int c = 0; c < 2; ++c) {
+      const int col = cg * 64 + c * 32;
+      uint32_t v[32];
+      tmem_ld32(tP + lane_addr + (uint32_t)col, v);
+      ws_bias_act_rt(f.act0, v, cb0 + col * 4);
+      ws_split_store(tP + lane_addr + (uint32_t)col, v, 1.f);
+      if (c == 1) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(WB_AP + cg));      // the layer-1 MMAs of this 64-wide k group may start
       }
+      if (H1) { ws_store_rows(patch, v, H1, rbase, f.rows, col, lane); __syncwarp(); }
     }
     if (warp == 0) WS_STAMP(3);
-    // ---- output-layer weights as fp32 [256][np] in AUX (the X planes are dead: every layer-0 MMA has retired)
-    if (f.nout > 1) ws_store_wrow<NG * 16>(aux, threadIdx.x, np, w2r);
+    // ---- output-layer weights as fp32 [256][np] in AUX (the X planes are dead: every layer-0 MMA has retired); the
+    //      loads fly while layer 1 runs
+    if (f.nout > 1 && threadIdx.x < FW_H) {
+      float w2r[NG * 16];
+      ws_load_wrow<NG * 16>(th + oW2, threadIdx.x, f.nout, w2r);
+      ws_store_wrow<NG * 16>(aux, threadIdx.x, np, w2r);
+    }
     epi_bar();
     if (warp == 0) WS_STAMP(4);
     // ---- epilogue 1: h2 = act1(D1 + b1) [+ saved h2]; out = h2 . W2 + b2 on CUDA cores (exact fp32)
@@ -390,10 +473,9 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
     float qacc = 0.f;
     auto head_chunk = [&](uint32_t (&v)[32], int col) {       // out += h2[row, col..col+31] . W2[col..col+31, :]
       if (f.nout == 1) {
-        const float4* wp = reinterpret_cast<const float4*>(th + oW2 + col);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 t4 = __ldg(wp + j);
+          const float4 t4 = lds128(cw2 + (uint32_t)(col + 4 * j) * 4);
           qacc = fmaf(__uint_as_float(v[4 * j]), t4.x, qacc); qacc = fmaf(__uint_as_float(v[4 * j + 1]), t4.y, qacc);
           qacc = fmaf(__uint_as_float(v[4 * j + 2]), t4.z, qacc); qacc = fmaf(__uint_as_float(v[4 * j + 3]), t4.w, qacc);
         }
@@ -414,55 +496,55 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
       }
     };
 #pragma unroll 1
-    for (int cp = 0; cp < 2; ++cp) {
-      const int col = half * 128 + cp * 64;
-      uint32_t va[32], vb[32];
-      tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, va);
-      tmem_ld32_nw(tQ + lane_addr + (uint32_t)(col + 32), vb);
-      tmem_ld_wait();
-      ws_bias_act_rt(f.act1, va, th + ob1 + col);
-      ws_bias_act_rt(f.act1, vb, th + ob1 + col + 32);
-      if (H2) {
-        ws_store_rows(patch, va, H2, rbase, f.rows, col, lane); __syncwarp();
-        ws_store_rows(patch, vb, H2, rbase, f.rows, col + 32, lane); __syncwarp();
-      }
-      head_chunk(va, col);
-      head_chunk(vb, col + 32);
+    for (int c = 0; c < 2; ++c) {
+      const int col = cg * 64 + c * 32;
+      uint32_t v[32];
+      tmem_ld32(tQ + lane_addr + (uint32_t)col, v);
+      ws_bias_act_rt(f.act1, v, cb1 + col * 4);
+      if (H2) { ws_store_rows(patch, v, H2, rbase, f.rows, col, lane); __syncwarp(); }
+      head_chunk(v, col);
     }
     if (warp == 0) WS_STAMP(6);
-    // ---- sum of the two column halves + bias -> Out
+    // ---- fixed-order sum of the four column groups + bias -> Out
+    const uint32_t red = aux + WS_RED;               // [3 groups][128 rows] scratch (one output column at a time is enough for q)
     if (f.nout == 1) {
-      const uint32_t red = aux + WS_RED;
-      if (half == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (uint32_t)(q * 32 + lane) * 4), "f"(qacc) : "memory");
+      if (cg > 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (uint32_t)((cg - 1) * TC_BM + q * 32 + lane) * 4), "f"(qacc) : "memory");
       epi_bar();
-      if (half == 0 && grow < f.rows) Out[(long long)grow * f.ldo] = (qacc + lds32(red + (uint32_t)(q * 32 + lane) * 4)) + __ldg(th + ob2);
+      if (cg == 0 && grow < f.rows) {
+        const uint32_t r = red + (uint32_t)(q * 32 + lane) * 4;
+        Out[(long long)grow * f.ldo] = ((qacc + lds32(r)) + (lds32(r + TC_BM * 4) + lds32(r + 2 * TC_BM * 4))) + lds32(cb2);
+      }
     } else {
-      const uint32_t other = patch_base + (uint32_t)(warp + 4) * 32 * WS_PSTR * 4;     // patch of the warp with the same rows, half 1
+      // groups 1..3 park their partial rows in their patch (column index rotated by the lane: conflict-free), group 0 adds
 #pragma unroll
       for (int r0 = 0; r0 < NG * 16; r0 += 32) {
         if (r0 < f.nout) {
-          if (half == 1) {
+          if (cg > 0) {
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc)
-              if (r0 + cc < NG * 16) asm volatile("st.shared.f32 [%0], %1;" ::"r"(patch + (uint32_t)(lane * WS_PSTR + cc) * 4), "f"(acc[(r0 + cc) < NG * 16 ? r0 + cc : 0]) : "memory");
+              if (r0 + cc < NG * 16) asm volatile("st.shared.f32 [%0], %1;" ::"r"(patch + (uint32_t)(lane * 32 + ((cc + lane) & 31)) * 4), "f"(acc[(r0 + cc) < NG * 16 ? r0 + cc : 0]) : "memory");
           }
           epi_bar();
-          if (half == 0 && grow < f.rows) {
+          if (cg == 0 && grow < f.rows) {
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc) {
-              if (r0 + cc < NG * 16 && r0 + cc < f.nout)
-                Out[(long long)grow * f.ldo + r0 + cc] = (acc[(r0 + cc) < NG * 16 ? r0 + cc : 0] + lds32(other + (uint32_t)(lane * WS_PSTR + cc) * 4)) + __ldg(th + ob2 + r0 + cc);
+              if (r0 + cc < NG * 16 && r0 + cc < f.nout) {
+                const uint32_t o = (uint32_t)(lane * 32 + ((cc + lane) & 31)) * 4;
+                const float p1 = lds32(patch_base + (uint32_t)(warp + 4) * WS_PATCH1 + o), p2 = lds32(patch_base + (uint32_t)(warp + 8) * WS_PATCH1 + o),
+                            p3 = lds32(patch_base + (uint32_t)(warp + 12) * WS_PATCH1 + o);
+                Out[(long long)grow * f.ldo + r0 + cc] = ((acc[(r0 + cc) < NG * 16 ? r0 + cc : 0] + p1) + (p2 + p3)) + lds32(cb2 + (uint32_t)(r0 + cc) * 4);
+              }
             }
           }
           if (r0 + 32 < f.nout) epi_bar();
         }
       }
     }
+    if (warp == 0) WS_STAMP(7);
   }
-  if (warp == 0) WS_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WS_NEW + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
 }
@@ -470,7 +552,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
 // ==========================================================================================
 // backward chain (weights fixed):
 //     dH2 = (dOut W2[:, :kout]^T) * act1'(H2);   dH1 = (dH2 W1^T) * act0'(H1);   dXa = dH1 W0[S:S+A, :]^T
-// grid (row tiles, agents * nnet), 320 threads.  NG = ceil(kout / 16), NA = ceil(a_cols / 16) (0: no dXa).
+// grid (row tiles, agents * nnet), 576 threads.  NG = ceil(kout / 16), NA = ceil(a_cols / 16) (0: no dXa).
 // ==========================================================================================
 struct BwdW {
   const float* dOut; int ldd; long long sDa, sDn; int kout;
@@ -502,7 +584,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == WS_NEW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -512,7 +594,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
   const uint32_t tmem = lds_u32(tslot);
   const uint32_t tP = tmem, tQ = tmem + 256;
 
-  if (warp == 8) {
+  if (warp == WS_NEW) {
     // TMA producer: stage (h, s) = rows i in [128h, 128h+128) of the 64-wide j slab s, K-major: 4 KB pieces (t, plane, s)
     if (lane == 0) {
       const uint8_t* w1 = f.planes + agent * f.sPa + net * f.sPn + (long long)n0 * WS_STAGE;
@@ -526,7 +608,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
                      w1 + (long long)(4 * h + tt) * WS_STAGE + pl * 16384 + sj * 4096, 4096, bar(WB_FULL + s));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WS_NEW + 1) {
     if (lane == 0) {
       for (int it = 0; it < 8; ++it) {          // D1[:, 128h..] (tQ) = dH2' . W1^T, contraction over the j slab sj
         const int h = it >> 2, sj = it & 3, s = it % WS_NST;
@@ -550,9 +632,9 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       }
     }
   } else {
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cg = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t patch = patch_base + (uint32_t)warp * 32 * WS_PSTR * 4;
+    const uint32_t patch = patch_base + (uint32_t)warp * WS_PATCH1;
     const int rbase = row0 + q * 32, grow = rbase + lane;
     const bool rvalid = grow < f.rows;
     const float* __restrict__ dOut = f.dOut + agent * f.sDa + net * f.sDn;
@@ -563,24 +645,27 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     float* dH1 = f.dH1 ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
     float* dH2 = f.dH2 ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
     const bool want_cs = f.dbpart && dH2 && dH1;
-    const bool outer = (f.kout == 1);
     const int kp = (f.kout + 3) & ~3;
-    const uint32_t wmax_s = aux + WS_RED - 256;            // [<=36] column maxima of |W2| (int bit patterns)
+    const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
     if (warp == 0) WS_STAMP(0);
+    float4 hq[8];                                          // saved-activation rows of the next chunk, in flight
+    ws_rows_issue(H2, rbase, f.rows, cg * 64, lane, hq);
     // ---- stage W2[:, :kout] as fp32 [256][kp]; max |W2| over the block bounds every row of dOut . W2^T (row scale)
     if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wmax_s), "r"(0u) : "memory");
-    float d[NG * 16];
-    {
-      float wr[NG * 16];
-      ws_load_wrow<NG * 16>(th + oW2, threadIdx.x, f.nout, wr);          // hidden unit j = threadIdx.x
+    constexpr int ND = NG > 0 ? NG * 16 : 1;               // NG == 0: single output (critics), the first step is an outer product
+    float d[ND];
 #pragma unroll
-      for (int cc = 0; cc < NG * 16; ++cc) d[cc] = (rvalid && cc < f.kout) ? __ldg(dOut + (long long)grow * f.ldd + cc) : 0.f;
-      epi_bar();
+    for (int cc = 0; cc < ND; ++cc) d[cc] = (rvalid && cc < f.kout) ? __ldg(dOut + (long long)grow * f.ldd + cc) : 0.f;
+    epi_bar();
+    if (threadIdx.x < FW_H) {
+      float wr[NG > 0 ? NG * 16 : 4];
+      ws_load_wrow<(NG > 0 ? NG * 16 : 4)>(th + oW2, threadIdx.x, f.nout, wr);          // hidden unit j = threadIdx.x
       float m = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < NG * 16; ++cc) { if (cc >= f.kout) wr[cc] = 0.f; m = fmaxf(m, fabsf(wr[cc])); }
-      if (!outer) ws_store_wrow<NG * 16>(aux, threadIdx.x, kp, wr);
+      for (int cc = 0; cc < (NG > 0 ? NG * 16 : 4); ++cc) { if (cc >= f.kout) wr[cc] = 0.f; m = fmaxf(m, fabsf(wr[cc])); }
+      if (NG > 0) ws_store_wrow<(NG > 0 ? NG * 16 : 4)>(aux, threadIdx.x, kp, wr);
+      else asm volatile("st.shared.f32 [%0], %1;" ::"r"(aux + threadIdx.x * 4), "f"(wr[0]) : "memory");
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       if (lane == 0) atomicMax(reinterpret_cast<int*>(smem_raw + (wmax_s - smem_u32(smem_raw))), __float_as_int(m));
     }
@@ -588,18 +673,23 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     // this row's upstream gradient and its scale: |dH2[row, j]| <= sum_c |dOut[row, c]| * max |W2|
     float bound = 0.f;
 #pragma unroll
-    for (int cc = 0; cc < NG * 16; ++cc) bound += fabsf(d[cc]);
+    for (int cc = 0; cc < ND; ++cc) bound += fabsf(d[cc]);
     bound *= __int_as_float((int)lds_u32(wmax_s));
     const float scale = ws_row_scale(bound), inv_scale = 1.f / scale;
     if (warp == 0) WS_STAMP(1);
 
     // ---- epilogue 0: dH2 = (dOut . W2^T) * act1'(H2) on CUDA cores -> scaled fp16 hi/lo A operand (tP) [+ saved dH2, column sums]
-    auto first_chunk = [&](uint32_t (&v)[32], int col) {
-      if (outer) {
-        const float4* wp = reinterpret_cast<const float4*>(th + oW2 + col);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int col = cg * 64 + c * 32;
+      ws_rows_commit_p(patch, lane, hq);
+      if (c == 0) ws_rows_issue(H2, rbase, f.rows, col + 32, lane, hq);      // chunk 1 flies during the math of chunk 0
+      else ws_rows_issue(H1, rbase, f.rows, cg * 64, lane, hq);              // first H1 chunk of epilogue 1 flies during the MMAs
+      uint32_t v[32];
+      if (NG == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 t4 = __ldg(wp + j);
+          const float4 t4 = lds128(aux + (uint32_t)(col + 4 * j) * 4);
           v[4 * j] = __float_as_uint(d[0] * t4.x); v[4 * j + 1] = __float_as_uint(d[0] * t4.y);
           v[4 * j + 2] = __float_as_uint(d[0] * t4.z); v[4 * j + 3] = __float_as_uint(d[0] * t4.w);
         }
@@ -612,29 +702,20 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
           for (int g4 = 0; g4 < NG * 4; ++g4) {
             if (g4 * 4 < kp) {
               const float4 w = lds128(wrow + g4 * 16);
-              a = fmaf(d[4 * g4], w.x, a); a = fmaf(d[4 * g4 + 1], w.y, a); a = fmaf(d[4 * g4 + 2], w.z, a); a = fmaf(d[4 * g4 + 3], w.w, a);
+              a = fmaf(d[(4 * g4) % ND], w.x, a); a = fmaf(d[(4 * g4 + 1) % ND], w.y, a);
+              a = fmaf(d[(4 * g4 + 2) % ND], w.z, a); a = fmaf(d[(4 * g4 + 3) % ND], w.w, a);
             }
           }
           v[jj] = __float_as_uint(a);
         }
       }
-    };
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int col = half * 128 + c * 32;
-      float hx[32];
-      ws_load_rows(patch, H2, rbase, f.rows, col, lane, hx);
-      uint32_t v[32], hi[16], lo[16];
-      first_chunk(v, col);
-      ws_mul_dact_rt(f.act1, v, hx, 1.f);
-      ws_split_f16(v, scale, hi, lo);
-      tmem_st16(tP + lane_addr + (uint32_t)col, hi);
-      tmem_st16(tP + lane_addr + (uint32_t)(col + 16), lo);
-      if (c & 1) {
+      ws_mul_dact_p_rt(f.act1, v, patch, lane, 1.f);
+      ws_split_store(tP + lane_addr + (uint32_t)col, v, scale);
+      if (c == 1) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(WB_AP + half * 2 + (c >> 1)));
+        if (lane == 0) mbar_arrive(bar(WB_AP + cg));
       }
       if (dH2) {
         ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane);
@@ -647,92 +728,93 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const int ap = (f.a_cols + 3) & ~3;
     if (NA > 0) {
       epi_bar();
-      const int j = threadIdx.x;
-      for (int a = 0; a < ap; ++a) {
-        const float w = a < f.a_cols ? __ldg(th + (long long)(f.s_cols + a) * FW_H + j) : 0.f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(aux + (uint32_t)(j * ap + a) * 4), "f"(w) : "memory");
+      if (threadIdx.x < FW_H) {
+        const int j = threadIdx.x;
+        for (int a = 0; a < ap; ++a) {
+          const float w = a < f.a_cols ? __ldg(th + (long long)(f.s_cols + a) * FW_H + j) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(aux + (uint32_t)(j * ap + a) * 4), "f"(w) : "memory");
+        }
       }
       epi_bar();
     }
     // ---- epilogue 1: dH1 = (D1 / scale) * act0'(H1) [+ saved dH1, column sums]; dXa = dH1 . W0a^T on CUDA cores
     if (warp == 0) WS_STAMP(3);
-    mbar_wait(bar(half ? WB_D1 : WB_D0), 0);
+    mbar_wait(bar(cg >= 2 ? WB_D1 : WB_D0), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) WS_STAMP(4);
-    if (warp == 4) WS_STAMP(12);
+    if (warp == 8) WS_STAMP(12);
     float xa[NA > 0 ? NA * 16 : 1];
 #pragma unroll
     for (int i = 0; i < (NA > 0 ? NA * 16 : 1); ++i) xa[i] = 0.f;
-    auto dxa_chunk = [&](const uint32_t (&v)[32], int col) {
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const float g = __uint_as_float(v[jj]);
-        const uint32_t wrow = aux + (uint32_t)((col + jj) * ap) * 4;
-#pragma unroll
-        for (int g4 = 0; g4 < (NA > 0 ? NA * 4 : 1); ++g4) {
-          if (NA > 0 && g4 * 4 < ap) {
-            const float4 w = lds128(wrow + g4 * 16);
-            xa[4 * g4] = fmaf(g, w.x, xa[4 * g4]); xa[4 * g4 + 1] = fmaf(g, w.y, xa[4 * g4 + 1]);
-            xa[4 * g4 + 2] = fmaf(g, w.z, xa[4 * g4 + 2]); xa[4 * g4 + 3] = fmaf(g, w.w, xa[4 * g4 + 3]);
-          }
-        }
-      }
-    };
 #pragma unroll 1
-    for (int cp = 0; cp < 2; ++cp) {
-      const int col = half * 128 + cp * 64;
-      uint32_t va[32], vb[32];
-      tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, va);
-      tmem_ld32_nw(tQ + lane_addr + (uint32_t)(col + 32), vb);
-      float hx[32];
-      ws_load_rows(patch, H1, rbase, f.rows, col, lane, hx);       // the saved-activation read overlaps the TMEM loads
+    for (int c = 0; c < 2; ++c) {
+      const int col = cg * 64 + c * 32;
+      uint32_t v[32];
+      tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, v);
+      ws_rows_commit_p(patch, lane, hq);
+      if (c == 0) ws_rows_issue(H1, rbase, f.rows, col + 32, lane, hq);
       tmem_ld_wait();
-      ws_mul_dact_rt(f.act0, va, hx, inv_scale);
+      ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
       if (dH1) {
-        ws_store_rows(patch, va, dH1, rbase, f.rows, col, lane);
+        ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane);
         if (want_cs) ws_colsum(patch, cs1, q, rbase, f.rows, col, lane);
         __syncwarp();
       }
-      if (NA > 0) dxa_chunk(va, col);
-      ws_load_rows(patch, H1, rbase, f.rows, col + 32, lane, hx);
-      ws_mul_dact_rt(f.act0, vb, hx, inv_scale);
-      if (dH1) {
-        ws_store_rows(patch, vb, dH1, rbase, f.rows, col + 32, lane);
-        if (want_cs) ws_colsum(patch, cs1, q, rbase, f.rows, col + 32, lane);
-        __syncwarp();
+      if (NA > 0) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float g = __uint_as_float(v[jj]);
+          const uint32_t wrow = aux + (uint32_t)((col + jj) * ap) * 4;
+#pragma unroll
+          for (int g4 = 0; g4 < (NA > 0 ? NA * 4 : 1); ++g4) {
+            if (g4 * 4 < ap) {
+              const float4 w = lds128(wrow + g4 * 16);
+              xa[4 * g4] = fmaf(g, w.x, xa[4 * g4]); xa[4 * g4 + 1] = fmaf(g, w.y, xa[4 * g4 + 1]);
+              xa[4 * g4 + 2] = fmaf(g, w.z, xa[4 * g4 + 2]); xa[4 * g4 + 3] = fmaf(g, w.w, xa[4 * g4 + 3]);
+            }
+          }
+        }
       }
-      if (NA > 0) dxa_chunk(vb, col + 32);
     }
     if (warp == 0) WS_STAMP(5);
-    if (warp == 4) WS_STAMP(13);
-    if (NA > 0) {      // sum of the two column halves -> dXa[row, :a_cols]
-      const uint32_t other = patch_base + (uint32_t)(warp + 4) * 32 * WS_PSTR * 4;
-      if (half == 1) {
+    if (warp == 8) WS_STAMP(13);
+    if (NA > 0) {      // fixed-order sum of the four column groups -> dXa[row, :a_cols]
+      if (cg > 0) {
 #pragma unroll
-        for (int cc = 0; cc < NA * 16; ++cc) asm volatile("st.shared.f32 [%0], %1;" ::"r"(patch + (uint32_t)(lane * WS_PSTR + cc) * 4), "f"(xa[cc]) : "memory");
+        for (int cc = 0; cc < (NA > 0 ? NA * 16 : 1); ++cc)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(patch + (uint32_t)(lane * 32 + ((cc + lane) & 31)) * 4), "f"(xa[cc]) : "memory");
       }
       epi_bar();
-      if (half == 0 && rvalid) {
+      if (cg == 0 && rvalid) {
         float* o = f.dXa + agent * f.sXa + net * f.sXn + (long long)grow * f.a_cols;
 #pragma unroll
-        for (int cc = 0; cc < NA * 16; ++cc) if (cc < f.a_cols) o[cc] = xa[cc] + lds32(other + (uint32_t)(lane * WS_PSTR + cc) * 4);
+        for (int cc = 0; cc < (NA > 0 ? NA * 16 : 1); ++cc) {
+          if (cc < f.a_cols) {
+            const uint32_t po = (uint32_t)(lane * 32 + ((cc + lane) & 31)) * 4;
+            const float p1 = lds32(patch_base + (uint32_t)(warp + 4) * WS_PATCH1 + po), p2 = lds32(patch_base + (uint32_t)(warp + 8) * WS_PATCH1 + po),
+                        p3 = lds32(patch_base + (uint32_t)(warp + 12) * WS_PATCH1 + po);
+            o[cc] = (xa[cc] + p1) + (p2 + p3);
+          }
+        }
       }
     }
     if (want_cs) {     // fixed-order sum of the four row quarters -> per-tile bias-gradient partials
       epi_bar();
-      const int t = threadIdx.x;
+      if (threadIdx.x < FW_H) {
+        const int t = threadIdx.x;
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t b = (which ? cs1 : cs2) + (uint32_t)t * 4;
-        const float s = ((lds32(b) + lds32(b + FW_H * 4)) + lds32(b + 2 * FW_H * 4)) + lds32(b + 3 * FW_H * 4);
-        f.dbpart[(((long long)z * gridDim.x + blockIdx.x) * 2 + which) * FW_H + t] = s;
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t b = (which ? cs1 : cs2) + (uint32_t)t * 4;
+          const float s = ((lds32(b) + lds32(b + FW_H * 4)) + lds32(b + 2 * FW_H * 4)) + lds32(b + 3 * FW_H * 4);
+          f.dbpart[(((long long)z * gridDim.x + blockIdx.x) * 2 + which) * FW_H + t] = s;
+        }
       }
     }
+    if (warp == 0) WS_STAMP(7);
   }
-  if (warp == 0) WS_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WS_NEW + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
 }
@@ -748,8 +830,8 @@ static inline cudaError_t mlp_ws_init() {
   cudaError_t e;
 #define WS_ATTR(K) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_BYTES); if (e) return e;
   WS_ATTR(k_mlp_fwd_ws<1>) WS_ATTR(k_mlp_fwd_ws<2>) WS_ATTR(k_mlp_fwd_ws<3>)
-  WS_ATTR((k_mlp_bwd_ws<1, 0>)) WS_ATTR((k_mlp_bwd_ws<1, 1>)) WS_ATTR((k_mlp_bwd_ws<1, 2>))
-  WS_ATTR((k_mlp_bwd_ws<2, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0>))
+  WS_ATTR((k_mlp_bwd_ws<0, 0>)) WS_ATTR((k_mlp_bwd_ws<0, 1>)) WS_ATTR((k_mlp_bwd_ws<0, 2>))
+  WS_ATTR((k_mlp_bwd_ws<1, 0>)) WS_ATTR((k_mlp_bwd_ws<2, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0>))
 #undef WS_ATTR
   done = true;
   return cudaSuccess;
@@ -765,19 +847,21 @@ static inline cudaError_t mlp_fwd_ws_launch(const FwdW& f, int nagents, cudaStre
   else k_mlp_fwd_ws<3><<<grid, WS_NT, WS_BYTES, st>>>(f);
   return cudaPeekAtLastError();
 }
-// the backward variants that exist: (kout groups, action groups) in {(1,0),(1,1),(1,2),(2,0),(3,0)}
+// the backward variants that exist: single-output nets (critics) with 0 / 1 / 2 action groups, multi-output nets
+// (actor, kout = nout) without an input gradient
 static inline bool mlp_bwd_ws_eligible(int h1, int h2, int kout, int nout, bool want_dxa, int a_cols, const float* theta, long long sTa,
                                        long long sTn) {
   if (!(h1 == FW_H && h2 == FW_H && kout >= 1 && kout <= WS_MAXOUT && kout <= nout)) return false;
-  if (want_dxa && (kout > 16 || a_cols < 1 || a_cols > 32)) return false;
+  if (want_dxa && (kout != 1 || a_cols < 1 || a_cols > 32)) return false;
   return ((reinterpret_cast<uintptr_t>(theta) & 15) == 0) && ((sTa & 3) == 0) && ((sTn & 3) == 0);
 }
 static inline cudaError_t mlp_bwd_ws_launch(const BwdW& f, int nagents, cudaStream_t st) {
   dim3 grid((f.rows + TC_BM - 1) / TC_BM, nagents * f.nnet);
-  const int ng = (f.kout + 15) / 16, na = f.dXa ? (f.a_cols + 15) / 16 : 0;
-  if (ng == 1 && na == 0) k_mlp_bwd_ws<1, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 1 && na == 1) k_mlp_bwd_ws<1, 1><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 1 && na == 2) k_mlp_bwd_ws<1, 2><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  const int ng = f.kout == 1 ? 0 : (f.kout + 15) / 16, na = f.dXa ? (f.a_cols + 15) / 16 : 0;
+  if (ng == 0 && na == 0) k_mlp_bwd_ws<0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0 && na == 1) k_mlp_bwd_ws<0, 1><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0) k_mlp_bwd_ws<0, 2><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 1) k_mlp_bwd_ws<1, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
   else if (ng == 2) k_mlp_bwd_ws<2, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
   else k_mlp_bwd_ws<3, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
   return cudaPeekAtLastError();
