@@ -87,7 +87,8 @@ typedef struct saceo_config {
                                  [2] != 0 disables the fused backward-chain kernel; [3] != 0 disables the fused model-term kernel;
                                  [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path;
                                  [5] != 0 disables the warp-specialised TMA-fed fused kernels and their weight planes
-                                 (round-1 fused kernels are used instead) */
+                                 (round-1 fused kernels are used instead); [6] != 0 keeps the whole update on one stream (no
+                                 concurrent actor-phase branch) */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */

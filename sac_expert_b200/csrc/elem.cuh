@@ -29,6 +29,7 @@ struct KCtx {
   float *Xpi, *aH1, *aH2, *aOut, *daOut, *daH2, *daH1, *dls;
   float *Xc, *cH1, *cH2, *cQ, *cdQ, *cdH2, *cdH1, *cdXa;
   float *Xc2;        // live-critic input [N_s(s) | N_a(a)] (Xc holds the target-critic input [N_s(sp) | N_a(a')])
+  float *Xc3;        // actor-phase critic input [N_s(s) | N_a(pi(s))]: state columns written by the gather, action columns by the head
   float *Xm, *mH1, *mH2, *mOut, *mdOut, *mdH2, *mdH1, *mdXa;
   float *y, *nlp;
   float *g_q, *g_actor;
@@ -184,7 +185,11 @@ __global__ void k_gather(KCtx c, const long long* __restrict__ idx, float* __res
       const int i = 4 * v + j;
       if (i < c.L.off_a) {
         if (out_s) out_s[ob * S + i] = w[j];
-        if (stage) c.Xc2[ob * c.ldXc + i] = (w[j] - nr[c.L.off_s_mean + i]) / nstd(nr[c.L.off_s_std + i]);
+        if (stage) {
+          const float x = (w[j] - nr[c.L.off_s_mean + i]) / nstd(nr[c.L.off_s_std + i]);
+          c.Xc2[ob * c.ldXc + i] = x;
+          c.Xc3[ob * c.ldXc + i] = x;
+        }
       } else if (i < c.L.off_sp) {
         const int a = i - c.L.off_a;
         if (out_a) out_a[ob * A + a] = w[j];
@@ -471,7 +476,8 @@ __global__ void k_lsv_reduce(KCtx c, int nrows) {
 
 // Keras Adam (epsilon outside the bias correction) fused with the Polyak target update
 // (SAC_expert.py:243,250,338; 362-373).  grid: (ceil(n/256), nnet, n_agents)
-__global__ void k_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+// launch bounds: <= 40 registers, so that an Adam CTA fits next to a resident fused-MLP CTA of the other stream (576 x 96)
+__global__ void __launch_bounds__(256, 6) k_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                        const float* __restrict__ g, float* __restrict__ target,
                        const float* __restrict__ lrt, const float* __restrict__ hyper, int hyper_stride,
                        int opt0, long long n, long long stride, int nnet, int do_polyak,

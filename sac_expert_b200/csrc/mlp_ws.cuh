@@ -53,6 +53,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps only
 // MN-major SWIZZLE_128B descriptor of a weight-plane stage: LBO = 4096 (next 64-wide n atom), SBO = 1024 (next 8 k rows)
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
@@ -97,19 +100,31 @@ __device__ __forceinline__ uint32_t ws_pa(uint32_t patch, int r, int c) {
   return patch + (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
 }
 // v (this lane's row, 32 columns) -> global tile rows through the warp-private patch (whole 128-byte segments per request)
+// cs != 0: the column sums of the valid rows of the tile go to cs[q][col + c] (floats) - summed from the values each lane
+// handles anyway (8 rows x 4 columns), finished with two shuffle steps in a fixed order
 __device__ __forceinline__ void ws_store_rows(uint32_t patch, const uint32_t (&v)[32], float* __restrict__ G, int rbase,
-                                              int rows, int col, int lane) {
+                                              int rows, int col, int lane, uint32_t cs = 0, int q = 0) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) sts128(ws_pa(patch, lane, 4 * j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
   __syncwarp();
   const int lr = lane >> 3, lc = (lane & 7) * 4;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int rr = 0; rr < 32; rr += 4) {
     const int r = rr + lr, grow = rbase + r;
     if (grow < rows) {
       const float4 t4 = lds128(ws_pa(patch, r, lc));
       *reinterpret_cast<float4*>(G + (long long)grow * FW_H + col + lc) = t4;
+      sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
     }
+  }
+  if (cs) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+      sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+    }
+    if (lane < 8) sts128f(cs + (uint32_t)(q * FW_H + col + lc) * 4, sum.x, sum.y, sum.z, sum.w);
   }
 }
 // column sums of the tile left in the patch by ws_store_rows (valid rows only) -> cs[q][col + lane]
@@ -346,6 +361,8 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
         mbar_wait(bar(WB_EMPTY + s), (uint32_t)(((it / WS_NST) & 1) ^ 1));
         mbar_expect_tx(bar(WB_FULL + s), WS_STAGE);
         bulk_g2s(ring + s * WS_STAGE, img + (long long)it * WS_STAGE, WS_STAGE, bar(WB_FULL + s));
+        if (it == WS_NST - 1)      // ring primed: pull the rest of the image into L2 so that the refills are L2 hits
+          for (int j = WS_NST; j < total; ++j) bulk_prefetch_l2(img + (long long)j * WS_STAGE, WS_STAGE);
       }
       WS_STAMP(11);
     }
@@ -583,6 +600,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     mbar_init(bar(WB_D0), 1); mbar_init(bar(WB_D1), 1);                 // accumulator halves 0 / 1
     for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(aux + WS_RED - 256), "r"(0u) : "memory");     // max |W2| accumulator
   }
   if (warp == WS_NEW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
@@ -606,6 +624,8 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
           for (int tt = 0; tt < 4; ++tt)
             bulk_g2s(ring + s * WS_STAGE + pl * 16384 + tt * 4096,
                      w1 + (long long)(4 * h + tt) * WS_STAGE + pl * 16384 + sj * 4096, 4096, bar(WB_FULL + s));
+        if (it == WS_NST - 1)
+          for (int t = 0; t < 8; ++t) bulk_prefetch_l2(w1 + (long long)t * WS_STAGE, WS_STAGE);
       }
     }
   } else if (warp == WS_NEW + 1) {
@@ -652,12 +672,10 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     float4 hq[8];                                          // saved-activation rows of the next chunk, in flight
     ws_rows_issue(H2, rbase, f.rows, cg * 64, lane, hq);
     // ---- stage W2[:, :kout] as fp32 [256][kp]; max |W2| over the block bounds every row of dOut . W2^T (row scale)
-    if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wmax_s), "r"(0u) : "memory");
     constexpr int ND = NG > 0 ? NG * 16 : 1;               // NG == 0: single output (critics), the first step is an outer product
     float d[ND];
 #pragma unroll
     for (int cc = 0; cc < ND; ++cc) d[cc] = (rvalid && cc < f.kout) ? __ldg(dOut + (long long)grow * f.ldd + cc) : 0.f;
-    epi_bar();
     if (threadIdx.x < FW_H) {
       float wr[NG > 0 ? NG * 16 : 4];
       ws_load_wrow<(NG > 0 ? NG * 16 : 4)>(th + oW2, threadIdx.x, f.nout, wr);          // hidden unit j = threadIdx.x
@@ -718,8 +736,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         if (lane == 0) mbar_arrive(bar(WB_AP + cg));
       }
       if (dH2) {
-        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane);
-        if (want_cs) ws_colsum(patch, cs2, q, rbase, f.rows, col, lane);
+        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
         __syncwarp();
       }
     }
@@ -756,8 +773,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       tmem_ld_wait();
       ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
       if (dH1) {
-        ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane);
-        if (want_cs) ws_colsum(patch, cs1, q, rbase, f.rows, col, lane);
+        ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
         __syncwarp();
       }
       if (NA > 0) {

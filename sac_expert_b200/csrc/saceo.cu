@@ -67,6 +67,11 @@ struct saceo_ctx {
   // weight-plane images maintained by k_adam / k_planes_build (warp-specialised fused kernels, mlp_ws.cuh)
   uint8_t *pl_actor = nullptr, *pl_q = nullptr, *pl_qt = nullptr;
   int planes_dirty = 3;                // bit 0: actor image stale, bit 1: critic / target images stale
+  // actor-phase buffers of their own (input operands, head outputs, neglogp, critic input with pi(s)), so that the
+  // critic-independent half of the actor phase can run on a second stream next to the critic phase
+  float *Xpi2 = nullptr, *aOut2 = nullptr, *nlp2 = nullptr, *Xc3 = nullptr;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -183,6 +188,10 @@ static void carve(saceo_ctx* x, char* base) {
   k.dls = b.get<float>("dls", n * R * A);
   k.Xc = b.get<float>("Xc", n * B * rup(SA, 4));
   k.Xc2 = b.get<float>("Xc2", n * B * rup(SA, 4));
+  x->Xc3 = k.Xc3 = b.get<float>("Xc3", n * B * rup(SA, 4));
+  x->Xpi2 = b.get<float>("Xpi2", n * R * rup(S, 4));
+  x->aOut2 = b.get<float>("aOut2", n * R * L.Ao);
+  x->nlp2 = b.get<float>("nlp2", n * R);
   k.cH1 = b.get<float>("cH1", n * 2 * B * c.critic_hidden[0]);  k.cH2 = b.get<float>("cH2", n * 2 * B * c.critic_hidden[1]);
   k.cQ = b.get<float>("cQ", n * 2 * B);                          k.cdQ = b.get<float>("cdQ", n * 2 * B);
   k.cdH2 = b.get<float>("cdH2", n * 2 * B * c.critic_hidden[1]); k.cdH1 = b.get<float>("cdH1", n * 2 * B * c.critic_hidden[0]);
@@ -304,6 +313,9 @@ static int create_fill(saceo_ctx* x, const saceo_config* cfg) {
     for (int a = 0; a < cfg->n_agents; ++a) for (int i = 0; i < k.E; ++i) pm[(size_t)a * k.E + i] = i;
     CU(cudaMemcpy(k.perm, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  CU(cudaStreamCreateWithFlags(&x->s2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
   CU(tc_gemm_init());
   CU(mlp_fwd_tc_init());
   CU(mlp_ws_init());
@@ -316,6 +328,9 @@ extern "C" int saceo_destroy(saceo_ctx* x) {
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) if (x->graph[i][j]) cudaGraphExecDestroy(x->graph[i][j]);
   if (x->ws) cudaFree(x->ws);
   if (x->fit_ws) cudaFree(x->fit_ws);
+  if (x->s2) cudaStreamDestroy(x->s2);
+  if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+  if (x->ev_join) cudaEventDestroy(x->ev_join);
   for (cudaEvent_t e : x->prof_ev) cudaEventDestroy(e);
   delete x;
   return 0;
@@ -358,11 +373,11 @@ static int ensure_planes(saceo_ctx* x, cudaStream_t st) {
   const saceo_config& c = x->cfg; const int n = c.n_agents;
   auto items = [](int K0) { return (((K0 + 31) / 32) * 32 + 256) * 32; };
   if (x->pl_actor && (x->planes_dirty & 1)) {
-    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S), 256), n), 256, 0, st, x->k.T.actor, x->L.na_stride, x->pl_actor, c.S);
+    k_planes_build<<<dim3(cdiv(items(c.S), 256), n), 256, 0, st>>>(x->k.T.actor, x->L.na_stride, x->pl_actor, c.S);   // maintenance: not counted as a launch of the step
   }
   if (x->pl_q && (x->planes_dirty & 2)) {
-    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st, x->k.T.q, x->L.nc_stride, x->pl_q, c.S + c.A);
-    LAUNCH(x, k_planes_build, dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st, x->k.T.qt, x->L.nc_stride, x->pl_qt, c.S + c.A);
+    k_planes_build<<<dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st>>>(x->k.T.q, x->L.nc_stride, x->pl_q, c.S + c.A);
+    k_planes_build<<<dim3(cdiv(items(c.S + c.A), 256), 2 * n), 256, 0, st>>>(x->k.T.qt, x->L.nc_stride, x->pl_qt, c.S + c.A);
   }
   x->planes_dirty = 0;
   cudaError_t e = cudaPeekAtLastError();
@@ -666,29 +681,27 @@ static int phase_critic_apply(saceo_ctx* x, int do_polyak, cudaStream_t st) {
   return check_launch();
 }
 
-// phase 2: actor gradients (policy loss through the UPDATED critics + expert-observation term)
-// bc: behaviour cloning (BC.py:309-363) - the expert weight is forced to 1 and the policy-loss half (critic forward /
-// backward-to-action on the B minibatch rows) is skipped: those rows then carry exactly-zero output gradients.
-static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+// The actor phase works on buffers of its own (Xpi2 = [N_s(s); N_s(sE)], aOut2, nlp2, Xc3 = [N_s(s) | N_a(pi(s))]), so
+// that its critic-independent half (actor forward, head, expert-observation term through the frozen models) can run on
+// a second stream next to the critic phase: only pi(s) -> Q(s, pi(s)) needs the UPDATED critics (SAC_expert.py:312-317).
+static KCtx actor_view(const saceo_ctx* x, bool bc = false) {
   KCtx kk = x->k;
+  kk.Xpi = x->Xpi2; kk.aOut = x->aOut2; kk.nlp = x->nlp2; kk.Xc2 = x->Xc3;
   if (bc) kk.eps_force = 1.f;
+  return kk;
+}
+
+// phase 2a: everything of the actor step that does not depend on the critics
+static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+  const KCtx kk = actor_view(x, bc);
   const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
   int rc;
-  NetD an = actor_net(x), qn = critic_net(x, false);
+  NetD an = actor_net(x);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
   rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
-         (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) replaces the action columns of Xc2
-  if (!bc) {
-    rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
-    LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
-    rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
-                      k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
-    if (rc) return rc;
-  } else {
-    CU(cudaMemsetAsync(k.cdXa, 0, sizeof(float) * (size_t)n * 2 * B * A, st));
-  }
+         (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
     if (model_term_launch(k, k.mse_part, st) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
@@ -740,12 +753,36 @@ static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
       rc = gemm(x, false, true, false, p, n, st); if (rc) return rc;
     }
   }
+  return check_launch();
+}
+
+// phase 2b: policy loss through the UPDATED critics, head backward, actor backward and weight gradients
+// bc: behaviour cloning (BC.py:309-363) - the expert weight is forced to 1 and the policy-loss half (critic forward /
+// backward-to-action on the B minibatch rows) is skipped: those rows then carry exactly-zero output gradients.
+static int phase_actor_post(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+  const KCtx kk = actor_view(x, bc);
+  const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, R = k.R, Rs = k.Rs;
+  int rc;
+  NetD an = actor_net(x), qn = critic_net(x, false);
+  if (!bc) {
+    rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+    LAUNCH(x, k_actor_q, dim3(n), 256, 0, st, k);
+    rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
+                      k.cdH2, k.cdH1, nullptr, 0, 0, k.cdXa, S, A, 2LL * B * A, (long long)B * A, st);
+    if (rc) return rc;
+  } else {
+    CU(cudaMemsetAsync(k.cdXa, 0, sizeof(float) * (size_t)n * 2 * B * A, st));
+  }
   LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
   rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
                     k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
   return check_launch();
+}
+static int phase_actor_grads(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+  int rc = phase_actor_pre(x, st, bc); if (rc) return rc;
+  return phase_actor_post(x, st, bc);
 }
 
 static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
@@ -758,7 +795,8 @@ static int phase_actor_apply(saceo_ctx* x, cudaStream_t st) {
 
 // phase 4/5: temperature (forward of the UPDATED actor on s with fresh noise u5)
 static int phase_alpha(saceo_ctx* x, int apply, cudaStream_t st) {
-  const KCtx& k = x->k; const int n = k.n_agents, B = k.B, A = k.A;
+  const KCtx kk = actor_view(x);          // Xpi2 still holds N_s(s) from the actor phase
+  const KCtx& k = kk; const int n = k.n_agents, B = k.B, A = k.A;
   NetD an = actor_net(x);
   int rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)k.Rs * k.ldXp, 0, B, k.aH1, k.aH2, k.Rs, k.aOut, k.Ao,
                        (long long)k.Rs * k.Ao, 0, st, false); if (rc) return rc;
@@ -777,9 +815,23 @@ static int step_once(saceo_ctx* x, int use_rng, int do_polyak, cudaStream_t st) 
     LAUNCH(x, k_rng_fill, dim3(cdiv(items > k.B ? items : k.B, 256), k.n_agents), 256, 0, st, k, use_rng == 2 ? 1 : 0);
   }
   if ((rc = phase_gather(x, st))) return rc;
+  // fork: the critic-independent half of the actor phase on the second stream (captured into the same graph).
+  // reserved[6]: 0 = on, 1 = off (single stream; also used by the per-kernel profile)
+  // Only with the warp-specialised fused kernels: the fallback engines write their hidden activations of the
+  // TD-target actor pass into the buffers the actor phase saves into.
+  const bool fork = x->cfg.reserved[6] == 0 && !x->prof && x->s2 != nullptr && x->pl_actor != nullptr && x->pl_q != nullptr &&
+                    x->cfg.reserved[1] == 0;
+  if (fork) {
+    CU(cudaEventRecord(x->ev_fork, st));
+    CU(cudaStreamWaitEvent(x->s2, x->ev_fork, 0));
+    if ((rc = phase_actor_pre(x, x->s2))) return rc;
+    CU(cudaEventRecord(x->ev_join, x->s2));
+  }
   if ((rc = phase_critic_grads(x, st))) return rc;
   if ((rc = phase_critic_apply(x, do_polyak, st))) return rc;
-  if ((rc = phase_actor_grads(x, st))) return rc;
+  if (fork) { CU(cudaStreamWaitEvent(st, x->ev_join, 0)); }
+  else if ((rc = phase_actor_pre(x, st))) return rc;
+  if ((rc = phase_actor_post(x, st))) return rc;
   if ((rc = phase_actor_apply(x, st))) return rc;
   if ((rc = phase_alpha(x, 1, st))) return rc;
   return 0;

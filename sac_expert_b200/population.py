@@ -50,6 +50,7 @@ class PopulationSpec:
     fuse_model: bool = True        # fused expert-observation term (model forward + MSE + backward to action)
     use_graph: bool = True         # one update = one CUDA-graph replay
     ws_kernels: bool = True        # warp-specialised TMA-fed fused kernels on optimiser-maintained weight planes (round 2)
+    fork_actor: bool = True        # critic-independent half of the actor phase on a second stream (needs ws_kernels)
     device: int = 0
 
     def to_config(self) -> _l.Config:
@@ -83,6 +84,7 @@ class PopulationSpec:
         c.reserved[2] = 0 if self.fuse_backward else 1
         c.reserved[3] = 0 if self.fuse_model else 1
         c.reserved[5] = 0 if self.ws_kernels else 1
+        c.reserved[6] = 0 if self.fork_actor else 1
         return c
 
 

@@ -139,7 +139,7 @@ def test_profile_step_reports_every_launch():
             prof = pop.profile_step(0, use_device_rng=False)
             assert len(prof) == pop.launches - l0 and len(prof) >= 20
             names = {n for n, _ in prof}
-            assert {"k_mlp_fwd_tc", "k_mlp_bwd_tc", "k_adam", "k_model_term", "k_gather"} <= names
+            assert {"k_mlp_fwd_ws", "k_mlp_bwd_ws", "k_adam", "k_model_term", "k_gather"} <= names
             assert all(us > 0 for _, us in prof) and sum(us for _, us in prof) < 1e6
         else:
             pop.update(1, num_timesteps=0, use_device_rng=False)
