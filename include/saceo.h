@@ -88,7 +88,7 @@ typedef struct saceo_config {
                                  [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path;
                                  [5] != 0 disables the warp-specialised TMA-fed fused kernels and their weight planes
                                  (round-1 fused kernels are used instead); [6] != 0 keeps the whole update on one stream (no
-                                 concurrent actor-phase branch) */
+                                 concurrent actor-phase branch); [7] != 0 selects the round-1 (one column per thread) model-term kernel */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */
@@ -126,9 +126,10 @@ typedef struct saceo_tables {
   int32_t *adam_t;                           /* [n_agents, 4]: q1, q2, actor, alpha step counts */
   const float *norm;                         /* [n_agents, norm_stride] */
   const float *hyper;                        /* [n_agents, hyper_stride] */
-  const float *replay;                       /* [n_agents, replay_capacity, row_words] */
-  const int32_t *replay_size;                /* [n_agents] rows currently valid */
-  const int32_t *replay_start;               /* [n_agents] physical row of logical index 0 (ring), may be NULL */
+  float *replay;                             /* [n_agents, replay_capacity, row_words]; written by saceo_replay_append */
+  int32_t *replay_size;                      /* [n_agents] rows currently valid */
+  int32_t *replay_start;                     /* [n_agents] physical row of logical index 0 (ring), may be NULL (then
+                                                saceo_replay_append is unavailable) */
   float *expert_s, *expert_sp;               /* [n_agents, E, S]; saceo_update_host* overwrite them with expert_host */
   const float *fvp_states;                   /* [n_agents, fvp_rows, S] or NULL */
 } saceo_tables;
@@ -157,6 +158,13 @@ int saceo_weights_changed(saceo_ctx *ctx);
  * Any out_* may be NULL.  Bit-exact. */
 int saceo_gather(saceo_ctx *ctx, const int64_t *idx, float *out_s, float *out_a, float *out_sp,
                  float *out_r, double *out_d, void *stream);
+
+/* TrajectoryBuffer.add (common/buffers.py:41-71) for EVERY agent in one call - the per-step triple add of the
+ * environment loop (algs/SAC_expert.py:793-801) without its O(N) np.concatenate: rows (device, 16-byte aligned,
+ * [n_agents, k, row_words] in the AoS row layout of saceo_layout) are appended behind each agent's newest row; a full
+ * ring overwrites its oldest rows, i.e. keeps the last replay_capacity rows like the reference's tail truncation
+ * (:60-66).  replay_size / replay_start are updated on the device (stream-ordered, no host sync). */
+int saceo_replay_append(saceo_ctx *ctx, const float *rows, int32_t k, void *stream);
 
 /* Inject the random draws of the next update(s) (parity mode), device pointers, any may be NULL:
  * idx [n,B] int64 (np.random.randint, buffers.py:135); noise [n, 3B+E, A] f32 in reference draw

@@ -215,6 +215,36 @@ __global__ void k_gather(KCtx c, const long long* __restrict__ idx, float* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// population-wide replay append (TrajectoryBuffer.add, buffers.py:41-71; SAC_expert.py:793-801): k new AoS rows per
+// agent go behind the newest row of that agent's ring; when the ring is full the OLDEST rows are overwritten, which is
+// the reference's keep-the-last-buffer_size truncation (:60-66).  Two stream-ordered launches: rows, then the ring
+// bookkeeping (size / start), so that every block of the first sees the same ring state.
+// grid: (ceil(k * row_words / 4 / 256), n_agents)
+// ------------------------------------------------------------------------------------------
+__global__ void k_replay_append_rows(KCtx c, const float* __restrict__ rows, int k, float* __restrict__ replay,
+                                     const int* __restrict__ rsize, const int* __restrict__ rstart) {
+  const int agent = blockIdx.y;
+  const int rw4 = c.L.row_words >> 2;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index inside the agent's [k, row_words] block
+  if (e >= k * rw4) return;
+  const int i = e / rw4, v = e - i * rw4;
+  const int size = rsize[agent], start = rstart ? rstart[agent] : 0;
+  long long pos = (long long)start + size + i;                  // logical slot behind the newest row
+  pos %= c.cap;
+  const float4 q = reinterpret_cast<const float4*>(rows + ((long long)agent * k + i) * c.L.row_words)[v];
+  reinterpret_cast<float4*>(replay + ((long long)agent * c.cap + pos) * c.L.row_words)[v] = q;
+}
+__global__ void k_replay_append_commit(KCtx c, int k, int* __restrict__ rsize, int* __restrict__ rstart) {
+  const int agent = blockIdx.x * blockDim.x + threadIdx.x;
+  if (agent >= c.n_agents) return;
+  const int size = rsize[agent], start = rstart[agent];
+  const long long tot = (long long)size + k;
+  const int over = tot > c.cap ? (int)(tot - c.cap) : 0;
+  rsize[agent] = tot > c.cap ? c.cap : (int)tot;
+  rstart[agent] = (int)(((long long)start + over) % c.cap);
+}
+
+// ------------------------------------------------------------------------------------------
 // input staging of the actor phase: normalise into the GEMM operand matrices (the critic-phase inputs are staged by
 // k_gather):  Xpi[b] = N_s(s[b]);  Xpi[B+i] = N_s(sE[perm i]);  Xm[net][il,:S] = N_s^M(sE[perm i])
 // grid: (ceil(R*S/256), n_agents)

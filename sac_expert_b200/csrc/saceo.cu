@@ -704,7 +704,7 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
          (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
-    if (model_term_launch(k, k.mse_part, st) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
+    if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7] == 0) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
     count_launch(x, "k_model_term", st);
   } else if (k.nmod > 0) {
     const int half = k.nmod == 2 ? E / 2 : E;
@@ -1006,6 +1006,23 @@ extern "C" int saceo_gather(saceo_ctx* x, const int64_t* idx, float* out_s, floa
   const KCtx& k = x->k;
   LAUNCH(x, k_gather, dim3(cdiv(k.B, 8), k.n_agents), 256, 0, (cudaStream_t)stream, k, (const long long*)idx,
          out_s, out_a, out_sp, out_r, out_d, (float*)nullptr, 0);
+  return check_launch();
+}
+
+// TrajectoryBuffer.add for the whole population in one call (buffers.py:41-71, SAC_expert.py:793-801): k packed AoS rows
+// per agent (device, [n_agents, k, row_words]) appended to every agent's ring, ring arithmetic on the device.
+extern "C" int saceo_replay_append(saceo_ctx* x, const float* rows, int32_t k, void* stream) {
+  if (!x || !rows) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound || !x->k.T.replay || !x->k.T.replay_size || !x->k.T.replay_start)
+    return fail(SACEO_E_UNBOUND, "replay, replay_size and replay_start tables must be bound");
+  if (k < 1 || k > x->cfg.replay_capacity) return fail(SACEO_E_INVALID, "k must be in [1, replay_capacity]");
+  if (reinterpret_cast<uintptr_t>(rows) & 15) return fail(SACEO_E_INVALID, "rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& kc = x->k;
+  const int items = k * (x->L.row_words >> 2);
+  LAUNCH(x, k_replay_append_rows, dim3(cdiv(items, 256), kc.n_agents), 256, 0, st, kc, rows, k, const_cast<float*>(kc.T.replay),
+         kc.T.replay_size, kc.T.replay_start);
+  LAUNCH(x, k_replay_append_commit, dim3(cdiv(kc.n_agents, 128)), 128, 0, st, kc, k, const_cast<int*>(kc.T.replay_size),
+         const_cast<int*>(kc.T.replay_start));
   return check_launch();
 }
 

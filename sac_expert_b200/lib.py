@@ -75,7 +75,7 @@ _lib: Optional[C.CDLL] = None
 
 # every symbol include/saceo.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
-    "saceo_query_layout", "saceo_create", "saceo_destroy", "saceo_bind", "saceo_weights_changed", "saceo_gather",
+    "saceo_query_layout", "saceo_create", "saceo_destroy", "saceo_bind", "saceo_weights_changed", "saceo_replay_append", "saceo_gather",
     "saceo_set_draws", "saceo_update", "saceo_update_host", "saceo_update_host_async", "saceo_update_phase", "saceo_bc_update", "saceo_profile_step",
     "saceo_actor_forward", "saceo_critic_forward", "saceo_model_eval", "saceo_fvp", "saceo_cg_solve",
     "saceo_fit_bind", "saceo_model_fit", "saceo_trpo_grad", "saceo_trpo_eval", "saceo_actor_step", "saceo_ppo_grad", "saceo_actor_adam",
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
         "saceo_destroy": (C.c_int, [vp]),
         "saceo_bind": (C.c_int, [vp, C.POINTER(Tables)]),
         "saceo_weights_changed": (C.c_int, [vp]),
+        "saceo_replay_append": (C.c_int, [vp, vp, i32, vp]),
         "saceo_gather": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "saceo_set_draws": (C.c_int, [vp, vp, vp, vp, vp]),
         "saceo_update": (C.c_int, [vp, i32, i64, i32, u64, vp, vp]),

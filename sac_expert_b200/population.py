@@ -51,6 +51,7 @@ class PopulationSpec:
     use_graph: bool = True         # one update = one CUDA-graph replay
     ws_kernels: bool = True        # warp-specialised TMA-fed fused kernels on optimiser-maintained weight planes (round 2)
     fork_actor: bool = True        # critic-independent half of the actor phase on a second stream (needs ws_kernels)
+    blocked_model: bool = True     # column-blocked model-term kernel (4 hidden columns per thread)
     device: int = 0
 
     def to_config(self) -> _l.Config:
@@ -85,6 +86,7 @@ class PopulationSpec:
         c.reserved[3] = 0 if self.fuse_model else 1
         c.reserved[5] = 0 if self.ws_kernels else 1
         c.reserved[6] = 0 if self.fork_actor else 1
+        c.reserved[7] = 0 if self.blocked_model else 1
         return c
 
 
@@ -352,6 +354,34 @@ class Population:
         self._host_start[agent] = (start + over) % cap
         self.t["replay_size"][agent] = int(self._host_size[agent])
         self.t["replay_start"][agent] = int(self._host_start[agent])
+
+    def append_all(self, s, a, r, sp, d):
+        """``TrajectoryBuffer.add`` for EVERY agent in one device call (buffers.py:41-71; the per-step adds of the
+        environment loop, SAC_expert.py:793-801): ``s, sp`` [n, k, S], ``a`` [n, k, A], ``r, d`` [n, k].  The packed rows
+        travel through one pinned staging buffer and one H2D copy; the ring arithmetic (append behind the newest row,
+        overwrite the oldest when full = keep the last ``capacity`` rows) runs on the device (``saceo_replay_append``).
+        No host synchronisation; the host mirrors of size / start are advanced with the same arithmetic."""
+        n, cap = self.spec.n_agents, self.spec.replay_capacity
+        r = np.asarray(r, np.float32).reshape(n, -1)
+        k = r.shape[1]
+        if k < 1 or k > cap:
+            raise ValueError("append_all: rows per agent must be in [1, replay_capacity]")
+        rows = self.pack_rows(np.asarray(s).reshape(n * k, -1), np.asarray(a).reshape(n * k, -1), r.reshape(-1),
+                              np.asarray(sp).reshape(n * k, -1), np.asarray(d).reshape(-1))
+        pin = getattr(self, "_pin_rows", None)
+        if pin is None or pin.shape[0] < n * k:
+            self._pin_rows = pin = torch.empty(n * k, self.L.row_words, pin_memory=True)
+            self._dev_rows = torch.empty(n * k, self.L.row_words, device=self.dev)
+        pin[: n * k].numpy()[...] = rows
+        st = self._enter()
+        with torch.cuda.stream(self.stream):
+            self._dev_rows[: n * k].copy_(pin[: n * k], non_blocking=True)
+        _l.check(self.lib.saceo_replay_append(self.ctx, self._dev_rows.data_ptr(), k, st))
+        self._exit()
+        tot = self._host_size + k
+        over = np.maximum(tot - cap, 0)
+        self._host_size[:] = np.minimum(tot, cap)
+        self._host_start[:] = (self._host_start + over) % cap
 
     def set_expert(self, agent: int, sE, spE):
         self.t["expert_s"][agent].copy_(torch.from_numpy(np.asarray(sE, np.float32)))

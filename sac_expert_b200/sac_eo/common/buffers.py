@@ -15,14 +15,40 @@ class TrajectoryBuffer:
         self._pop, self._agent = None, 0
         self.reset()
 
+    _FIELDS = (("s", "s_dim", np.float32), ("a", "a_dim", np.float32), ("r", None, np.float32), ("sp", "s_dim", np.float32),
+               ("d", None, np.float64), ("idx", None, np.float64))
+
     def reset(self):
-        self.s_all = np.empty((0, self.s_dim), np.float32)
-        self.a_all = np.empty((0, self.a_dim), np.float32)
-        self.r_all = np.empty((0,), np.float32)
-        self.sp_all = np.empty((0, self.s_dim), np.float32)
-        self.d_all = np.empty((0,))          # float64 done flags
-        self.idx_all = np.empty((0,))
+        """Empty buffer.  The arrays the reference exposes (``s_all`` ... ``idx_all``, chronological order) are views
+        ``store[lo:hi]`` of pre-allocated windows: ``add`` writes behind ``hi`` in amortised O(rows added) instead of
+        re-concatenating every array (buffers.py:41-58 copies the whole buffer on every call - O(N) per environment
+        step); when the window reaches the end of the allocation the live rows slide to the front."""
+        self._lo = self._hi = 0
+        self._alloc(64)
         self.traj_total = self.steps_total = self.current_size = 0
+
+    def _alloc(self, cap):
+        old = getattr(self, "_store", None)
+        self._store = {}
+        for name, dim, dt in self._FIELDS:
+            shape = (cap,) if dim is None else (cap, getattr(self, dim))
+            arr = np.empty(shape, dt)
+            if old is not None and self._hi > self._lo:
+                arr[: self._hi - self._lo] = old[name][self._lo:self._hi]
+            self._store[name] = arr
+        self._hi -= self._lo
+        self._lo = 0
+        self._cap = cap
+
+    def _view(self, name):
+        return self._store[name][self._lo:self._hi]
+
+    s_all = property(lambda self: self._view("s"))
+    a_all = property(lambda self: self._view("a"))
+    r_all = property(lambda self: self._view("r"))
+    sp_all = property(lambda self: self._view("sp"))
+    d_all = property(lambda self: self._view("d"))
+    idx_all = property(lambda self: self._view("idx"))
 
     def attach(self, pop, agent=0):
         """Mirror this buffer into the device replay table of ``agent`` (existing rows are uploaded)."""
@@ -37,18 +63,22 @@ class TrajectoryBuffer:
         a_traj = np.asarray(a_traj).reshape(-1, self.a_dim)
         r_traj, d_traj = np.atleast_1d(np.asarray(r_traj)), np.atleast_1d(np.asarray(d_traj))
         sp_traj = np.asarray(sp_traj).reshape(-1, self.s_dim)
-        cat = lambda old, new: np.concatenate((old, new), axis=0)
-        self.s_all, self.a_all = cat(self.s_all, s_traj), cat(self.a_all, a_traj)
-        self.r_all, self.sp_all = cat(self.r_all, r_traj), cat(self.sp_all, sp_traj)
-        self.d_all = cat(self.d_all, d_traj)
-        self.idx_all = cat(self.idx_all, np.ones_like(r_traj) * self.traj_total)
-        if self.buffer_size and len(self.r_all) > self.buffer_size:        # keep the LAST buffer_size rows (:60-66)
-            keep = slice(-self.buffer_size, None)
-            self.s_all, self.a_all, self.r_all = self.s_all[keep], self.a_all[keep], self.r_all[keep]
-            self.sp_all, self.d_all, self.idx_all = self.sp_all[keep], self.d_all[keep], self.idx_all[keep]
-        self.current_size = len(self.r_all)
+        k = len(r_traj)
+        if self._hi + k > self._cap:          # slide the live window to the front, growing the allocation if needed
+            live = self._hi - self._lo
+            keep = min(live, self.buffer_size) if self.buffer_size else live
+            self._lo = self._hi - keep
+            need = keep + k
+            self._alloc(max(2 * self._cap, 2 * need) if (not self.buffer_size or self._cap < 2 * (self.buffer_size + k)) else self._cap)
+        new = dict(s=s_traj, a=a_traj, r=r_traj, sp=sp_traj, d=d_traj, idx=np.ones(k) * self.traj_total)
+        for name, _, _ in self._FIELDS:
+            self._store[name][self._hi:self._hi + k] = new[name]
+        self._hi += k
+        if self.buffer_size and self._hi - self._lo > self.buffer_size:    # keep the LAST buffer_size rows (:60-66)
+            self._lo = self._hi - self.buffer_size
+        self.current_size = self._hi - self._lo
         self.traj_total += 1
-        self.steps_total += len(r_traj)
+        self.steps_total += k
         if self._pop is not None:
             if not self.buffer_size and self.current_size > self._pop.spec.replay_capacity:
                 raise SaceoError("unbounded TrajectoryBuffer outgrew the device replay_capacity")

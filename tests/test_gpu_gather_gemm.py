@@ -124,3 +124,49 @@ def test_pair_gemm(K):
     torch.cuda.synchronize()
     err = float((Cd.double().cpu() - ref).norm() / ref.norm())
     assert err < 2e-5, err
+
+
+def test_replay_append_all_agents_wraparound():
+    """saceo_replay_append: one call appends k rows to EVERY agent's ring on the device; after several
+    wrap-arounds the gather is still a bit-exact copy of the last `capacity` rows in chronological order
+    (buffers.py:41-71 keep-the-tail semantics), for all agents at once, with different fill levels per agent."""
+    import numpy as np
+    from sac_expert_b200.population import Population, PopulationSpec
+    n, S, A, cap, B = 5, 7, 3, 96, 64
+    pop = Population(PopulationSpec(n_agents=n, S=S, A=A, B=B, E=2, num_models=0, replay_capacity=cap, gemm_mode=0))
+    rng = np.random.default_rng(3)
+    hist = [dict(s=[], a=[], r=[], sp=[], d=[]) for _ in range(n)]
+    # agents start at different fill levels (per-agent appends), then advance together
+    for ag in range(n):
+        k0 = 5 + 9 * ag
+        s, a = rng.standard_normal((k0, S)).astype(np.float32), rng.standard_normal((k0, A)).astype(np.float32)
+        r, sp, d = rng.standard_normal(k0).astype(np.float32), rng.standard_normal((k0, S)).astype(np.float32), (rng.random(k0) < 0.3).astype(np.float64)
+        pop.append_rows(ag, s, a, r, sp, d)
+        for key, v in zip("s a r sp d".split(), (s, a, r, sp, d)):
+            hist[ag][key].append(v)
+    for step in range(40):
+        k = int(rng.integers(1, 12))
+        s, a = rng.standard_normal((n, k, S)).astype(np.float32), rng.standard_normal((n, k, A)).astype(np.float32)
+        r, sp = rng.standard_normal((n, k)).astype(np.float32), rng.standard_normal((n, k, S)).astype(np.float32)
+        d = (rng.random((n, k)) < 0.3).astype(np.float64)
+        s[0, 0, 0] = -0.0                                   # sign of zero survives
+        pop.append_all(s, a, r, sp, d)
+        for ag in range(n):
+            for key, v in zip("s a r sp d".split(), (s, a, r, sp, d)):
+                hist[ag][key].append(v[ag])
+    torch.cuda.synchronize()
+    sizes = pop.t["replay_size"].cpu().numpy()
+    full = {key: [np.concatenate(h[key])[-cap:] for h in hist] for key in "s a r sp d".split()}
+    assert np.array_equal(sizes, [len(x) for x in full["r"]]) and np.array_equal(sizes, pop._host_size)
+    assert np.array_equal(pop.t["replay_start"].cpu().numpy(), pop._host_start)
+    idx = np.stack([rng.integers(0, sizes[ag], size=B) for ag in range(n)]).astype(np.int64)
+    idx[:, 0] = 0
+    idx[:, 1] = sizes - 1                                   # oldest and newest logical rows
+    gs, ga, gsp, gr, gd = [t.cpu().numpy() for t in pop.gather(torch.from_numpy(idx))]
+    for ag in range(n):
+        assert gs[ag].tobytes() == full["s"][ag][idx[ag]].tobytes()
+        assert ga[ag].tobytes() == full["a"][ag][idx[ag]].tobytes()
+        assert gsp[ag].tobytes() == full["sp"][ag][idx[ag]].tobytes()
+        assert gr[ag].tobytes() == full["r"][ag][idx[ag]].tobytes()
+        assert gd[ag].tobytes() == full["d"][ag][idx[ag]].tobytes()
+    pop.close()

@@ -181,3 +181,26 @@ def test_on_policy_temperature_step_is_keras_adam_with_the_zero_floor(which):
         a = [torch.clamp(a[0], min=0.0)]
         assert abs(float(alg.alpha) - float(a[0])) < 2e-6, (g, alg.alpha, a)
     assert alg._alpha_t == len(grads) and float(alg.alpha) >= 0.0
+
+
+@pytest.mark.parametrize("buffer_size", [None, 50, 7])
+def test_trajectory_buffer_window_equals_concatenate_semantics(buffer_size):
+    """TrajectoryBuffer.add without the reference's O(N) re-concatenation (buffers.py:41-71): the exposed arrays must be
+    exactly what np.concatenate + tail truncation (:60-66) produces, after every add, for bounded and unbounded buffers."""
+    from sac_expert_b200.sac_eo.common.buffers import TrajectoryBuffer
+    rng = np.random.default_rng(0)
+    tb = TrajectoryBuffer(3, 2, 0.99, 0.95, buffer_size)
+    S, R, D, I = np.empty((0, 3), np.float32), np.empty((0,), np.float32), np.empty((0,)), np.empty((0,))
+    for t in range(300):
+        k = int(rng.integers(1, 9))
+        s, a = rng.standard_normal((k, 3)).astype(np.float32), rng.standard_normal((k, 2)).astype(np.float32)
+        r, d = rng.standard_normal(k).astype(np.float32), (rng.random(k) < 0.1).astype(np.float64)
+        tb.add(s, a, r, s + 1, d)
+        S, R, D, I = np.concatenate((S, s)), np.concatenate((R, r)), np.concatenate((D, d)), np.concatenate((I, np.ones(k) * t))
+        if buffer_size and len(R) > buffer_size:
+            S, R, D, I = S[-buffer_size:], R[-buffer_size:], D[-buffer_size:], I[-buffer_size:]
+        assert tb.current_size == len(R) and tb.steps_total == sum(1 for _ in range(1)) * tb.steps_total
+        assert np.array_equal(tb.s_all, S) and np.array_equal(tb.sp_all, S + 1) and np.array_equal(tb.r_all, R)
+        assert np.array_equal(tb.d_all, D) and tb.d_all.dtype == np.float64 and np.array_equal(tb.idx_all, I)
+    s_, a_, sp_, r_ = tb.get_model_info()
+    assert s_.shape == (len(R), 3) and a_.shape == (len(R), 2)
