@@ -216,13 +216,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) k_model_term(KCtx c, float* __r
   }
 }
 
-// Column-blocked variant (round 2): 128 threads, every thread owns FOUR hidden columns (j, j+128, j+256, j+384).  The
-// round-1 kernel above was bound by shared-memory bandwidth, not by HBM or FMAs: each broadcast float4 of the row
-// activations fed 4 FMAs, i.e. 2 MS LDS.128 (4 LSU cycles each) per 8 MS FMAs per warp - 360 us of LSU time per step
-// for the 256-agent population (ncu: L1/TEX 84 %).  With four columns per thread the same broadcast feeds 16 FMAs.
-constexpr int MT4_THREADS = 128, MT4_CPT = 4;
+// Column-blocked variant (round 2 experiment, opt-in through reserved[7]): every thread owns MT4_CPT hidden columns, so
+// that one broadcast float4 of the row activations feeds 4 x MT4_CPT FMAs instead of 4.  ncu of the round-1 kernel:
+// L1/TEX 90 % busy with 62 M shared-memory wavefronts + 66 M global sectors per launch (profiles/r2_model_term_ncu.txt).
+// Measured on the 256-agent step: 4 columns x 128 threads 571 us (shared wavefronts 62 M -> 22 M, but 16 warps per SM
+// leave the FMAs waiting on LDS: short-scoreboard stalls dominate), 2 columns x 256 threads 465 us, round-1 kernel
+// 467 us.  Not a win; kept for the record and for small hidden sizes.
+constexpr int MT4_THREADS = 256, MT4_CPT = 2;
 template <int MS>
-__global__ void __launch_bounds__(MT4_THREADS, 4) k_model_term4(KCtx c, float* __restrict__ mse_part) {
+__global__ void __launch_bounds__(MT4_THREADS, 3) k_model_term4(KCtx c, float* __restrict__ mse_part) {
   extern __shared__ float msm[];
   const int net = blockIdx.x, agent = blockIdx.y;
   const int S = c.S, A = c.A, SA = S + A, H1 = c.mh1, H2 = c.mh2, mo = c.mo, E = c.E;

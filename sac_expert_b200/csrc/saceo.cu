@@ -704,7 +704,7 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
          (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
-    if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7] == 0) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
+    if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7] != 0) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
     count_launch(x, "k_model_term", st);
   } else if (k.nmod > 0) {
     const int half = k.nmod == 2 ? E / 2 : E;
