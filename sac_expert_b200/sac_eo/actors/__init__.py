@@ -1,0 +1,1 @@
+from .init_actor import init_actor

@@ -7,7 +7,9 @@ What the reference keeps in tf.Variables / Keras optimizers / NumPy lives in a s
 for many agents).  The random draws are made on the HOST with the same calls, in the same order, as the
 reference (``np.random.randint`` for the minibatch, ``np.random.normal`` for the three / five action-noise
 draws, ``self.rng.shuffle`` for the expert split) and injected, so the NumPy RNG streams are consumed
-identically.  The environment loop (``train``) is out of scope."""
+identically.  ``train`` is the reference's environment loop (host Python) around that call."""
+import time
+
 import numpy as np
 import torch
 
@@ -16,6 +18,7 @@ from ...population import Population, PopulationSpec
 from ..common.buffers import TrajectoryBuffer
 from ..common.logger import Logger
 from ..common.normalizer import RunningNormalizers
+from ..common.samplers import trajectory_sampler
 from ..envs.synthetic import flatdim
 
 _DEFAULTS = dict(gamma=0.995, lam=0.97, init_temperature=0.1, q_crit_lr=3e-4, mbpo_actor_lr=1e-4, mbpo_alpha_lr=1e-4,
@@ -24,7 +27,9 @@ _DEFAULTS = dict(gamma=0.995, lam=0.97, init_temperature=0.1, q_crit_lr=3e-4, mb
                  epsilon=1e-3, scale_epsilon_by_true_MSE=False, use_expert_actions=False, scale_max_disc=False,
                  scale_median_disc=False, scale_total_disc=False, exp_mult=False, min_mult=False, mult_coeff=1.0,
                  expert_buffer_size=20, expert_batch_size=None, model_buffer_size=100000, device_replay_capacity=100000,
-                 gemm_mode=_l.GEMM_TCGEN05_BF16X3, device=0, save_path="./logs", checkpoint_file="TEMPLOG")
+                 gemm_mode=_l.GEMM_TCGEN05_BF16X3, device=0, save_path="./logs", checkpoint_file="TEMPLOG",
+                 save_freq=None, eval_freq=None, eval_num_traj=5, env_horizon=1000, env_batch_type="steps",
+                 env_batch_size_init=5000, env_batch_size=3000, exp_batch_type="steps", total_timesteps=5e5)
 
 
 class SAC:
@@ -65,6 +70,13 @@ class SAC:
         self.expert_buffer_size = int(kw["expert_buffer_size"]) if kw["expert_buffer_size"] else None
         self.expert_batch_size = kw["expert_batch_size"]
         self.save_path, self.checkpoint_file = kw["save_path"], kw["checkpoint_file"]
+        self.save_freq, self.eval_freq, self.eval_num_traj = kw["save_freq"], kw["eval_freq"], int(kw["eval_num_traj"])
+        self.env_horizon, self.env_batch_type = int(kw["env_horizon"]), kw["env_batch_type"]
+        self.env_batch_size_init, self.env_batch_size = int(kw["env_batch_size_init"]), int(kw["env_batch_size"])
+        self.exp_batch_type = kw["exp_batch_type"]
+        self._max_episode_steps = self.env_horizon               # base_onpolicy_alg.py:104
+        self.corruptor = None                                    # state-noise corruption (common/corruptor.py) is out of scope
+        self.last_eval = 0
 
     def _n_models(self):
         return 0
@@ -162,8 +174,120 @@ class SAC:
         """Polyak averaging is fused into the critic Adam kernel, gated on
         ``num_timesteps % target_update_int == 0`` like SAC.py:246-248; nothing to do here."""
 
+    # ------------------------------------------------------------------ environment loop (host; callers of the hot path)
+    def _evaluate(self, num_timesteps):
+        """``_evaluate`` (base_onpolicy_alg.py:174-197)."""
+        t0 = time.time()
+        J = [trajectory_sampler(self.env_eval, self.actor, self.env_horizon, eval=True, deterministic=True)[-1]
+             for _ in range(self.eval_num_traj)]
+        self.logger.log_train({"J_tot_eval": np.mean(J), "steps_eval": num_timesteps - self.last_eval,
+                               "time_eval": time.time() - t0})
+        self.last_eval = num_timesteps
+
+    def _data_sinks(self):
+        return [self.env_data]
+
+    def _collect_env_data(self, num_timesteps, update_normalizers=True, only_model_normalizer=False):
+        """``_collect_env_data`` (SAC_expert.py:625-683 / SAC.py): whole rollouts with the current actor before the
+        per-step loop starts."""
+        t0 = time.time()
+        batch_size = self.env_batch_size_init if num_timesteps == 0 else self.env_batch_size
+        steps_start, traj_start = self.env_data.steps_total, self.env_data.traj_total
+        cur, J_all = 0, []
+        while cur < batch_size:
+            horizon = min(batch_size - cur, self.env_horizon) if self.env_batch_type == "steps" else self.env_horizon
+            s, a, r, sp, d, J = trajectory_sampler(self.env, self.actor, horizon, eval=True, corruptor=self.corruptor)
+            if update_normalizers:
+                (self.model_normalizer if only_model_normalizer else self.normalizer).update_rms(s, a, r, sp)
+            for sink in self._data_sinks():
+                sink.add(s, a, r, sp, d)
+            if horizon == self.env_horizon:
+                J_all.append(J)
+            cur = (self.env_data.steps_total - steps_start) if self.env_batch_type == "steps" \
+                else (self.env_data.traj_total - traj_start)
+        steps_new = self.env_data.steps_total - steps_start
+        self.current_reward = np.mean(J_all) if J_all else float("nan")
+        self.logger.log_train({"J_tot": self.current_reward, "steps": steps_new,
+                               "traj": self.env_data.traj_total - traj_start, "time_env_data": time.time() - t0})
+        return steps_new
+
+    def _episode_start(self):
+        """Per-episode work before the first step (SAC_exp: model fitting + adaptive expert weight)."""
+        return None
+
+    def _step_update(self, num_timesteps, episode_ctx):
+        self._update(num_timesteps)
+
+    def _dump_and_save(self, params):
+        """``_dump_and_save`` (base_onpolicy_alg.py:366-374)."""
+        self.logger.log_params(params)
+        self.logger.log_final(self._dump_stats())
+        self.logger.dump_and_save(self.save_path, self.checkpoint_name)
+        self.logger.reset()
+
+    def _train_prologue(self):
+        self._set_rms()
+
     def train(self, total_timesteps, params):
-        raise NotImplementedError("the environment loop is a caller of the hot path (SURVEY.md §8f); drive _update() directly")
+        """The reference's training loop (SAC_expert.py:685-824; SAC.py:254-385): initial data collection, then one
+        environment step + one ``_update`` per iteration, per-episode bookkeeping, evaluation and checkpoints.  Host
+        Python; every network call inside is a device call.  Returns the checkpoint name."""
+        total_timesteps = int(total_timesteps)
+        self._train_prologue()
+        pts = lambda f: np.concatenate((np.arange(0, total_timesteps, f)[1:], [total_timesteps]))
+        checkpoints = np.array([total_timesteps]) if self.save_freq is None else pts(self.save_freq)
+        evaluate = self.eval_freq is not None
+        eval_points = pts(self.eval_freq) if evaluate else None
+        checkpt_idx = eval_idx = 0
+        num_timesteps = 0
+        if evaluate:
+            self._evaluate(num_timesteps)
+        num_timesteps += self._collect_env_data(num_timesteps, update_normalizers=self.update_normalizers,
+                                                only_model_normalizer=self.only_model_normalizer)
+        new_traj = TrajectoryBuffer(self.s_dim, self.a_dim, self.gamma, self.lam)
+        episode_step, episode, episode_reward, done = 0, 0, 0.0, True
+        t0 = time.time()
+        ctx = None
+        while num_timesteps < total_timesteps:
+            if done:
+                if self.update_normalizers and episode > 0:
+                    s_, a_, sp_, r_ = new_traj.get_model_info()
+                    if self.only_model_normalizer:
+                        self.model_normalizer.update_rms(s_, a_, r_, sp_)
+                    else:
+                        self.normalizer.update_rms(s_, a_, r_, sp_)
+                        self.model_normalizer.update_rms(s_, a_, r_, sp_)
+                    new_traj.reset()
+                if episode > 0:
+                    self.logger.log_train({"J_tot": episode_reward, "steps": episode_step, "traj": 1,
+                                           "time_env_data": time.time() - t0})
+                    self.current_reward = episode_reward
+                obs = self.env.reset()
+                done, episode_reward, episode_step = False, 0.0, 0
+                episode += 1
+                ctx = self._episode_start()
+                t0 = time.time()
+            a = np.asarray(self.actor.sample(obs, deterministic=not self.random_act).numpy())      # SAC_expert.py:779
+            self._step_update(num_timesteps, ctx)
+            next_obs, r, done, _ = self.env.step(self.actor.clip(a))
+            done_no_max = False if episode_step + 1 == self._max_episode_steps else done
+            episode_reward += r
+            row = (np.array([obs]), np.array([a]), np.array([r]), np.array([next_obs]), np.array([done_no_max]))
+            for sink in self._data_sinks():
+                sink.add(*row)
+            if self.update_normalizers:
+                new_traj.add(*row)
+            obs = next_obs
+            episode_step += 1
+            num_timesteps += 1
+            if evaluate and num_timesteps >= eval_points[eval_idx]:
+                self._evaluate(num_timesteps)
+                eval_idx += 1
+            if num_timesteps >= checkpoints[checkpt_idx]:
+                self._dump_and_save(params)
+                checkpt_idx += 1
+        self._dump_and_save(params)
+        return self.checkpoint_name
 
     def _dump_stats(self):
         """{'actor_weights','critic_weights','rms_stats'} checkpoint payload (base_onpolicy_alg.py:351-364)."""

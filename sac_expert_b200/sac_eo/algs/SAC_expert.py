@@ -2,10 +2,13 @@
 (``/root/reference/sac_eo/algs/SAC_expert.py``).  ``_update(num_timesteps, expert_reg)`` is the seam the CUDA
 path sits behind; ``expert_reg = (s_expert, a_expert, sp_expert, epsilon_coef, use_expert_actions)`` as built by
 ``_expert_preprocess`` (:375-424)."""
+import time
+
 import numpy as np
 import torch
 
 from .SAC import SAC
+from ..common.samplers import trajectory_sampler
 from ..common.buffers import TrajectoryBuffer
 from ..common.normalizer import RunningNormalizers
 
@@ -40,6 +43,53 @@ class SAC_exp(SAC):
         kw = {**self._kw_pre}
         e = kw.get("expert_batch_size") or kw.get("expert_buffer_size") or 20
         return int(e)
+
+    # ------------------------------------------------------------------ environment loop pieces (host)
+    def _data_sinks(self):
+        return [self.env_data, self.model_data]          # the per-step double add (SAC_expert.py:793-798)
+
+    def _collect_expert_data(self):
+        """``_collect_expert_data`` (:156-209): deterministic rollouts of the expert policy into ``expert_data``."""
+        t0 = time.time()
+        cur, J_all = 0, []
+        while cur < self.expert_buffer_size:
+            horizon = min(self.expert_buffer_size - cur, self.env_horizon) if self.exp_batch_type == "steps" else self.env_horizon
+            s, a, r, sp, d, J = trajectory_sampler(self.env_expert, self.expert, horizon, eval=True, deterministic=True,
+                                                   corruptor=self.corruptor)
+            self.expert_data.add(s, a, r, sp, d)
+            if horizon == self.env_horizon:
+                J_all.append(J)
+            cur = self.expert_data.steps_total if self.exp_batch_type == "steps" else self.expert_data.traj_total
+        self.expert_reward = np.mean(J_all) if J_all else self.expert_reward
+        self.logger.log_train({"expert_J_tot": self.expert_reward, "expert_steps": self.expert_data.steps_total,
+                               "expert_traj": self.expert_data.traj_total, "time_expert_data": time.time() - t0})
+
+    def _train_prologue(self):
+        self._set_rms()
+        self._bind_expert()
+        self._collect_expert_data()
+
+    def _bind_expert(self):
+        """The expert policy is only ever rolled out (never updated): it gets a single-agent device population of its
+        own for its forward passes, with its own normaliser statistics (``init_expert_rms_stats``, :128-133)."""
+        if self.expert is None or getattr(self.expert, "_pop", None) is not None:
+            return
+        from ...population import Population, PopulationSpec
+        e = self.expert
+        spec = PopulationSpec(n_agents=1, S=self.s_dim, A=self.a_dim, actor_hidden=e.layers, critic_hidden=(8, 8),
+                              model_hidden=(8, 8), actor_acts=e.activations, per_state_std=e.per_state_std, num_models=0,
+                              B=self.sac_batch_size, E=2, replay_capacity=16, std_mult=e.std_mult,
+                              gemm_mode=self.alg_kwargs["gemm_mode"], device=self.alg_kwargs["device"])
+        self._expert_pop = Population(spec)
+        e._bind(self._expert_pop, 0, "actor")
+        e.set_rms(self.expert_normalizer)
+
+    def _episode_start(self):
+        self._update_models()
+        return self._expert_preprocess()
+
+    def _step_update(self, num_timesteps, expert_reg):
+        self._update(num_timesteps, expert_reg)
 
     # ------------------------------------------------------------------ hot path
     def _update(self, num_timesteps, expert_reg):

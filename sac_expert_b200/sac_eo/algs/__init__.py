@@ -1,0 +1,1 @@
+from .init_alg import init_alg

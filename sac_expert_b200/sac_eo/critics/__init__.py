@@ -1,0 +1,1 @@
+from .init_critic import init_critics

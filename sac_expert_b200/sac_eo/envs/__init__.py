@@ -1,0 +1,1 @@
+from .init_env import init_env

@@ -204,3 +204,24 @@ def test_trajectory_buffer_window_equals_concatenate_semantics(buffer_size):
         assert np.array_equal(tb.d_all, D) and tb.d_all.dtype == np.float64 and np.array_equal(tb.idx_all, I)
     s_, a_, sp_, r_ = tb.get_model_info()
     assert s_.shape == (len(R), 3) and a_.shape == (len(R), 2)
+
+
+def test_train_parser_groups_and_seed_derivation():
+    """The kwarg groups `train()` consumes carry the reference's flag names and defaults
+    (/root/reference/sac_eo/common/train_parser.py) and the per-run seeds follow train.py:116-147."""
+    from sac_expert_b200.sac_eo import train as T
+    from sac_expert_b200.sac_eo.common.train_parser import all_kwargs, create_train_parser
+    args = create_train_parser().parse_args(["--env_type", "synthetic", "--env_name", "ant", "--actor_squash", "--runs", "3",
+                                             "--no_model_batch_shuffle", "--alg_seed", "5"])
+    inputs = T.build_inputs(args)
+    assert len(inputs) == 3 and [i["setup_kwargs"]["idx"] for i in inputs] == [0, 1, 2]
+    a = inputs[0]["alg_kwargs"]
+    assert (a["gamma"], a["soft_tau"], a["sac_batch_size"], a["epsilon"], a["expert_buffer_size"], a["alg_type"]) == \
+        (0.995, 5e-3, 256, 1e-3, 20, "sac_imit")
+    assert a["model_batch_shuffle"] is False and a["init_rms_stats"] is None and a["save_path"] == "./logs"
+    assert inputs[0]["model_kwargs"]["model_layers"] == [512, 512] and inputs[0]["critic_kwargs"]["num_models"] == 2
+    seeds = np.random.SeedSequence(0).generate_state(5)
+    assert inputs[1]["setup_kwargs"]["sim_seed"] == int(np.random.SeedSequence(seeds[1]).generate_state(3)[1])
+    assert all(i["setup_kwargs"]["algorithm_seed"] == 5 for i in inputs)
+    assert set(all_kwargs) == {"setup_kwargs", "env_kwargs", "actor_kwargs", "critic_kwargs", "model_kwargs",
+                               "model_setup_kwargs", "alg_kwargs", "mf_update_kwargs"}
