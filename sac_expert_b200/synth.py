@@ -126,10 +126,26 @@ def algorithmic_bytes(sp, L) -> float:
     return float(4 * (2 * 6 * L.nc + 2 * 2 * L.nc + 6 * L.na + sp.num_models * nm) + 4 * B * (2 * S + A + 2) + 4 * E * 2 * S)
 
 
-def kernel_algorithmic_bytes(sp, L) -> dict:
-    """Compulsory HBM bytes PER AGENT-UPDATE of the launches of each hot kernel (what every launch must read and write
-    even with perfect on-chip reuse: the weights of the nets it applies once, its input rows, the outputs another kernel
-    consumes).  Used by bench.py for the per-kernel roofline next to the live per-launch times."""
+def kernel_compulsory_bytes(sp, L) -> dict:
+    """SURVEY.md 8d's compulsory bytes per agent-update, apportioned to the kernels that MUST move them: every
+    parameter and optimiser slot once per update belongs to the optimiser kernel (theta, m, v read + write, targets read +
+    write), the frozen model weights once to the expert-observation term, the minibatch rows to the gather.  The fused
+    forward / backward / weight-gradient kernels have NO compulsory HBM traffic in that model (with perfect on-chip
+    reuse the weights would be touched by the optimiser only): everything they move is overhead of the design, reported
+    as ``bandwidth_util`` of ``kernel_design_bytes`` and never as a roofline fraction."""
+    S, A, B = sp.S, sp.A, sp.B
+    E = sp.E if sp.num_models > 0 else 0
+    return {
+        "k_adam": float(4 * (2 * 6 * L.nc + 2 * 2 * L.nc + 6 * L.na)),
+        "k_model_term": float(4 * (sp.num_models * L.nm + E * 2 * S)) if sp.num_models > 0 else 0.0,
+        "k_gather": float(4 * B * (2 * S + A + 2)),
+    }
+
+
+def kernel_design_bytes(sp, L) -> dict:
+    """HBM bytes PER AGENT-UPDATE the launches of each hot kernel move BY DESIGN (weights of the nets each pass applies,
+    input rows, saved activations, gradients written for the optimiser to read): the denominator of a bandwidth
+    utilisation, not of a roofline fraction - summed over the kernels it is about 2.8x SURVEY.md 8d's compulsory bytes."""
     S, A, B, SA = sp.S, sp.A, sp.B, sp.S + sp.A
     E = sp.E if sp.num_models > 0 else 0
     R, H, Ao = B + E, sp.critic_hidden[0], L.Ao
@@ -142,9 +158,12 @@ def kernel_algorithmic_bytes(sp, L) -> dict:
         + (L.na + 2 * R * sp.actor_hidden[0] + 2 * R * sp.actor_hidden[0] + R * Ao))
     dw = (2 * (B * SA + 4 * B * H + L.nc)) + (R * S + 4 * R * sp.actor_hidden[0] + R * Ao + L.na)   # activations in, gradients out
     return {
-        "k_mlp_fwd_tc": float(w * fwd),
-        "k_mlp_bwd_tc": float(w * bwd),
+        "k_mlp_fwd_tc": float(w * fwd), "k_mlp_fwd_ws": float(w * fwd),
+        "k_mlp_bwd_tc": float(w * bwd), "k_mlp_bwd_ws": float(w * bwd),
         "k_model_term": float(w * (sp.num_models * L.nm + E * (2 * S + A))) if sp.num_models > 0 else 0.0,
-        "k_adam": float(w * (2 * 9 * L.nc + 7 * L.na)),
+        "k_adam": float(w * (2 * 11 * L.nc + 8 * L.na)),        # + the fp16 hi/lo weight planes of theta and of the targets
         "k_gemm_tc+k_gemm_skinny": float(w * dw),
     }
+
+
+kernel_algorithmic_bytes = kernel_design_bytes      # round-1 name
