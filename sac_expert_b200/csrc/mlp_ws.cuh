@@ -114,7 +114,7 @@ __device__ __forceinline__ void ws_store_rows(uint32_t patch, const uint32_t (&v
     const int r = rr + lr, grow = rbase + r;
     if (grow < rows) {
       const float4 t4 = lds128(ws_pa(patch, r, lc));
-      *reinterpret_cast<float4*>(G + (long long)grow * FW_H + col + lc) = t4;
+      if (G) *reinterpret_cast<float4*>(G + (long long)grow * FW_H + col + lc) = t4;
       sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
     }
   }
@@ -176,6 +176,21 @@ __device__ __forceinline__ void ws_load_rows(uint32_t patch, const float* __rest
     aux[4 * j] = t4.x; aux[4 * j + 1] = t4.y; aux[4 * j + 2] = t4.z; aux[4 * j + 3] = t4.w;
   }
   __syncwarp();
+}
+// this lane's row b (32 consecutive columns starting at col) -> bf16 hi / lo planes of the [rows x 256] activation image
+// (same layout as the weight images: ws_image_off(row, 16-byte chunk)); read back by k_dw_planes as an MN-major operand
+__device__ __forceinline__ void ws_store_planes_bf16(uint8_t* __restrict__ img, int row, int col, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]);
+    uint4 hi, lo;
+    split8<false>(x, hi, lo);
+    uint8_t* dst = img + ws_image_off(row, (col >> 3) + ch);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + 16384) = lo;
+  }
 }
 // tcgen05.ld without the wait: two chunks are requested back to back, then waited for once
 __device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t (&v)[32]) {
@@ -317,6 +332,7 @@ struct FwdW {
   const float* theta; long long sTa, sTn;
   const uint8_t* planes; long long sPa, sPn;      // plane images (bytes): per agent / per net strides
   float* H1; float* H2; long long sHa, sHn;       // optional saved activations [rows, 256]
+  uint8_t* H1p; long long sQa, sQn;               // optional bf16 hi/lo plane image of h1 (operand of k_dw_planes), bytes
   float* Out; int ldo; long long sOa, sOn;
   int rows, K0, nout, nnet, act0, act1;
   unsigned long long* dbg;                         // optional per-CTA phase stamps (16 per CTA, globaltimer ns)
@@ -469,6 +485,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
         if (lane == 0) mbar_arrive(bar(WB_AP + cg));      // the layer-1 MMAs of this 64-wide k group may start
       }
       if (H1) { ws_store_rows(patch, v, H1, rbase, f.rows, col, lane); __syncwarp(); }
+      if (f.H1p && grow < f.rows) ws_store_planes_bf16(f.H1p + agent * f.sQa + net * f.sQn, grow, col, v);
     }
     if (warp == 0) WS_STAMP(3);
     // ---- output-layer weights as fp32 [256][np] in AUX (the X planes are dead: every layer-0 MMA has retired); the
@@ -577,6 +594,7 @@ struct BwdW {
   const uint8_t* planes; long long sPa, sPn;
   const float* H1; const float* H2; long long sHa, sHn;
   float* dH2; float* dH1;
+  uint8_t* dH2p; long long sQa, sQn;               // optional bf16 hi/lo plane image of dH2 (replaces the fp32 dH2), bytes
   float* dXa; int s_cols, a_cols; long long sXa, sXn;
   int rows, nnet, act0, act1;
   float* dbpart;
@@ -664,7 +682,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const float* H2 = f.H2 + agent * f.sHa + net * f.sHn;
     float* dH1 = f.dH1 ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
     float* dH2 = f.dH2 ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
-    const bool want_cs = f.dbpart && dH2 && dH1;
+    const bool want_cs = f.dbpart && (dH2 || f.dH2p) && dH1;
     const int kp = (f.kout + 3) & ~3;
     const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
@@ -735,9 +753,10 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(WB_AP + cg));
       }
-      if (dH2) {
-        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
+      if (dH2 || f.dH2p) {
+        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);      // dH2 == null: column sums only
         __syncwarp();
+        if (f.dH2p && rvalid) ws_store_planes_bf16(f.dH2p + agent * f.sQa + net * f.sQn, grow, col, v);
       }
     }
     if (warp == 0) WS_STAMP(2);
@@ -835,6 +854,107 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
   }
 }
 
+// ==========================================================================================
+// Weight gradient of the hidden-to-hidden layer from the activation plane images:
+//     dW1[i, j] = sum_b h1[b, i] * dH2[b, j]          (one CTA per (agent, net): the whole 256 x 256 block)
+// Both operands arrive by TMA as bf16 hi/lo planes written by the fused forward (h1) and backward (dH2) kernels -
+// MN-major SWIZZLE_128B operands with the batch row as the contraction index, 32 rows (64 KB: A + B) per stage - so
+// the kernel converts nothing: producer warp, MMA thread (two 128-row accumulator blocks = all 512 TMEM columns,
+// 3 MMAs per product), 16 epilogue warps that write the fp32 gradient block through the transposition patches.
+// Replaces the cp.async + in-kernel-conversion GEMM for this shape (85 + 170 us per step at 256 agents -> see DESIGN).
+// ==========================================================================================
+struct DwP {
+  const uint8_t* Ap; long long sAa, sAn;      // h1 planes  [rows(pad 32) x 256]
+  const uint8_t* Bp; long long sBa, sBn;      // dH2 planes
+  float* G; long long sGa, sGn;               // gradient block W1 of the flat layout (pitch 256)
+  int rows, nnet;
+};
+constexpr int DW_STAGE = 2 * WS_STAGE, DW_NST = 3;
+constexpr int DW_MAIN = DW_NST * DW_STAGE;                       // 192 KB; the epilogue patches overlay the ring
+constexpr int DW_BYTES = DW_MAIN + 1024 + 256;
+constexpr uint32_t DW_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(WS_NT, 1) k_dw_planes(DwP f) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring = sb, bars = sb + DW_MAIN, tslot = bars + 8 * 16;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };          // [0..3) full, [3..6) empty, [6] done
+  const int z = blockIdx.x, agent = z / f.nnet, net = z - agent * f.nnet;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = (f.rows + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * DW_NST + 1; ++s) mbar_init(bar(s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WS_NEW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = lds_u32(tslot);
+  if (warp == WS_NEW) {
+    if (lane == 0) {
+      const uint8_t* A = f.Ap + agent * f.sAa + net * f.sAn;
+      const uint8_t* B = f.Bp + agent * f.sBa + net * f.sBn;
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % DW_NST;
+        mbar_wait(bar(DW_NST + s), (uint32_t)(((it / DW_NST) & 1) ^ 1));
+        mbar_expect_tx(bar(s), DW_STAGE);
+        bulk_g2s(ring + s * DW_STAGE, A + (long long)it * WS_STAGE, WS_STAGE, bar(s));
+        bulk_g2s(ring + s * DW_STAGE + WS_STAGE, B + (long long)it * WS_STAGE, WS_STAGE, bar(s));
+      }
+    }
+  } else if (warp == WS_NEW + 1) {
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % DW_NST;
+        mbar_wait(bar(s), (uint32_t)((it / DW_NST) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = ring + s * DW_STAGE, sbb = sa + WS_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t ko = (uint32_t)kk * 2048;
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {          // accumulator block mb: gradient rows i in [128 mb, 128 mb + 128)
+            const uint32_t a_hi = sa + mb * 8192 + ko, a_lo = a_hi + 16384, b_hi = sbb + ko, b_lo = b_hi + 16384;
+            const uint32_t d = tmem + 256 * mb, acc = (it | kk) ? 1u : 0u;
+            umma_f16(d, umma_desc_mn(a_hi), umma_desc_mn(b_hi), DW_IDESC, acc);
+            umma_f16(d, umma_desc_mn(a_hi), umma_desc_mn(b_lo), DW_IDESC, 1u);
+            umma_f16(d, umma_desc_mn(a_lo), umma_desc_mn(b_hi), DW_IDESC, 1u);
+          }
+        }
+        umma_commit(bar(DW_NST + s));
+      }
+      umma_commit(bar(2 * DW_NST));
+    }
+  } else {
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t patch = ring + (uint32_t)warp * WS_PATCH1;         // the operand ring is dead once the last MMA has retired
+    float* G = f.G + agent * f.sGa + net * f.sGn;
+    mbar_wait(bar(2 * DW_NST), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col = cg * 64 + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + (uint32_t)(256 * mb + col), v);
+        ws_store_rows(patch, v, G, mb * 128 + q * 32, 256, col, lane);
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == WS_NEW + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -849,6 +969,7 @@ static inline cudaError_t mlp_ws_init() {
   WS_ATTR((k_mlp_bwd_ws<0, 0>)) WS_ATTR((k_mlp_bwd_ws<0, 1>)) WS_ATTR((k_mlp_bwd_ws<0, 2>))
   WS_ATTR((k_mlp_bwd_ws<1, 0>)) WS_ATTR((k_mlp_bwd_ws<2, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0>))
 #undef WS_ATTR
+  e = cudaFuncSetAttribute(k_dw_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_BYTES); if (e) return e;
   done = true;
   return cudaSuccess;
 }

@@ -70,8 +70,11 @@ struct saceo_ctx {
   // actor-phase buffers of their own (input operands, head outputs, neglogp, critic input with pi(s)), so that the
   // critic-independent half of the actor phase can run on a second stream next to the critic phase
   float *Xpi2 = nullptr, *aOut2 = nullptr, *nlp2 = nullptr, *Xc3 = nullptr;
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // bf16 hi/lo plane images of h1 / dH2 (actor: Rs rows, critics: B rows per net): operands of k_dw_planes
+  uint8_t *aH1p = nullptr, *adH2p = nullptr, *cH1p = nullptr, *cdH2p = nullptr;
+  long long a_img = 0, c_img = 0;      // bytes per (agent, net) image
+  cudaStream_t s2 = nullptr, s3 = nullptr, s4 = nullptr;      // s3 / s4: the three independent weight-gradient GEMMs of a backward pass side by side
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_g = nullptr, ev_g3 = nullptr, ev_g4 = nullptr;
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -217,12 +220,17 @@ static void carve(saceo_ctx* x, char* base) {
   }
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
   x->pl_actor = x->pl_q = x->pl_qt = nullptr;
+  x->aH1p = x->adH2p = x->cH1p = x->cdH2p = nullptr;
+  x->a_img = (long long)(R / 32) * WS_STAGE; x->c_img = (long long)(rup(B, 32) / 32) * WS_STAGE;
   if (c.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && c.reserved[5] == 0) {
-    if (c.actor_hidden[0] == FW_H && c.actor_hidden[1] == FW_H)
+    if (c.actor_hidden[0] == FW_H && c.actor_hidden[1] == FW_H) {
       x->pl_actor = b.get<uint8_t>("pl_actor", n * ws_image_bytes(S));
+      x->aH1p = b.get<uint8_t>("aH1p", n * x->a_img); x->adH2p = b.get<uint8_t>("adH2p", n * x->a_img);
+    }
     if (c.critic_hidden[0] == FW_H && c.critic_hidden[1] == FW_H) {
       x->pl_q = b.get<uint8_t>("pl_q", n * 2 * ws_image_bytes(SA));
       x->pl_qt = b.get<uint8_t>("pl_qt", n * 2 * ws_image_bytes(SA));
+      x->cH1p = b.get<uint8_t>("cH1p", n * 2 * x->c_img); x->cdH2p = b.get<uint8_t>("cdH2p", n * 2 * x->c_img);
     }
   }
   x->idx_stage = b.get<long long>("idx_stage", n * B);
@@ -316,6 +324,11 @@ static int create_fill(saceo_ctx* x, const saceo_config* cfg) {
   CU(cudaStreamCreateWithFlags(&x->s2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&x->s3, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&x->s4, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&x->ev_g, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&x->ev_g3, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&x->ev_g4, cudaEventDisableTiming));
   CU(tc_gemm_init());
   CU(mlp_fwd_tc_init());
   CU(mlp_ws_init());
@@ -331,6 +344,9 @@ extern "C" int saceo_destroy(saceo_ctx* x) {
   if (x->s2) cudaStreamDestroy(x->s2);
   if (x->ev_fork) cudaEventDestroy(x->ev_fork);
   if (x->ev_join) cudaEventDestroy(x->ev_join);
+  if (x->s3) cudaStreamDestroy(x->s3);
+  if (x->s4) cudaStreamDestroy(x->s4);
+  for (cudaEvent_t e : {x->ev_g, x->ev_g3, x->ev_g4}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : x->prof_ev) cudaEventDestroy(e);
   delete x;
   return 0;
@@ -462,7 +478,8 @@ static int mlp_forward_unfused(saceo_ctx* x, const NetD& n, const float* X, int 
 // stay in TMEM between layers; h1/h2 reach HBM only when save_h), leftover rows through the GEMM chain.
 static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, long long sXa, long long sXn,
                        int rows, float* H1, float* H2, long long rowsAllocH, float* Out, int ldo,
-                       long long sOa, long long sOn, cudaStream_t st, bool save_h = true) {
+                       long long sOa, long long sOn, cudaStream_t st, bool save_h = true,
+                       uint8_t* H1p = nullptr, long long sQa = 0, long long sQn = 0) {
   int row0 = 0;
   if (n.planes && x->cfg.reserved[1] == 0 && mlp_fwd_ws_eligible(n.h1, n.h2, n.out, n.in, n.theta, n.sa, n.sn)) {
     // warp-specialised kernel on the TMA-fed weight planes: every row (partial tiles are masked)
@@ -472,6 +489,7 @@ static int mlp_forward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lon
     f.planes = n.planes; f.sPa = n.pa; f.sPn = n.pn;
     f.H1 = save_h ? H1 : nullptr; f.H2 = save_h ? H2 : nullptr;
     f.sHa = (long long)n.nnet * rowsAllocH * n.h1; f.sHn = rowsAllocH * n.h1;
+    f.H1p = save_h ? H1p : nullptr; f.sQa = sQa; f.sQn = sQn;
     f.Out = Out; f.ldo = ldo; f.sOa = sOa; f.sOn = sOn;
     f.rows = rows; f.K0 = n.in; f.nout = n.out; f.nnet = n.nnet; f.act0 = n.act0; f.act1 = n.act1;
     f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
@@ -507,7 +525,8 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
                         const float* dOut, int ldd, long long sDa, long long sDn, int out_cols,
                         float* dH2, float* dH1, float* grads, long long sGa, long long sGn,
                         float* dXa, int S_cols, int A_cols, long long sXaA, long long sXaN, cudaStream_t st,
-                        bool kpad = false) {
+                        bool kpad = false, const uint8_t* H1p = nullptr, uint8_t* dH2p = nullptr, long long sQa = 0,
+                        long long sQn = 0) {
   const int na = x->cfg.n_agents;
   // kpad: the caller guarantees that rows [rows, rowsAllocH) of X, H1, H2, dOut, dH2, dH1 are zero, so the
   // weight-gradient contractions may run over a row count rounded up to the 32-row slabs of the streaming kernel
@@ -517,7 +536,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   int rc;
   GemmP p{};
   // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
-  bool fused = false, bias_done = false;
+  bool fused = false, bias_done = false, dw1_planes = false;
   if (n.planes && x->cfg.reserved[2] == 0 &&
       mlp_bwd_ws_eligible(n.h1, n.h2, out_cols, n.out, dXa != nullptr, A_cols, n.theta, n.sa, n.sn)) {
     BwdW f{};
@@ -531,6 +550,9 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     const int tiles = (rows + TC_BM - 1) / TC_BM;
     const bool db_fits = (long long)na * n.nnet * tiles * 2 * FW_H <= x->dbpart_cap;
     f.dbpart = (grads && x->dbpart && db_fits && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
+    // hidden-to-hidden weight gradient from bf16 plane images (k_dw_planes): dH2 then leaves the kernel as planes only
+    dw1_planes = grads && f.dbpart && H1p && dH2p;
+    if (dw1_planes) { f.dH2 = nullptr; f.dH2p = dH2p; f.sQa = sQa; f.sQn = sQn; }
     f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
     if (mlp_bwd_ws_launch(f, na, st) != cudaSuccess) return fail(SACEO_E_CUDA, "fused backward launch failed");
     count_launch(x, "k_mlp_bwd_ws", st);
@@ -565,13 +587,22 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
       bias_done = true;
     }
   }
+  // the three weight-gradient GEMMs are independent of each other: with the fused chain they fan out over three streams
+  // (captured into the graph as parallel branches) - at small populations each is one under-filled, latency-bound wave
+  const bool fan = fused && grads && x->cfg.reserved[6] == 0 && !x->prof && x->s3 && x->s4;
+  cudaStream_t st2 = st, st0 = st;
+  if (fan) {
+    CU(cudaEventRecord(x->ev_g, st));
+    CU(cudaStreamWaitEvent(x->s3, x->ev_g, 0)); CU(cudaStreamWaitEvent(x->s4, x->ev_g, 0));
+    st2 = x->s3; st0 = x->s4;
+  }
   if (grads) {   // [dW2; db2] = [H2,1]^T . dOut
     p = GemmP{}; p.nnet = n.nnet;
     p.A = H2; p.lda = n.h2; p.sAa = sH2a; p.sAn = sH2n;
     p.B = dOut; p.ldb = ldd; p.sBa = sDa; p.sBn = sDn;
     p.C = grads + n.oW2(); p.ldc = n.out; p.sCa = sGa; p.sCn = sGn;
     p.M = n.h2 + 1; p.N = n.out; p.K = krows; p.epi = EPI_NONE;
-    rc = gemm(x, true, false, true, p, na, st); if (rc) return rc;
+    rc = gemm(x, true, false, true, p, na, st2); if (rc) return rc;
   }
   if (!fused) {
   // dH2 = (dOut . W2[:, :out_cols]^T) * act1'(H2)
@@ -582,7 +613,13 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   p.M = rows; p.N = n.h2; p.K = out_cols; p.epi = EPI_MUL_DACT; p.act = n.act1;
   rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
   }
-  if (grads) {   // [dW1; db1] = [H1,1]^T . dH2
+  if (grads && dw1_planes) {   // dW1 = H1^T . dH2 from the plane images (db1 came from the kernel's column sums)
+    DwP d{};
+    d.Ap = H1p; d.sAa = sQa; d.sAn = sQn; d.Bp = dH2p; d.sBa = sQa; d.sBn = sQn;
+    d.G = grads + n.oW1(); d.sGa = sGa; d.sGn = sGn; d.rows = rows; d.nnet = n.nnet;
+    k_dw_planes<<<na * n.nnet, WS_NT, DW_BYTES, st>>>(d);
+    count_launch(x, "k_dw_planes", st);
+  } else if (grads) {   // [dW1; db1] = [H1,1]^T . dH2
     p = GemmP{}; p.nnet = n.nnet;
     p.A = H1; p.lda = n.h1; p.sAa = sH1a; p.sAn = sH1n;
     p.B = dH2; p.ldb = n.h2; p.sBa = sH2a; p.sBn = sH2n;
@@ -605,7 +642,11 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     p.B = dH1; p.ldb = n.h1; p.sBa = sH1a; p.sBn = sH1n;
     p.C = grads + n.oW0(); p.ldc = n.h1; p.sCa = sGa; p.sCn = sGn;
     p.M = bias_done ? n.in : n.in + 1; p.N = n.h1; p.K = krows; p.epi = EPI_NONE;
-    rc = gemm(x, true, false, !bias_done, p, na, st); if (rc) return rc;
+    rc = gemm(x, true, false, !bias_done, p, na, st0); if (rc) return rc;
+  }
+  if (fan) {
+    CU(cudaEventRecord(x->ev_g3, x->s3)); CU(cudaEventRecord(x->ev_g4, x->s4));
+    CU(cudaStreamWaitEvent(st, x->ev_g3, 0)); CU(cudaStreamWaitEvent(st, x->ev_g4, 0));
   }
   if (dXa && !fused) {     // dX[:, S:S+A] = dH1 . W0[S:S+A, :]^T
     p = GemmP{}; p.nnet = n.nnet;
@@ -666,10 +707,12 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   rc = mlp_forward(x, tn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
   LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
-  rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st); if (rc) return rc;
+  rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, true,
+                   x->cH1p, 2 * x->c_img, x->c_img); if (rc) return rc;
   LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
   rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
-                    k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st);
+                    k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st, false,
+                    x->cH1p, x->cdH2p, 2 * x->c_img, x->c_img);
   if (rc) return rc;
   return check_launch();
 }
@@ -698,7 +741,8 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   int rc;
   NetD an = actor_net(x);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
-  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st);
+  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st, true,
+                   x->aH1p, x->a_img, 0);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
          (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
@@ -775,7 +819,8 @@ static int phase_actor_post(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   }
   LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
   rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
-                    k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true);
+                    k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true,
+                    x->aH1p, x->adH2p, x->a_img, 0);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
   return check_launch();
