@@ -177,20 +177,56 @@ __device__ __forceinline__ void ws_load_rows(uint32_t patch, const float* __rest
   }
   __syncwarp();
 }
-// this lane's row b (32 consecutive columns starting at col) -> bf16 hi / lo planes of the [rows x 256] activation image
-// (same layout as the weight images: ws_image_off(row, 16-byte chunk)); read back by k_dw_planes as an MN-major operand
-__device__ __forceinline__ void ws_store_planes_bf16(uint8_t* __restrict__ img, int row, int col, const uint32_t (&v)[32]) {
+// Activation plane images (bf16 hi / lo, layout ws_image_off(row, 16-byte chunk)): the [32 rows x 32 cols] tile of a warp
+// goes through the warp's transposition patch, so that every request touches whole 64-byte row segments (4 lanes per
+// row, 8 rows per request) instead of 32 different lines.  k_dw_planes reads the images as MN-major operands.
+//   store: the patch holds the fp32 tile (written lane-per-row, __syncwarp done)
+__device__ __forceinline__ void ws_store_planes_p(uint32_t patch, uint8_t* __restrict__ img, int rbase, int rows, int col, int lane) {
+  const int lr = lane >> 2, c8 = lane & 3;
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]);
-    uint4 hi, lo;
-    split8<false>(x, hi, lo);
-    uint8_t* dst = img + ws_image_off(row, (col >> 3) + ch);
-    *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + 16384) = lo;
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + lr, grow = rbase + r;
+    if (grow < rows) {
+      const float4 a = lds128(ws_pa(patch, r, 8 * c8)), b = lds128(ws_pa(patch, r, 8 * c8 + 4));
+      const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint4 hi, lo;
+      split8<false>(x, hi, lo);
+      uint8_t* dst = img + ws_image_off(grow, (col >> 3) + c8);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + 16384) = lo;
+    }
   }
+}
+//   load, two-phase: request the tile early (8 x 16 bytes per lane), decode it into the patch (fp32) when needed
+__device__ __forceinline__ void ws_planes_issue(const uint8_t* __restrict__ img, int rbase, int rows, int col, int lane, float4 (&t)[8]) {
+  const int lr = lane >> 2, c8 = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int grow = rbase + 8 * i + lr;
+    t[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * i + 1] = t[2 * i];
+    if (grow < rows) {
+      const uint8_t* src = img + ws_image_off(grow, (col >> 3) + c8);
+      t[2 * i] = __ldg(reinterpret_cast<const float4*>(src));
+      t[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(src + 16384));
+    }
+  }
+}
+__device__ __forceinline__ void ws_planes_commit_p(uint32_t patch, int lane, const float4 (&t)[8]) {
+  const int lr = lane >> 2, c8 = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t hw[4] = {__float_as_uint(t[2 * i].x), __float_as_uint(t[2 * i].y), __float_as_uint(t[2 * i].z), __float_as_uint(t[2 * i].w)};
+    const uint32_t lw[4] = {__float_as_uint(t[2 * i + 1].x), __float_as_uint(t[2 * i + 1].y), __float_as_uint(t[2 * i + 1].z), __float_as_uint(t[2 * i + 1].w)};
+    float h[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+      h[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+    }
+    sts128f(ws_pa(patch, 8 * i + lr, 8 * c8), h[0], h[1], h[2], h[3]);
+    sts128f(ws_pa(patch, 8 * i + lr, 8 * c8 + 4), h[4], h[5], h[6], h[7]);
+  }
+  __syncwarp();
 }
 // tcgen05.ld without the wait: two chunks are requested back to back, then waited for once
 __device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t (&v)[32]) {
@@ -484,8 +520,13 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(WB_AP + cg));      // the layer-1 MMAs of this 64-wide k group may start
       }
-      if (H1) { ws_store_rows(patch, v, H1, rbase, f.rows, col, lane); __syncwarp(); }
-      if (f.H1p && grow < f.rows) ws_store_planes_bf16(f.H1p + agent * f.sQa + net * f.sQn, grow, col, v);
+      if (f.H1p) {          // h1 leaves as a bf16 hi/lo plane image only (operand of k_dw_planes, read back by the backward chain)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(ws_pa(patch, lane, 4 * j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        __syncwarp();
+        ws_store_planes_p(patch, f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
+        __syncwarp();
+      } else if (H1) { ws_store_rows(patch, v, H1, rbase, f.rows, col, lane); __syncwarp(); }
     }
     if (warp == 0) WS_STAMP(3);
     // ---- output-layer weights as fp32 [256][np] in AUX (the X planes are dead: every layer-0 MMA has retired); the
@@ -595,6 +636,7 @@ struct BwdW {
   const float* H1; const float* H2; long long sHa, sHn;
   float* dH2; float* dH1;
   uint8_t* dH2p; long long sQa, sQn;               // optional bf16 hi/lo plane image of dH2 (replaces the fp32 dH2), bytes
+  const uint8_t* H1p;                              // optional: h1 as a bf16 hi/lo plane image (then H1 is not read), strides sQa / sQn
   float* dXa; int s_cols, a_cols; long long sXa, sXn;
   int rows, nnet, act0, act1;
   float* dbpart;
@@ -720,7 +762,8 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       const int col = cg * 64 + c * 32;
       ws_rows_commit_p(patch, lane, hq);
       if (c == 0) ws_rows_issue(H2, rbase, f.rows, col + 32, lane, hq);      // chunk 1 flies during the math of chunk 0
-      else ws_rows_issue(H1, rbase, f.rows, cg * 64, lane, hq);              // first H1 chunk of epilogue 1 flies during the MMAs
+      else if (!f.H1p) ws_rows_issue(H1, rbase, f.rows, cg * 64, lane, hq);  // first H1 chunk of epilogue 1 flies during the MMAs
+      else ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, cg * 64, lane, hq);
       uint32_t v[32];
       if (NG == 0) {
 #pragma unroll
@@ -755,8 +798,8 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       }
       if (dH2 || f.dH2p) {
         ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);      // dH2 == null: column sums only
+        if (f.dH2p) ws_store_planes_p(patch, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
         __syncwarp();
-        if (f.dH2p && rvalid) ws_store_planes_bf16(f.dH2p + agent * f.sQa + net * f.sQn, grow, col, v);
       }
     }
     if (warp == 0) WS_STAMP(2);
@@ -787,10 +830,17 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       const int col = cg * 64 + c * 32;
       uint32_t v[32];
       tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, v);
-      ws_rows_commit_p(patch, lane, hq);
-      if (c == 0) ws_rows_issue(H1, rbase, f.rows, col + 32, lane, hq);
-      tmem_ld_wait();
-      ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
+      if (f.H1p) {        // h1 from its plane image, decoded into the patch
+        ws_planes_commit_p(patch, lane, hq);
+        if (c == 0) ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col + 32, lane, hq);
+        tmem_ld_wait();
+        ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
+      } else {
+        ws_rows_commit_p(patch, lane, hq);
+        if (c == 0) ws_rows_issue(H1, rbase, f.rows, col + 32, lane, hq);
+        tmem_ld_wait();
+        ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
+      }
       if (dH1) {
         ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
         __syncwarp();

@@ -552,7 +552,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     f.dbpart = (grads && x->dbpart && db_fits && x->cfg.reserved[4] == 0) ? x->dbpart : nullptr;
     // hidden-to-hidden weight gradient from bf16 plane images (k_dw_planes): dH2 then leaves the kernel as planes only
     dw1_planes = grads && f.dbpart && H1p && dH2p;
-    if (dw1_planes) { f.dH2 = nullptr; f.dH2p = dH2p; f.sQa = sQa; f.sQn = sQn; }
+    if (dw1_planes) { f.dH2 = nullptr; f.dH2p = dH2p; f.H1p = H1p; f.sQa = sQa; f.sQn = sQn; }
     f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
     if (mlp_bwd_ws_launch(f, na, st) != cudaSuccess) return fail(SACEO_E_CUDA, "fused backward launch failed");
     count_launch(x, "k_mlp_bwd_ws", st);
@@ -659,6 +659,16 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   return 0;
 }
 
+// Will mlp_backward(grads) of this net on `rows` rows take the plane path (fused chain + column-sum biases + k_dw_planes)?
+// The forward pass that saves the activations asks the same question: it then writes h1 ONLY as a plane image.
+static bool dw_planes_ok(const saceo_ctx* x, const NetD& n, int rows, int out_cols, const uint8_t* H1p, const uint8_t* dH2p) {
+  if (!n.planes || x->cfg.reserved[2] != 0 || x->cfg.reserved[1] != 0 || x->cfg.reserved[4] != 0 || !H1p || !dH2p || !x->dbpart) return false;
+  if (!mlp_bwd_ws_eligible(n.h1, n.h2, out_cols, n.out, false, 0, n.theta, n.sa, n.sn)) return false;
+  if (!mlp_fwd_ws_eligible(n.h1, n.h2, n.out, n.in, n.theta, n.sa, n.sn)) return false;
+  const int tiles = (rows + TC_BM - 1) / TC_BM;
+  return (long long)x->cfg.n_agents * n.nnet * tiles * 2 * FW_H <= x->dbpart_cap;
+}
+
 static NetD actor_net(const saceo_ctx* x) {
   const saceo_config& c = x->cfg;
   NetD d{x->k.T.actor, x->L.na_stride, 0, 1, c.S, c.actor_hidden[0], c.actor_hidden[1], x->L.Ao,
@@ -707,12 +717,13 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
          (float*)nullptr, (float*)nullptr, 0LL, 0);
   rc = mlp_forward(x, tn, k.Xc, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, false); if (rc) return rc;
   LAUNCH(x, k_td_target, dim3(cdiv(B, 128), n), 128, 0, st, k);
+  const bool cpl = dw_planes_ok(x, qn, B, 1, x->cH1p, x->cdH2p);
   rc = mlp_forward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cQ, 1, 2LL * B, B, st, true,
-                   x->cH1p, 2 * x->c_img, x->c_img); if (rc) return rc;
+                   cpl ? x->cH1p : nullptr, 2 * x->c_img, x->c_img); if (rc) return rc;
   LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
   rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                     k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st, false,
-                    x->cH1p, x->cdH2p, 2 * x->c_img, x->c_img);
+                    cpl ? x->cH1p : nullptr, cpl ? x->cdH2p : nullptr, 2 * x->c_img, x->c_img);
   if (rc) return rc;
   return check_launch();
 }
@@ -742,7 +753,7 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   NetD an = actor_net(x);
   LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
   rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st, true,
-                   x->aH1p, x->a_img, 0);
+                   dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->aH1p : nullptr, x->a_img, 0);
   if (rc) return rc;
   LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
          (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
@@ -820,7 +831,8 @@ static int phase_actor_post(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   LAUNCH(x, k_head_bwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R);
   rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
                     k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true,
-                    x->aH1p, x->adH2p, x->a_img, 0);
+                    dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->aH1p : nullptr,
+                    dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->adH2p : nullptr, x->a_img, 0);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
   return check_launch();
