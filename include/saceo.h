@@ -88,7 +88,8 @@ typedef struct saceo_config {
                                  [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path;
                                  [5] != 0 disables the warp-specialised TMA-fed fused kernels and their weight planes
                                  (round-1 fused kernels are used instead); [6] != 0 keeps the whole update on one stream (no
-                                 concurrent actor-phase branch); [7] != 0 selects the column-blocked model-term kernel (2 hidden columns per thread; measured equal to the default) */
+                                 concurrent actor-phase branch); [7] expert-term kernel: 0 = hidden layer on mma.sync tf32 hi/lo x3 (default where the
+                                 shape allows), 1 = column-blocked CUDA-core kernel, 2 = round-1 CUDA-core kernel */
 } saceo_config;
 
 /* Strides/offsets (in 4-byte words unless stated) derived from a config. */

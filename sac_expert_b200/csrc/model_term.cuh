@@ -8,6 +8,7 @@
 // 2 x (W0 + W1 + W2) HBM read - the compulsory traffic of this term - instead of seven latency-bound launches.
 #pragma once
 #include "elem.cuh"
+#include "model_term_mma.cuh"
 
 namespace saceo {
 
@@ -501,16 +502,36 @@ static inline cudaError_t model_term_init() {
 #define MT_ATTR(MSV) e = cudaFuncSetAttribute(k_model_term4<MSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e) return e;
   MT_ATTR(4) MT_ATTR(8) MT_ATTR(12) MT_ATTR(16)
 #undef MT_ATTR
+#define MT_ATTR(MSV) e = cudaFuncSetAttribute(k_model_term_mma<MSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); if (e) return e;
+  MT_ATTR(4) MT_ATTR(8) MT_ATTR(12) MT_ATTR(16)
+#undef MT_ATTR
   done = true;
   return cudaSuccess;
 }
 static inline size_t model_term_smem(const KCtx& c, int ms) {
   return (size_t)ms * (c.S + c.A + c.mh1 + c.mh2 + c.mo + c.S) * sizeof(float);
 }
-static inline cudaError_t model_term_launch(const KCtx& c, float* mse_part, cudaStream_t st, bool blocked = true) {
+// variant 0: hidden layer on the tensor cores (k_model_term_mma) where the shape allows, else the round-1 kernel;
+// 1: column-blocked CUDA-core kernel; 2: round-1 kernel.
+static inline bool model_term_mma_ok(const KCtx& c) {
+  const int half = c.nmod == 2 ? c.E / 2 : c.E;
+  return half <= 16 && (c.mh1 % 32) == 0 && (c.mh2 % 32) == 0 && ((c.L.nm_stride % 4) == 0) &&
+         (((long long)(c.S + c.A) * c.mh1 + c.mh1) % 4) == 0 && c.mo <= 32 && model_term_mma_smem(c, 16) <= 224 * 1024;
+}
+static inline cudaError_t model_term_launch(const KCtx& c, float* mse_part, cudaStream_t st, int variant = 0) {
   const int half = c.nmod == 2 ? c.E / 2 : c.E;
   dim3 grid(c.nmod, c.n_agents);
-  if (blocked && half <= 16) {      // column-blocked kernel (4 hidden columns per thread)
+  if (variant == 0 && model_term_mma_ok(c)) {
+    const int nthr = MTM_THREADS;
+#define MT_GOM(MSV) do { k_model_term_mma<MSV><<<grid, nthr, model_term_mma_smem(c, MSV), st>>>(c, mse_part, g_mt_dbg); } while (0)
+    if (half <= 4) MT_GOM(4);
+    else if (half <= 8) MT_GOM(8);
+    else if (half <= 12) MT_GOM(12);
+    else MT_GOM(16);
+#undef MT_GOM
+    return cudaPeekAtLastError();
+  }
+  if (variant == 1 && half <= 16) {      // column-blocked kernel (4 hidden columns per thread)
 #define MT_GO4(MSV) do { k_model_term4<MSV><<<grid, MT4_THREADS, model_term_smem(c, MSV), st>>>(c, mse_part); } while (0)
     if (half <= 4) MT_GO4(4);
     else if (half <= 8) MT_GO4(8);

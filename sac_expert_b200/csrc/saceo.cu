@@ -759,7 +759,7 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
          (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
-    if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7] != 0) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
+    if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7]) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
     count_launch(x, "k_model_term", st);
   } else if (k.nmod > 0) {
     const int half = k.nmod == 2 ? E / 2 : E;
@@ -1379,6 +1379,8 @@ extern "C" int saceo_actor_step(saceo_ctx* x, const float* theta_ref, const floa
 // ------------------------------------------------------------------------------------------
 // test-only: per-CTA phase timestamps of the tcgen05 streaming kernel (dbg = device buffer, 8 u64 per CTA)
 extern "C" int saceo_test_set_tc_debug(void* dbg) { g_tc_dbg = (unsigned long long*)dbg; return 0; }
+// test-only: 8 phase stamps per CTA of the tensor-core expert-term kernel
+extern "C" int saceo_test_set_mt_debug(void* dbg) { g_mt_dbg = (unsigned long long*)dbg; return 0; }
 // test-only: the sel-th warp-specialised fused launch from now on writes 16 phase stamps per CTA into dbg
 extern "C" int saceo_test_set_ws_debug(void* dbg, int32_t sel) { g_ws_dbg = (unsigned long long*)dbg; g_ws_sel = sel; g_ws_count = 0; return 0; }
 

@@ -51,7 +51,7 @@ class PopulationSpec:
     use_graph: bool = True         # one update = one CUDA-graph replay
     ws_kernels: bool = True        # warp-specialised TMA-fed fused kernels on optimiser-maintained weight planes (round 2)
     fork_actor: bool = True        # critic-independent half of the actor phase on a second stream (needs ws_kernels)
-    blocked_model: bool = False    # column-blocked model-term kernel (2 hidden columns per thread; measured equal to the default)
+    model_variant: int = 0         # expert-term kernel: 0 hidden layer on mma.sync tf32 hi/lo (default), 1 column-blocked CUDA-core, 2 round-1 CUDA-core
     device: int = 0
 
     def to_config(self) -> _l.Config:
@@ -86,7 +86,7 @@ class PopulationSpec:
         c.reserved[3] = 0 if self.fuse_model else 1
         c.reserved[5] = 0 if self.ws_kernels else 1
         c.reserved[6] = 0 if self.fork_actor else 1
-        c.reserved[7] = 1 if self.blocked_model else 0
+        c.reserved[7] = int(self.model_variant)
         return c
 
 

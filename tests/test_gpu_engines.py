@@ -85,13 +85,46 @@ def test_relu_mask_stability_tcgen05(seed, fuse):
     min(Q1,Q2) selection agree with the fp32 oracle; with bf16 planes these seeds gave g_actor errors of 6e-3.
     Gradients are held to 2e-4 here (5x tighter than the 1e-3 bar) to catch a regression of the plane format."""
     cfg = NetCfg(S=27, A=8)
+    # seed 31 holds an exact tie in a frozen MODEL (test_model_relu_tie_is_confined below): the fp32 CUDA-core expert
+    # term keeps this test about the actor / critic operand planes
     pop, probs = build(cfg, n_agents=2, B=256, E=20, N=2000, seed=seed, gemm_mode=L.GEMM_TCGEN05_BF16X3,
-                       fuse_forward=fuse, fuse_backward=fuse)
+                       fuse_forward=fuse, fuse_backward=fuse, model_variant=2 if seed == 31 else 0)
     w = compare_update(pop, cfg, probs)
     pop.close()
     for k in ("g_q1", "g_q2", "g_actor", "y", "L_pi"):
         assert w[k] < 2e-4, (k, w[k])
     assert max(w.values()) < TOL, w
+
+
+def test_model_relu_tie_is_confined():
+    """Seed 31 of the test above: one hidden pre-activation of one 2x512 ReLU model sits at 4.6e-8 of the magnitude of
+    its summed terms - below fp32 epsilon, so the summation order alone decides the ReLU branch (the oracle, the fp32
+    CUDA-core kernel and the tensor-core kernel are three orders).  The tensor-core expert term may take the other
+    branch for THAT expert row; every other row must agree with the fp32 kernel to rounding, and the row that differs
+    must be one whose fp64 pre-activations really contain such a tie."""
+    cfg = NetCfg(S=27, A=8)
+    n, E, SA, H = 2, 20, 35, 512
+    outs = {}
+    for variant in (0, 2):
+        pop, probs = build(cfg, n_agents=n, B=256, E=E, N=2000, seed=31, gemm_mode=L.GEMM_TCGEN05_BF16X3, model_variant=variant)
+        pop.update(1, num_timesteps=0, use_device_rng=False)
+        torch.cuda.synchronize()
+        outs[variant] = pop.debug("mdXa").cpu().numpy().reshape(n, 2, E, cfg.A)[:, :, :E // 2].copy()
+        if variant == 0:
+            Xm = pop.debug("Xm").cpu().numpy().reshape(n, 2, E, SA)[:, :, :E // 2].astype(np.float64)
+            th = pop.t["model"].cpu().numpy().astype(np.float64).reshape(n, 2, -1)
+        pop.close()
+    d = np.abs(outs[0] - outs[2]).max(-1) / (np.abs(outs[2]).max(-1) + 1e-30)       # [agent, model, row]
+    bad = np.argwhere(d > 1e-5)
+    assert len(bad) <= 1, d
+    for a, m, r in bad:
+        t = th[a, m]
+        W0 = t[:SA * H].reshape(SA, H); b0 = t[SA * H:SA * H + H]; o = SA * H + H
+        W1 = t[o:o + H * H].reshape(H, H); b1 = t[o + H * H:o + H * H + H]
+        h1 = np.maximum(Xm[a, m, r] @ W0 + b0, 0)
+        z2 = h1 @ W1 + b1
+        scale = np.abs(h1) @ np.abs(W1) + np.abs(b1)
+        assert (np.abs(z2) / scale).min() < 2e-7, (a, m, r, (np.abs(z2) / scale).min())
 
 
 def test_host_buffer_paths_agree():
@@ -148,3 +181,30 @@ def test_profile_step_reports_every_launch():
         pop.close()
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("hidden,acts,E,nm", [((512, 512), ("relu", "relu"), 20, 2), ((512, 512), ("tanh", "tanh"), 20, 2),
+                                               ((64, 96), ("relu", "tanh"), 8, 2), ((96, 32), ("tanh", "relu"), 16, 1),
+                                               ((256, 256), ("relu", "relu"), 32, 2), ((64, 64), ("relu", "relu"), 6, 2)])
+def test_model_term_tensor_core_hidden_layer(hidden, acts, E, nm):
+    """Expert term, hidden layer on mma.sync tf32 hi/lo x3 (model_variant 0, the default) against the fp32 CUDA-core
+    kernels (variants 1, 2): the gradient w.r.t. the expert actions (mdXa) and the per-model MSE agree to fp32 rounding,
+    and the whole update agrees with the oracle (compare_update)."""
+    cfg = NetCfg(S=11, A=3, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=hidden, model_acts=acts, num_models=nm,
+                 delta_clip_pred=3.0)
+    outs = {}
+    for variant in (0, 1, 2):
+        pop, probs = build(cfg, n_agents=3, B=64, E=E, N=600, seed=13, model_variant=variant)
+        if variant == 0:
+            w = compare_update(pop, cfg, probs)
+            assert max(v for k, v in w.items() if not k.startswith("oracle32")) < TOL, w
+        else:
+            pop.update(1, num_timesteps=0, use_device_rng=False)
+        torch.cuda.synchronize()
+        outs[variant] = (pop.debug("mdXa").cpu().numpy().copy(), pop.debug("mse_part").cpu().numpy().copy(),
+                         pop.t["actor"].cpu().numpy().copy())
+        pop.close()
+    for variant in (1, 2):
+        assert rel(outs[0][0], outs[variant][0]) < 1e-5, (variant, rel(outs[0][0], outs[variant][0]), rel(outs[1][0], outs[2][0]))
+        assert np.allclose(outs[0][1], outs[variant][1], rtol=1e-5, atol=1e-9)
+        assert rel(outs[0][2], outs[variant][2]) < 1e-5
