@@ -224,10 +224,11 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
   __half* plo = phi + MTM_ROWS * ldh;
   float* part = reinterpret_cast<float*>(phi);          // [nwarp][16][32] partial output tiles, aliases the planes
   float* stg = reinterpret_cast<float*>(plo + MTM_ROWS * ldh);   // staged small weights: W0|b0, then W2|b2, then W0's action rows
-  float* xs = stg + mtm_nstg(S, A, H1, H2, mo);                  // [MS][SA]
-  float* ob = xs + MS * SA;             // [MS][mo]   model output
-  float* dd = ob + MS * mo;             // [MS][S]    d(eps*MSE)/d(delta)
-  float* wmx = dd + MS * S;             // [16 warps][MS] row maxima, then [MS] scales at wmx[512..]
+  const int SAp = (SA + 3) & ~3, Sp = (S + 3) & ~3;      // row strides of xs / dd: float4 broadcasts, zero padding
+  float* xs = stg + mtm_nstg(S, A, H1, H2, mo);                  // [MS][SAp]
+  float* dd = xs + MS * SAp;            // [MS][Sp]   d(eps*MSE)/d(delta)
+  float* ob = dd + MS * Sp;             // [MS][mo]   model output
+  float* wmx = ob + MS * mo;            // [16 warps][MS] row maxima, then [MS] scales at wmx[16 MS ..]; later layer-0^T partials
   __shared__ float red[32];
   const float* th = c.T.model + ((long long)agent * 2 + net) * c.L.nm_stride;
   const float* W0 = th; const float* b0 = W0 + (long long)SA * H1;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
     const int nh0 = (H1 >> 4) < MTM_PF ? (H1 >> 4) : MTM_PF;
     bulk_prefetch_l2(W1, (uint32_t)(nh0 * 16 * H2 * sizeof(float)));
   }
-  for (int e = tid; e < MS * SA; e += NT) { const int r = e / SA; xs[e] = r < half ? Xm[e] : 0.f; }
+  for (int e = tid; e < MS * SAp; e += NT) { const int r = e / SAp, k = e - r * SAp; xs[e] = (r < half && k < SA) ? Xm[r * SA + k] : 0.f; }
   // the tensor-core tiles read 16 rows: rows >= MS of the planes and of h2 are zeros, never written again
   for (int e = tid; e < MTM_ROWS * ldh; e += NT) reinterpret_cast<uint32_t*>(phi)[e] = 0u;     // both planes (2 x 16 x ldh halves)
   if (MS < MTM_ROWS)
@@ -256,16 +257,15 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
     const float bj = stg[SA * H1 + j];
 #pragma unroll
     for (int r = 0; r < MS; ++r) acc[r] = bj;
-    for (int k = 0; k < SA; k += 8) {
-      float w[8];
+    for (int k = 0; k < SA; k += 4) {                    // one broadcast float4 of the row feeds 4 FMAs
+      float w[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = (k + u < SA) ? stg[(k + u) * H1 + j] : 0.f;
+      for (int u = 0; u < 4; ++u) w[u] = (k + u < SA) ? stg[(k + u) * H1 + j] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (k + u < SA) {
-#pragma unroll
-          for (int r = 0; r < MS; ++r) acc[r] = fmaf(xs[r * SA + k + u], w[u], acc[r]);
-        }
+      for (int r = 0; r < MS; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + r * SAp + k);
+        acc[r] = fmaf(x.x, w[0], acc[r]); acc[r] = fmaf(x.y, w[1], acc[r]);
+        acc[r] = fmaf(x.z, w[2], acc[r]); acc[r] = fmaf(x.w, w[3], acc[r]);
       }
     }
 #pragma unroll
@@ -315,10 +315,10 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
   const float eps = agent_eps(c, agent);
   const float inv = 1.f / (float)half;
   float part_l = 0.f;
-  for (int e = tid; e < MS * S; e += NT) {
-    const int i = e / S, j = e - i * S;
+  for (int e = tid; e < MS * Sp; e += NT) {
+    const int i = e / Sp, j = e - i * Sp;
     float g = 0.f;
-    if (i < half) {
+    if (i < half && j < S) {
       const int src = c.perm[(long long)agent * E + net * half + i];
       float delta = ob[i * mo + j];
       float cm = 1.f;
@@ -347,16 +347,15 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
       float acc[MS];
 #pragma unroll
       for (int r = 0; r < MS; ++r) acc[r] = 0.f;
-      for (int cc = 0; cc < S; cc += 8) {
-        float w[8];
+      for (int cc = 0; cc < S; cc += 4) {
+        float w[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = (cc + u < S) ? stg[j * mo + cc + u] : 0.f;
+        for (int u = 0; u < 4; ++u) w[u] = (cc + u < S) ? stg[j * mo + cc + u] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (cc + u < S) {
-#pragma unroll
-            for (int r = 0; r < MS; ++r) acc[r] = fmaf(dd[r * S + cc + u], w[u], acc[r]);
-          }
+        for (int r = 0; r < MS; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(dd + r * Sp + cc);
+          acc[r] = fmaf(x.x, w[0], acc[r]); acc[r] = fmaf(x.y, w[1], acc[r]);
+          acc[r] = fmaf(x.z, w[2], acc[r]); acc[r] = fmaf(x.w, w[3], acc[r]);
         }
       }
 #pragma unroll
@@ -408,20 +407,24 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
   mtm_stage_wait();
   __syncthreads();
   MTM_STAMP(6);
-  // ---- layer 0 transposed, action rows only: one warp per action ------------------------------
+  // ---- layer 0 transposed, action rows only: nsp warps per action, partial sums combined in a fixed order ----
   float* out = c.mdXa + ((long long)agent * 2 + net) * E * A;
-  for (int a = warp; a < A; a += nwarp) {
+  int nsp = 1;
+  while (nsp < 4 && A * nsp * 2 <= nwarp && (H1 % (64 * nsp)) == 0) nsp *= 2;
+  const int seg = H1 / nsp;
+  for (int it = warp; it < A * nsp; it += nwarp) {
+    const int a = it / nsp, sp = it - a * nsp;
     float acc[MS];
 #pragma unroll
     for (int r = 0; r < MS; ++r) acc[r] = 0.f;
     const float* wrow = stg + a * H1;
-    for (int j0 = lane; j0 < H1; j0 += 256) {
+    for (int j0 = sp * seg + lane; j0 < (sp + 1) * seg; j0 += 256) {
       float w[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = (j0 + 32 * u < H1) ? wrow[j0 + 32 * u] : 0.f;
+      for (int u = 0; u < 8; ++u) w[u] = (j0 + 32 * u < (sp + 1) * seg) ? wrow[j0 + 32 * u] : 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (j0 + 32 * u < H1) {
+        if (j0 + 32 * u < (sp + 1) * seg) {
 #pragma unroll
           for (int r = 0; r < MS; ++r) acc[r] = fmaf(h1[r * H1 + j0 + 32 * u], w[u], acc[r]);
         }
@@ -431,8 +434,15 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
     for (int r = 0; r < MS; ++r) {
       float v = acc[r];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && r < half) out[r * A + a] = v;
+      if (lane == 0) wmx[(a * 4 + sp) * MS + r] = v;
     }
+  }
+  __syncthreads();
+  for (int e = tid; e < A * MS; e += NT) {
+    const int a = e / MS, r = e - a * MS;
+    float v = 0.f;
+    for (int sp = 0; sp < nsp; ++sp) v += wmx[(a * 4 + sp) * MS + r];
+    if (r < half) out[r * A + a] = v;
   }
   MTM_STAMP(7);
 }
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(MTM_THREADS, 1) k_model_term_mma(KCtx c, float
 static inline size_t model_term_mma_smem(const KCtx& c, int ms) {
   const int hm = c.mh1 > c.mh2 ? c.mh1 : c.mh2;
   return ((size_t)ms * c.mh1 + (size_t)MTM_ROWS * (c.mh2 + MTM_PAD)) * sizeof(float) + (size_t)2 * MTM_ROWS * mtm_ldh(hm) * 2 +
-         (size_t)mtm_nstg(c.S, c.A, c.mh1, c.mh2, c.mo) * sizeof(float) + (size_t)ms * (c.S + c.A + c.mo + c.S + 17) * sizeof(float);
+         (size_t)mtm_nstg(c.S, c.A, c.mh1, c.mh2, c.mo) * sizeof(float) + (size_t)ms * (((c.S + c.A + 3) & ~3) + ((c.S + 3) & ~3) + c.mo + (4 * c.A > 17 ? 4 * c.A : 17)) * sizeof(float);
 }
 
 }  // namespace saceo
