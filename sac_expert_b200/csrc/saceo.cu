@@ -19,7 +19,6 @@
 #include "mlp_ws.cuh"
 #include "model_term.cuh"
 #include "model_fit.cuh"
-#include "pair_gemm.cuh"
 
 using namespace saceo;
 
@@ -1397,18 +1396,5 @@ extern "C" int saceo_test_gemm(int32_t gemm_mode, int32_t batch, int32_t M, int3
       return fail(SACEO_E_INVALID, "shape not eligible for the tcgen05 engine");
   }
   int rc = gemm(&tmp, transA != 0, transB != 0, false, p, batch, (cudaStream_t)stream); if (rc) return rc;
-  return check_launch();
-}
-
-// CTA-pair (cta_group::2) GEMM building block, test surface only: C[b] = A[b] (256 x K) . B[b]^T (B: 256 x K), K % 64 == 0.
-extern "C" int saceo_test_pair_gemm(int32_t batch, int32_t K, const float* A, const float* Bm, float* C, void* stream) {
-  if (!A || !Bm || !C || batch < 1 || K < 64 || (K % 64) != 0) return fail(SACEO_E_INVALID, "bad argument");
-  static bool attr = false;
-  if (!attr) { CU(cudaFuncSetAttribute(k_pair_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_BYTES)); attr = true; }
-  TcP q{}; GemmP& p = q.g;
-  p.nnet = 1; p.A = A; p.B = Bm; p.C = C; p.M = 256; p.N = 256; p.K = K; p.lda = K; p.ldb = K; p.ldc = 256;
-  p.sAa = 256LL * K; p.sBa = 256LL * K; p.sCa = 256LL * 256; p.epi = EPI_NONE;
-  q.m_rows = 256; q.dbg = nullptr;
-  k_pair_gemm<<<2 * batch, PG_NT, PG_BYTES, (cudaStream_t)stream>>>(q);
   return check_launch();
 }

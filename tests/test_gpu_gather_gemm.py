@@ -104,28 +104,6 @@ def test_tcgen05_bf16x3_gemm(ta, tb, M, N, K, variant):
     assert err < 5e-5, float(err)     # ~2^-16 per product; single-pass bf16 would sit at ~4e-3
 
 
-@pytest.mark.parametrize("K", [64, 256, 512])
-def test_pair_gemm(K):
-    """CTA-pair building block (tcgen05 cta_group::2, M = 256 across two SMs, each CTA stages half of B; multicast
-    commit) against an fp64 matmul - the mechanism of the weight-stationary design."""
-    import ctypes as C
-    lib = L.load()
-    fn = lib.saceo_test_pair_gemm
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    g = torch.Generator(device="cpu").manual_seed(K)
-    batch = 5
-    A = torch.randn(batch, 256, K, generator=g)
-    B = torch.randn(batch, 256, K, generator=g)
-    ref = torch.matmul(A.double(), B.double().transpose(1, 2))
-    Ad, Bd = A.cuda().contiguous(), B.cuda().contiguous()
-    Cd = torch.full((batch, 256, 256), float("nan"), device="cuda")
-    L.check(fn(batch, K, Ad.data_ptr(), Bd.data_ptr(), Cd.data_ptr(), torch.cuda.current_stream().cuda_stream))
-    torch.cuda.synchronize()
-    err = float((Cd.double().cpu() - ref).norm() / ref.norm())
-    assert err < 2e-5, err
-
-
 def test_replay_append_all_agents_wraparound():
     """saceo_replay_append: one call appends k rows to EVERY agent's ring on the device; after several
     wrap-arounds the gather is still a bit-exact copy of the last `capacity` rows in chronological order

@@ -198,3 +198,47 @@ def test_data_parallel_two_gpus_2x256():
            "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "dp_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_weights_changed_contract():
+    """include/saceo.h: the tcgen05 engine computes from fp16 hi/lo images of the actor / q / qt tables.  (1) a write
+    through ``pop.t[...]`` is picked up automatically; (2) a write through a tensor the caller kept is picked up after
+    ``saceo_weights_changed``; in both cases the tensor-core forward then agrees with the exact-fp32 engine holding the
+    same weights, and differs from the forward before the write."""
+    from sac_expert_b200.population import PopulationSpec
+    from sac_expert_b200.synth import fill_synthetic
+    n, S, A = 3, 27, 8
+    pops = {}
+    for mode in (L.GEMM_TCGEN05_BF16X3, L.GEMM_FP32_SIMT):
+        pops[mode] = Population(PopulationSpec(n_agents=n, S=S, A=A, B=256, E=20, replay_capacity=600, gemm_mode=mode,
+                                               use_graph=False))
+        fill_synthetic(pops[mode], seed=11, replay_rows=500)
+    tc, ex = pops[L.GEMM_TCGEN05_BF16X3], pops[L.GEMM_FP32_SIMT]
+    obs = torch.randn(n, 256, S, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    act = torch.tanh(torch.randn(n, 256, A, device="cuda", generator=torch.Generator("cuda").manual_seed(6)))
+    a0, q0 = tc.actor_forward(obs).clone(), tc.critic_forward(obs, act).clone()
+    assert rel(a0.cpu(), ex.actor_forward(obs).cpu()) < 1e-5
+    # (1) through the table accessor
+    for p in (tc, ex):
+        p.t["actor"].mul_(0.7)
+        p.t["q"].mul_(1.3)
+    a1, q1 = tc.actor_forward(obs).clone(), tc.critic_forward(obs, act).clone()
+    assert rel(a1.cpu(), a0.cpu()) > 1e-2 and rel(q1.cpu(), q0.cpu()) > 1e-2
+    assert rel(a1.cpu(), ex.actor_forward(obs).cpu()) < 1e-5 and rel(q1.cpu(), ex.critic_forward(obs, act).cpu()) < 1e-5
+    # (2) through tensors the caller kept: announce the write explicitly
+    wa, wq = tc.t["actor"], tc.t["q"]
+    tc.actor_forward(obs)                         # consumes the automatic mark
+    assert not tc.t.dirty
+    wa.mul_(1.2); wq.mul_(0.8)
+    ex.t["actor"].mul_(1.2); ex.t["q"].mul_(0.8)
+    L.check(tc.lib.saceo_weights_changed(tc.ctx))
+    a2, q2 = tc.actor_forward(obs), tc.critic_forward(obs, act)
+    assert rel(a2.cpu(), a1.cpu()) > 1e-2
+    assert rel(a2.cpu(), ex.actor_forward(obs).cpu()) < 1e-5 and rel(q2.cpu(), ex.critic_forward(obs, act).cpu()) < 1e-5
+    # and one update on top of the externally written weights still matches the exact engine
+    for p in (tc, ex):
+        p.update(1, num_timesteps=0, use_device_rng=True, seed=3)
+    torch.cuda.synchronize()
+    assert rel(tc.t["actor"].cpu(), ex.t["actor"].cpu()) < 1e-4 and rel(tc.t["q"].cpu(), ex.t["q"].cpu()) < 1e-4
+    for p in pops.values():
+        p.close()

@@ -11,7 +11,7 @@ lib.saceo_test_set_ws_debug.argtypes = [C.c_void_p, C.c_int32]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 27
 A = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-pop = Population(PopulationSpec(n_agents=n, S=S, A=A, B=256, E=20, replay_capacity=2000, gemm_mode=1, use_graph=False))
+pop = Population(PopulationSpec(n_agents=n, S=S, A=A, B=256, E=20, replay_capacity=2000, gemm_mode=1, use_graph=False, fork_actor=False))   # one stream: the launch order below
 fill_synthetic(pop, seed=1)
 for w in range(3):
     pop.update(1, num_timesteps=w, use_device_rng=True, seed=3)
