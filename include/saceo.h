@@ -296,6 +296,26 @@ int saceo_trpo_grad(saceo_ctx *ctx, const float *act, const float *adv, const fl
 int saceo_ppo_grad(saceo_ctx *ctx, const float *act, const float *adv, const float *nlp_old, const float *alpha,
                    float eps_clip, float max_grad_norm, float *grad_out, float *stats_out, void *stream);
 
+/* Expert-observation gradient of the on-policy classes: the second tape of TRPO.update's two-model branch
+ * (algs/model_free/trpo.py:113-149) and the MSE half of PPO._apply_actor_grad's expert branch (ppo.py:176-213, models[0]):
+ * counterfactual actions a = GaussianActor.sample(sE) = mean + exp(logstd) u (actors/continuous_actors.py:103-123, the
+ * _forward parameterisation with cfg.std_mult; clip_actions != 0: actor.tf_clip to +-act_limit, :128-129), next-state
+ * prediction through the frozen model(s) (models/continuous_models.py:244-254), MSE = mean_i 0.5 sum_j (s'E - pred)^2
+ * over the rows of one model (n_models = 2: the two halves of the shuffled expert rows through models 0 and 1, the two
+ * means added; n_models = 1: all E rows through model 0).  Expert rows = tables.expert_s / expert_sp; the shuffle
+ * (expert_perm) and the noise (rows [2B, 2B+E) of the noise block = the u3 | u4 slots) are the draws last injected with
+ * saceo_set_draws.  grad_out [n, na_stride] (device, 16-byte aligned) = d MSE / d(actor trainable), UNWEIGHTED;
+ * stats_out [n, 8] (may be NULL): [0] = MSE. */
+int saceo_onpolicy_expert_grad(saceo_ctx *ctx, int32_t n_models, int32_t clip_actions, float *grad_out, float *stats_out,
+                               void *stream);
+
+/* grad_final = (1 - eps) neg_pg + eps mse_grad (trpo.py:150-158; ppo.py:213 after the tape) per agent, eps [n] (device);
+ * out [n, na_stride] may alias neg_pg.  stats_out [n, 8] (may be NULL): [6] = norm_pg, [7] = norm_MSE as the reference
+ * logs them (sums of per-tensor L2 norms, trpo.py:160-163), [4] / [5] = global norm of the result before / after
+ * tf.clip_by_global_norm(max_grad_norm) (ppo.py:226-231; max_grad_norm <= 0: no clipping). */
+int saceo_grad_blend(saceo_ctx *ctx, const float *neg_pg, const float *mse_grad, const float *eps, float max_grad_norm,
+                     float *out, float *stats_out, void *stream);
+
 /* actor_optimizer.apply_gradients(zip(neg_pg, actor.trainable)) (ppo.py:234): one Keras-Adam step of the ACTOR
  * optimiser (tables.actor / actor_m / actor_v, adam_t[.,2], learning rate hyper[3]) with grad [n, na_stride]
  * (device, 16-byte aligned).  No other optimiser advances. */

@@ -720,6 +720,25 @@ def trpo_expert_blend(cfg: NetCfg, theta: Sequence[Tensor], neg_pg: Sequence[Ten
     return [f.detach() for f in final], mse.detach(), norm_pg, norm_mse
 
 
+def ppo_expert_blend(cfg: NetCfg, theta: Sequence[Tensor], neg_pg: Sequence[Tensor], batch: Dict, eps: float, st: Dict):
+    """Expert branch of ``PPO._apply_actor_grad`` (ppo.py:176-213, ``use_expert_actions = False``): ALL expert rows (in
+    order, no shuffle) through ``tf_clip(actor.sample(s_expert))`` (continuous_actors.py:103-129, clip to the action
+    limits) and ``models[0].sample``; ``MSE = mean(0.5 sum (s'E - pred)^2)``; the tape differentiates ``(1 - eps)
+    pg_loss + eps MSE``, i.e. ``neg_pg_final = (1 - eps) neg_pg + eps MSE_grads``.  ``batch["u3"]`` holds the [E, A]
+    noise of the one ``actor.sample`` call.  Returns (grad_final, mse)."""
+    dt = theta[0].dtype
+    sE, spE = torch.as_tensor(batch["sE"]).to(dt), torch.as_tensor(batch["spE"]).to(dt)
+    th = _req(theta)
+    lim = torch.as_tensor(np.asarray(st["act_limit"])).to(dt)
+    a = gaussian_sample(cfg, th, sE, batch["u3"], st)
+    a = torch.maximum(torch.minimum(a, lim), -lim)                         # tf.clip_by_value: gradient on the closed interval
+    p = model_sample(cfg, st["m1"], sE, a, st)
+    mse = (0.5 * ((spE - p) ** 2).sum(-1)).mean()
+    g = torch.autograd.grad(mse, th, allow_unused=True)
+    g = [x if x is not None else torch.zeros_like(q) for x, q in zip(g, th)]
+    return [((1 - eps) * a_ + eps * b_).detach() for a_, b_ in zip(neg_pg, g)], mse.detach()
+
+
 def backtrack(trial, eta_v, kl_maxfactor: float, delta: float):
     """Control flow of ``TRPO._backtrack`` (trpo.py:251-301).  ``trial(step) -> (theta, stats, improve)`` applies
     ``theta_k + step`` and evaluates it (``stats`` needs "kl", "tv").  Returns (theta, stats, improve, adj, step, tv_pre,

@@ -744,18 +744,11 @@ static KCtx actor_view(const saceo_ctx* x, bool bc = false) {
   return kk;
 }
 
-// phase 2a: everything of the actor step that does not depend on the critics
-static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
-  const KCtx kk = actor_view(x, bc);
-  const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
+// Expert-observation term on the staged model inputs Xm: forward through the frozen model(s), MSE against s'E, backward
+// to the action columns (mdXa, mse_part).  Shared by the SAC-EO / BC actor phase and the on-policy expert gradient.
+static int model_term_phase(saceo_ctx* x, const KCtx& k, cudaStream_t st) {
+  const int n = k.n_agents, S = k.S, A = k.A, SA = S + A, E = k.E;
   int rc;
-  NetD an = actor_net(x);
-  LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
-  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st, true,
-                   dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->aH1p : nullptr, x->a_img, 0);
-  if (rc) return rc;
-  LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
-         (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
   if (k.nmod > 0 && x->cfg.reserved[3] == 0 && model_term_eligible(k)) {
     // fused expert-observation term: model forward, MSE, backward to the action columns in one kernel
     if (model_term_launch(k, k.mse_part, st, x->cfg.reserved[7]) != cudaSuccess) return fail(SACEO_E_CUDA, "model-term launch failed");
@@ -807,6 +800,22 @@ static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
       rc = gemm(x, false, true, false, p, n, st); if (rc) return rc;
     }
   }
+  return 0;
+}
+
+// phase 2a: everything of the actor step that does not depend on the critics
+static int phase_actor_pre(saceo_ctx* x, cudaStream_t st, bool bc = false) {
+  const KCtx kk = actor_view(x, bc);
+  const KCtx& k = kk; const int n = k.n_agents, B = k.B, S = k.S, A = k.A, SA = S + A, R = k.R, E = k.E, Rs = k.Rs;
+  int rc;
+  NetD an = actor_net(x);
+  LAUNCH(x, k_stage, dim3(cdiv((long long)R * S, 256), n), 256, 0, st, k);
+  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st, true,
+                   dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->aH1p : nullptr, x->a_img, 0);
+  if (rc) return rc;
+  LAUNCH(x, k_head_fwd, dim3(cdiv(R, 128), n), 128, 0, st, k, R, B, k.noise, (3LL * B + E) * A, B, 2,
+         (float*)nullptr, (float*)nullptr, 0LL, 0);      // pi(s) -> the action columns of Xc3
+  rc = model_term_phase(x, k, st); if (rc) return rc;
   return check_launch();
 }
 
@@ -1336,6 +1345,53 @@ extern "C" int saceo_ppo_grad(saceo_ctx* x, const float* act, const float* adv, 
   if (!(eps_clip >= 0.f)) return fail(SACEO_E_INVALID, "eps_clip must be >= 0");
   if (!nlp_old) return fail(SACEO_E_INVALID, "nlp_old is required");
   return surrogate_grad(x, act, adv, nlp_old, alpha, eps_clip, max_grad_norm, true, grad_out, stats_out, (cudaStream_t)stream);
+}
+
+// Expert-observation gradient of the on-policy classes (trpo.py:92-158, ppo.py:176-213): see trpo.cuh.  Draws (noise
+// rows [2B, 2B+E), expert permutation) are the ones last injected with saceo_set_draws.
+extern "C" int saceo_onpolicy_expert_grad(saceo_ctx* x, int32_t n_models, int32_t clip_actions, float* grad_out,
+                                          float* stats_out, void* stream) {
+  if (!x || !grad_out) return fail(SACEO_E_INVALID, "null argument");
+  if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
+  if (n_models < 1 || n_models > x->cfg.num_models) return fail(SACEO_E_INVALID, "n_models must be in [1, num_models]");
+  if (x->k.E < 1 || (n_models == 2 && (x->k.E & 1))) return fail(SACEO_E_INVALID, "needs E >= 1 expert rows (even for two models)");
+  if (reinterpret_cast<uintptr_t>(grad_out) & 15) return fail(SACEO_E_INVALID, "grad_out must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  { int rcp = ensure_planes(x, st); if (rcp) return rcp; }
+  KCtx kk = actor_view(x, true);            // expert weight forced to 1: the blend is applied by saceo_grad_blend
+  kk.nmod = n_models; kk.g_actor = grad_out;
+  const KCtx& k = kk; const int n = k.n_agents, E = k.E, Rs = k.Rs;
+  NetD an = actor_net(x);
+  int rc;
+  CU(cudaMemsetAsync(grad_out, 0, sizeof(float) * (size_t)n * x->L.na_stride, st));
+  LAUNCH(x, k_exp_stage, dim3(cdiv((long long)E * k.S, 256), n), 256, 0, st, k);
+  rc = mlp_forward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, E, k.aH1, k.aH2, Rs, k.aOut, k.Ao, (long long)Rs * k.Ao, 0, st, true);
+  if (rc) return rc;
+  LAUNCH(x, k_ghead, dim3(cdiv(E, 128), n), 128, 0, st, k, x->cfg.std_mult, clip_actions, 0);
+  rc = model_term_phase(x, k, st); if (rc) return rc;
+  LAUNCH(x, k_ghead, dim3(cdiv(E, 128), n), 128, 0, st, k, x->cfg.std_mult, clip_actions, 1);
+  rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, E, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
+                    k.Ao, k.daH2, k.daH1, grad_out, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st);
+  if (rc) return rc;
+  if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(k.A, 32), 0, st, k, E);
+  if (stats_out) LAUNCH(x, k_exp_stats, dim3(cdiv(n, 128)), 128, 0, st, k, stats_out);
+  return check_launch();
+}
+
+// grad_final = (1 - eps) neg_pg + eps mse_grad per agent, the reference's logged norms, and (max_grad_norm > 0, PPO)
+// tf.clip_by_global_norm of the result.  out may alias neg_pg.
+extern "C" int saceo_grad_blend(saceo_ctx* x, const float* neg_pg, const float* mse_grad, const float* eps, float max_grad_norm,
+                                float* out, float* stats_out, void* stream) {
+  if (!x || !neg_pg || !mse_grad || !eps || !out) return fail(SACEO_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream; const KCtx& k = x->k;
+  NetD an = actor_net(x);
+  BlendSeg sg{};
+  const long long bnd[8] = {0, an.ob0(), an.oW1(), an.ob1(), an.oW2(), an.ob2(), an.ob2() + an.out, x->L.na};
+  sg.nseg = (x->L.na > bnd[6]) ? 7 : 6;           // + the state-independent logstd variable
+  for (int i = 0; i < 8; ++i) sg.b[i] = bnd[i];
+  LAUNCH(x, k_grad_blend, dim3(k.n_agents), 256, 0, st, k, sg, neg_pg, mse_grad, eps, out, stats_out);
+  if (max_grad_norm > 0.f || stats_out) LAUNCH(x, k_grad_clip, dim3(k.n_agents), 256, 0, st, k, out, max_grad_norm, stats_out);
+  return check_launch();
 }
 
 // One Keras-Adam step of the actor optimiser with a caller-supplied gradient (ppo.py:234): only the actor's step

@@ -139,4 +139,98 @@ __global__ void k_grad_clip(KCtx c, float* __restrict__ g, float max_norm, float
   if (threadIdx.x == 0 && stats) { stats[agent * 8 + 4] = norm; stats[agent * 8 + 5] = post; }
 }
 
+// ------------------------------------------------------------------------------------------
+// Expert-observation term of the on-policy classes (trpo.py:92-158 two-model branch, ppo.py:176-213 with models[0]):
+//   counterfactual a = GaussianActor.sample(sE) = mean + exp(logstd) u   (continuous_actors.py:103-123, _forward
+//   parameterisation, NO squash; clip != 0: actor.tf_clip to the action limits, :128-129), through the frozen model(s),
+//   MSE = mean_i 0.5 sum_j (s'E - pred)^2, gradient w.r.t. the actor's trainable variables.
+// The E expert rows occupy rows [0, E) of the actor-phase buffers (Xpi, aOut, daOut, dls, Xm); the model term itself
+// is the SAC-EO kernel (model_term.cuh) with the expert weight forced to 1.
+// ------------------------------------------------------------------------------------------
+// Xpi[i] = N_s(sE[perm i]);  Xm[net][il, :S] = N_s^M(sE[perm i]).  grid: (ceil(E*S/256), n_agents)
+__global__ void k_exp_stage(KCtx c) {
+  const int agent = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = c.S, SA = S + c.A;
+  if (e >= c.E * S) return;
+  const int i = e / S, j = e - i * S;
+  const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
+  const int src = c.perm[(long long)agent * c.E + i];
+  const float x = c.expert_s[((long long)agent * c.E + src) * S + j];
+  c.Xpi[((long long)agent * c.Rs + i) * c.ldXp + j] = (x - nr[c.L.off_s_mean + j]) / nstd(nr[c.L.off_s_std + j]);
+  const int half = c.nmod == 2 ? c.E / 2 : c.E;
+  const int net = i / half, il = i - net * half;
+  c.Xm[(((long long)agent * 2 + net) * c.E + il) * SA + j] = (x - nr[c.L.off_m_s_mean + j]) / nstd(nr[c.L.off_m_s_std + j]);
+}
+
+// forward: action columns of Xm.  backward (bwd != 0): d(out) from mdXa.  One thread per expert row.
+// noise: rows [2B, 2B + E) of the per-agent block (the u3 | u4 slots of the SAC-EO draw order).  grid: (ceil(E/128), n_agents)
+__global__ void k_ghead(KCtx c, float std_mult, int clip, int bwd) {
+  const int agent = blockIdx.y;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= c.E) return;
+  const int A = c.A, Ao = c.Ao, S = c.S, SA = S + A, B = c.B, E = c.E;
+  const float* out = c.aOut + ((long long)agent * c.Rs + row) * Ao;
+  const float* theta = c.T.actor + (long long)agent * c.L.na_stride;
+  const float* nr = c.T.norm + (long long)agent * c.L.norm_stride;
+  const float* u = c.noise + (long long)agent * ((3LL * B + E) * A) + (long long)(2 * B + row) * A;
+  const float ls_init = c.per_state_std ? logf(std_mult) - logf(kLog2) : logf(std_mult);
+  const float floor_ls = logf(1e-3f);
+  const int half = c.nmod == 2 ? E / 2 : E;
+  const int net = row / half, il = row - net * half;
+  float* dout = c.daOut + ((long long)agent * c.Rs + row) * Ao;
+  for (int j = 0; j < A; ++j) {
+    const GaussRow g = gauss_row(c, out, theta, j, ls_init, floor_ls);
+    const float sd = expf(g.ls);
+    float a = g.mean + sd * u[j];
+    float cm = 1.f;
+    if (clip) {          // tf.clip_by_value: the gradient passes on the closed interval
+      const float lim = nr[c.L.off_act_limit + j];
+      cm = (a >= -lim && a <= lim) ? 1.f : 0.f;
+      a = fminf(fmaxf(a, -lim), lim);
+    }
+    const float inv_sd = 1.f / nstd(nr[c.L.off_m_a_std + j]);
+    if (!bwd) {
+      c.Xm[(((long long)agent * 2 + net) * E + il) * SA + S + j] = (a - nr[c.L.off_m_a_mean + j]) * inv_sd;
+    } else {
+      const float da = c.mdXa[(((long long)agent * 2 + net) * E + il) * A + j] * inv_sd * cm;
+      dout[j] = da;
+      const float dl = da * sd * u[j] * g.dls;
+      if (c.per_state_std) dout[A + j] = dl;
+      else c.dls[((long long)agent * c.Rs + row) * A + j] = dl;
+    }
+  }
+}
+
+// stats[agent*8 + 0] = MSE (sum over the models of their per-half means).  grid: (ceil(n/128)), block 128
+__global__ void k_exp_stats(KCtx c, float* __restrict__ stats) {
+  const int agent = blockIdx.x * blockDim.x + threadIdx.x;
+  if (agent >= c.n_agents) return;
+  stats[agent * 8] = c.mse_part[agent * 2] + (c.nmod == 2 ? c.mse_part[agent * 2 + 1] : 0.f);
+}
+
+// grad_final = (1 - eps) neg_pg + eps mse_grad (two rounded products, one rounded sum, like the reference's eager ops,
+// trpo.py:150-158 / ppo.py:213), with the reference's logged norms: sums of per-tensor L2 norms (trpo.py:160-163).
+// seg[0..nseg] = tensor boundaries in the flat layout.  stats[agent*8 + {6: norm_pg, 7: norm_MSE}].  grid: (n_agents), block 256
+struct BlendSeg { int nseg; long long b[8]; };
+__global__ void k_grad_blend(KCtx c, BlendSeg sg, const float* __restrict__ neg_pg, const float* __restrict__ mse_g,
+                             const float* __restrict__ eps, float* __restrict__ out, float* __restrict__ stats) {
+  __shared__ float sh[32];
+  const int agent = blockIdx.x;
+  const long long o = (long long)agent * c.L.na_stride;
+  const float e = eps[agent], om = (float)(1.0 - (double)e);
+  float npg = 0.f, nms = 0.f;
+  for (int t = 0; t < sg.nseg; ++t) {
+    float a2 = 0.f, b2 = 0.f;
+    for (long long i = sg.b[t] + threadIdx.x; i < sg.b[t + 1]; i += blockDim.x) {
+      const float a = neg_pg[o + i], b = mse_g[o + i];
+      a2 += a * a; b2 += b * b;
+      out[o + i] = __fadd_rn(__fmul_rn(om, a), __fmul_rn(e, b));
+    }
+    npg += sqrtf(block_sum(a2, sh)); nms += sqrtf(block_sum(b2, sh));
+  }
+  for (long long i = c.L.na + threadIdx.x; i < c.L.na_stride; i += blockDim.x) out[o + i] = 0.f;
+  if (threadIdx.x == 0 && stats) { stats[agent * 8 + 6] = npg; stats[agent * 8 + 7] = nms; }
+}
+
 }  // namespace saceo

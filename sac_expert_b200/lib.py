@@ -78,7 +78,7 @@ EXPORTS = [
     "saceo_query_layout", "saceo_create", "saceo_destroy", "saceo_bind", "saceo_weights_changed", "saceo_replay_append", "saceo_gather",
     "saceo_set_draws", "saceo_update", "saceo_update_host", "saceo_update_host_async", "saceo_update_phase", "saceo_bc_update", "saceo_profile_step",
     "saceo_actor_forward", "saceo_critic_forward", "saceo_model_eval", "saceo_fvp", "saceo_cg_solve",
-    "saceo_fit_bind", "saceo_model_fit", "saceo_trpo_grad", "saceo_trpo_eval", "saceo_actor_step", "saceo_ppo_grad", "saceo_actor_adam",
+    "saceo_fit_bind", "saceo_model_fit", "saceo_trpo_grad", "saceo_trpo_eval", "saceo_actor_step", "saceo_ppo_grad", "saceo_actor_adam", "saceo_onpolicy_expert_grad", "saceo_grad_blend",
     "saceo_debug_ptr", "saceo_launch_count", "saceo_test_gemm", "saceo_last_error", "saceo_abi_version",
 ]
 
@@ -121,6 +121,8 @@ def load() -> C.CDLL:
         "saceo_actor_step": (C.c_int, [vp, vp, vp, vp, vp]),
         "saceo_ppo_grad": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
         "saceo_actor_adam": (C.c_int, [vp, vp, vp]),
+        "saceo_onpolicy_expert_grad": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp, vp]),
+        "saceo_grad_blend": (C.c_int, [vp, vp, vp, vp, f32, vp, vp, vp]),
         "saceo_debug_ptr": (vp, [vp, C.c_char_p, C.POINTER(i64)]),
         "saceo_launch_count": (i64, [vp]),
         "saceo_test_gemm": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

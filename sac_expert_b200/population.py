@@ -630,6 +630,35 @@ class Population:
         self._exit()
         return grad, stats
 
+    def onpolicy_expert_grad(self, n_models: int = 2, clip_actions: bool = False):
+        """Second tape of ``TRPO.update``'s expert branch / the MSE half of ``PPO._apply_actor_grad``'s (trpo.py:113-149,
+        ppo.py:176-213): d MSE / d(actor trainable) through ``GaussianActor.sample`` and the frozen model(s), on the bound
+        expert rows with the draws last injected by ``set_draws(noise=..., perm=...)`` (noise rows [2B, 2B+E)).
+        Returns (grad [n, na_stride], mse [n])."""
+        n = self.spec.n_agents
+        grad = torch.empty(n, self.L.na_stride, device=self.dev)
+        stats = torch.zeros(n, 8, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_onpolicy_expert_grad(self.ctx, int(n_models), int(bool(clip_actions)), grad.data_ptr(),
+                                                     stats.data_ptr(), st))
+        self._exit()
+        return grad, stats[:, 0]
+
+    def grad_blend(self, neg_pg, mse_grad, eps, max_grad_norm=None):
+        """``grad_final = (1 - eps) neg_pg + eps MSE_grads`` per agent (trpo.py:150-158) + optional global-norm clip
+        (ppo.py:226-231).  Returns (grad_final [n, na_stride], stats [n, 8]: [6] norm_pg, [7] norm_MSE as the reference
+        logs them, [4] / [5] global norm before / after clipping)."""
+        n = self.spec.n_agents
+        eps = torch.as_tensor(np.broadcast_to(np.asarray(eps, np.float32), (n,)).copy()).to(self.dev)
+        out = torch.empty(n, self.L.na_stride, device=self.dev)
+        stats = torch.zeros(n, 8, device=self.dev)
+        st = self._enter()
+        _l.check(self.lib.saceo_grad_blend(self.ctx, neg_pg.data_ptr(), mse_grad.data_ptr(), eps.data_ptr(),
+                                           float(max_grad_norm) if max_grad_norm is not None else 0.0, out.data_ptr(),
+                                           stats.data_ptr(), st))
+        self._exit()
+        return out, stats
+
     def ppo_grad(self, act, adv, nlp_old, alpha=None, eps_clip=0.2, max_grad_norm=None):
         """Gradient of ``PPO._apply_actor_grad`` (ppo.py:132-147, :226-231) on the bound ``fvp_states``: clipped surrogate
         + entropy regulariser, then ``clip_by_global_norm``.  Returns (neg_pg [n, na_stride], stats [n, 8] with
@@ -688,13 +717,15 @@ class Population:
         self._exit()
 
     def trpo_update(self, act, adv, *, delta=0.01, cg_iters=20, trust_damp=0.01, kl_maxfactor=1.5, alpha=None,
-                    adv_center=True, adv_scale=True, residual_tol=1e-10):
+                    adv_center=True, adv_scale=True, residual_tol=1e-10, expert_eps=None):
         """``TRPO.update`` (trpo.py:36-198) + ``TRPO._backtrack`` (:229-317) for every agent of the population on its
         bound ``fvp_states`` (trust_sub = 1): surrogate gradient, CG solve with the Fisher-vector product, step length
         ``sqrt(2 delta / vFv)`` and the back-tracking line search, each agent with its own accept / shrink decisions.
         ``adv`` [n, N] raw advantages (host); centred / scaled per agent with NumPy like the reference (:41-48, and a
-        second time inside ``_backtrack`` :243-249).  The gradient blend is its epsilon = 0 slice (``grad_final =
-        neg_pg``).  Returns one log dict per agent (``ent, tv_pre, kl_pre, tv, kl, adj, improve``)."""
+        second time inside ``_backtrack`` :243-249).  ``expert_eps`` (scalar or [n]; None: the epsilon = 0 slice
+        ``grad_final = neg_pg``): the two-model expert blend ``grad_final = (1 - eps) neg_pg + eps MSE_grads``
+        (:113-158) on the bound expert rows with the draws last injected by ``set_draws(noise=..., perm=...)``.
+        Returns one log dict per agent (``ent, tv_pre, kl_pre, tv, kl, adj, improve`` [+ ``mse, norm_pg, norm_MSE``])."""
         n, N = self.spec.n_agents, self.spec.fvp_rows
         adv = np.asarray(adv, np.float32).reshape(n, N)
 
@@ -713,6 +744,11 @@ class Population:
         nlp_old, kl_ref = first["nlp"], first["kl_info"]
         ent = first["stats"][:, 3].cpu().numpy()
         neg_pg, _ = self.trpo_grad(act, adv1, nlp_old, alpha)
+        extra = None
+        if expert_eps is not None:
+            g_mse, mse = self.onpolicy_expert_grad(n_models=2, clip_actions=False)
+            neg_pg, bst = self.grad_blend(neg_pg, g_mse, expert_eps)
+            extra = (mse.cpu().numpy(), bst.cpu().numpy())
         pg = -neg_pg
         theta_ref = self.t["actor"].clone()
         if delta == 0.0:
@@ -734,6 +770,10 @@ class Population:
             return s, s[:, 0] - surr_before
 
         adj, stats, improve, tv_pre, kl_pre = backtrack_population(lambda a: trial(eta * a), n, kl_maxfactor, delta)
-        return [dict(ent=float(ent[i]), tv_pre=float(tv_pre[i]), kl_pre=float(kl_pre[i]), tv=float(stats[i, 2]),
+        logs = [dict(ent=float(ent[i]), tv_pre=float(tv_pre[i]), kl_pre=float(kl_pre[i]), tv=float(stats[i, 2]),
                      kl=float(stats[i, 1]), adj=float(adj[i]), improve=float(improve[i])) for i in range(n)]
+        if extra is not None:
+            for i in range(n):
+                logs[i].update(mse=float(extra[0][i]), norm_pg=float(extra[1][i, 6]), norm_MSE=float(extra[1][i, 7]))
+        return logs
 

@@ -5,9 +5,10 @@ with the entropy regulariser and ``clip_by_global_norm`` (``saceo_ppo_grad``) an
 rate.  The host keeps what the reference keeps in NumPy: the shuffle (``np.random.shuffle``, same global-RNG
 consumption), the per-minibatch advantage statistics, the temperature scalar and the learning-rate adaptation.
 
-Scope: ``expert_reg = None`` (or a zero expert weight).  The reference's expert branch reads ``sp_pred`` before
-assignment when ``use_expert_actions`` is set (:196-199 vs :211-212); with a non-zero weight this class raises instead
-of guessing."""
+With ``expert_reg`` the loss becomes ``(1 - epsilon) pg_loss + epsilon MSE`` (:176-213): the MSE gradient through
+``tf_clip(actor.sample(s_expert))`` and ``models[0]`` comes from ``saceo_onpolicy_expert_grad``, the blend and the
+global-norm clip from ``saceo_grad_blend``; one ``np.random.normal`` draw per minibatch step, like the reference.  The
+reference's ``use_expert_actions`` branch reads ``sp_pred`` before assignment (:196-199 vs :211-212) and is refused."""
 import numpy as np
 import torch
 
@@ -49,8 +50,12 @@ class PPO(BaseOnPolicyUpdate):
         lr_t = np.float32(self.alpha_lr * np.sqrt(1 - 0.999 ** self._alpha_t) / (1 - 0.9 ** self._alpha_t))
         self.alpha = np.float32(max(self.alpha - lr_t * self._alpha_m / (np.sqrt(self._alpha_v) + 1e-7), 0.0))
 
-    def _population(self, s_rows):
-        F = make_F(self.actor, s_rows, 1, 0.0, gemm_mode=self._gemm_mode, device=self._device)
+    def _population(self, s_rows, expert_reg=None):
+        kw = {}
+        if expert_reg is not None:
+            kw = dict(models=list(expert_reg[4])[:1], expert=(expert_reg[0], expert_reg[2]))     # models[0] only, ppo.py:202
+        F = make_F(self.actor, s_rows, 1, 0.0, gemm_mode=self._gemm_mode, device=self._device, **kw)
+        self._F = F
         pop = F.pop
         pop.set_hyper(0, lr_pi=self.actor_lr)
         if self._m is not None:
@@ -59,8 +64,10 @@ class PPO(BaseOnPolicyUpdate):
         return pop
 
     def update(self, rollout_data, expert_reg=None):
-        if expert_reg is not None and float(expert_reg[3]) != 0.0:
-            raise NotImplementedError("the expert-observation blend of PPO._apply_actor_grad (ppo.py:149-216) is not built")
+        if expert_reg is not None and expert_reg[5]:
+            raise NotImplementedError("use_expert_actions: the reference's branch reads sp_pred before assignment "
+                                      "(ppo.py:196-199 vs :211-212) and raises UnboundLocalError")
+        eps_exp = None if expert_reg is None else float(expert_reg[3])
         s_all = np.asarray(rollout_data[0], np.float32)
         a_all = np.asarray(rollout_data[1], np.float32)
         adv_all = np.asarray(rollout_data[2])
@@ -74,7 +81,8 @@ class PPO(BaseOnPolicyUpdate):
         nlp_old_all = nlp_old_dev[0].cpu().numpy()
         ent = float(first["stats"][0, 3])
 
-        mb = self._population(s_all[:n_batch])
+        mb = self._population(s_all[:n_batch], expert_reg)
+        mbF = self._F
         mb.t["actor"].copy_(full.t["actor"])
         pre_all = post_all = 0.0
         nb = 0
@@ -93,11 +101,25 @@ class PPO(BaseOnPolicyUpdate):
                 if self.adv_scale:
                     adv = adv / adv_std
                 mb.t["fvp_states"][0].copy_(torch.from_numpy(s_all[b]))
-                grad, stats = mb.ppo_grad(a_all[b][None], np.asarray(adv, np.float32)[None], nlp_old_all[b][None],
-                                          np.asarray([self.alpha], np.float32), self.eps, self.max_grad_norm)
-                stats = stats[0].cpu().numpy()
-                if self.ent_reg:                                            # :221-224, alpha_grad = -(ent - ent_targ)
-                    self._alpha_step(float(stats[3]) - self.ent_targ)
+                if eps_exp is None:
+                    grad, stats = mb.ppo_grad(a_all[b][None], np.asarray(adv, np.float32)[None], nlp_old_all[b][None],
+                                              np.asarray([self.alpha], np.float32), self.eps, self.max_grad_norm)
+                    stats = stats[0].cpu().numpy()
+                    w_pg = 1.0
+                else:
+                    # pg_loss = (1 - epsilon) pg_loss + epsilon MSE(models[0].sample(sE, tf_clip(actor.sample(sE)))) (:190-213);
+                    # the clip by global norm follows the blend (:226-231)
+                    E = len(expert_reg[0])
+                    mbF.set_expert_draws(np.arange(E), np.random.normal(size=(E, self.actor.a_dim)))      # actor.sample, :191
+                    grad, stats = mb.ppo_grad(a_all[b][None], np.asarray(adv, np.float32)[None], nlp_old_all[b][None],
+                                              np.asarray([self.alpha], np.float32), self.eps, None)
+                    g_mse, _ = mb.onpolicy_expert_grad(n_models=1, clip_actions=True)
+                    grad, bst = mb.grad_blend(grad, g_mse, eps_exp, self.max_grad_norm)
+                    stats = stats[0].cpu().numpy()
+                    stats[4:6] = bst[0, 4:6].cpu().numpy()
+                    w_pg = 1.0 - eps_exp
+                if self.ent_reg:                                            # :221-224, alpha_grad = -(1 - eps)(ent - ent_targ)
+                    self._alpha_step(w_pg * (float(stats[3]) - self.ent_targ))
                 mb.actor_adam(grad)                                         # :234
                 pre_all += float(stats[4]); post_all += float(stats[5])
                 nb += 1

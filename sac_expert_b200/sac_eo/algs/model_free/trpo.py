@@ -4,9 +4,12 @@ step length ``sqrt(2 delta / vFv)`` and the back-tracking line search - all on t
 ``saceo_trpo_grad`` / ``saceo_cg_solve`` / ``saceo_trpo_eval`` / ``saceo_actor_step`` (include/saceo.h); the host keeps
 only the scalars the reference keeps in NumPy (advantage statistics, the accept / shrink decisions, the temperature).
 
-Scope: the policy-gradient part of the update.  The reference builds ``grad_final`` only inside its expert branches
-(:107-111, :154-158) as ``(1 - epsilon) neg_pg + epsilon MSE_grads``; this class implements its ``epsilon = 0`` slice
-(``grad_final = neg_pg``) and refuses an ``expert_reg`` with a non-zero weight instead of silently dropping the term.
+The reference builds ``grad_final`` only inside its expert branches (:107-111, :154-158) as ``(1 - epsilon) neg_pg +
+epsilon MSE_grads``: with ``expert_reg`` and two models this class runs that blend on the device
+(``saceo_onpolicy_expert_grad`` + ``saceo_grad_blend``, same RNG consumption: ``rng.shuffle`` of the expert rows,
+then one ``np.random.normal`` per half for ``actor.sample``); without ``expert_reg`` it implements the ``epsilon = 0``
+slice (``grad_final = neg_pg``; the reference raises NameError there).  The single-model branch (:77-111) raises in the
+reference (``epsilon * None`` for the temperature gradient, :111) and is refused here.
 ``trust_sub`` must be 1 (the Fisher rows are the rollout rows).  The temperature uses Keras-Adam on one scalar
 (:29-32, :169-172), kept on the host like the reference's other per-update scalars."""
 import numpy as np
@@ -48,16 +51,28 @@ class TRPO(BaseOnPolicyUpdate):
     def update(self, rollout_data, expert_reg=None):
         if self.trust_sub != 1:
             raise ValueError("trust_sub must be 1: the Fisher rows are the rollout rows on the device path")
-        if expert_reg is not None and float(expert_reg[3]) != 0.0:
-            raise NotImplementedError("the expert-observation blend of TRPO.update (trpo.py:92-158) is not built; "
-                                      "SAC_exp / BC carry the expert term on the device path")
         s_all, a_all, adv_all = rollout_data[0], rollout_data[1], rollout_data[2]
-        F = make_F(self.actor, s_all, 1, self.trust_damp, gemm_mode=self._gemm_mode, device=self._device)
+        eps = None
+        if expert_reg is not None:
+            s_expert, _, sp_expert, epsilon, models, _, rng = expert_reg[:7]
+            if len(models) != 2:
+                raise NotImplementedError("TRPO.update with one model: the reference's own branch raises TypeError at "
+                                          "trpo.py:111 ((1 - epsilon) * alpha_grad + epsilon * None)")
+            F = make_F(self.actor, s_all, 1, self.trust_damp, gemm_mode=self._gemm_mode, device=self._device,
+                       models=models, expert=(s_expert, sp_expert))
+            idx = np.arange(len(s_expert))
+            rng.shuffle(idx)                                                  # :115-116
+            sections = np.array_split(idx, 2)
+            u = [np.random.normal(size=(len(sec), self.actor.a_dim)) for sec in sections]   # actor.sample x2, :135-136
+            F.set_expert_draws(np.concatenate(sections), np.concatenate(u))
+            eps = float(epsilon)
+        else:
+            F = make_F(self.actor, s_all, 1, self.trust_damp, gemm_mode=self._gemm_mode, device=self._device)
         pop = F.pop
         logs = pop.trpo_update(np.asarray(a_all, np.float32)[None], np.asarray(adv_all, np.float32)[None],
                                delta=self.delta, cg_iters=self.cg_it, trust_damp=self.trust_damp,
                                kl_maxfactor=self.kl_maxfactor, alpha=np.asarray([self.alpha], np.float32),
-                               adv_center=self.adv_center, adv_scale=self.adv_scale)
+                               adv_center=self.adv_center, adv_scale=self.adv_scale, expert_eps=eps)
         if self.ent_reg:
             # alpha_grad = -(mean entropy - ent_targ) at the pre-update policy; apply_gradients([alpha_grad * -1]) (:169-172).
             # The surrogate tape above saw the temperature before this step, as in the reference.

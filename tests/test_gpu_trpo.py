@@ -252,3 +252,187 @@ def test_ppo_class_interface():
     # optimiser slots persist into the next update, as the Keras optimiser's do
     alg.update((s, a, adv, None, None, None))
     assert alg._t == 12
+
+
+# ----------------------------------------------------------------------------------------------------------
+# expert-observation blend of the on-policy updates (trpo.py:92-158, ppo.py:176-213)
+# ----------------------------------------------------------------------------------------------------------
+def _setup_expert(per_state_std, acts, num_models, n=2, N=96, E=10, gemm_mode=lib.GEMM_FP32_SIMT, hidden=(64, 48),
+                  model_hidden=(64, 64), S=9, A=3, seed=30, act_limit=None, model_acts=("relu", "tanh")):
+    cfg = O.NetCfg(S=S, A=A, actor_hidden=hidden, critic_hidden=(16, 16), model_hidden=model_hidden, num_models=num_models,
+                   per_state_std=per_state_std, actor_acts=acts, model_acts=model_acts, std_mult=0.7, delta_clip_pred=3.0)
+    B = 8
+    pop = Population(spec_from_cfg(cfg, n, B, E, 16, fvp_rows=N, gemm_mode=gemm_mode))
+    probs = []
+    rng = np.random.default_rng(seed)
+    noise = np.zeros((n, 3 * B + E, A), np.float32)
+    perm = np.zeros((n, E), np.int32)
+    for i in range(n):
+        st, replay, expert, hyper = O.make_problem(cfg, B, E, 300, seed=seed + i, perturb=0.2)
+        if act_limit is not None:
+            st["act_limit"] = np.full(A, act_limit, np.float32)
+        batch = O.draw_batch(cfg, replay, expert, B, seed=seed + 100 + i)
+        pop.load_agent(i, st, hyper)
+        pop.set_expert(i, expert["sE"], expert["spE"])
+        s = replay["s"][:N]
+        th = O.to_torch_state(st, torch.float64)
+        with torch.no_grad():
+            mean, ls = O.gaussian_forward(cfg, th["actor"], torch.as_tensor(s, dtype=torch.float64), th)
+        a = (mean + torch.exp(ls) * torch.from_numpy(rng.standard_normal((N, A)))).numpy().astype(np.float32)
+        pop.t["fvp_states"][i].copy_(torch.from_numpy(s))
+        if num_models == 2:
+            noise[i, 2 * B:2 * B + E] = np.concatenate([batch["u3"], batch["u4"]])
+            perm[i] = np.concatenate([batch["I1"], batch["I2"]])
+        else:
+            noise[i, 2 * B:2 * B + E] = batch["u3"]
+            perm[i] = np.arange(E)
+        probs.append((st, s, a, rng.standard_normal(N).astype(np.float32) * (1 + i), batch))
+    pop.set_draws(noise=noise, perm=perm)
+    return cfg, pop, probs
+
+
+@pytest.mark.parametrize("per_state_std,acts,num_models,mode", [
+    (True, ("tanh", "tanh"), 2, lib.GEMM_FP32_SIMT), (False, ("relu", "tanh"), 2, lib.GEMM_FP32_SIMT),
+    (True, ("tanh", "relu"), 1, lib.GEMM_FP32_SIMT), (False, ("tanh", "tanh"), 1, lib.GEMM_FP32_SIMT),
+    (True, ("tanh", "tanh"), 2, lib.GEMM_TCGEN05_BF16X3), (False, ("tanh", "tanh"), 1, lib.GEMM_TCGEN05_BF16X3)])
+def test_onpolicy_expert_gradient_matches_the_oracle(per_state_std, acts, num_models, mode):
+    """saceo_onpolicy_expert_grad: d MSE / d(actor trainable) through GaussianActor.sample and the frozen model(s) against
+    autograd (oracle.trpo_expert_blend for the two-model TRPO form, oracle.ppo_expert_blend for the clipped one-model PPO
+    form; action limit 0.6 so that some counterfactual actions really are clipped)."""
+    big = dict(hidden=(256, 256), model_hidden=(512, 512), S=27, A=8, E=20, N=128) if mode == lib.GEMM_TCGEN05_BF16X3 else {}
+    cfg, pop, probs = _setup_expert(per_state_std, acts, num_models, gemm_mode=mode,
+                                    act_limit=0.6 if num_models == 1 else None, **big)
+    L = pop.L
+    grad, mse = pop.onpolicy_expert_grad(n_models=num_models, clip_actions=num_models == 1)
+    grad, mse = grad.cpu().numpy(), mse.cpu().numpy()
+    clipped = 0
+    for i, (st, s, a, adv, batch) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        zero = [torch.zeros_like(t) for t in th["actor"]]
+        if num_models == 2:
+            g_ref, mse_ref, _, _ = O.trpo_expert_blend(cfg, th["actor"], zero, batch, 1.0, th)
+        else:
+            g_ref, mse_ref = O.ppo_expert_blend(cfg, th["actor"], zero, batch, 1.0, th)
+            with torch.no_grad():
+                c = O.gaussian_sample(cfg, th["actor"], torch.as_tensor(batch["sE"], dtype=torch.float64), batch["u3"], th)
+            clipped += int((c.abs() > 0.6).sum())
+        assert rel(grad[i, :L.na], O.flat(g_ref).numpy()) < 1e-3, i
+        assert np.all(grad[i, L.na:] == 0)
+        assert abs(mse[i] - float(mse_ref)) <= 1e-4 * abs(float(mse_ref))
+    if num_models == 1:
+        assert clipped > 0
+    pop.close()
+
+
+@pytest.mark.parametrize("per_state_std", [True, False])
+def test_grad_blend_norms_and_clip(per_state_std):
+    """saceo_grad_blend: (1 - eps) a + eps b with two rounded products and one rounded sum (bit-exact against NumPy fp32),
+    the reference's norm bookkeeping (sums of per-tensor L2 norms, trpo.py:160-163) and tf.clip_by_global_norm."""
+    cfg, pop, probs = _setup_expert(per_state_std, ("tanh", "tanh"), 2)
+    n, L = 2, pop.L
+    g = torch.Generator().manual_seed(3)
+    a = torch.zeros(n, L.na_stride); b = torch.zeros(n, L.na_stride)
+    a[:, :L.na] = torch.randn(n, L.na, generator=g) * 0.1; b[:, :L.na] = torch.randn(n, L.na, generator=g)
+    eps = np.array([0.3, 0.0], np.float32)
+    for max_norm in (None, 0.5):
+        out, stats = pop.grad_blend(a.cuda(), b.cuda(), eps, max_norm)
+        out, stats = out.cpu().numpy(), stats.cpu().numpy()
+        an, bn = a.numpy(), b.numpy()
+        for i in range(n):
+            ref = (np.float32(1.0 - float(eps[i])) * an[i]).astype(np.float32) + (eps[i] * bn[i]).astype(np.float32)
+            shapes = [w.shape for w in probs[i][0]["actor"]]
+            sizes = np.cumsum([0] + [int(np.prod(sh)) for sh in shapes])
+            n_pg = sum(np.linalg.norm(an[i, sizes[k]:sizes[k + 1]].astype(np.float64)) for k in range(len(shapes)))
+            n_ms = sum(np.linalg.norm(bn[i, sizes[k]:sizes[k + 1]].astype(np.float64)) for k in range(len(shapes)))
+            assert abs(stats[i, 6] - n_pg) < 1e-5 * n_pg and abs(stats[i, 7] - n_ms) < 1e-5 * n_ms
+            gn = np.linalg.norm(ref[:L.na].astype(np.float64))
+            assert abs(stats[i, 4] - gn) < 1e-5 * gn
+            if max_norm is None:
+                assert np.array_equal(out[i], ref)
+                assert abs(stats[i, 5] - gn) < 1e-5 * gn
+            else:
+                scale = max_norm / max(gn, max_norm)
+                assert rel(out[i], ref * scale) < 1e-6 and abs(stats[i, 5] - gn * scale) < 1e-5 * gn
+    pop.close()
+
+
+@pytest.mark.parametrize("per_state_std,eps", [(True, 0.5), (False, 0.2)])
+def test_trpo_update_with_expert_blend_matches_the_oracle(per_state_std, eps):
+    cfg, pop, probs = _setup_expert(per_state_std, ("tanh", "tanh"), 2, n=3, N=128)
+    L = pop.L
+    act = np.stack([p[2] for p in probs]); adv = np.stack([p[3] for p in probs])
+    before = pop.t["actor"].cpu().numpy().copy()
+    logs = pop.trpo_update(act, adv, delta=0.02, cg_iters=5, trust_damp=0.01, kl_maxfactor=1.5, expert_eps=eps)
+    after = pop.t["actor"].cpu().numpy()
+    for i, (st, s, a, ad, batch) in enumerate(probs):
+        th = O.to_torch_state(st, torch.float64)
+        new, log, _, _ = O.trpo_update(cfg, th["actor"], s, a, ad, th, delta=0.02, cg_iters=5, trust_damp=0.01,
+                                       kl_maxfactor=1.5, expert=batch, eps=eps)
+        plain, _, _, _ = O.trpo_update(cfg, th["actor"], s, a, ad, th, delta=0.02, cg_iters=5, trust_damp=0.01, kl_maxfactor=1.5)
+        assert abs(logs[i]["adj"] - log["adj"]) < 1e-6, (logs[i], log)
+        step_ref = (O.flat(new) - O.flat(th["actor"])).numpy()
+        step_plain = (O.flat(plain) - O.flat(th["actor"])).numpy()
+        assert rel(step_ref, step_plain) > 1e-2                                    # the expert term really moves the step
+        if log["adj"] != 0:
+            assert rel(after[i, :L.na] - before[i, :L.na], step_ref) < 1e-2
+        for key in ("ent", "tv_pre", "kl_pre", "tv", "kl", "improve"):
+            assert abs(logs[i][key] - log[key]) <= 2e-2 * max(abs(log[key]), 1e-3), (key, logs[i], log)
+        assert logs[i]["mse"] > 0 and logs[i]["norm_MSE"] > 0 and logs[i]["norm_pg"] > 0
+    pop.close()
+
+
+def test_onpolicy_classes_take_expert_reg():
+    """``TRPO.update(rollout, expert_reg)`` / ``PPO.update(rollout, expert_reg)`` through the mirror classes: same RNG
+    consumption as the reference (rng.shuffle + two actor.sample draws; one draw per PPO minibatch step), the expert
+    weight changes the update, epsilon = 0 reproduces the plain update bit for bit."""
+    from sac_expert_b200.sac_eo.actors.init_actor import init_actor
+    from sac_expert_b200.sac_eo.algs.model_free.ppo import PPO
+    from sac_expert_b200.sac_eo.algs.model_free.trpo import TRPO
+    from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
+    from sac_expert_b200.sac_eo.models.init_world_models import init_world_models
+    env = SyntheticEnv(7, 2)
+    rng0 = np.random.default_rng(1)
+    N, E = 80, 10
+    s = rng0.standard_normal((N, 7)).astype(np.float32); a = rng0.standard_normal((N, 2)).astype(np.float32)
+    adv = rng0.standard_normal(N).astype(np.float32)
+    sE = rng0.standard_normal((E, 7)).astype(np.float32); spE = (sE + 0.1 * rng0.standard_normal((E, 7))).astype(np.float32)
+    tkw = dict(adv_center=True, adv_scale=True, delta_trpo=0.02, cg_it=5, trust_sub=1, trust_damp=0.01, kl_maxfactor=1.5,
+               ent_reg=False, ent_targ=0.0, alpha_lr=0.01)
+    pkw = dict(adv_center=True, adv_scale=True, eps_ppo=0.2, max_grad_norm=0.5, actor_lr=3e-4, actor_update_it=2,
+               actor_nminibatch=2, adaptlr=False, adapt_factor=0.03, adapt_minthresh=0.0, adapt_maxthresh=1.0,
+               ent_reg=False, ent_targ=0.0, alpha_lr=0.01)
+
+    def fresh():
+        np.random.seed(0)
+        actor = init_actor(env, [32, 32], ["tanh"], 0.01, 1.0, "orthogonal", False, None, actor_per_state_std=True,
+                           actor_squash=True)
+        models = init_world_models(env, [32, 32], ["relu"], 1.0, 1.0, None, [32, 32], ["relu"], 1.0, None, 2, False,
+                                   dict(separate_reward_nn=False, reward_loss_coef=1.0, scale_model_loss=False,
+                                        delta_clip_loss=None, reward_clip_loss=None, delta_clip_pred=3.0,
+                                        reward_clip_pred=None))
+        return actor, models
+
+    def flat(actor):
+        return np.concatenate([w.ravel() for w in actor.get_weights()])
+
+    for cls, kw in ((TRPO, tkw), (PPO, pkw)):
+        res = {}
+        for eps in (None, 0.0, 0.6):
+            actor, models = fresh()
+            w0 = flat(actor)
+            alg = cls(actor, kw)
+            np.random.seed(5)
+            reg = None if eps is None else (sE, None, spE, eps, models, False, np.random.default_rng(9))
+            log = alg.update((s, a, adv, None, None, None), expert_reg=reg)
+            res[eps] = (flat(actor) - w0, np.random.random(), log)            # the next global draw = how much was consumed
+        if cls is TRPO:      # the draws of the expert branch do not feed back into the TRPO step: epsilon = 0 is the plain update
+            assert rel(res[0.0][0], res[None][0]) < 1e-6, rel(res[0.0][0], res[None][0])
+        # (PPO: the actor.sample draws advance the global stream that also shuffles the minibatches, so epsilon = 0
+        # follows other minibatches than the plain update - as in the reference)
+        assert rel(res[0.6][0], res[0.0][0]) > 1e-2
+        assert np.isfinite(res[0.6][0]).all()
+        if cls is TRPO:
+            assert res[0.6][2]["epsilon"] == 0.6 and res[0.6][2]["norm_MSE"] > 0
+        # the expert branch consumes the global NumPy stream (actor.sample), the plain one does not (TRPO) / less (PPO)
+        assert res[0.6][1] != res[None][1]
+        assert res[0.6][1] == res[0.0][1]
