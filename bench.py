@@ -446,7 +446,8 @@ def run_b200(a):
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "agents_per_gpu": n_local, "total_agents": n_global, "batch": B,
                    "gemm_engine": ("tcgen05 fp16 hi/lo x3 (fp32 accumulation in TMEM): warp-specialised fused 3-layer forward / backward "
-                                   "kernels fed by cp.async.bulk from optimiser-maintained weight planes; bf16 hi/lo x3 weight-gradient GEMMs"
+                                   "kernels fed by cp.async.bulk from optimiser-maintained weight planes; bf16 hi/lo x3 weight-gradient GEMMs; "
+                                   "expert term: 2x512 models on mma.sync m16n8k16 fp16 hi/lo x3 streamed from HBM (10 rows per model)"
                                    if gemm_mode == 1 and not a.no_ws else
                                    "tcgen05 16-bit hi/lo x3, round-1 fused kernels" if gemm_mode == 1 else "fp32 SIMT"),
                    "cuda_graph": not a.no_graph, "second_stream_branch": not a.no_fork, "rng": "in-kernel Philox4x32-10",
