@@ -88,7 +88,7 @@ typedef struct saceo_config {
                                  [4] != 0 keeps the hidden-layer bias gradients on the ones-row GEMM path;
                                  [5] != 0 disables the warp-specialised TMA-fed fused kernels and their weight planes
                                  (round-1 fused kernels are used instead); [6] != 0 keeps the whole update on one stream (no
-                                 concurrent actor-phase branch); [7] expert-term kernel: 0 = hidden layer on mma.sync tf32 hi/lo x3 (default where the
+                                 concurrent actor-phase branch); [7] expert-term kernel: 0 = hidden layer on mma.sync fp16 hi/lo x3 (default where the
                                  shape allows), 1 = column-blocked CUDA-core kernel, 2 = round-1 CUDA-core kernel */
 } saceo_config;
 
@@ -245,7 +245,8 @@ int saceo_model_eval(saceo_ctx *ctx, const float *obs, const float *act, int32_t
  * (sac_eo/models/base_world_model.py:65-87).  Replaces self.model_optimizer (one tf.keras Adam over the
  * tensors of ALL models, mbrl_onpolicy_alg.py:48-49) and tf.clip_by_global_norm (:315-317).
  * GaussianModel.get_loss (continuous_models.py:101-131) is used instead when the logstd tables are given.
- * Single-network models only (separate_reward_nn == 0).  fit_hyper per agent (8 floats):
+ * With separate_reward_nn the reward prediction comes from the reward network bound in saceo_fit_tables (the model
+ * network then predicts the S delta columns only).  fit_hyper per agent (8 floats):
  *   [0] model_lr  [1] reward_loss_coef  [2] delta_clip_loss (0 = off)  [3] reward_clip_loss (0 = off)
  *   [4] model_max_grad_norm (0 = None)  [5] r_rms mean  [6] r_rms std  [7] scale_model_loss (0/1, Gaussian only) */
 #define SACEO_FIT_HYPER 8
@@ -257,6 +258,13 @@ typedef struct saceo_fit_tables {
   /* GaussianModel only (all three NULL => MSEModel loss): the trainable logstd variable [n_agents, 2, S]
    * (continuous_models.py:24-27, initial value log(std_mult)) and its Adam slots; part of the same joint optimiser */
   float *model_logstd, *model_logstd_m, *model_logstd_v;
+  /* separate_reward_nn only (base_world_model.py:34-38, continuous_models.py:216-219): the reward network of every model,
+   * input S+A, two hidden layers reward_hidden with activations reward_act (SACEO_ACT_*), one output, flat Keras layout
+   * [W0|b0|W1|b1|W2|b2], [n_agents, 2, reward_stride] (reward_stride % 32 == 0), and its Adam slots.  Its tensors join
+   * the same joint optimiser and the same global-norm clip (model.trainable = model_trainable + reward_trainable). */
+  float *reward, *reward_m, *reward_v;
+  int32_t reward_hidden[2], reward_act[2];
+  int64_t reward_stride;
 } saceo_fit_tables;
 
 /* Binds the fit tables and allocates the fitting workspace for minibatches of model_batch rows

@@ -110,6 +110,8 @@ class NetCfg:
     delta_clip_pred: float = 0.0          # 0/None => no clip (base_world_model.py:80-82)
     num_models: int = 2                   # 0 => plain SAC (SAC.py), 1 or 2 => SAC-EO branches
     std_mult: float = 1.0                 # only used by the GaussianActor._forward (CG) path
+    reward_hidden: Optional[Tuple[int, int]] = None   # separate_reward_nn: the reward net (None: like the model net)
+    reward_acts: Optional[Tuple[str, str]] = None
 
     @property
     def Ao(self) -> int:
@@ -375,13 +377,16 @@ def model_loss(cfg: NetCfg, theta_m, s_: Tensor, a_: Tensor, sp_: Tensor, r_: Te
     Gaussian: ``logstd`` [1,S] (trainable, NOT clipped): neglogp = 0.5*sum_j(((dn-dp)/exp(ls))^2 + 2 ls +
               log 2pi); loss = mean_b(scale*neglogp + coef*0.5*(rn-rp)^2), scale = stop_gradient(mean(
               exp(ls)^2)) with ``scale_model_loss`` else 1.
-    Single-network models only (``separate_reward_nn`` is not restated)."""
-    if cfg.separate_reward_nn:
-        raise ValueError("model fitting with separate_reward_nn is not restated")
+    ``separate_reward_nn`` (base_world_model.py:72-74): ``theta_m`` = the model net's six tensors followed by the reward
+    net's six; the model net predicts the S delta columns, the reward net (same normalised input) the reward."""
     sa = torch.cat([normalize(s_, st["m_s_mean"], st["m_s_std"]),
                     normalize(a_, st["m_a_mean"], st["m_a_std"])], -1)
-    pred = mlp(theta_m, sa.to(s_.dtype), cfg.model_acts)
-    delta_pred, r_pred = pred[:, :-1], pred[:, -1]
+    if cfg.separate_reward_nn:
+        delta_pred = mlp(theta_m[:6], sa.to(s_.dtype), cfg.model_acts)
+        r_pred = mlp(theta_m[6:12], sa.to(s_.dtype), cfg.reward_acts or cfg.model_acts).squeeze(-1)
+    else:
+        pred = mlp(theta_m, sa.to(s_.dtype), cfg.model_acts)
+        delta_pred, r_pred = pred[:, :-1], pred[:, -1]
     delta_norm = normalize(sp_ - s_, st["m_d_mean"], st["m_d_std"])
     if delta_clip_loss:
         delta_norm = torch.clamp(delta_norm, -delta_clip_loss, delta_clip_loss)
@@ -407,7 +412,9 @@ def apply_model_grads(cfg: NetCfg, models: List[List[Tensor]], adam: Dict, batch
     (lr ``model_lr``, one shared step counter) applies it to every model's tensors.
     ``adam`` = dict(m=[per model lists], v=[...], t=int); ``batches[k]`` = dict(s,a,sp,r) tensors.
     ``GaussianModel``: pass each model's tensor list with the ``logstd`` [1,S] variable appended
-    (``model_trainable = nn weights + [logstd]``, continuous_models.py:27) and ``fit["gaussian"] = True``."""
+    (``model_trainable = nn weights + [logstd]``, continuous_models.py:27) and ``fit["gaussian"] = True``.
+    ``separate_reward_nn`` (MSE loss): each model's list = model net tensors + reward net tensors
+    (``trainable = model_trainable + reward_trainable``, continuous_models.py:216-219)."""
     dt = models[0][0].dtype
     gauss = bool(fit.get("gaussian", False))
     live = [[w.detach().clone().requires_grad_(True) for w in th] for th in models]

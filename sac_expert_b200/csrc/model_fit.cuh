@@ -26,6 +26,11 @@ struct FitCtx {
   float *lrt;            // [n_agents] bias-corrected Adam step size
   int S, mb, mbs, nmod, use_clip;     // mbs: row stride of the minibatch buffers (mb rounded up to 32, pad rows stay zero)
   long long nm, nm_stride;
+  // separate_reward_nn: the reward network of every model (caller tables + workspace), NULL otherwise
+  float *rw, *rw_m, *rw_v, *g_r;
+  float *rH1, *rH2, *rOut, *rdOut, *rdH2, *rdH1;
+  int rh1, rh2, ract0, ract1;
+  long long nr, nr_stride;
 };
 
 // Adam step counter and step size of the joint model optimiser.  grid: ceil(n_agents/128)
@@ -91,7 +96,8 @@ __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
   __shared__ float w[512];              // exp(-2 ls_j) per output column (S <= 512 checked at bind time)
   __shared__ float sc_s, lsum_s;
   const int agent = blockIdx.y, net = blockIdx.x;
-  const int S = c.S, mo = S + 1;
+  const int S = c.S, mt = S + 1;                 // target rows: [delta (S) | reward]
+  const int mo = f.rw ? S : S + 1;               // model output width (separate_reward_nn: delta columns only)
   const long long an = (long long)agent * 2 + net;
   const float* hy = f.hyper + (long long)agent * FIT_HYPER;
   const float coef = hy[FIT_RCOEF];
@@ -114,7 +120,7 @@ __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
   float acc = 0.f;
   for (int row = threadIdx.x; row < f.mb; row += blockDim.x) {
     const float* P = f.Out + (an * f.mbs + row) * mo;
-    const float* T = f.T + (an * f.mbs + row) * mo;
+    const float* T = f.T + (an * f.mbs + row) * mt;
     float* dP = f.dOut + (an * f.mbs + row) * mo;
     float dl = 0.f;
     for (int j = 0; j < S; ++j) {
@@ -122,8 +128,9 @@ __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
       dl += e * e * w[j];
       dP[j] = sc * e * w[j] * inv;
     }
-    const float er = P[S] - T[S];
-    dP[S] = coef * er * inv;
+    const float er = (f.rw ? f.rOut[an * f.mbs + row] : P[S]) - T[S];
+    if (f.rw) f.rdOut[an * f.mbs + row] = coef * er * inv;
+    else dP[S] = coef * er * inv;
     acc += sc * (0.5f * (dl + lsum_s)) + coef * (0.5f * er * er);
   }
   acc = block_sum(acc, sh);
@@ -136,7 +143,7 @@ __global__ void k_fit_loss(KCtx c, FitCtx f, float* __restrict__ losses_out) {
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
       float g = 0.f;
       for (int row = 0; row < f.mb; ++row) {
-        const float e = f.Out[(an * f.mbs + row) * mo + j] - f.T[(an * f.mbs + row) * mo + j];
+        const float e = f.Out[(an * f.mbs + row) * mo + j] - f.T[(an * f.mbs + row) * mt + j];
         g += 1.f - e * e * w[j];
       }
       f.g_ls[an * S + j] = sc * g * inv;
@@ -157,6 +164,10 @@ __global__ void k_fit_gnorm(FitCtx f) {
       const float* gl = f.g_ls + ((long long)agent * 2 + net) * f.S;
       for (int i = threadIdx.x; i < f.S; i += blockDim.x) { const float x = gl[i]; acc += x * x; }
     }
+    if (f.rw) {
+      const float* gr = f.g_r + ((long long)agent * 2 + net) * f.nr_stride;
+      for (long long i = threadIdx.x; i < f.nr; i += blockDim.x) { const float x = gr[i]; acc += x * x; }
+    }
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
@@ -171,10 +182,12 @@ __global__ void k_fit_gnorm(FitCtx f) {
 }
 
 // joint Keras Adam over all model tensors (one step counter per agent).  grid: (ceil(ceil(nm/4)/256), nmod, n_agents)
-__global__ void k_fit_adam(FitCtx f) {
+// reward != 0: the same step on the reward networks' tensors (separate_reward_nn).
+__global__ void k_fit_adam(FitCtx f, int reward) {
   const int agent = blockIdx.z, net = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const float lr_t = f.lrt[agent];
+  if (reward) { f.model = f.rw; f.m = f.rw_m; f.v = f.rw_v; f.g = f.g_r; f.nm = f.nr; f.nm_stride = f.nr_stride; f.ls = nullptr; }
   if (f.ls && blockIdx.x == 0) {                           // the logstd variable rides in the first block
     for (int j = threadIdx.x; j < f.S; j += blockDim.x) {
       const long long o = ((long long)agent * 2 + net) * f.S + j;

@@ -1158,7 +1158,16 @@ extern "C" int saceo_model_eval(saceo_ctx* x, const float* obs, const float* act
 extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t model_batch, int32_t use_grad_clip) {
   if (!x || !t) return fail(SACEO_E_INVALID, "null argument");
   if (x->cfg.num_models < 1) return fail(SACEO_E_INVALID, "model fitting needs num_models >= 1");
-  if (x->cfg.separate_reward_nn) return fail(SACEO_E_INVALID, "model fitting with separate_reward_nn is not supported");
+  const bool sep = x->cfg.separate_reward_nn != 0;
+  if (sep) {
+    if (!t->reward || !t->reward_m || !t->reward_v) return fail(SACEO_E_INVALID, "separate_reward_nn: the reward tables of saceo_fit_tables are required");
+    if (t->reward_hidden[0] < 1 || t->reward_hidden[1] < 1) return fail(SACEO_E_INVALID, "reward_hidden must be positive");
+    for (int i = 0; i < 2; ++i)
+      if (t->reward_act[i] < 0 || t->reward_act[i] > SACEO_ACT_ELU) return fail(SACEO_E_INVALID, "bad reward activation");
+    const long long nr_ = (long long)(x->cfg.S + x->cfg.A) * t->reward_hidden[0] + t->reward_hidden[0] +
+                          (long long)t->reward_hidden[0] * t->reward_hidden[1] + t->reward_hidden[1] + t->reward_hidden[1] + 1;
+    if (t->reward_stride < nr_ || (t->reward_stride % 32) != 0) return fail(SACEO_E_INVALID, "reward_stride must be a multiple of 32 and >= %lld", nr_);
+  }
   if (model_batch < 1) return fail(SACEO_E_INVALID, "model_batch must be >= 1");
   if (!t->model || !t->model_m || !t->model_v || !t->model_t || !t->fit_hyper)
     return fail(SACEO_E_INVALID, "a required fit table pointer is NULL");
@@ -1174,10 +1183,16 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
   f.ls = t->model_logstd; f.ls_m = t->model_logstd_m; f.ls_v = t->model_logstd_v; f.S = c.S;
   f.mb = model_batch; f.mbs = (int)rup(model_batch, 32); f.nmod = c.num_models; f.use_clip = use_grad_clip;
   f.nm = x->L.nm; f.nm_stride = x->L.nm_stride;
+  if (sep) {
+    f.rw = t->reward; f.rw_m = t->reward_m; f.rw_v = t->reward_v;
+    f.rh1 = t->reward_hidden[0]; f.rh2 = t->reward_hidden[1]; f.ract0 = t->reward_act[0]; f.ract1 = t->reward_act[1];
+    f.nr_stride = t->reward_stride;
+    f.nr = (long long)(c.S + c.A) * f.rh1 + f.rh1 + (long long)f.rh1 * f.rh2 + f.rh2 + f.rh2 + 1;
+  }
   const long long n2 = 2LL * c.n_agents, mb = f.mbs, SA = c.S + c.A, mo = x->L.model_out;
   for (int pass = 0; pass < 2; ++pass) {
     Bump b{pass ? (char*)x->fit_ws : nullptr, 0, pass ? &x->names : nullptr};
-    f.X = b.get<float>("fit_X", n2 * mb * SA);        f.T = b.get<float>("fit_T", n2 * mb * mo);
+    f.X = b.get<float>("fit_X", n2 * mb * SA);        f.T = b.get<float>("fit_T", n2 * mb * (c.S + 1));
     f.H1 = b.get<float>("fit_H1", n2 * mb * c.model_hidden[0]); f.H2 = b.get<float>("fit_H2", n2 * mb * c.model_hidden[1]);
     f.Out = b.get<float>("fit_Out", n2 * mb * mo);    f.dOut = b.get<float>("fit_dOut", n2 * mb * mo);
     f.dH2 = b.get<float>("fit_dH2", n2 * mb * c.model_hidden[1]); f.dH1 = b.get<float>("fit_dH1", n2 * mb * c.model_hidden[0]);
@@ -1186,6 +1201,12 @@ extern "C" int saceo_fit_bind(saceo_ctx* x, const saceo_fit_tables* t, int32_t m
     f.g_ls = b.get<float>("g_model_logstd", n2 * c.S);
     f.gscale = b.get<float>("fit_gscale", c.n_agents); f.gnorm = b.get<float>("fit_gnorm", c.n_agents);
     f.lrt = b.get<float>("fit_lrt", c.n_agents);
+    if (sep) {
+      f.rH1 = b.get<float>("fit_rH1", n2 * mb * f.rh1); f.rH2 = b.get<float>("fit_rH2", n2 * mb * f.rh2);
+      f.rOut = b.get<float>("fit_rOut", n2 * mb);       f.rdOut = b.get<float>("fit_rdOut", n2 * mb);
+      f.rdH2 = b.get<float>("fit_rdH2", n2 * mb * f.rh2); f.rdH1 = b.get<float>("fit_rdH1", n2 * mb * f.rh1);
+      f.g_r = b.get<float>("g_reward", n2 * f.nr_stride);
+    }
     if (!pass) {
       const long long bytes = rup(b.off, 256);
       if (cudaMalloc(&x->fit_ws, (size_t)bytes) != cudaSuccess) {
@@ -1217,14 +1238,27 @@ extern "C" int saceo_model_fit(saceo_ctx* x, int32_t n_steps, const int64_t* idx
     int rc = mlp_forward(x, net, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.H1, f.H2, ms, f.Out, mo,
                          2LL * ms * mo, (long long)ms * mo, st, true);
     if (rc) return rc;
+    NetD rnet{f.rw, 2 * f.nr_stride, f.nr_stride, f.nmod, SA, f.rh1, f.rh2, 1, f.ract0, f.ract1};
+    if (f.rw) {      // the reward network sees the same normalised input (base_world_model.py:72-74)
+      rc = mlp_forward(x, rnet, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.rH1, f.rH2, ms, f.rOut, 1,
+                       2LL * ms, (long long)ms, st, true);
+      if (rc) return rc;
+    }
     LAUNCH(x, k_fit_loss, dim3(f.nmod, n), 256, 0, st, k, f,
            losses_out ? losses_out + (long long)s * n * f.nmod : (float*)nullptr);
     rc = mlp_backward(x, net, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.H1, f.H2, ms, f.dOut, mo,
                       2LL * ms * mo, (long long)ms * mo, mo, f.dH2, f.dH1, f.g, 2 * x->L.nm_stride, x->L.nm_stride,
                       nullptr, 0, 0, 0, 0, st, false);    // K = 200 on the register-staged kernel beats K = 224 streamed (measured)
     if (rc) return rc;
+    if (f.rw) {
+      rc = mlp_backward(x, rnet, f.X, SA, 2LL * ms * SA, (long long)ms * SA, mb, f.rH1, f.rH2, ms, f.rdOut, 1,
+                        2LL * ms, (long long)ms, 1, f.rdH2, f.rdH1, f.g_r, 2 * f.nr_stride, f.nr_stride,
+                        nullptr, 0, 0, 0, 0, st, false);
+      if (rc) return rc;
+    }
     if (f.use_clip) LAUNCH(x, k_fit_gnorm, n, 1024, 0, st, f);
-    LAUNCH(x, k_fit_adam, dim3(cdiv(cdiv(f.nm, 4), 256), f.nmod, n), 256, 0, st, f);
+    LAUNCH(x, k_fit_adam, dim3(cdiv(cdiv(f.nm, 4), 256), f.nmod, n), 256, 0, st, f, 0);
+    if (f.rw) LAUNCH(x, k_fit_adam, dim3(cdiv(cdiv(f.nr, 4), 256), f.nmod, n), 256, 0, st, f, 1);
   }
   return check_launch();
 }

@@ -64,7 +64,11 @@ class Tables(C.Structure):
 class FitTables(C.Structure):
     """saceo_fit_tables (include/saceo.h): dynamics-model fitting state."""
     _fields_ = [(n, C.c_void_p) for n in ("model", "model_m", "model_v", "model_t", "fit_hyper",
-                                          "model_logstd", "model_logstd_m", "model_logstd_v")]
+                                          "model_logstd", "model_logstd_m", "model_logstd_v",
+                                          "reward", "reward_m", "reward_v")] + \
+               [("reward_hidden", C.c_int32 * 2), ("reward_act", C.c_int32 * 2), ("reward_stride", C.c_int64)]
+    POINTERS = ("model", "model_m", "model_v", "model_t", "fit_hyper", "model_logstd", "model_logstd_m", "model_logstd_v",
+                "reward", "reward_m", "reward_v")
 
 
 FIT_HYPER = 8

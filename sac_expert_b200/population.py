@@ -35,6 +35,8 @@ class PopulationSpec:
     model_acts: Tuple[str, str] = ("relu", "relu")
     per_state_std: bool = True
     separate_reward_nn: bool = False
+    reward_hidden: Optional[Tuple[int, int]] = None     # separate_reward_nn: the reward network (default: model_hidden / model_acts)
+    reward_acts: Optional[Tuple[str, str]] = None
     num_models: int = 2            # 0 = plain SAC
     delta_clip_pred: float = 0.0
     B: int = 256
@@ -199,9 +201,14 @@ class Population:
             actor=net_shapes(spec.S, spec.actor_hidden, L.Ao) + ([] if spec.per_state_std else [(1, spec.A)]),
             q=net_shapes(spec.S + spec.A, spec.critic_hidden, 1),
             model=net_shapes(spec.S + spec.A, spec.model_hidden, L.model_out),
+            reward=net_shapes(spec.S + spec.A, tuple(spec.reward_hidden or spec.model_hidden), 1),
         )
         self._host_size = np.zeros(n, np.int64)
         self._host_start = np.zeros(n, np.int64)
+        if spec.separate_reward_nn and spec.num_models > 0:      # reward networks: fitted by model_fit, unused by the update
+            nr = sum(int(np.prod(sh)) for sh in self.shapes["reward"])
+            self.nr_stride = (nr + 31) // 32 * 32
+            self.t["reward"] = torch.zeros(n, 2, self.nr_stride, device=self.dev)
         self.ctx = C.c_void_p()
         torch.cuda.synchronize(self.dev)
         _l.check(self.lib.saceo_create(C.byref(self.cfg), C.byref(self.ctx)))
@@ -265,6 +272,8 @@ class Population:
             return self.t["qt"], "q", int(name[1]) - 1
         if name in ("m1", "m2"):
             return self.t["model"], "model", int(name[1]) - 1
+        if name in ("r1", "r2"):      # reward networks of the models (separate_reward_nn, bound by fit_bind)
+            return self.t["reward"], "reward", int(name[1]) - 1
         raise KeyError(name)
 
     def set_net(self, agent: int, name: str, weights: Sequence[np.ndarray], table: Optional[str] = None):
@@ -552,6 +561,12 @@ class Population:
         self.t["fit_hyper"][:, 0] = 1e-3      # --model_lr
         self.t["fit_hyper"][:, 1] = 1.0       # --reward_loss_coef
         self.t["fit_hyper"][:, 6] = 1.0       # identity r_rms
+        if self.spec.separate_reward_nn:
+            nr = sum(int(np.prod(sh)) for sh in self.shapes["reward"])
+            self.nr_stride = (nr + 31) // 32 * 32
+            keep = self.t.get("reward")
+            self.t.update(reward=keep if keep is not None and keep.shape[-1] == self.nr_stride else z(n, 2, self.nr_stride),
+                          reward_m=z(n, 2, self.nr_stride), reward_v=z(n, 2, self.nr_stride))
         if gaussian:
             self.t.update(model_logstd=torch.full((n, 2, self.spec.S), float(np.log(std_mult)), device=self.dev),
                           model_logstd_m=z(n, 2, self.spec.S), model_logstd_v=z(n, 2, self.spec.S))
@@ -559,8 +574,16 @@ class Population:
             for k in ("model_logstd", "model_logstd_m", "model_logstd_v"):
                 self.t.pop(k, None)
         ft = _l.FitTables()
-        for name, _ in _l.FitTables._fields_:
+        for name in _l.FitTables.POINTERS:
             setattr(ft, name, self.t[name].data_ptr() if name in self.t else None)
+        if self.spec.separate_reward_nn:
+            rh = tuple(self.spec.reward_hidden or self.spec.model_hidden)
+            ra = tuple(self.spec.reward_acts or self.spec.model_acts)
+            for i in range(2):
+                if ra[i] not in _l.ACT_IDS:
+                    raise ValueError("activations must be relu, tanh, or elu")
+                ft.reward_hidden[i] = int(rh[i]); ft.reward_act[i] = _l.ACT_IDS[ra[i]]
+            ft.reward_stride = self.nr_stride
         torch.cuda.synchronize(self.dev)
         _l.check(self.lib.saceo_fit_bind(self.ctx, C.byref(ft), int(model_batch), int(bool(use_grad_clip))))
         self.model_batch = int(model_batch)
@@ -574,7 +597,7 @@ class Population:
 
     def reset_model_optimizer(self):
         """``reset_model_optimizer`` (SAC_expert.py:551-553): fresh Adam slots and step count."""
-        for k in ("model_m", "model_v", "model_t", "model_logstd_m", "model_logstd_v"):
+        for k in ("model_m", "model_v", "model_t", "model_logstd_m", "model_logstd_v", "reward_m", "reward_v"):
             if k in self.t:
                 self.t[k].zero_()
 

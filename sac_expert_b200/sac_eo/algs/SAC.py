@@ -94,6 +94,8 @@ class SAC:
             model_hidden=m.layers if m else (8, 8), actor_acts=a.activations, critic_acts=q.activations,
             model_acts=m.activations if m else ("relu", "relu"), per_state_std=a.per_state_std,
             separate_reward_nn=m.separate_reward_nn if m else False, num_models=nm,
+            reward_hidden=getattr(m, "reward_layers", None) if m else None,
+            reward_acts=getattr(m, "reward_activations", None) if m else None,
             delta_clip_pred=(m.delta_clip_pred or 0.0) if m else 0.0, B=self.sac_batch_size, E=max(self._expert_rows(), 2),
             target_update_int=self.target_update_int, replay_capacity=cap, std_mult=a.std_mult,
             gemm_mode=kw["gemm_mode"], device=kw["device"])

@@ -121,6 +121,9 @@ class SAC_exp(SAC):
             raise NotImplementedError("the device joint optimiser covers the two models of the update path")
         gaussian = bool(getattr(self.models[0], "gaussian", False))
         self.pop.fit_bind(self.model_batch_size, use_grad_clip=self.model_max_grad_norm is not None, gaussian=gaussian)
+        if getattr(self.models[0], "separate_reward_nn", False):      # the reward networks join the joint optimiser
+            for k in range(self._n_models()):
+                self.pop.set_net(0, "r%d" % (k + 1), self.models[k]._reward_weights)
         if gaussian:                           # GaussianModel.logstd (continuous_models.py:24-25) joins the device optimiser
             for k in range(self._n_models()):
                 self.pop.t["model_logstd"][0, k].copy_(torch.from_numpy(np.asarray(self.models[k]._logstd, np.float32)[0]))

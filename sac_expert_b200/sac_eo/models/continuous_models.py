@@ -29,7 +29,9 @@ class MSEModel(DeviceNet):
         self.scale_model_loss = bool(model_setup_kwargs.get("scale_model_loss", False))
         out = self.s_dim if self.separate_reward_nn else self.s_dim + 1
         self._host_weights = create_nn_weights(self.s_dim + self.a_dim, out, self.layers, model_gain)
-        self._reward_weights = (create_nn_weights(self.s_dim + self.a_dim, 1, check_two_hidden(reward_layers), reward_gain)
+        self.reward_layers = check_two_hidden(reward_layers) if self.separate_reward_nn else None
+        self.reward_activations = broadcast_activations(reward_layers, reward_activations) if self.separate_reward_nn else None
+        self._reward_weights = (create_nn_weights(self.s_dim + self.a_dim, 1, self.reward_layers, reward_gain)
                                 if self.separate_reward_nn else None)
         self._logstd = np.ones((1, self.s_dim), np.float32) * np.log(std_mult) if self.gaussian else None
         self.trainable = ["W0", "b0", "W1", "b1", "W2", "b2"] + (["logstd"] if self.gaussian else [])
@@ -69,12 +71,24 @@ class MSEModel(DeviceNet):
                 dev.copy_(torch.from_numpy(self._logstd[0]))
         super().set_weights(weights, from_flat, increment)
 
+    def _device_reward(self):
+        """The reward network lives in the device fit tables once the joint optimiser is bound (separate_reward_nn)."""
+        if self.separate_reward_nn and self._pop is not None and "reward_m" in self._pop.t:
+            return "r%d" % int(self._table[1])
+        return None
+
     def get_reward_weights(self):
+        name = self._device_reward()
+        if name is not None:
+            self._reward_weights = self._pop.get_net(self._agent, name)
         return self._reward_weights
 
     def set_reward_weights(self, weights):
         if self.separate_reward_nn:
             self._reward_weights = [np.asarray(w, np.float32) for w in weights]
+            name = self._device_reward()
+            if name is not None:
+                self._pop.set_net(self._agent, name, self._reward_weights)
 
     def sample(self, s, a, deterministic=True):
         if self.gaussian and not deterministic:

@@ -246,6 +246,49 @@ def test_update_models_gaussian_mirror():
             assert rel(np.asarray(gw) - np.asarray(old), ref.numpy() - np.asarray(old)) < 1e-3
 
 
+def test_update_models_separate_reward_nn_mirror():
+    """--separate_reward_nn through the class interface: the reward networks are uploaded when the joint optimiser is
+    bound, one _apply_model_grads call matches the oracle on BOTH networks of both models, and
+    get_reward_weights() / set_reward_weights() reach the device tables."""
+    from oracle.sac_eo_oracle import apply_model_grads
+    S, A, B, E = 11, 3, 32, 8
+    np.random.seed(0)
+    env = SyntheticEnv(S, A)
+    actor = init_actor(env, [32, 32], ["relu"], 0.01, 1.0, "orthogonal", False, None, True, True, False)
+    critics, q_targets, q_critics = init_critics(env, [32, 32], ["relu"], 1.0, None, 2, False, "orthogonal", False)
+    setup = dict(SETUP, separate_reward_nn=True, reward_loss_coef=0.6)
+    models = init_world_models(env, [48, 48], ["tanh"], 0.01, 1.0, None, [32, 40], ["relu"], 0.01, None, 2, False, setup)
+    kw = dict(alg_type="sac_imit", sac_batch_size=B, expert_buffer_size=E, gamma=0.99, alg_seed=5, epsilon=0.2,
+              device_replay_capacity=1000, gemm_mode=L.GEMM_FP32_SIMT, model_batch_size=40, model_lr=1e-3)
+    alg = init_alg(0, env, env, env, actor, critics, q_targets, q_critics, models, kw, {}, None, None)
+    rng = np.random.default_rng(1)
+    n = 200
+    rows = (rng.standard_normal((n, S)).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32),
+            rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32), rng.random(n) < 0.05)
+    alg.env_data.add(*rows)
+    alg.model_data.add(*rows)
+    w0 = [m.get_weights() for m in alg.models]
+    r0 = [[w.copy() for w in m.get_reward_weights()] for m in alg.models]
+    assert [w.shape for w in r0[0]] == [(S + A, 32), (32,), (32, 40), (40,), (40, 1), (1,)] and w0[0][-2].shape == (48, S)
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 32), critic_hidden=(32, 32), model_hidden=(48, 48), model_acts=("tanh", "tanh"),
+                 separate_reward_nn=True, reward_hidden=(32, 40), reward_acts=("relu", "relu"))
+    st = to_torch_state(snapshot(alg, cfg))
+    idx = np.stack([rng.permutation(n)[:40] for _ in range(2)])
+    losses = alg._apply_model_grads(idx)
+    mods = [[torch.from_numpy(np.asarray(w, np.float32)) for w in list(w0[k]) + list(r0[k])] for k in range(2)]
+    adam = dict(m=[[torch.zeros_like(w) for w in m] for m in mods], v=[[torch.zeros_like(w) for w in m] for m in mods], t=0)
+    d = alg.model_data
+    b = [{k: torch.as_tensor(getattr(d, k + "_all")[idx[m]]) for k in ("s", "a", "sp", "r")} for m in range(2)]
+    out = apply_model_grads(cfg, mods, adam, b, st, dict(model_lr=1e-3, reward_loss_coef=0.6))
+    for m in range(2):
+        assert abs(float(losses[0, 0, m]) - float(out["losses"][m])) < 1e-4 * abs(float(out["losses"][m]))
+        got = list(alg.models[m].get_weights()) + list(alg.models[m].get_reward_weights())
+        for gw, ref, old in zip(got, out["models"][m], mods[m]):
+            assert rel(np.asarray(gw) - old.numpy(), ref.numpy() - old.numpy()) < 1e-3
+    alg.models[0].set_reward_weights(r0[0])
+    assert all(np.array_equal(a_, b_) for a_, b_ in zip(alg.models[0].get_reward_weights(), r0[0]))
+
+
 def test_bc_alg_update_matches_oracle_with_reference_rng_order():
     """init_alg(alg_type='bc'): BC._update -> _update_actor, RNG order of BC.py:329-341."""
     from oracle.sac_eo_oracle import bc_update

@@ -193,11 +193,86 @@ def test_model_fit_multi_step_call_matches_single_steps():
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("gemm_mode", [L.GEMM_FP32_SIMT, L.GEMM_TCGEN05_BF16X3])
+def test_model_fit_separate_reward_nn(gemm_mode):
+    """separate_reward_nn (base_world_model.py:34-38, 72-74; continuous_models.py:216-219): the model net predicts the S
+    delta columns, a second net the reward; both nets of both models sit in ONE joint optimiser with ONE global-norm
+    clip.  Three steps against the oracle: losses, gradients of both nets, the clip norm, parameters and Adam slots."""
+    from oracle.sac_eo_oracle import init_net
+    big = gemm_mode == L.GEMM_TCGEN05_BF16X3
+    cfg = NetCfg(S=11 if big else 5, A=3 if big else 2, model_hidden=(512, 512) if big else (64, 48), model_acts=("tanh", "relu"),
+                 separate_reward_nn=True, reward_hidden=(256, 256) if big else (32, 40), reward_acts=("relu", "tanh"))
+    n, mb, N, S, A = 2, 200 if big else 24, 600, cfg.S, cfg.A
+    fit = dict(model_lr=2e-3, reward_loss_coef=0.7, delta_clip_loss=3.0, reward_clip_loss=2.0, model_max_grad_norm=0.4)
+    pop = Population(spec_from_cfg(cfg, n, 32, 4, N, gemm_mode=gemm_mode, reward_hidden=cfg.reward_hidden, reward_acts=cfg.reward_acts))
+    pop.fit_bind(mb, use_grad_clip=True)
+    rng = np.random.default_rng(77)
+    agents = []
+    for i in range(n):
+        st, replay, expert, hyper = make_problem(cfg, 32, 4, N, seed=50 + 13 * i, perturb=0.05)
+        st["m_r_mean"], st["m_r_std"] = np.float32(0.2 * i), np.float32(1.3)
+        pop.load_agent(i, st, hyper)
+        pop.append_rows(i, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+        pop.set_fit_hyper(i, r_mean=st["m_r_mean"], r_std=st["m_r_std"], **fit)
+        rw = []
+        for k in range(2):
+            w = [x + (0.05 * rng.standard_normal(x.shape)).astype(np.float32) for x in init_net(rng, S + A, cfg.reward_hidden, 1, 0.01)]
+            pop.set_net(i, "r%d" % (k + 1), w)
+            rw.append(w)
+        T = to_torch_state(st)
+        models = [T["m%d" % (k + 1)] + [torch.from_numpy(x) for x in rw[k]] for k in range(2)]
+        adam = dict(m=[[torch.zeros_like(w) for w in m] for m in models], v=[[torch.zeros_like(w) for w in m] for m in models], t=0)
+        agents.append([T, replay, models, adam])
+    worst = {}
+
+    def upd(k, v):
+        worst[k] = max(worst.get(k, 0.0), float(v))
+
+    for step in range(3):
+        idx = np.stack([model_fit_batches(N, 2, mb, True, rng)[0] for _ in range(n)])
+        losses = pop.model_fit(idx)
+        torch.cuda.synchronize()
+        g = pop.debug("g_model").cpu().numpy().reshape(n, 2, pop.L.nm_stride)
+        gr = pop.debug("g_reward").cpu().numpy().reshape(n, 2, pop.nr_stride)
+        for i, (T, replay, models, adam) in enumerate(agents):
+            b = [{k: torch.as_tensor(replay[k][idx[i, m]]) for k in ("s", "a", "sp", "r")} for m in range(2)]
+            o = apply_model_grads(cfg, models, adam, b, T, fit)
+            scale = float(pop.debug("fit_gscale").cpu()[i])
+            upd("gnorm", abs(float(pop.debug("fit_gnorm").cpu()[i]) - float(o["gnorm"])) / float(o["gnorm"]))
+            for m in range(2):
+                upd("loss", abs(float(losses[0, i, m]) - float(o["losses"][m])) / abs(float(o["losses"][m])))
+                ref = np.concatenate([x.numpy().ravel() for x in o["grads"][m][:6]])
+                upd("grad", rel(g[i, m, :ref.size] * scale, ref))
+                ref_r = np.concatenate([x.numpy().ravel() for x in o["grads"][m][6:]])
+                upd("grad_reward", rel(gr[i, m, :ref_r.size] * scale, ref_r))
+                for name, sl, tabs in (("m%d" % (m + 1), slice(0, 6), ("model_m", "model_v")),
+                                       ("r%d" % (m + 1), slice(6, 12), ("reward_m", "reward_v"))):
+                    for gw, nw, ow in zip(pop.get_net(i, name), o["models"][m][sl], models[m][sl]):
+                        upd("dtheta_" + name[0], rel(gw - ow.numpy(), nw.numpy() - ow.numpy()))
+                    for gw, nw in zip(pop.get_net(i, name, table=tabs[0]), o["m"][m][sl]):
+                        upd("adam_m_" + name[0], rel(gw, nw.numpy()))
+                    for gw, nw in zip(pop.get_net(i, name, table=tabs[1]), o["v"][m][sl]):
+                        upd("adam_v_" + name[0], rel(gw, nw.numpy()))
+            # continue from the device state
+            agents[i][2] = [[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1)) + pop.get_net(i, "r%d" % (m + 1))] for m in range(2)]
+            agents[i][3] = dict(m=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_m") + pop.get_net(i, "r%d" % (m + 1), table="reward_m")] for m in range(2)],
+                                v=[[torch.from_numpy(w.copy()) for w in pop.get_net(i, "m%d" % (m + 1), table="model_v") + pop.get_net(i, "r%d" % (m + 1), table="reward_v")] for m in range(2)],
+                                t=o["t"])
+    pop.close()
+    assert max(worst.values()) < (3e-3 if big else TOL), worst
+
+
 def test_model_fit_errors():
     cfg = NetCfg(S=4, A=2, model_hidden=(32, 32), separate_reward_nn=True)
     pop = Population(spec_from_cfg(cfg, 1, 16, 4, 32))
+    ft = L.FitTables()                       # separate_reward_nn without the reward tables
+    for name in ("model",):
+        setattr(ft, name, pop.t["model"].data_ptr())
+    z = torch.zeros(1, 2, pop.L.nm_stride, device="cuda"); zt = torch.zeros(1, dtype=torch.int32, device="cuda"); zh = torch.zeros(1, 8, device="cuda")
+    ft.model_m, ft.model_v, ft.model_t, ft.fit_hyper = z.data_ptr(), z.data_ptr(), zt.data_ptr(), zh.data_ptr()
+    import ctypes as C
     with pytest.raises(SaceoError):
-        pop.fit_bind(8)
+        L.check(pop.lib.saceo_fit_bind(pop.ctx, C.byref(ft), 8, 0))
     pop.close()
     cfg = NetCfg(S=4, A=2, model_hidden=(32, 32))
     pop = Population(spec_from_cfg(cfg, 1, 16, 4, 32))
