@@ -197,6 +197,44 @@ __device__ __forceinline__ void ws_store_planes_p(uint32_t patch, uint8_t* __res
     }
   }
 }
+//   store + column sums in ONE pass over the patch (the gradient tiles whose fp32 form is not kept): v -> patch -> planes,
+//   the column sums of the valid rows to cs[q][col + c] from the 4 rows x 8 columns each lane converts anyway, finished
+//   with three shuffle steps in a fixed order
+__device__ __forceinline__ void ws_store_planes_cs(uint32_t patch, const uint32_t (&v)[32], uint8_t* __restrict__ img, int rbase, int rows,
+                                                   int col, int lane, uint32_t cs, int q) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sts128(ws_pa(patch, lane, 4 * j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  __syncwarp();
+  const int lr = lane >> 2, c8 = lane & 3;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + lr, grow = rbase + r;
+    if (grow < rows) {
+      const float4 a = lds128(ws_pa(patch, r, 8 * c8)), b = lds128(ws_pa(patch, r, 8 * c8 + 4));
+      const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint4 hi, lo;
+      split8<false>(x, hi, lo);
+      uint8_t* dst = img + ws_image_off(grow, (col >> 3) + c8);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + 16384) = lo;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += x[j];
+    }
+  }
+  if (cs) {
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if (lane < 4) {
+      sts128f(cs + (uint32_t)(q * FW_H + col + 8 * c8) * 4, s[0], s[1], s[2], s[3]);
+      sts128f(cs + (uint32_t)(q * FW_H + col + 8 * c8 + 4) * 4, s[4], s[5], s[6], s[7]);
+    }
+  }
+}
 //   load, two-phase: request the tile early (8 x 16 bytes per lane), decode it into the patch (fp32) when needed
 __device__ __forceinline__ void ws_planes_issue(const uint8_t* __restrict__ img, int rbase, int rows, int col, int lane, float4 (&t)[8]) {
   const int lr = lane >> 2, c8 = lane & 3;
@@ -636,6 +674,7 @@ struct BwdW {
   const float* H1; const float* H2; long long sHa, sHn;
   float* dH2; float* dH1;
   uint8_t* dH2p; long long sQa, sQn;               // optional bf16 hi/lo plane image of dH2 (replaces the fp32 dH2), bytes
+  uint8_t* dH1p;                                   // optional plane image of dH1 (operand of k_dw0_planes; same strides)
   const uint8_t* H1p;                              // optional: h1 as a bf16 hi/lo plane image (then H1 is not read), strides sQa / sQn
   float* dXa; int s_cols, a_cols; long long sXa, sXn;
   int rows, nnet, act0, act1;
@@ -724,7 +763,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const float* H2 = f.H2 + agent * f.sHa + net * f.sHn;
     float* dH1 = f.dH1 ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
     float* dH2 = f.dH2 ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
-    const bool want_cs = f.dbpart && (dH2 || f.dH2p) && dH1;
+    const bool want_cs = f.dbpart && (dH2 || f.dH2p) && (dH1 || f.dH1p);
     const int kp = (f.kout + 3) & ~3;
     const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
@@ -796,8 +835,11 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(WB_AP + cg));
       }
-      if (dH2 || f.dH2p) {
-        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);      // dH2 == null: column sums only
+      if (f.dH2p && !dH2) {
+        ws_store_planes_cs(patch, v, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
+        __syncwarp();
+      } else if (dH2 || f.dH2p) {
+        ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
         if (f.dH2p) ws_store_planes_p(patch, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
         __syncwarp();
       }
@@ -841,8 +883,12 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         tmem_ld_wait();
         ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
       }
-      if (dH1) {
+      if (f.dH1p && !dH1) {
+        ws_store_planes_cs(patch, v, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
+        __syncwarp();
+      } else if (dH1 || f.dH1p) {
         ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
+        if (f.dH1p) ws_store_planes_p(patch, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
         __syncwarp();
       }
       if (NA > 0) {
@@ -1005,6 +1051,128 @@ __global__ void __launch_bounds__(WS_NT, 1) k_dw_planes(DwP f) {
   }
 }
 
+// ==========================================================================================
+// Weight gradient of the first layer from the dH1 plane image:
+//     dW0[i, j] = sum_b X[b, i] * dH1[b, j]           (one CTA per (agent, net), in <= 64 inputs)
+// B = dH1 planes by TMA exactly like k_dw_planes; A = the input rows X (fp32, a few dozen columns), converted ONCE by the
+// epilogue warps into bf16 hi/lo MN-major stages in shared memory (8 KB per 32 batch rows: [plane][32 rows][64 inputs])
+// while the first dH1 stages are in flight.  One 128-row accumulator of which rows [0, in) are the gradient block (the M
+// atom stride of the shared descriptor form makes rows 64.. a by-product of the neighbouring plane; never read).
+// Replaces the cp.async + in-kernel-conversion GEMM for this shape (82 + 47 us per step at 256 agents).
+// ==========================================================================================
+struct Dw0P {
+  const float* X; int ldx; long long sXa, sXn;     // input rows [rows x in] (row stride ldx floats, 16-byte aligned)
+  const uint8_t* Bp; long long sBa, sBn;           // dH1 planes
+  float* G; long long sGa, sGn;                    // gradient block W0 of the flat layout (pitch 256)
+  int rows, in, nnet;
+};
+constexpr int DW0_NST = 3, DW0_RING = DW0_NST * WS_STAGE, DW0_XST = 8192, DW0_MAXST = 14;
+constexpr int DW0_BYTES = DW0_RING + DW0_MAXST * DW0_XST + 4096 + 1024 + 256;
+
+__global__ void __launch_bounds__(WS_NT, 1) k_dw0_planes(Dw0P f) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring = sb, xs = sb + DW0_RING, bars = xs + DW0_MAXST * DW0_XST + 4096, tslot = bars + 8 * 16;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };          // [0..3) full, [3..6) empty, [6] done, [7] X stages ready
+  const int z = blockIdx.x, agent = z / f.nnet, net = z - agent * f.nnet;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = (f.rows + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2 * DW0_NST + 2; ++s) mbar_init(bar(s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WS_NEW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = lds_u32(tslot);
+  if (warp == WS_NEW) {
+    if (lane == 0) {
+      const uint8_t* B = f.Bp + agent * f.sBa + net * f.sBn;
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % DW0_NST;
+        mbar_wait(bar(DW0_NST + s), (uint32_t)(((it / DW0_NST) & 1) ^ 1));
+        mbar_expect_tx(bar(s), WS_STAGE);
+        bulk_g2s(ring + s * WS_STAGE, B + (long long)it * WS_STAGE, WS_STAGE, bar(s));
+      }
+    }
+  } else if (warp < WS_NEW) {
+    // X -> bf16 hi/lo MN-major stages: item = (batch row, 8-input chunk); zeros beyond rows / in
+    const float* X = f.X + agent * f.sXa + net * f.sXn;
+    for (int it = threadIdx.x; it < nst * 32 * 8; it += WS_NEPI) {
+      const int b = it >> 3, c8 = it & 7, t = b >> 5, r = b & 31;
+      float x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = 0.f;
+      if (b < f.rows && 8 * c8 < f.in) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(X + (long long)b * f.ldx + 8 * c8));
+        const float4 c = 8 * c8 + 4 < f.in ? __ldg(reinterpret_cast<const float4*>(X + (long long)b * f.ldx + 8 * c8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x8[j] = 8 * c8 + j < f.in ? v8[j] : 0.f;
+      }
+      uint4 hi, lo;
+      split8<false>(x8, hi, lo);
+      const uint32_t dst = xs + (uint32_t)t * DW0_XST + (uint32_t)r * 128 + (uint32_t)((c8 ^ (r & 7)) << 4);
+      sts128(dst, hi); sts128(dst + 4096, lo);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar();                                       // the 16 conversion warps only (the producer is busy with its ring)
+    if (threadIdx.x == 0) mbar_arrive(bar(2 * DW0_NST + 1));          // the X stages are complete and visible to the tensor core
+  }
+  if (warp == WS_NEW + 1) {
+    if (lane == 0) {
+      mbar_wait(bar(2 * DW0_NST + 1), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % DW0_NST;
+        mbar_wait(bar(s), (uint32_t)((it / DW0_NST) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = xs + (uint32_t)it * DW0_XST, sbb = ring + s * WS_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t ko = (uint32_t)kk * 2048;
+          const uint32_t a_hi = sa + ko, a_lo = a_hi + 4096, b_hi = sbb + ko, b_lo = b_hi + 16384, acc = (it | kk) ? 1u : 0u;
+          umma_f16(tmem, umma_desc_mn(a_hi), umma_desc_mn(b_hi), DW_IDESC, acc);
+          umma_f16(tmem, umma_desc_mn(a_hi), umma_desc_mn(b_lo), DW_IDESC, 1u);
+          umma_f16(tmem, umma_desc_mn(a_lo), umma_desc_mn(b_hi), DW_IDESC, 1u);
+        }
+        umma_commit(bar(DW0_NST + s));
+      }
+      umma_commit(bar(2 * DW0_NST));
+    }
+  } else if (warp < WS_NEW) {
+    const int q = warp & 3, cg = warp >> 2;
+    if (q * 32 < f.in) {                              // lane quarters beyond the input width hold nothing
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const uint32_t patch = ring + (uint32_t)warp * WS_PATCH1;       // the operand ring is dead once the last MMA has retired
+      float* G = f.G + agent * f.sGa + net * f.sGn;
+      mbar_wait(bar(2 * DW0_NST), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col = cg * 64 + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+        ws_store_rows(patch, v, G, q * 32, f.in, col, lane);
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == WS_NEW + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+  }
+}
+static inline bool dw0_planes_eligible(int in, int rows, int ldx, const float* X, long long sXa, long long sXn) {
+  return in >= 1 && in <= 64 && ((rows + 31) >> 5) <= DW0_MAXST && (ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+         (sXa % 4) == 0 && (sXn % 4) == 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1020,6 +1188,7 @@ static inline cudaError_t mlp_ws_init() {
   WS_ATTR((k_mlp_bwd_ws<1, 0>)) WS_ATTR((k_mlp_bwd_ws<2, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0>))
 #undef WS_ATTR
   e = cudaFuncSetAttribute(k_dw_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_BYTES); if (e) return e;
+  e = cudaFuncSetAttribute(k_dw0_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, DW0_BYTES); if (e) return e;
   done = true;
   return cudaSuccess;
 }

@@ -70,10 +70,17 @@ struct saceo_ctx {
   // critic-independent half of the actor phase can run on a second stream next to the critic phase
   float *Xpi2 = nullptr, *aOut2 = nullptr, *nlp2 = nullptr, *Xc3 = nullptr;
   // bf16 hi/lo plane images of h1 / dH2 (actor: Rs rows, critics: B rows per net): operands of k_dw_planes
-  uint8_t *aH1p = nullptr, *adH2p = nullptr, *cH1p = nullptr, *cdH2p = nullptr;
+  uint8_t *aH1p = nullptr, *adH2p = nullptr, *cH1p = nullptr, *cdH2p = nullptr, *adH1p = nullptr, *cdH1p = nullptr;
   long long a_img = 0, c_img = 0;      // bytes per (agent, net) image
   cudaStream_t s2 = nullptr, s3 = nullptr, s4 = nullptr;      // s3 / s4: the three independent weight-gradient GEMMs of a backward pass side by side
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_g = nullptr, ev_g3 = nullptr, ev_g4 = nullptr;
+  // saceo_update_host_async: the H2D copies of step t+1 ride a copy stream into one of two device staging sets while step
+  // t computes; the update stream then only does device-to-device copies into the bound tables
+  cudaStream_t sc = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  char* hstage[2] = {nullptr, nullptr};
+  bool hstage_used[2] = {false, false};
+  int hslot = 0;
   FitCtx fit;             // dynamics-model fitting (saceo_fit_bind)
   bool fit_bound = false;
   void* fit_ws = nullptr;
@@ -219,17 +226,19 @@ static void carve(saceo_ctx* x, char* base) {
   }
   k.step_ctr = b.get<unsigned long long>("step_ctr", 2);
   x->pl_actor = x->pl_q = x->pl_qt = nullptr;
-  x->aH1p = x->adH2p = x->cH1p = x->cdH2p = nullptr;
+  x->aH1p = x->adH2p = x->cH1p = x->cdH2p = x->adH1p = x->cdH1p = nullptr;
   x->a_img = (long long)(R / 32) * WS_STAGE; x->c_img = (long long)(rup(B, 32) / 32) * WS_STAGE;
   if (c.gemm_mode == SACEO_GEMM_TCGEN05_BF16X3 && c.reserved[5] == 0) {
     if (c.actor_hidden[0] == FW_H && c.actor_hidden[1] == FW_H) {
       x->pl_actor = b.get<uint8_t>("pl_actor", n * ws_image_bytes(S));
       x->aH1p = b.get<uint8_t>("aH1p", n * x->a_img); x->adH2p = b.get<uint8_t>("adH2p", n * x->a_img);
+      x->adH1p = b.get<uint8_t>("adH1p", n * x->a_img);
     }
     if (c.critic_hidden[0] == FW_H && c.critic_hidden[1] == FW_H) {
       x->pl_q = b.get<uint8_t>("pl_q", n * 2 * ws_image_bytes(SA));
       x->pl_qt = b.get<uint8_t>("pl_qt", n * 2 * ws_image_bytes(SA));
       x->cH1p = b.get<uint8_t>("cH1p", n * 2 * x->c_img); x->cdH2p = b.get<uint8_t>("cdH2p", n * 2 * x->c_img);
+      x->cdH1p = b.get<uint8_t>("cdH1p", n * 2 * x->c_img);
     }
   }
   x->idx_stage = b.get<long long>("idx_stage", n * B);
@@ -345,6 +354,12 @@ extern "C" int saceo_destroy(saceo_ctx* x) {
   if (x->ev_join) cudaEventDestroy(x->ev_join);
   if (x->s3) cudaStreamDestroy(x->s3);
   if (x->s4) cudaStreamDestroy(x->s4);
+  if (x->sc) cudaStreamDestroy(x->sc);
+  for (int i = 0; i < 2; ++i) {
+    if (x->ev_h2d[i]) cudaEventDestroy(x->ev_h2d[i]);
+    if (x->ev_free[i]) cudaEventDestroy(x->ev_free[i]);
+    if (x->hstage[i]) cudaFree(x->hstage[i]);
+  }
   for (cudaEvent_t e : {x->ev_g, x->ev_g3, x->ev_g4}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : x->prof_ev) cudaEventDestroy(e);
   delete x;
@@ -525,7 +540,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
                         float* dH2, float* dH1, float* grads, long long sGa, long long sGn,
                         float* dXa, int S_cols, int A_cols, long long sXaA, long long sXaN, cudaStream_t st,
                         bool kpad = false, const uint8_t* H1p = nullptr, uint8_t* dH2p = nullptr, long long sQa = 0,
-                        long long sQn = 0) {
+                        long long sQn = 0, uint8_t* dH1p = nullptr) {
   const int na = x->cfg.n_agents;
   // kpad: the caller guarantees that rows [rows, rowsAllocH) of X, H1, H2, dOut, dH2, dH1 are zero, so the
   // weight-gradient contractions may run over a row count rounded up to the 32-row slabs of the streaming kernel
@@ -535,7 +550,7 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   int rc;
   GemmP p{};
   // fused gradient chain (dH2, dH1, dXa) on tensor cores with the tile resident in TMEM
-  bool fused = false, bias_done = false, dw1_planes = false;
+  bool fused = false, bias_done = false, dw1_planes = false, dw0_planes = false;
   if (n.planes && x->cfg.reserved[2] == 0 &&
       mlp_bwd_ws_eligible(n.h1, n.h2, out_cols, n.out, dXa != nullptr, A_cols, n.theta, n.sa, n.sn)) {
     BwdW f{};
@@ -552,6 +567,9 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
     // hidden-to-hidden weight gradient from bf16 plane images (k_dw_planes): dH2 then leaves the kernel as planes only
     dw1_planes = grads && f.dbpart && H1p && dH2p;
     if (dw1_planes) { f.dH2 = nullptr; f.dH2p = dH2p; f.H1p = H1p; f.sQa = sQa; f.sQn = sQn; }
+    // first-layer weight gradient from the dH1 plane image (k_dw0_planes): dH1 then leaves the kernel as planes only
+    dw0_planes = dw1_planes && dH1p && dw0_planes_eligible(n.in, rows, ldx, X, sXa, sXn);
+    if (dw0_planes) { f.dH1 = nullptr; f.dH1p = dH1p; }
     f.dbg = (g_ws_dbg && g_ws_count++ == g_ws_sel) ? g_ws_dbg : nullptr;
     if (mlp_bwd_ws_launch(f, na, st) != cudaSuccess) return fail(SACEO_E_CUDA, "fused backward launch failed");
     count_launch(x, "k_mlp_bwd_ws", st);
@@ -635,7 +653,13 @@ static int mlp_backward(saceo_ctx* x, const NetD& n, const float* X, int ldx, lo
   p.M = rows; p.N = n.h1; p.K = n.h2; p.epi = EPI_MUL_DACT; p.act = n.act0;
   rc = gemm(x, false, true, false, p, na, st); if (rc) return rc;
   }
-  if (grads) {   // [dW0; db0] = [X,1]^T . dH1
+  if (grads && dw0_planes) {   // dW0 = X^T . dH1 from the plane image (db0 came from the kernel's column sums)
+    Dw0P d{};
+    d.X = X; d.ldx = ldx; d.sXa = sXa; d.sXn = sXn; d.Bp = dH1p; d.sBa = sQa; d.sBn = sQn;
+    d.G = grads + n.oW0(); d.sGa = sGa; d.sGn = sGn; d.rows = rows; d.in = n.in; d.nnet = n.nnet;
+    k_dw0_planes<<<na * n.nnet, WS_NT, DW0_BYTES, st0>>>(d);
+    count_launch(x, "k_dw0_planes", st0);
+  } else if (grads) {   // [dW0; db0] = [X,1]^T . dH1
     p = GemmP{}; p.nnet = n.nnet;
     p.A = X; p.lda = ldx; p.sAa = sXa; p.sAn = sXn;
     p.B = dH1; p.ldb = n.h1; p.sBa = sH1a; p.sBn = sH1n;
@@ -722,7 +746,7 @@ static int phase_critic_grads(saceo_ctx* x, cudaStream_t st) {
   LAUNCH(x, k_critic_loss, dim3(2, n), 256, 0, st, k);
   rc = mlp_backward(x, qn, k.Xc2, k.ldXc, (long long)B * k.ldXc, 0, B, k.cH1, k.cH2, B, k.cdQ, 1, 2LL * B, B, 1,
                     k.cdH2, k.cdH1, k.g_q, 2 * x->L.nc_stride, x->L.nc_stride, nullptr, 0, 0, 0, 0, st, false,
-                    cpl ? x->cH1p : nullptr, cpl ? x->cdH2p : nullptr, 2 * x->c_img, x->c_img);
+                    cpl ? x->cH1p : nullptr, cpl ? x->cdH2p : nullptr, 2 * x->c_img, x->c_img, cpl ? x->cdH1p : nullptr);
   if (rc) return rc;
   return check_launch();
 }
@@ -840,7 +864,8 @@ static int phase_actor_post(saceo_ctx* x, cudaStream_t st, bool bc = false) {
   rc = mlp_backward(x, an, k.Xpi, k.ldXp, (long long)Rs * k.ldXp, 0, R, k.aH1, k.aH2, Rs, k.daOut, k.Ao, (long long)Rs * k.Ao, 0,
                     k.Ao, k.daH2, k.daH1, k.g_actor, x->L.na_stride, 0, nullptr, 0, 0, 0, 0, st, true,
                     dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->aH1p : nullptr,
-                    dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->adH2p : nullptr, x->a_img, 0);
+                    dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->adH2p : nullptr, x->a_img, 0,
+                    dw_planes_ok(x, an, R, k.Ao, x->aH1p, x->adH2p) ? x->adH1p : nullptr);
   if (rc) return rc;
   if (!k.per_state_std) LAUNCH(x, k_lsv_reduce, dim3(n), 32 * cdiv(A, 32), 0, st, k, R);
   return check_launch();
@@ -1012,17 +1037,46 @@ static int update_host_impl(saceo_ctx* x, int64_t num_timesteps, uint64_t seed, 
   if (!x) return fail(SACEO_E_INVALID, "null ctx");
   if (!x->bound) return fail(SACEO_E_UNBOUND, "saceo_bind() has not been called");
   cudaStream_t st = (cudaStream_t)stream; KCtx& k = x->k;
-  if (expert_host && k.E > 0) {
-    const long long ne = (long long)k.n_agents * k.E * k.S;
-    // host layout [2, n, E, S] (all sE rows, then all s'E rows) -> the BOUND expert tables (like Population.set_expert
-    // followed by an update): the kernels and the captured graphs keep reading the tables saceo_bind() gave them
-    CU(cudaMemcpyAsync(k.T.expert_s, expert_host, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(k.T.expert_sp, expert_host + ne, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
-  }
+  const bool want_e = expert_host && k.E > 0;
+  const long long ne = (long long)k.n_agents * k.E * k.S;
+  const size_t idx_bytes = sizeof(long long) * (size_t)k.n_agents * k.B, exp_bytes = sizeof(float) * 2 * (size_t)ne;
   int rc;
+  if (!sync && (want_e || idx_host)) {
+    // pipelined host path: H2D on the copy stream into staging set `s` (overlaps the previous step, which still reads the
+    // bound tables), then stream-ordered device-to-device copies into the bound tables / the index buffer
+    if (!x->sc) {
+      CU(cudaStreamCreateWithFlags(&x->sc, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&x->ev_free[i], cudaEventDisableTiming));
+        CU(cudaMalloc(&x->hstage[i], idx_bytes + exp_bytes + 256));
+      }
+    }
+    const int s = x->hslot; x->hslot ^= 1;
+    char* sidx = x->hstage[s]; char* sexp = x->hstage[s] + ((idx_bytes + 255) & ~(size_t)255);
+    if (x->hstage_used[s]) CU(cudaStreamWaitEvent(x->sc, x->ev_free[s], 0));     // its last consumer has copied out of it
+    if (want_e) CU(cudaMemcpyAsync(sexp, expert_host, exp_bytes, cudaMemcpyHostToDevice, x->sc));
+    if (idx_host) CU(cudaMemcpyAsync(sidx, idx_host, idx_bytes, cudaMemcpyHostToDevice, x->sc));
+    CU(cudaEventRecord(x->ev_h2d[s], x->sc));
+    CU(cudaStreamWaitEvent(st, x->ev_h2d[s], 0));
+    if (want_e) {
+      CU(cudaMemcpyAsync(k.T.expert_s, sexp, sizeof(float) * ne, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(k.T.expert_sp, sexp + sizeof(float) * ne, sizeof(float) * ne, cudaMemcpyDeviceToDevice, st));
+    }
+    if (idx_host) CU(cudaMemcpyAsync(k.idx, sidx, idx_bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(x->ev_free[s], st));
+    x->hstage_used[s] = true;
+  } else {
+    if (want_e) {
+      // host layout [2, n, E, S] (all sE rows, then all s'E rows) -> the BOUND expert tables (like Population.set_expert
+      // followed by an update): the kernels and the captured graphs keep reading the tables saceo_bind() gave them
+      CU(cudaMemcpyAsync(k.T.expert_s, expert_host, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(k.T.expert_sp, expert_host + ne, sizeof(float) * ne, cudaMemcpyHostToDevice, st));
+    }
+    if (idx_host) CU(cudaMemcpyAsync(k.idx, idx_host, idx_bytes, cudaMemcpyHostToDevice, st));
+  }
   if (idx_host) {
     // host indices (np.random.randint, buffers.py:135) + device noise / expert shuffle
-    CU(cudaMemcpyAsync(k.idx, idx_host, sizeof(long long) * k.n_agents * k.B, cudaMemcpyHostToDevice, st));
     rc = saceo_update(x, 1, num_timesteps, 2, seed, nullptr, stream); if (rc) return rc;
   } else {
     rc = saceo_update(x, 1, num_timesteps, 1, seed, nullptr, stream); if (rc) return rc;
