@@ -393,7 +393,8 @@ def run_b200(a):
             if w == 0:
                 continue                       # first un-graphed step: lazy module loads
             for name, us in prof:
-                key = "k_gemm_tc+k_gemm_skinny" if name.startswith("k_gemm") else name
+                # the weight-gradient contractions: dW1 (k_dw_planes), dW0 (k_dw0_planes), dW2 / fallbacks (k_gemm_*)
+                key = "k_dw_planes+k_dw0_planes+k_gemm" if name.startswith(("k_gemm", "k_dw")) else name
                 kern_us[key] = kern_us.get(key, 0.0) + us / reps
 
     # ---- strong-scaling sub-record: the SAME 256-agent population sharded over the ranks (BASELINE configs[2]) --------
@@ -446,7 +447,7 @@ def run_b200(a):
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "agents_per_gpu": n_local, "total_agents": n_global, "batch": B,
                    "gemm_engine": ("tcgen05 fp16 hi/lo x3 (fp32 accumulation in TMEM): warp-specialised fused 3-layer forward / backward "
-                                   "kernels fed by cp.async.bulk from optimiser-maintained weight planes; bf16 hi/lo x3 weight-gradient GEMMs; "
+                                   "kernels fed by cp.async.bulk from optimiser-maintained weight planes; TMA-fed bf16 hi/lo x3 weight-gradient kernels on activation plane images; "
                                    "expert term: 2x512 models on mma.sync m16n8k16 fp16 hi/lo x3 streamed from HBM (10 rows per model)"
                                    if gemm_mode == 1 and not a.no_ws else
                                    "tcgen05 16-bit hi/lo x3, round-1 fused kernels" if gemm_mode == 1 else "fp32 SIMT"),

@@ -162,7 +162,7 @@ def kernel_design_bytes(sp, L) -> dict:
         "k_mlp_bwd_tc": float(w * bwd), "k_mlp_bwd_ws": float(w * bwd),
         "k_model_term": float(w * (sp.num_models * L.nm + E * (2 * S + A))) if sp.num_models > 0 else 0.0,
         "k_adam": float(w * (2 * 11 * L.nc + 8 * L.na)),        # + the fp16 hi/lo weight planes of theta and of the targets
-        "k_gemm_tc+k_gemm_skinny": float(w * dw),
+        "k_dw_planes+k_dw0_planes+k_gemm": float(w * dw), "k_gemm_tc+k_gemm_skinny": float(w * dw),
     }
 
 
