@@ -146,6 +146,19 @@ __device__ __forceinline__ void ws_rows_issue(const float* __restrict__ Hs, int 
     if (grow < rows) t[i] = __ldg(reinterpret_cast<const float4*>(Hs + (long long)grow * FW_H + col + lc));
   }
 }
+// L2 prefetch of the same tiles (one 128-byte line per lane): the backward kernel asks for the saved activations early
+// WITHOUT holding 32 registers for them across the epilogue math (the 96-register cap of an 18-warp CTA made that
+// prefetch buffer spill: 1.6 M local loads + 1.5 M local stores per launch at 17 % L1 hit rate, profiles/r2_step_ncu_full_summary.txt)
+__device__ __forceinline__ void ws_rows_prefetch(const float* __restrict__ Hs, int rbase, int rows, int col, int lane) {
+  if (rbase + lane < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(Hs + (long long)(rbase + lane) * FW_H + col));
+}
+__device__ __forceinline__ void ws_planes_prefetch(const uint8_t* __restrict__ img, int rbase, int rows, int col, int lane) {
+  if (rbase + lane < rows) {
+    const uint8_t* p = img + ws_image_off(rbase + lane, (col >> 6) << 3);     // the 128-byte row segment holding these 32 columns
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 16384));
+  }
+}
 __device__ __forceinline__ void ws_rows_commit(uint32_t patch, int lane, const float4 (&t)[8], float (&aux)[32]) {
   const int lr = lane >> 3, lc = (lane & 7) * 4;
 #pragma unroll
@@ -768,8 +781,8 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
     if (warp == 0) WS_STAMP(0);
-    float4 hq[8];                                          // saved-activation rows of the next chunk, in flight
-    ws_rows_issue(H2, rbase, f.rows, cg * 64, lane, hq);
+    ws_rows_prefetch(H2, rbase, f.rows, cg * 64, lane);     // saved activations of both chunks -> L2 while W2 is staged
+    ws_rows_prefetch(H2, rbase, f.rows, cg * 64 + 32, lane);
     // ---- stage W2[:, :kout] as fp32 [256][kp]; max |W2| over the block bounds every row of dOut . W2^T (row scale)
     constexpr int ND = NG > 0 ? NG * 16 : 1;               // NG == 0: single output (critics), the first step is an outer product
     float d[ND];
@@ -799,10 +812,15 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int col = cg * 64 + c * 32;
-      ws_rows_commit_p(patch, lane, hq);
-      if (c == 0) ws_rows_issue(H2, rbase, f.rows, col + 32, lane, hq);      // chunk 1 flies during the math of chunk 0
-      else if (!f.H1p) ws_rows_issue(H1, rbase, f.rows, cg * 64, lane, hq);  // first H1 chunk of epilogue 1 flies during the MMAs
-      else ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, cg * 64, lane, hq);
+      {
+        float4 hq[8];
+        ws_rows_issue(H2, rbase, f.rows, col, lane, hq);
+        ws_rows_commit_p(patch, lane, hq);
+      }
+      if (c == 1) {        // the H1 tiles of epilogue 1 -> L2 during the MMAs
+        if (!f.H1p) { ws_rows_prefetch(H1, rbase, f.rows, cg * 64, lane); ws_rows_prefetch(H1, rbase, f.rows, cg * 64 + 32, lane); }
+        else ws_planes_prefetch(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, cg * 64, lane);
+      }
       uint32_t v[32];
       if (NG == 0) {
 #pragma unroll
@@ -872,17 +890,18 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       const int col = cg * 64 + c * 32;
       uint32_t v[32];
       tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, v);
-      if (f.H1p) {        // h1 from its plane image, decoded into the patch
-        ws_planes_commit_p(patch, lane, hq);
-        if (c == 0) ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col + 32, lane, hq);
-        tmem_ld_wait();
-        ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
-      } else {
-        ws_rows_commit_p(patch, lane, hq);
-        if (c == 0) ws_rows_issue(H1, rbase, f.rows, col + 32, lane, hq);
-        tmem_ld_wait();
-        ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
+      {
+        float4 hq[8];
+        if (f.H1p) {      // h1 from its plane image, decoded into the patch
+          ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, hq);
+          ws_planes_commit_p(patch, lane, hq);
+        } else {
+          ws_rows_issue(H1, rbase, f.rows, col, lane, hq);
+          ws_rows_commit_p(patch, lane, hq);
+        }
       }
+      tmem_ld_wait();
+      ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
       if (f.dH1p && !dH1) {
         ws_store_planes_cs(patch, v, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
         __syncwarp();
