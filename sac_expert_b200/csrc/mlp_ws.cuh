@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
     for (int s = 0; s < 2 * WS_NST; ++s) mbar_init(bar(s), 1);
     mbar_init(bar(WB_XFULL), WS_NEW); mbar_init(bar(WB_XEMPTY), 1);
     mbar_init(bar(WB_D0), 1); mbar_init(bar(WB_D1), 1);
-    for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 4);
+    for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 8);     // 4 lane quarters x the 2 warps converting the group's two chunks
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WS_NEW + 1) {
@@ -558,18 +558,21 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_fwd_ws(FwdW f) {
     mbar_wait(bar(WB_D0), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) WS_STAMP(2);
+    // chunk order by k group: in step c the 16 warps convert k groups 2c and 2c+1 (warp pair cg>>1 takes one group, cg&1 its
+    // 32-column half), so the layer-1 MMAs of groups 0 / 1 - and the W1 stages behind them - start after HALF of this
+    // epilogue instead of at its end (the W1 stream through the 3-deep ring was two TMA round trips behind the last group)
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      const int col = cg * 64 + c * 32;
+      const int kg = 2 * c + (cg >> 1), col = kg * 64 + (cg & 1) * 32;
       uint32_t v[32];
       tmem_ld32(tP + lane_addr + (uint32_t)col, v);
       ws_bias_act_rt(f.act0, v, cb0 + col * 4);
       ws_split_store(tP + lane_addr + (uint32_t)col, v, 1.f);
-      if (c == 1) {
+      {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(WB_AP + cg));      // the layer-1 MMAs of this 64-wide k group may start
+        if (lane == 0) mbar_arrive(bar(WB_AP + kg));      // the layer-1 MMAs of this 64-wide k group may start
       }
       if (f.H1p) {          // h1 leaves as a bf16 hi/lo plane image only (operand of k_dw_planes, read back by the backward chain)
 #pragma unroll
