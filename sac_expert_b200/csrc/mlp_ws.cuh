@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2 * WS_NST; ++s) mbar_init(bar(s), 1);
     mbar_init(bar(WB_D0), 1); mbar_init(bar(WB_D1), 1);                 // accumulator halves 0 / 1
-    for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 4);
+    for (int g = 0; g < 4; ++g) mbar_init(bar(WB_AP + g), 8);     // 4 lane quarters x the 2 warps converting the group's two chunks
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(aux + WS_RED - 256), "r"(0u) : "memory");     // max |W2| accumulator
   }
@@ -784,8 +784,10 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
     if (warp == 0) WS_STAMP(0);
-    ws_rows_prefetch(H2, rbase, f.rows, cg * 64, lane);     // saved activations of both chunks -> L2 while W2 is staged
-    ws_rows_prefetch(H2, rbase, f.rows, cg * 64 + 32, lane);
+    // chunk order of epilogue 0 by k group (as in the forward kernel): step c converts the j slabs 2c and 2c+1
+    const int col0_0 = (cg >> 1) * 64 + (cg & 1) * 32, col0_1 = (2 + (cg >> 1)) * 64 + (cg & 1) * 32;
+    ws_rows_prefetch(H2, rbase, f.rows, col0_0, lane);      // saved activations of both chunks -> L2 while W2 is staged
+    ws_rows_prefetch(H2, rbase, f.rows, col0_1, lane);
     // ---- stage W2[:, :kout] as fp32 [256][kp]; max |W2| over the block bounds every row of dOut . W2^T (row scale)
     constexpr int ND = NG > 0 ? NG * 16 : 1;               // NG == 0: single output (critics), the first step is an outer product
     float d[ND];
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     // ---- epilogue 0: dH2 = (dOut . W2^T) * act1'(H2) on CUDA cores -> scaled fp16 hi/lo A operand (tP) [+ saved dH2, column sums]
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      const int col = cg * 64 + c * 32;
+      const int col = c ? col0_1 : col0_0, kg = 2 * c + (cg >> 1);
       {
         float4 hq[8];
         ws_rows_issue(H2, rbase, f.rows, col, lane, hq);
@@ -850,11 +852,11 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       }
       ws_mul_dact_p_rt(f.act1, v, patch, lane, 1.f);
       ws_split_store(tP + lane_addr + (uint32_t)col, v, scale);
-      if (c == 1) {
+      {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(WB_AP + cg));
+        if (lane == 0) mbar_arrive(bar(WB_AP + kg));
       }
       if (f.dH2p && !dH2) {
         ws_store_planes_cs(patch, v, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
