@@ -698,7 +698,10 @@ struct BwdW {
   unsigned long long* dbg;
 };
 
-template <int NG, int NA>
+// MODE specialises the saved-activation / gradient-output forms at compile time (fewer live pointers and no dead
+// alternative paths under the 96-register cap): 0 = decided at run time; 1 = the training form (h1 read from its plane
+// image, dH2 and dH1 leave as plane images only); 2 = input gradient only (h1 from its plane image, nothing saved)
+template <int NG, int NA, int MODE>
 __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -777,9 +780,11 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
     const long long ob0 = (long long)f.K0 * FW_H, oW1 = ob0 + FW_H, ob1 = oW1 + (long long)FW_H * FW_H, oW2 = ob1 + FW_H;
     const float* H1 = f.H1 + agent * f.sHa + net * f.sHn;
     const float* H2 = f.H2 + agent * f.sHa + net * f.sHn;
-    float* dH1 = f.dH1 ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
-    float* dH2 = f.dH2 ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
-    const bool want_cs = f.dbpart && (dH2 || f.dH2p) && (dH1 || f.dH1p);
+    float* dH1 = (MODE == 0 && f.dH1) ? f.dH1 + agent * f.sHa + net * f.sHn : nullptr;
+    float* dH2 = (MODE == 0 && f.dH2) ? f.dH2 + agent * f.sHa + net * f.sHn : nullptr;
+    const bool pH1 = MODE != 0 || f.H1p != nullptr;
+    const bool pdH2 = MODE == 1 || (MODE == 0 && f.dH2p != nullptr), pdH1 = MODE == 1 || (MODE == 0 && f.dH1p != nullptr);
+    const bool want_cs = f.dbpart && (dH2 || pdH2) && (dH1 || pdH1);
     const int kp = (f.kout + 3) & ~3;
     const uint32_t wmax_s = aux + WS_RED - 256;            // max |W2| over the staged block (int bit pattern)
 
@@ -823,7 +828,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         ws_rows_commit_p(patch, lane, hq);
       }
       if (c == 1) {        // the H1 tiles of epilogue 1 -> L2 during the MMAs
-        if (!f.H1p) { ws_rows_prefetch(H1, rbase, f.rows, cg * 64, lane); ws_rows_prefetch(H1, rbase, f.rows, cg * 64 + 32, lane); }
+        if (!pH1) { ws_rows_prefetch(H1, rbase, f.rows, cg * 64, lane); ws_rows_prefetch(H1, rbase, f.rows, cg * 64 + 32, lane); }
         else ws_planes_prefetch(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, cg * 64, lane);
       }
       uint32_t v[32];
@@ -858,12 +863,12 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(WB_AP + kg));
       }
-      if (f.dH2p && !dH2) {
+      if (pdH2 && !dH2) {
         ws_store_planes_cs(patch, v, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
         __syncwarp();
-      } else if (dH2 || f.dH2p) {
+      } else if (dH2 || pdH2) {
         ws_store_rows(patch, v, dH2, rbase, f.rows, col, lane, want_cs ? cs2 : 0u, q);
-        if (f.dH2p) ws_store_planes_p(patch, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
+        if (pdH2) ws_store_planes_p(patch, f.dH2p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
         __syncwarp();
       }
     }
@@ -897,7 +902,7 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       tmem_ld32_nw(tQ + lane_addr + (uint32_t)col, v);
       {
         float4 hq[8];
-        if (f.H1p) {      // h1 from its plane image, decoded into the patch
+        if (pH1) {        // h1 from its plane image, decoded into the patch
           ws_planes_issue(f.H1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, hq);
           ws_planes_commit_p(patch, lane, hq);
         } else {
@@ -907,12 +912,12 @@ __global__ void __launch_bounds__(WS_NT, 1) k_mlp_bwd_ws(BwdW f) {
       }
       tmem_ld_wait();
       ws_mul_dact_p_rt(f.act0, v, patch, lane, inv_scale);
-      if (f.dH1p && !dH1) {
+      if (pdH1 && !dH1) {
         ws_store_planes_cs(patch, v, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
         __syncwarp();
-      } else if (dH1 || f.dH1p) {
+      } else if (dH1 || pdH1) {
         ws_store_rows(patch, v, dH1, rbase, f.rows, col, lane, want_cs ? cs1 : 0u, q);
-        if (f.dH1p) ws_store_planes_p(patch, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
+        if (pdH1) ws_store_planes_p(patch, f.dH1p + agent * f.sQa + net * f.sQn, rbase, f.rows, col, lane);
         __syncwarp();
       }
       if (NA > 0) {
@@ -1208,8 +1213,9 @@ static inline cudaError_t mlp_ws_init() {
   cudaError_t e;
 #define WS_ATTR(K) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_BYTES); if (e) return e;
   WS_ATTR(k_mlp_fwd_ws<1>) WS_ATTR(k_mlp_fwd_ws<2>) WS_ATTR(k_mlp_fwd_ws<3>)
-  WS_ATTR((k_mlp_bwd_ws<0, 0>)) WS_ATTR((k_mlp_bwd_ws<0, 1>)) WS_ATTR((k_mlp_bwd_ws<0, 2>))
-  WS_ATTR((k_mlp_bwd_ws<1, 0>)) WS_ATTR((k_mlp_bwd_ws<2, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0>))
+  WS_ATTR((k_mlp_bwd_ws<0, 0, 0>)) WS_ATTR((k_mlp_bwd_ws<0, 1, 0>)) WS_ATTR((k_mlp_bwd_ws<0, 2, 0>))
+  WS_ATTR((k_mlp_bwd_ws<1, 0, 0>)) WS_ATTR((k_mlp_bwd_ws<2, 0, 0>)) WS_ATTR((k_mlp_bwd_ws<3, 0, 0>))
+  WS_ATTR((k_mlp_bwd_ws<0, 0, 1>)) WS_ATTR((k_mlp_bwd_ws<1, 0, 1>)) WS_ATTR((k_mlp_bwd_ws<0, 1, 2>))
 #undef WS_ATTR
   e = cudaFuncSetAttribute(k_dw_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_BYTES); if (e) return e;
   e = cudaFuncSetAttribute(k_dw0_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, DW0_BYTES); if (e) return e;
@@ -1238,12 +1244,17 @@ static inline bool mlp_bwd_ws_eligible(int h1, int h2, int kout, int nout, bool 
 static inline cudaError_t mlp_bwd_ws_launch(const BwdW& f, int nagents, cudaStream_t st) {
   dim3 grid((f.rows + TC_BM - 1) / TC_BM, nagents * f.nnet);
   const int ng = f.kout == 1 ? 0 : (f.kout + 15) / 16, na = f.dXa ? (f.a_cols + 15) / 16 : 0;
-  if (ng == 0 && na == 0) k_mlp_bwd_ws<0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 0 && na == 1) k_mlp_bwd_ws<0, 1><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 0) k_mlp_bwd_ws<0, 2><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 1) k_mlp_bwd_ws<1, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else if (ng == 2) k_mlp_bwd_ws<2, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
-  else k_mlp_bwd_ws<3, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  // the shapes of the SAC / SAC-EO step get compile-time specialised forms (MODE 1 / 2)
+  const bool m1 = f.H1p && f.dH2p && f.dH1p && !f.dH2 && !f.dH1, m2 = f.H1p && !f.dH2p && !f.dH1p && !f.dH2 && !f.dH1;
+  if (ng == 0 && na == 0 && m1) k_mlp_bwd_ws<0, 0, 1><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 1 && na == 0 && m1) k_mlp_bwd_ws<1, 0, 1><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0 && na == 1 && m2) k_mlp_bwd_ws<0, 1, 2><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0 && na == 0) k_mlp_bwd_ws<0, 0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0 && na == 1) k_mlp_bwd_ws<0, 1, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 0) k_mlp_bwd_ws<0, 2, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 1) k_mlp_bwd_ws<1, 0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else if (ng == 2) k_mlp_bwd_ws<2, 0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
+  else k_mlp_bwd_ws<3, 0, 0><<<grid, WS_NT, WS_BYTES, st>>>(f);
   return cudaPeekAtLastError();
 }
 
