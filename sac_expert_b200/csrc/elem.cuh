@@ -506,8 +506,8 @@ __global__ void k_lsv_reduce(KCtx c, int nrows) {
 
 // Keras Adam (epsilon outside the bias correction) fused with the Polyak target update
 // (SAC_expert.py:243,250,338; 362-373).  grid: (ceil(n/256), nnet, n_agents)
-// launch bounds: <= 40 registers, so that an Adam CTA fits next to a resident fused-MLP CTA of the other stream (576 x 96)
-__global__ void __launch_bounds__(256, 6) k_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+// launch bounds: <= 64 registers (48 used, no spills; (256, 6) = 40 registers spilled 1.2 M local loads per launch)
+__global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                        const float* __restrict__ g, float* __restrict__ target,
                        const float* __restrict__ lrt, const float* __restrict__ hyper, int hyper_stride,
                        int opt0, long long n, long long stride, int nnet, int do_polyak,
