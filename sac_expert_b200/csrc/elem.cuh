@@ -47,6 +47,9 @@ constexpr float kLog2Pi = 1.8378770664093453f;
 constexpr float kLog2 = 0.6931471805599453f;
 constexpr float kMinLogStd = -5.0f, kMaxLogStd = 2.0f;   // continuous_actors.py:250-251
 constexpr float kB1 = 0.9f, kB2 = 0.999f, kAdamEps = 1e-7f;  // tf.keras Adam defaults
+// keras/optimizers/adam.py::update_step multiplies by the Python double (1 - beta) rounded to fp32 (0.001 -> 0.00100000005),
+// not by fp32(1) - fp32(beta) (0.00099998713): pinned by tests/test_reference_pin.py against the reference's own code
+constexpr float kOmB1 = (float)(1.0 - 0.9), kOmB2 = (float)(1.0 - 0.999);
 
 __device__ __forceinline__ float softplusf(float x) {
   return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
@@ -533,8 +536,8 @@ __global__ void __launch_bounds__(256, 4) k_adam(float* __restrict__ theta, floa
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (i4 + j < n) {          // words past n are padding (the actor's last pad word carries g_alpha): left untouched
-      mi[j] = kB1 * mi[j] + (1.f - kB1) * gi[j];
-      vi[j] = kB2 * vi[j] + (1.f - kB2) * gi[j] * gi[j];
+      mi[j] = kB1 * mi[j] + kOmB1 * gi[j];
+      vi[j] = kB2 * vi[j] + kOmB2 * gi[j] * gi[j];
       th[j] = th[j] - lr_t * mi[j] / (sqrtf(vi[j]) + kAdamEps);
       // NumPy fp32: two rounded products, one rounded sum (no FMA contraction)
       tg[j] = __fadd_rn(__fmul_rn(tg[j], one_m), __fmul_rn(th[j], tau));
@@ -574,8 +577,8 @@ __global__ void k_alpha_step(KCtx c, int apply) {
     c.g_actor[(long long)agent * c.L.na_stride + c.L.na_stride - 1] = g;   // last padded word: g_alpha (DP all-reduce rides along)
     if (apply) {
       const float lr_t = c.lrt[agent * 4 + 3];
-      const float mi = kB1 * c.T.alpha_m[agent] + (1.f - kB1) * g;
-      const float vi = kB2 * c.T.alpha_v[agent] + (1.f - kB2) * g * g;
+      const float mi = kB1 * c.T.alpha_m[agent] + kOmB1 * g;
+      const float vi = kB2 * c.T.alpha_v[agent] + kOmB2 * g * g;
       float a = alpha - lr_t * mi / (sqrtf(vi) + kAdamEps);
       a = fmaxf(a, 1e-5f);
       c.T.alpha_m[agent] = mi; c.T.alpha_v[agent] = vi; c.T.alpha[agent] = a;
@@ -589,8 +592,8 @@ __global__ void k_alpha_apply(KCtx c) {
   if (agent >= c.n_agents) return;
   const float g = c.g_actor[(long long)agent * c.L.na_stride + c.L.na_stride - 1];
   const float lr_t = c.lrt[agent * 4 + 3];
-  const float mi = kB1 * c.T.alpha_m[agent] + (1.f - kB1) * g;
-  const float vi = kB2 * c.T.alpha_v[agent] + (1.f - kB2) * g * g;
+  const float mi = kB1 * c.T.alpha_m[agent] + kOmB1 * g;
+  const float vi = kB2 * c.T.alpha_v[agent] + kOmB2 * g * g;
   float a = c.T.alpha[agent] - lr_t * mi / (sqrtf(vi) + kAdamEps);
   a = fmaxf(a, 1e-5f);
   c.T.alpha_m[agent] = mi; c.T.alpha_v[agent] = vi; c.T.alpha[agent] = a;

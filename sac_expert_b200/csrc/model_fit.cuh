@@ -192,8 +192,8 @@ __global__ void k_fit_adam(FitCtx f, int reward) {
     for (int j = threadIdx.x; j < f.S; j += blockDim.x) {
       const long long o = ((long long)agent * 2 + net) * f.S + j;
       const float gi = f.g_ls[o] * f.gscale[agent];
-      const float mi = kB1 * f.ls_m[o] + (1.f - kB1) * gi;
-      const float vi = kB2 * f.ls_v[o] + (1.f - kB2) * gi * gi;
+      const float mi = kB1 * f.ls_m[o] + kOmB1 * gi;
+      const float vi = kB2 * f.ls_v[o] + kOmB2 * gi * gi;
       f.ls[o] = f.ls[o] - lr_t * mi / (sqrtf(vi) + kAdamEps);
       f.ls_m[o] = mi; f.ls_v[o] = vi;
     }
@@ -211,8 +211,8 @@ __global__ void k_fit_adam(FitCtx f, int reward) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (i4 + j < f.nm) {
-      mi[j] = kB1 * mi[j] + (1.f - kB1) * gi[j];
-      vi[j] = kB2 * vi[j] + (1.f - kB2) * gi[j] * gi[j];
+      mi[j] = kB1 * mi[j] + kOmB1 * gi[j];
+      vi[j] = kB2 * vi[j] + kOmB2 * gi[j] * gi[j];
       th[j] = th[j] - lr_t * mi[j] / (sqrtf(vi[j]) + kAdamEps);
     }
   }

@@ -1,0 +1,263 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE.  Run in the build container only:
+
+    python tests/golden/make_golden_reference.py
+
+The reference's unmodified Python files are imported from /root/reference and executed over ``oracle/tfemu`` (an eager
+torch-CPU executor for the TensorFlow / gym symbols they import - TensorFlow itself is not installable here; what that
+does and does not pin is in oracle/tfemu/README.md).  For every case below the script
+
+  1. builds the reference's ``SquashedGaussianActor`` / ``QCritic`` x4 / ``MSEModel`` x{0,1,2} / ``SAC_exp`` (or ``SAC``)
+     through the reference's own parser defaults and factories (train.py:60-105 without ``init_env``),
+  2. loads an oracle problem (weights, Adam slots, normaliser statistics, replay and expert rows) into them,
+  3. runs ``alg._update(num_timesteps, expert_reg)`` K times with the global NumPy RNG seeded, RECORDING every
+     ``np.random.randint`` / ``np.random.normal`` call and every ``alg.rng.shuffle`` result in call order,
+  4. stores inputs (small cases) or the generating seed + an input checksum (benchmark-shaped case), the recorded draws,
+     and the reference's outputs per step: TD target, the gradients handed to each optimiser, logged losses, every
+     network / target / alpha value, and the final Adam slots.
+
+tests/test_reference_pin.py replays the recorded draws through oracle/sac_eo_oracle.py (CPU tier) and through
+libsaceo (GPU tier) and compares.  /root/reference does not exist on the GPU box: only the .npz files travel.
+"""
+import hashlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "tfemu"))
+sys.path.insert(0, REF)
+
+from oracle.sac_eo_oracle import NetCfg, make_problem  # noqa: E402
+
+
+class _Env:
+    """observation_space / action_space only; never stepped."""
+
+    def __init__(self, S, A):
+        import gym
+        self.observation_space = gym.spaces.Box(-np.inf, np.inf, (S,), np.float32)
+        self.action_space = gym.spaces.Box(-1.0, 1.0, (A,), np.float32)
+
+    def seed(self, s):
+        pass
+
+
+class _Recorder:
+    """Wraps the global NumPy RNG entry points the update path uses; keeps (kind, value) in call order."""
+
+    def __init__(self):
+        self.calls = []
+        self._randint, self._normal = np.random.randint, np.random.normal
+
+    def __enter__(self):
+        def randint(*a, **k):
+            v = self._randint(*a, **k)
+            self.calls.append(("randint", np.array(v)))
+            return v
+
+        def normal(*a, **k):
+            v = self._normal(*a, **k)
+            self.calls.append(("normal", np.array(v)))
+            return v
+        np.random.randint, np.random.normal = randint, normal
+        return self
+
+    def __exit__(self, *exc):
+        np.random.randint, np.random.normal = self._randint, self._normal
+        return False
+
+
+def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int):
+    from sac_eo.actors import init_actor
+    from sac_eo.algs import init_alg
+    from sac_eo.common.train_parser import create_train_parser
+    from sac_eo.common.train_utils import gather_inputs
+    from sac_eo.critics import init_critics
+    from sac_eo.models import init_world_models
+    alg_type = "sac_imit" if cfg.num_models > 0 else "sac"
+    inputs = gather_inputs(create_train_parser().parse_args(["--alg_type", alg_type]))
+    ak, ck, mk, msk, al = (inputs[k] for k in ("actor_kwargs", "critic_kwargs", "model_kwargs", "model_setup_kwargs",
+                                               "alg_kwargs"))
+    ak.update(actor_layers=list(cfg.actor_hidden), actor_activations=list(cfg.actor_acts), actor_weights=None,
+              actor_per_state_std=cfg.per_state_std, actor_squash=True, actor_std_mult=cfg.std_mult)
+    ck.update(critic_layers=list(cfg.critic_hidden), critic_activations=list(cfg.critic_acts), critic_weights=None)
+    mk.update(model_layers=list(cfg.model_hidden), model_activations=list(cfg.model_acts), model_weights=None,
+              reward_weights=None, num_models=max(cfg.num_models, 1), gaussian_model=False)
+    msk.update(separate_reward_nn=cfg.separate_reward_nn, delta_clip_pred=cfg.delta_clip_pred or None)
+    al.update(init_rms_stats=None, alg_seed=0, gamma=hyper["gamma"], soft_tau=hyper["tau"], q_crit_lr=hyper["lr_q"],
+              mbpo_actor_lr=hyper["lr_pi"], mbpo_alpha_lr=hyper["lr_alpha"], sac_batch_size=B,
+              target_update_int=target_update_int, only_model_normalizer=True, epsilon=hyper["eps"],
+              expert_buffer_size=len(expert["sE"]), env_buffer_size=len(replay["r"]))
+    env = _Env(cfg.S, cfg.A)
+    actor = init_actor(env, **ak)
+    expert_actor = init_actor(env, **ak)
+    critics, q_targets, q_critics = init_critics(env, **ck)
+    models = init_world_models(env, **mk, model_setup_kwargs=msk)
+    alg = init_alg(0, env, env, env, actor, critics, q_targets, q_critics, models, al, inputs["mf_update_kwargs"],
+                   expert_actor, None)
+    # ---- the oracle problem: weights, Adam slots, alpha ---------------------------------------------------------------
+    actor.set_weights([np.asarray(w) for w in st["actor"]])
+    for net, key in zip(q_critics, ("q1", "q2")):
+        net.set_weights([np.asarray(w) for w in st[key]])
+    for net, key in zip(q_targets, ("t1", "t2")):
+        net.set_weights([np.asarray(w) for w in st[key]])
+    for net, key in zip(models, ("m1", "m2")):
+        net.set_weights([np.asarray(w) for w in st[key]])
+    alg.alpha.assign(float(st["alpha"]))
+    import torch
+    for opt, variables, key in ((alg.q_critic1_optimizer, q_critics[0].trainable, "adam_q1"),
+                                (alg.q_critic2_optimizer, q_critics[1].trainable, "adam_q2"),
+                                (alg.actor_optimizer, actor.trainable, "adam_actor")):
+        opt.iterations = int(st[key]["t"])
+        for v, m_, v_ in zip(variables, st[key]["m"], st[key]["v"]):
+            opt.slots[id(v)] = (torch.tensor(np.asarray(m_)).reshape(tuple(v.shape)).clone(),
+                                torch.tensor(np.asarray(v_)).reshape(tuple(v.shape)).clone())
+    alg.alpha_optimizer.iterations = int(st["adam_alpha"]["t"])
+    alg.alpha_optimizer.slots[id(alg.alpha)] = (torch.tensor(np.float32(st["adam_alpha"]["m"])),
+                                               torch.tensor(np.float32(st["adam_alpha"]["v"])))
+    # ---- normaliser statistics: the running normalisers' attributes, then shared the reference's way -----------------
+    nz = alg.normalizer
+    nz.s_rms.mean, nz.s_rms.std = st["s_mean"].copy(), st["s_std"].copy()
+    nz.a_rms.mean, nz.a_rms.std = st["a_mean"].copy(), st["a_std"].copy()
+    nz.ret_rms.std = np.float32(st["ret_std"])
+    mz = alg.model_normalizer
+    mz.s_rms.mean, mz.s_rms.std = st["m_s_mean"].copy(), st["m_s_std"].copy()
+    mz.a_rms.mean, mz.a_rms.std = st["m_a_mean"].copy(), st["m_a_std"].copy()
+    mz.delta_rms.mean, mz.delta_rms.std = st["m_d_mean"].copy(), st["m_d_std"].copy()
+    alg._set_rms()
+    alg.env_data.add(replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    assert alg.env_data.current_size == len(replay["r"])
+    expert_reg = (expert["sE"], expert["aE"], expert["spE"], hyper["eps"], False)
+    return alg, expert_reg
+
+
+def flat(ws):
+    return np.concatenate([np.asarray(w, np.float32).ravel() for w in ws])
+
+
+def run_case(name, cfg: NetCfg, B, E, N, seed, K, eps, target_update_int, store_inputs, proj_dim=0):
+    st, replay, expert, hyper = make_problem(cfg, B, E, N, seed=seed, perturb=0.05)
+    hyper["eps"] = eps
+    alg, expert_reg = build(cfg, st, replay, expert, hyper, B, target_update_int)
+    out = dict(meta=np.array([cfg.S, cfg.A, B, E, N, seed, K, target_update_int, cfg.num_models], np.int64),
+               eps=np.float64(eps))
+    h = hashlib.sha256()
+    for k in ("actor", "q1", "q2", "t1", "t2", "m1", "m2"):
+        h.update(flat(st[k]).tobytes())
+    for k in ("s", "a", "sp", "r", "d"):
+        h.update(np.ascontiguousarray(replay[k]).tobytes())
+    out["input_sha256"] = np.frombuffer(h.digest(), np.uint8)
+    if store_inputs:
+        for k in ("actor", "q1", "q2", "t1", "t2", "m1", "m2"):
+            for i, w in enumerate(st[k]):
+                out[f"in_{k}_{i}"] = np.asarray(w, np.float32)
+        for k in ("q1", "q2", "actor"):
+            for i, (m_, v_) in enumerate(zip(st["adam_" + k]["m"], st["adam_" + k]["v"])):
+                out[f"in_adam_{k}_m_{i}"], out[f"in_adam_{k}_v_{i}"] = m_, v_
+        for k in ("s_mean", "s_std", "a_mean", "a_std", "ret_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std",
+                  "m_d_mean", "m_d_std", "alpha"):
+            out["in_" + k] = np.asarray(st[k])
+        for k, v in replay.items():
+            out["in_replay_" + k] = v
+        for k, v in expert.items():
+            out["in_expert_" + k] = v
+
+    def snap(step):
+        nets = dict(actor=alg.actor.get_weights(), q1=alg.q_critics[0].get_weights(), q2=alg.q_critics[1].get_weights(),
+                    t1=alg.q_targets[0].get_weights(), t2=alg.q_targets[1].get_weights())
+        for k, ws in nets.items():
+            f = flat(ws)
+            if proj_dim:        # benchmark-sized nets: fixed random projections + norm instead of 1.4 MB of weights
+                R = np.random.default_rng(12345).standard_normal((proj_dim, f.size))
+                out[f"step{step}_proj_{k}"] = R @ (f.astype(np.float64) - flat(st[k]).astype(np.float64))
+                out[f"step{step}_dnorm_{k}"] = np.float64(np.linalg.norm(f.astype(np.float64) - flat(st[k])))
+            else:
+                out[f"step{step}_theta_{k}"] = f
+        out[f"step{step}_alpha"] = np.float32(alg.alpha.numpy())
+
+    ys = []
+    orig_target = alg._get_Q_target
+
+    def spy_target(sp, r, done):
+        y = orig_target(sp, r, done)
+        ys.append(np.array(y.numpy()))
+        return y
+    alg._get_Q_target = spy_target
+    shuffles = []
+    orig_shuffle = alg.rng.shuffle
+
+    class _Rng:             # alg.rng.shuffle(idx) in place (SAC_expert.py:301-303): keep the permutation it produced
+        def shuffle(self_, x):
+            orig_shuffle(x)
+            shuffles.append(np.array(x))
+
+        def __getattr__(self_, k):
+            return getattr(alg.rng.__class__, k).__get__(alg.rng)
+    real_rng, alg.rng = alg.rng, _Rng()
+    np.random.seed(1000 + seed)
+    for step in range(K):
+        with _Recorder() as rec:
+            if cfg.num_models > 0:
+                alg._update(step, expert_reg)
+            else:
+                alg._update(step)
+        kinds = [k for k, _ in rec.calls]
+        want = ["randint", "normal", "normal"] + ["normal"] * cfg.num_models + ["normal"]
+        assert kinds == want, (kinds, want)                  # consumption order of SURVEY.md App. A
+        vals = [v for _, v in rec.calls]
+        out[f"step{step}_idx"] = vals[0].astype(np.int64)
+        for j, v in enumerate(vals[1:]):
+            out[f"step{step}_normal{j}"] = v                 # float64, as drawn
+        if cfg.num_models == 2:
+            out[f"step{step}_perm"] = shuffles[-1].astype(np.int64)
+        out[f"step{step}_y"] = ys[-1]
+        g1, g2, ga = (alg.q_critic1_optimizer.last_grads, alg.q_critic2_optimizer.last_grads,
+                      alg.actor_optimizer.last_grads)
+        if proj_dim:
+            for k, g in (("q1", g1), ("q2", g2), ("actor", ga)):
+                f = flat(g).astype(np.float64)
+                R = np.random.default_rng(54321).standard_normal((proj_dim, f.size))
+                out[f"step{step}_gproj_{k}"], out[f"step{step}_gnorm_{k}"] = R @ f, np.float64(np.linalg.norm(f))
+        else:
+            out[f"step{step}_g_q1"], out[f"step{step}_g_q2"], out[f"step{step}_g_actor"] = flat(g1), flat(g2), flat(ga)
+        out[f"step{step}_g_alpha"] = np.float32(alg.alpha_optimizer.last_grads[0])
+        if cfg.num_models > 0:       # SAC.py keeps its losses local (the log_train call is commented out, SAC.py:217)
+            out[f"step{step}_p_loss"] = np.float32(alg.logger.train_dict["p_loss"][-1])
+            out[f"step{step}_alpha_loss"] = np.float32(alg.logger.train_dict["alpha_loss"][-1])
+        snap(step)
+    alg.rng = real_rng
+    if not proj_dim:
+        for key, opt, variables in (("q1", alg.q_critic1_optimizer, alg.q_critics[0].trainable),
+                                    ("actor", alg.actor_optimizer, alg.actor.trainable)):
+            ms, vs = zip(*(opt.get_slot_arrays(v) for v in variables))
+            out[f"final_adam_{key}_m"], out[f"final_adam_{key}_v"] = flat(ms), flat(vs)
+    path = os.path.join(OUT, f"ref_{name}.npz")
+    buf = io.BytesIO()
+    np.savez_compressed(buf, **out)
+    open(path, "wb").write(buf.getvalue())
+    print(f"{name}: {len(buf.getvalue()) / 1024:.0f} KiB, alpha per step {[float(out[f'step{i}_alpha']) for i in range(K)]}")
+
+
+CASES = dict(
+    # name: (cfg, B, E, N, seed, K, eps, target_update_int, store_inputs, proj_dim)
+    saceo2_relu=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(32, 24), num_models=2),
+                 32, 8, 300, 11, 3, 0.3, 2, True, 0),
+    saceo1_tanh_elu_sis=(NetCfg(S=6, A=3, actor_hidden=(24, 32), critic_hidden=(32, 32), model_hidden=(24, 24),
+                                actor_acts=("tanh", "tanh"), critic_acts=("elu", "elu"), model_acts=("tanh", "tanh"),
+                                per_state_std=False, num_models=1, delta_clip_pred=0.05),
+                         24, 6, 200, 12, 3, 0.25, 1, True, 0),
+    sac_plain_relu=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(8, 8),
+                           num_models=0), 32, 8, 300, 13, 3, 0.0, 2, True, 0),
+    saceo2_hopper_256=(NetCfg(S=11, A=3), 256, 20, 2000, 14, 2, 1e-3, 1, False, 48),
+)
+
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or CASES):
+        cfg, *rest = CASES[name]
+        run_case(name, cfg, *rest)

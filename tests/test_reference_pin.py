@@ -1,0 +1,230 @@
+"""Pins against the REFERENCE'S OWN CODE: tests/golden/ref_*.npz were produced by the reference's unmodified
+``SAC_exp._update`` / ``SAC._update`` (SAC_expert.py:463-477, SAC.py:236-250) executed over oracle/tfemu
+(tests/golden/make_golden_reference.py; oracle/tfemu/README.md says what that does and does not pin).
+
+CPU tier: the oracle restatement replays the recorded draws and must reproduce the reference's TD target, the gradients
+handed to every optimiser, the logged losses and every parameter / target / alpha value after each of K consecutive
+updates (fp32 rounding only), with the Polyak gate alternating.  GPU tier: the CUDA path through the C ABI against the
+same vectors.  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sac_eo_oracle import NetCfg, gather, make_problem, sac_eo_update, to_torch_state
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# must equal CASES of tests/golden/make_golden_reference.py (the meta / checksum entries of each file verify it)
+CFGS = dict(
+    saceo2_relu=NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(32, 24), num_models=2),
+    saceo1_tanh_elu_sis=NetCfg(S=6, A=3, actor_hidden=(24, 32), critic_hidden=(32, 32), model_hidden=(24, 24),
+                               actor_acts=("tanh", "tanh"), critic_acts=("elu", "elu"), model_acts=("tanh", "tanh"),
+                               per_state_std=False, num_models=1, delta_clip_pred=0.05),
+    sac_plain_relu=NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(8, 8), num_models=0),
+    saceo2_hopper_256=NetCfg(S=11, A=3),
+)
+NETS = ("actor", "q1", "q2", "t1", "t2")
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def flat(ws):
+    return np.concatenate([np.asarray(w.numpy() if hasattr(w, "numpy") else w, np.float32).ravel() for w in ws])
+
+
+def load_case(name):
+    """-> (cfg, golden, problem pieces, meta).  Small cases take their inputs from the file; the benchmark-shaped case
+    regenerates them from the seed and both verify the stored checksum."""
+    import hashlib
+    g = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    cfg = CFGS[name]
+    S, A, B, E, N, seed, K, tui, nm = (int(x) for x in g["meta"])
+    assert (S, A, nm) == (cfg.S, cfg.A, cfg.num_models)
+    st, replay, expert, hyper = make_problem(cfg, B, E, N, seed=seed, perturb=0.05)
+    hyper["eps"] = float(g["eps"])
+    if "in_actor_0" in g.files:
+        for k in ("actor", "q1", "q2", "t1", "t2", "m1", "m2"):
+            st[k] = [g[f"in_{k}_{i}"] for i in range(len(st[k]))]
+        for k in ("q1", "q2", "actor"):
+            st["adam_" + k]["m"] = [g[f"in_adam_{k}_m_{i}"] for i in range(len(st[k]))]
+            st["adam_" + k]["v"] = [g[f"in_adam_{k}_v_{i}"] for i in range(len(st[k]))]
+        for k in ("s_mean", "s_std", "a_mean", "a_std", "ret_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean",
+                  "m_d_std", "alpha"):
+            st[k] = g["in_" + k] if g["in_" + k].ndim else g["in_" + k][()]
+        replay = {k: g["in_replay_" + k] for k in replay}
+        expert = {k: g["in_expert_" + k] for k in expert}
+    h = hashlib.sha256()
+    for k in ("actor", "q1", "q2", "t1", "t2", "m1", "m2"):
+        h.update(np.concatenate([np.asarray(w, np.float32).ravel() for w in st[k]]).tobytes())
+    for k in ("s", "a", "sp", "r", "d"):
+        h.update(np.ascontiguousarray(replay[k]).tobytes())
+    assert bytes(g["input_sha256"]) == h.digest(), "inputs differ from those the reference was run on"
+    return cfg, g, (st, replay, expert, hyper), dict(B=B, E=E, N=N, K=K, tui=tui, nm=nm)
+
+
+def step_batch(g, step, replay, expert, m):
+    """The draws the reference made in update ``step``, in the oracle's batch layout (SURVEY.md App. A order)."""
+    idx = g[f"step{step}_idx"]
+    s, a, sp, r, d = gather(replay, idx)
+    nrm = [g[f"step{step}_normal{j}"].astype(np.float32) for j in range(3 + m["nm"])]
+    b = dict(idx=idx, s=s, a=a, sp=sp, r=r, d=d, u1=nrm[0], u2=nrm[1], u5=nrm[-1])
+    if m["nm"] == 2:
+        b["I1"], b["I2"] = np.array_split(g[f"step{step}_perm"], 2)        # SAC_expert.py:301-309
+        b["u3"], b["u4"] = nrm[2], nrm[3]
+    elif m["nm"] == 1:
+        b["I1"], b["u3"] = np.arange(m["E"]), nrm[2]
+    if m["nm"]:
+        b["sE"], b["spE"] = expert["sE"], expert["spE"]
+    return b
+
+
+def proj(seed, dim, vec):
+    return np.random.default_rng(seed).standard_normal((dim, vec.size)) @ vec.astype(np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU tier: the oracle restatement against the reference's own code
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CFGS))
+def test_oracle_reproduces_reference_updates(name):
+    cfg, g, (st, replay, expert, hyper), m = load_case(name)
+    state = to_torch_state(st, torch.float32)
+    small = "step0_theta_actor" in g.files
+    for step in range(m["K"]):
+        hyper["do_polyak"] = (step % m["tui"] == 0)                       # SAC_expert.py:475
+        o = sac_eo_update(cfg, state, step_batch(g, step, replay, expert, m), hyper)
+        assert rel(o["y"].numpy(), g[f"step{step}_y"]) < 2e-6
+        assert abs(float(o["g_alpha"]) - float(g[f"step{step}_g_alpha"])) < 2e-6 * max(1.0, abs(float(o["g_alpha"])))
+        if m["nm"]:
+            assert abs(float(o["p_loss"]) - float(g[f"step{step}_p_loss"])) < 2e-6 * max(1.0, abs(float(o["p_loss"])))
+            assert abs(float(o["alpha_loss"]) - float(g[f"step{step}_alpha_loss"])) < 2e-6
+        assert abs(float(o["new"]["alpha"]) - float(g[f"step{step}_alpha"])) < 1e-7
+        for k in ("q1", "q2", "actor"):
+            got = flat(o["g_" + k])
+            if small:
+                assert rel(got, g[f"step{step}_g_{k}"]) < 5e-6, (k, step)
+            else:
+                assert abs(np.linalg.norm(got.astype(np.float64)) / float(g[f"step{step}_gnorm_{k}"]) - 1) < 5e-6
+                want = g[f"step{step}_gproj_{k}"]
+                assert rel(proj(54321, len(want), got), want) < 2e-5, (k, step)
+        for k in NETS:
+            got = flat(o["new"][k])
+            if small:
+                assert rel(got, g[f"step{step}_theta_{k}"]) < 1e-6, (k, step)
+            else:
+                d = got.astype(np.float64) - flat(st[k]).astype(np.float64)
+                want = g[f"step{step}_proj_{k}"]
+                assert rel(proj(12345, len(want), d), want) < 1e-3, (k, step)   # Δθ: Adam amplifies last-bit g noise
+                assert abs(np.linalg.norm(d) / float(g[f"step{step}_dnorm_{k}"]) - 1) < 1e-4
+        for k in NETS + ("alpha", "adam_q1", "adam_q2", "adam_actor", "adam_alpha"):
+            state[k] = o["new"][k]
+    if small:
+        for k in ("q1", "actor"):
+            assert rel(flat(state["adam_" + k]["m"]), g[f"final_adam_{k}_m"]) < 5e-6
+            assert rel(flat(state["adam_" + k]["v"]), g[f"final_adam_{k}_v"]) < 5e-6
+
+
+def test_polyak_gate_is_exercised():
+    """target_update_int = 2 in the relu cases: the reference left the targets untouched in update 1 and moved them in
+    updates 0 and 2."""
+    g = np.load(os.path.join(GOLD, "ref_saceo2_relu.npz"))
+    assert np.array_equal(g["step0_theta_t1"], g["step1_theta_t1"])
+    assert not np.array_equal(g["step1_theta_t1"], g["step2_theta_t1"])
+    assert not np.array_equal(g["in_t1_0"].ravel(), g["step0_theta_t1"][:g["in_t1_0"].size])
+
+
+def test_rng_consumption_recorded():
+    """The generator asserted the call order randint, normal x (3 + num_models) per update; here: the
+    shapes of what was drawn, and that the expert permutation is a permutation drawn from alg.rng."""
+    for name, cfg in CFGS.items():
+        g = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+        S, A, B, E, N, seed, K, tui, nm = (int(x) for x in g["meta"])
+        assert g["step0_idx"].shape == (B,) and g["step0_idx"].max() < N
+        shapes = [g[f"step0_normal{j}"].shape for j in range(3 + nm)]
+        if nm == 2:
+            assert shapes == [(B, A), (B, A), (E // 2, A), (E - E // 2, A), (B, A)]
+            assert sorted(g["step0_perm"].tolist()) == list(range(E))
+        elif nm == 1:
+            assert shapes == [(B, A), (B, A), (E, A), (B, A)]
+        else:
+            assert shapes == [(B, A), (B, A), (B, A)]
+        assert g["step0_normal0"].dtype == np.float64
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU tier: the CUDA path against the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_run(name, gemm_mode, use_graph, tol_g, tol_theta, tol_dtheta):
+    from sac_expert_b200 import lib as _lib
+    from tests.helpers import inject, spec_from_cfg
+    from sac_expert_b200.population import Population
+    cfg, g, (st, replay, expert, hyper), m = load_case(name)
+    mode = getattr(_lib, gemm_mode)
+    pop = Population(spec_from_cfg(cfg, 1, m["B"], m["E"], m["N"], gemm_mode=mode, use_graph=use_graph,
+                                   target_update_int=m["tui"]))
+    pop.load_agent(0, st, hyper)
+    pop.append_rows(0, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    if cfg.num_models > 0:
+        pop.set_expert(0, expert["sE"], expert["spE"])
+    L = pop.L
+    small = "step0_theta_actor" in g.files
+    worst = {}
+    for step in range(m["K"]):
+        inject(pop, cfg, [(st, replay, expert, hyper, step_batch(g, step, replay, expert, m))])
+        pop.update(1, num_timesteps=step, use_device_rng=False)
+        torch.cuda.synchronize()
+        losses = pop.losses.cpu().numpy()[0]
+        y = pop.debug("y").cpu().numpy().reshape(-1)[:m["B"]]
+        assert rel(y, g[f"step{step}_y"]) < tol_g, ("y", step)
+        if m["nm"]:
+            assert abs(losses[4] - float(g[f"step{step}_p_loss"])) < tol_g * max(1.0, abs(float(g[f"step{step}_p_loss"])))
+            assert abs(losses[5] - float(g[f"step{step}_alpha_loss"])) < tol_g * max(1.0, abs(float(g[f"step{step}_alpha_loss"])))
+        assert abs(losses[6] - float(g[f"step{step}_alpha"])) < 1e-6
+        g_q = pop.debug("g_q").cpu().numpy().reshape(2, L.nc_stride)
+        g_a = pop.debug("g_actor").cpu().numpy().reshape(L.na_stride)
+        for k, got_full in (("q1", g_q[0]), ("q2", g_q[1]), ("actor", g_a)):
+            if small:
+                want = g[f"step{step}_g_{k}"]
+                e = rel(got_full[:want.size], want)
+            else:
+                want = g[f"step{step}_gproj_{k}"]
+                n = sum(int(np.prod(w.shape)) for w in st[k])
+                e = rel(proj(54321, len(want), got_full[:n]), want)
+            worst["g_" + k] = max(worst.get("g_" + k, 0.0), e)
+            assert e < tol_g, (k, step, e)
+        for k in NETS:
+            got = flat(pop.get_net(0, k))
+            if small:
+                e = rel(got, g[f"step{step}_theta_{k}"])
+                assert e < tol_theta, (k, step, e)
+                d0 = flat(st[k]).astype(np.float64)
+                dref = g[f"step{step}_theta_{k}"].astype(np.float64) - d0
+                e = rel(got.astype(np.float64) - d0, dref)
+            else:
+                d = got.astype(np.float64) - flat(st[k]).astype(np.float64)
+                want = g[f"step{step}_proj_{k}"]
+                e = rel(proj(12345, len(want), d), want)
+            worst["dtheta_" + k] = max(worst.get("dtheta_" + k, 0.0), e)
+            assert e < tol_dtheta, (k, step, e)
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu"])
+def test_cuda_fp32_engine_reproduces_reference_updates(name):
+    """Three consecutive updates on the fp32 engine vs the reference's own outputs (gradients 2e-5, θ 1e-6, Δθ 2e-3)."""
+    _device_run(name, "GEMM_FP32_SIMT", False, 2e-5, 2e-6, 2e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_tcgen05_engine_reproduces_reference_updates_hopper():
+    """The benchmarked engine (tcgen05 fp16 hi/lo x3, fused kernels, CUDA graph) at the Hopper benchmark shape (2x256
+    / 2x512, B = 256, E = 20), two consecutive updates vs the reference's own outputs through fixed random projections of
+    the gradients and of Δθ."""
+    _device_run("saceo2_hopper_256", "GEMM_TCGEN05_BF16X3", True, 2e-4, None, 5e-3)
