@@ -341,8 +341,9 @@ class GradientTape:
                 e._t.requires_grad_(True)
 
     def gradient(self, target, sources, output_gradients=None):
-        single = not isinstance(sources, (list, tuple))
-        srcs = [sources] if single else list(sources)
+        """Sources may be a variable, a list, or a nested list (trpo.py:67 passes ``[actor.trainable, alpha]``); the
+        result has the same structure, ``None`` where a source is not connected to the target."""
+        srcs = list(_flatten(sources)) if isinstance(sources, (list, tuple)) else [sources]
         outer = any(t is not self for t in _TAPES)          # an enclosing tape must see the gradient computation
         tgt = target._t
         og = None
@@ -355,8 +356,13 @@ class GradientTape:
         else:
             grads = _torch.autograd.grad(tgt, [s._t for s in srcs], grad_outputs=og, retain_graph=True,
                                          create_graph=outer, allow_unused=True)
-        out = [None if g is None else Tensor(g if outer else g.detach()) for g in grads]
-        return out[0] if single else out
+        it = iter(None if g is None else Tensor(g if outer else g.detach()) for g in grads)
+
+        def pack(struct):
+            if isinstance(struct, (list, tuple)):
+                return [pack(e) for e in struct]
+            return next(it)
+        return pack(sources)
 
 
 def stop_gradient(x):

@@ -243,6 +243,111 @@ def run_case(name, cfg: NetCfg, B, E, N, seed, K, eps, target_update_int, store_
     print(f"{name}: {len(buf.getvalue()) / 1024:.0f} KiB, alpha per step {[float(out[f'step{i}_alpha']) for i in range(K)]}")
 
 
+def run_trpo_case(name, cfg: NetCfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp):
+    """``TRPO.update(rollout_data, expert_reg)`` (trpo.py:36-198: surrogate + entropy gradient, two-model expert blend,
+    ``_make_F``, ``cg``, step length, ``_backtrack``) on a ``GaussianActor``, plus one stand-alone Fisher-vector product."""
+    import torch
+    from sac_eo.actors import init_actor
+    from sac_eo.algs.model_free import trpo as trpo_mod
+    from sac_eo.common.normalizer import RunningNormalizers
+    from sac_eo.common.train_parser import create_train_parser
+    from sac_eo.common.train_utils import gather_inputs
+    from sac_eo.models import init_world_models
+    from oracle.sac_eo_oracle import gaussian_forward, to_torch_state
+    st, replay, expert, hyper = make_problem(cfg, 8, E, max(N, 300), seed=seed, perturb=0.2)
+    inputs = gather_inputs(create_train_parser().parse_args(["--alg_type", "mbrl"]))
+    ak, mk, msk, uk = (inputs[k] for k in ("actor_kwargs", "model_kwargs", "model_setup_kwargs", "mf_update_kwargs"))
+    ak.update(actor_layers=list(cfg.actor_hidden), actor_activations=list(cfg.actor_acts), actor_weights=None,
+              actor_per_state_std=cfg.per_state_std, actor_squash=False, actor_std_mult=cfg.std_mult)
+    mk.update(model_layers=list(cfg.model_hidden), model_activations=list(cfg.model_acts), model_weights=None,
+              reward_weights=None, num_models=2, gaussian_model=False)
+    msk.update(separate_reward_nn=False, delta_clip_pred=None)
+    uk.update(delta_trpo=delta, cg_it=cg_it, trust_sub=1, trust_damp=trust_damp, kl_maxfactor=kl_maxfactor,
+              ent_reg=False, ent_targ=-cfg.A, adv_center=True, adv_scale=True)
+    env = _Env(cfg.S, cfg.A)
+    actor = init_actor(env, **ak)
+    models = init_world_models(env, **mk, model_setup_kwargs=msk)
+    actor.set_weights([np.asarray(w) for w in st["actor"]])
+    for net, key in zip(models, ("m1", "m2")):
+        net.set_weights([np.asarray(w) for w in st[key]])
+    nz, mz = RunningNormalizers(cfg.S, cfg.A, 0.99), RunningNormalizers(cfg.S, cfg.A, 0.99)
+    nz.s_rms.mean, nz.s_rms.std = st["s_mean"].copy(), st["s_std"].copy()
+    mz.s_rms.mean, mz.s_rms.std = st["m_s_mean"].copy(), st["m_s_std"].copy()
+    mz.a_rms.mean, mz.a_rms.std = st["m_a_mean"].copy(), st["m_a_std"].copy()
+    mz.delta_rms.mean, mz.delta_rms.std = st["m_d_mean"].copy(), st["m_d_std"].copy()
+    actor.set_rms(nz)
+    for m_ in models:
+        m_.set_rms(mz)
+    algo = trpo_mod.TRPO(actor, uk)
+    # rollout: the policy's own actions (ratios near 1), random advantages
+    rng = np.random.default_rng(seed + 500)
+    s_all = replay["s"][:N]
+    th64 = to_torch_state(st, torch.float64)
+    with torch.no_grad():
+        mean, ls = gaussian_forward(cfg, th64["actor"], torch.as_tensor(s_all, dtype=torch.float64), th64)
+    a_all = (mean + torch.exp(ls) * torch.from_numpy(rng.standard_normal((N, cfg.A)))).numpy().astype(np.float32)
+    adv_all = (rng.standard_normal(N) * 1.5 + 0.3).astype(np.float32)
+    out = dict(meta=np.array([cfg.S, cfg.A, N, E, seed, cg_it, int(cfg.per_state_std)], np.int64),
+               hyper=np.array([eps, delta, kl_maxfactor, trust_damp, cfg.std_mult], np.float64),
+               s_all=s_all, a_all=a_all, adv_all=adv_all)
+    for k in ("actor", "m1", "m2"):
+        for i, w in enumerate(st[k]):
+            out[f"in_{k}_{i}"] = np.asarray(w, np.float32)
+    for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
+        out["in_" + k] = np.asarray(st[k])
+    for k, v in expert.items():
+        out["in_expert_" + k] = v
+    # ---- one Fisher-vector product of the untouched policy (trpo.py:200-227) ------------------------------------------
+    x = rng.standard_normal(int(actor.d)).astype(np.float32)
+    out["fvp_x"], out["fvp_Fx"] = x, algo._make_F(s_all)(x).numpy()
+    out["neglogp_old"] = actor.neglogp(s_all, a_all).numpy()
+    out["entropy"] = actor.entropy(s_all).numpy()
+    # ---- the update, with its internals observed -----------------------------------------------------------------------
+    seen = {}
+    orig_cg, orig_bt = trpo_mod.cg, algo._backtrack
+
+    def spy_cg(f_Ax, b, cg_iters=20, residual_tol=1e-10):
+        v = orig_cg(f_Ax, b, cg_iters=cg_iters, residual_tol=residual_tol)
+        seen["pg_vec"], seen["v_flat"] = np.array(b), np.array(v)
+        return v
+
+    def spy_bt(eta_v_flat, *a):
+        seen["eta_v_flat"] = np.array(eta_v_flat)
+        return orig_bt(eta_v_flat, *a)
+    trpo_mod.cg, algo._backtrack = spy_cg, spy_bt
+    alg_rng = np.random.default_rng(0)
+    perm_seen = []
+
+    class _Rng:
+        def shuffle(self_, v):
+            alg_rng.shuffle(v)
+            perm_seen.append(np.array(v))
+    np.random.seed(2000 + seed)
+    with _Recorder() as rec:
+        log = algo.update((s_all, a_all, adv_all, None, None, None),
+                          (expert["sE"], expert["aE"], expert["spE"], eps, models, False, _Rng()))
+    trpo_mod.cg = orig_cg
+    assert [k for k, _ in rec.calls] == ["normal", "normal"], [k for k, _ in rec.calls]
+    out["u3"], out["u4"] = rec.calls[0][1], rec.calls[1][1]
+    out["perm"] = perm_seen[0].astype(np.int64)
+    for k, v in seen.items():
+        out[k] = np.asarray(v)
+    for k in ("ent", "tv_pre", "kl_pre", "tv", "kl", "adj", "improve", "norm_pg", "norm_MSE"):
+        out["log_" + k] = np.float64(np.asarray(log[k]))
+    out["theta_new"] = flat(actor.get_weights())
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: adj {float(out['log_adj']):.4f} kl_pre {float(out['log_kl_pre']):.4g} kl {float(out['log_kl']):.4g} "
+          f"improve {float(out['log_improve']):.4g} |eta_v| {np.linalg.norm(out['eta_v_flat']):.4g}")
+
+
+TRPO_CASES = dict(
+    # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
+    trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
+                          actor_acts=("tanh", "tanh"), std_mult=0.7), 96, 8, 21, 0.5, 0.02, 10, 1.5, 0.01),
+    trpo_sis_relu=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=False,
+                          actor_acts=("relu", "relu"), std_mult=0.7), 96, 8, 22, 0.2, 0.02, 10, 0.6, 0.01),
+)
+
 CASES = dict(
     # name: (cfg, B, E, N, seed, K, eps, target_update_int, store_inputs, proj_dim)
     saceo2_relu=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(32, 24), num_models=2),
@@ -258,6 +363,10 @@ CASES = dict(
 
 
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or CASES):
-        cfg, *rest = CASES[name]
-        run_case(name, cfg, *rest)
+    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES)):
+        if name in CASES:
+            cfg, *rest = CASES[name]
+            run_case(name, cfg, *rest)
+        else:
+            cfg, *rest = TRPO_CASES[name]
+            run_trpo_case(name, cfg, *rest)
