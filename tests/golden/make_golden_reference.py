@@ -52,7 +52,7 @@ class _Recorder:
 
     def __init__(self):
         self.calls = []
-        self._randint, self._normal = np.random.randint, np.random.normal
+        self._randint, self._normal, self._shuffle = np.random.randint, np.random.normal, np.random.shuffle
 
     def __enter__(self):
         def randint(*a, **k):
@@ -64,11 +64,14 @@ class _Recorder:
             v = self._normal(*a, **k)
             self.calls.append(("normal", np.array(v)))
             return v
-        np.random.randint, np.random.normal = randint, normal
+        def shuffle(x):
+            self._shuffle(x)
+            self.calls.append(("shuffle", np.array(x)))
+        np.random.randint, np.random.normal, np.random.shuffle = randint, normal, shuffle
         return self
 
     def __exit__(self, *exc):
-        np.random.randint, np.random.normal = self._randint, self._normal
+        np.random.randint, np.random.normal, np.random.shuffle = self._randint, self._normal, self._shuffle
         return False
 
 
@@ -340,6 +343,62 @@ def run_trpo_case(name, cfg: NetCfg, N, E, seed, eps, delta, cg_it, kl_maxfactor
           f"improve {float(out['log_improve']):.4g} |eta_v| {np.linalg.norm(out['eta_v_flat']):.4g}")
 
 
+def run_fit_case(name, cfg: NetCfg, n_rows, E, seed, epochs, mbs, max_grad_norm, lr):
+    """``SAC_exp._update_models`` (SAC_expert.py:478-621: per-model shuffled minibatches, ``_apply_model_grads`` =
+    summed losses, global-norm clip, ONE shared Keras Adam; then the MSE-on-expert bookkeeping) followed by
+    ``_expert_preprocess`` with ``scale_epsilon_by_true_MSE`` (:375-404)."""
+    st, replay, expert, hyper = make_problem(cfg, 8, E, n_rows, seed=seed, perturb=0.05)
+    alg, _ = build(cfg, st, replay, expert, hyper, 8, 1)
+    rng = np.random.default_rng(seed + 900)
+    expert["rE"] = rng.standard_normal(E).astype(np.float32)
+    alg.model_data.add(replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    alg.expert_data.add(expert["sE"], expert["aE"], expert["rE"], expert["spE"], np.zeros(E))
+    alg.model_holdout_ratio, alg.model_num_epochs, alg.model_batch_size = 0.0, epochs, mbs
+    alg.model_batch_shuffle, alg.model_max_updates, alg.model_max_grad_norm = True, 10 ** 6, max_grad_norm
+    alg.reset_model_optimizer, alg.use_expert_actions = False, False
+    import tensorflow as tf
+    alg.model_optimizer = tf.keras.optimizers.Adam(learning_rate=lr)
+    out = dict(meta=np.array([cfg.S, cfg.A, n_rows, E, seed, epochs, mbs], np.int64),
+               hyper=np.array([max_grad_norm, lr], np.float64), in_expert_rE=expert["rE"])
+    for k in ("actor", "m1", "m2"):
+        for i, w in enumerate(st[k]):
+            out[f"in_{k}_{i}"] = np.asarray(w, np.float32)
+    for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
+        out["in_" + k] = np.asarray(st[k])
+    for k, v in replay.items():
+        out["in_replay_" + k] = v
+    for k in ("sE", "aE", "spE"):
+        out["in_expert_" + k] = expert[k]
+    np.random.seed(3000 + seed)
+    with _Recorder() as rec:
+        alg._update_models()
+    kinds = [k for k, _ in rec.calls]
+    assert kinds == ["shuffle"] * (2 * epochs) + ["normal"], kinds         # per-model shuffles per epoch, then actor.sample
+    out["shuffles"] = np.stack([v for k, v in rec.calls if k == "shuffle"]).astype(np.int64)
+    out["u_cf"] = rec.calls[-1][1]
+    for k, mdl in zip(("m1", "m2"), alg.models):
+        out["theta_" + k] = flat(mdl.get_weights())
+    out["mse_expert"] = np.float64(alg.model_MSE_on_expert_data[-1])
+    out["mse_counterfactual"] = np.float64(alg.model_MSE_on_expert_counterfactual_action[-1])
+    # adaptive expert weight from the bookkeeping above (SAC_expert.py:381-404)
+    alg.scale_epsilon_by_true_MSE, alg.epsilon, alg.min_mult, alg.exp_mult, alg.mult_coeff = True, 2.0, True, True, 0.75
+    alg.current_reward, alg.expert_reward, alg.expert_batch_size = 120.0, 400.0, None
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        reg = alg._expert_preprocess()
+    out["epsilon_coef"] = np.float64(reg[3])
+    out["adaptive"] = np.array([2.0, 0.75, 120.0, 400.0], np.float64)
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: {len(kinds) - 1} shuffles, mse_expert {float(out['mse_expert']):.5f} "
+          f"mse_cf {float(out['mse_counterfactual']):.5f} epsilon_coef {float(out['epsilon_coef']):.5f}")
+
+
+FIT_CASES = dict(
+    # name: (cfg, rows, E, seed, epochs, minibatch, max_grad_norm, lr)
+    fit_mse_relu=(NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2),
+                  72, 8, 31, 2, 16, 0.05, 1e-3),
+)
+
 TRPO_CASES = dict(
     # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
     trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
@@ -363,10 +422,13 @@ CASES = dict(
 
 
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES)):
+    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES)):
         if name in CASES:
             cfg, *rest = CASES[name]
             run_case(name, cfg, *rest)
+        elif name in FIT_CASES:
+            cfg, *rest = FIT_CASES[name]
+            run_fit_case(name, cfg, *rest)
         else:
             cfg, *rest = TRPO_CASES[name]
             run_trpo_case(name, cfg, *rest)

@@ -344,3 +344,83 @@ def test_cuda_reproduces_reference_trpo_update(name):
         ref = float(g["log_" + k])
         assert abs(log[k] - ref) <= (5e-2 if loose else 1e-2) * max(abs(ref), 1e-3), (k, log[k], ref)
     pop.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SAC_exp._update_models (SAC_expert.py:478-621) + _expert_preprocess (:375-404) - rows f1 and a13
+# ---------------------------------------------------------------------------------------------------------------------
+FIT_CFG = NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2)
+
+
+def load_fit_case():
+    g = np.load(os.path.join(GOLD, "ref_fit_mse_relu.npz"))
+    S, A, n_rows, E, seed, epochs, mbs = (int(x) for x in g["meta"])
+    st, replay, expert, hyper = make_problem(FIT_CFG, 8, E, n_rows, seed=seed, perturb=0.05)
+    for k in ("actor", "m1", "m2"):
+        st[k] = [g[f"in_{k}_{i}"] for i in range(len(st[k]))]
+    for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
+        st[k] = g["in_" + k]
+    replay = {k: g["in_replay_" + k] for k in replay}
+    # minibatches the reference drew: per epoch one permutation per model, split every mbs columns, ragged tail dropped
+    batches = []
+    for ep in range(epochs):
+        idx = g["shuffles"][2 * ep:2 * ep + 2]
+        sec = np.array_split(idx, np.arange(0, n_rows, mbs)[1:], axis=1)
+        batches += sec[:-1] if n_rows % mbs else sec
+    return g, st, replay, batches, dict(E=E, mgn=float(g["hyper"][0]), lr=float(g["hyper"][1]))
+
+
+def test_oracle_reproduces_reference_model_fitting():
+    from oracle import sac_eo_oracle as O
+    g, st, replay, batches, m = load_fit_case()
+    th = O.to_torch_state(st, torch.float32)
+    models = [th["m1"], th["m2"]]
+    adam = dict(m=[[torch.zeros_like(w) for w in ml] for ml in models], v=[[torch.zeros_like(w) for w in ml] for ml in models], t=0)
+    fit = dict(model_lr=m["lr"], model_max_grad_norm=m["mgn"])
+    clipped = 0
+    for idx in batches:
+        bs = [{k: torch.as_tensor(replay[k][idx[j]]) for k in ("s", "a", "sp", "r")} for j in range(2)]
+        o = O.apply_model_grads(FIT_CFG, models, adam, bs, th, fit)
+        clipped += float(o["gnorm"]) > m["mgn"] * 2
+        models, adam = o["models"], dict(m=o["m"], v=o["v"], t=o["t"])
+    assert len(batches) == 8 and 0 < clipped                                  # the global-norm clip was active
+    for k, ml in zip(("m1", "m2"), models):
+        d0 = flat(st[k]).astype(np.float64)
+        assert rel(flat(ml).astype(np.float64) - d0, g["theta_" + k].astype(np.float64) - d0) < 2e-4, k
+    th["m1"], th["m2"] = models
+    mse_e = O.model_mse_on_expert(FIT_CFG, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"], use_expert_actions=True)
+    mse_c = O.model_mse_on_expert(FIT_CFG, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"],
+                                  u=g["u_cf"].astype(np.float32))
+    assert abs(float(mse_e) - float(g["mse_expert"])) < 1e-5 * float(g["mse_expert"])
+    assert abs(float(mse_c) - float(g["mse_counterfactual"])) < 1e-5 * float(g["mse_counterfactual"])
+    eps, coeff, j_cur, j_exp = (float(x) for x in g["adaptive"])
+    got = O.adaptive_epsilon(eps, scale_by_true_mse=True, mse_cf=float(g["mse_counterfactual"]), j_cur=j_cur, j_exp=j_exp,
+                             min_mult=True, exp_mult=True, mult_coeff=coeff)
+    # np.float32 bookkeeping value x Python float: float32 arithmetic under NumPy >= 2, float64 under NumPy 1.x
+    assert abs(got - float(g["epsilon_coef"])) < 1e-7 * got
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_model_fitting():
+    """saceo_model_fit over the eight minibatches the reference's _update_models drew (per-model shuffles, global-norm
+    clip active, one joint Adam), then saceo_model_eval-free check of the final weights against the reference's."""
+    from sac_expert_b200.population import Population
+    from tests.helpers import spec_from_cfg
+    g, st, replay, batches, m = load_fit_case()
+    mbs = batches[0].shape[1]
+    pop = Population(spec_from_cfg(FIT_CFG, 1, 8, m["E"], len(replay["r"])))
+    pop.fit_bind(mbs, use_grad_clip=True)
+    _, _, _, hyper = make_problem(FIT_CFG, 8, m["E"], len(replay["r"]), seed=int(g["meta"][4]), perturb=0.05)
+    pop.load_agent(0, st, hyper)
+    pop.append_rows(0, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    pop.set_fit_hyper(0, model_lr=m["lr"], model_max_grad_norm=m["mgn"], r_mean=0.0, r_std=1.0)
+    pop.model_fit(np.stack(batches)[:, None])                        # [steps, agent, model, minibatch]
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k in ("m1", "m2"):
+        d0 = flat(st[k]).astype(np.float64)
+        e = rel(flat(pop.get_net(0, k)).astype(np.float64) - d0, g["theta_" + k].astype(np.float64) - d0)
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+    print(f"\n[fit_mse_relu] dtheta vs reference {worst:.2e}")
+    pop.close()
