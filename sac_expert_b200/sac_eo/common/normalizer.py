@@ -31,18 +31,22 @@ class RunningNormalizer:
         return data_norm * self._den() + self.mean if center else data_norm * self._den()
 
     def update(self, data):
-        """Merges a batch into the running mean / unbiased variance (parallel-variance merge; reproduces the
-        reference's conventions: max(1, n-1) denominators, std = 1 while only one sample was seen)."""
-        data = np.asarray(data, np.float64)
-        nb = data.shape[0]
-        mb = data.mean(axis=0)
-        sb = np.sum((data - mb) ** 2, axis=0)
+        """Merges a batch into the running mean / unbiased variance with the reference's arithmetic (normalizer.py:55-87):
+        the batch is first scaled by the CURRENT std, batch mean and sum of squares are taken in that scaled space and
+        scaled back, everything in the dtype NumPy promotion gives (float32 for float32 trajectories), max(1, n-1)
+        denominators, std = 1 while only one sample was seen.  Same operations in the same order, so the statistics are
+        bit-identical to the reference's (tests/test_reference_pin.py)."""
+        scale = self._den()
+        scale_sq = np.square(scale)
+        z = data / scale
+        nb = z.shape[0]
+        zb = z.mean(axis=0)
+        ssq = np.sum(np.square(z - zb), axis=0)
         n0, n = self.t_last, self.t_last + nb
-        m2 = np.asarray(self.var, np.float64) * max(1, n0 - 1) + sb + (nb * n0 / n) * (mb - self.mean) ** 2
-        mean = (n0 * np.asarray(self.mean, np.float64) + nb * mb) / n
-        var = m2 / max(1, n - 1)
-        self.mean = mean.astype(np.float32) if self.dim != 1 else np.float32(mean)
-        self.var = var.astype(np.float32) if self.dim != 1 else np.float32(var)
+        var = (scale_sq * ssq + self.var * np.maximum(1, n0 - 1)
+               + (nb / n) * n0 * scale_sq * np.square(zb - self.mean / scale)) / np.maximum(1, n - 1)
+        mean = (nb * zb * scale + n0 * self.mean) / n
+        self.mean, self.var = mean.astype("float32"), var.astype("float32")
         self.std = np.ones_like(self.var) if n == 1 else np.sqrt(self.var)
         self.t_last = n
         self.version += 1
@@ -78,9 +82,13 @@ class RunningNormalizers:
         self.a_rms.update(a_traj)
         self.r_rms.update(r_traj)
         self.delta_rms.update(sp_traj - s_traj)
-        ret, acc = np.zeros(len(r_traj)), 0.0
-        for i in range(len(r_traj) - 1, -1, -1):          # discounted return-to-go
-            acc = r_traj[i] + self.gamma * acc
+        # discounted return-to-go in float64, the recurrence scipy's lfilter([1], [1, -gamma]) runs on the reversed
+        # rewards (buffer_utils.py:8): y[i] = r[i] + gamma * y[i+1]
+        r64 = np.asarray(r_traj, np.float64)
+        ret, acc = np.zeros(len(r64)), np.float64(0.0)
+        g = np.float64(self.gamma)
+        for i in range(len(r64) - 1, -1, -1):
+            acc = r64[i] + g * acc
             ret[i] = acc
         self.ret_rms.update(ret)
 

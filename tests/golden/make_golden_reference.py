@@ -75,14 +75,14 @@ class _Recorder:
         return False
 
 
-def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int):
+def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int, alg_type=None):
     from sac_eo.actors import init_actor
     from sac_eo.algs import init_alg
     from sac_eo.common.train_parser import create_train_parser
     from sac_eo.common.train_utils import gather_inputs
     from sac_eo.critics import init_critics
     from sac_eo.models import init_world_models
-    alg_type = "sac_imit" if cfg.num_models > 0 else "sac"
+    alg_type = alg_type or ("sac_imit" if cfg.num_models > 0 else "sac")
     inputs = gather_inputs(create_train_parser().parse_args(["--alg_type", alg_type]))
     ak, ck, mk, msk, al = (inputs[k] for k in ("actor_kwargs", "critic_kwargs", "model_kwargs", "model_setup_kwargs",
                                                "alg_kwargs"))
@@ -399,6 +399,86 @@ FIT_CASES = dict(
                   72, 8, 31, 2, 16, 0.05, 1e-3),
 )
 
+def run_bc_case(name, cfg: NetCfg, E, seed, K):
+    """``BC._update`` (BC.py:298-363): K consecutive actor steps on the expert-observation MSE alone."""
+    st, replay, expert, hyper = make_problem(cfg, 8, E, 50, seed=seed, perturb=0.05)
+    alg, expert_reg = build(cfg, st, replay, expert, hyper, 8, 1, alg_type="bc")
+    out = dict(meta=np.array([cfg.S, cfg.A, E, seed, K], np.int64), lr_pi=np.float64(hyper["lr_pi"]))
+    for k in ("actor", "m1", "m2"):
+        for i, w in enumerate(st[k]):
+            out[f"in_{k}_{i}"] = np.asarray(w, np.float32)
+    for i, (m_, v_) in enumerate(zip(st["adam_actor"]["m"], st["adam_actor"]["v"])):
+        out[f"in_adam_actor_m_{i}"], out[f"in_adam_actor_v_{i}"] = m_, v_
+    out["in_adam_actor_t"] = np.int64(st["adam_actor"]["t"])
+    for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
+        out["in_" + k] = np.asarray(st[k])
+    for k, v in expert.items():
+        out["in_expert_" + k] = v
+    perms = []
+    orig = alg.rng.shuffle
+
+    class _Rng:
+        def shuffle(self_, x):
+            orig(x)
+            perms.append(np.array(x))
+    alg.rng = _Rng()
+    np.random.seed(4000 + seed)
+    for step in range(K):
+        with _Recorder() as rec:
+            alg._update(step, expert_reg)
+        assert [k for k, _ in rec.calls] == ["normal", "normal"]
+        out[f"step{step}_u3"], out[f"step{step}_u4"] = rec.calls[0][1], rec.calls[1][1]
+        out[f"step{step}_perm"] = perms[-1].astype(np.int64)
+        out[f"step{step}_g_actor"] = flat(alg.actor_optimizer.last_grads)
+        out[f"step{step}_mse"] = np.float32(alg.logger.train_dict["BC_MSE_loss"][-1])
+        out[f"step{step}_theta_actor"] = flat(alg.actor.get_weights())
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: BC_MSE_loss per step {[float(out[f'step{i}_mse']) for i in range(K)]}")
+
+
+BC_CASES = dict(
+    bc2_relu=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2), 8, 41, 3),
+)
+
+def run_host_case(name="host_buffers_normalizers"):
+    """The reference's pure-NumPy host classes, executed as they are (no emulation involved): TrajectoryBuffer append +
+    tail truncation + seeded minibatch draws (buffers.py:41-71, 126-144), RunningNormalizers.update_rms
+    (normalizer.py:55-87, 152-163)."""
+    from sac_eo.common.buffers import TrajectoryBuffer
+    from sac_eo.common.normalizer import RunningNormalizers
+    S, A, cap = 4, 2, 50
+    rng = np.random.default_rng(77)
+    buf = TrajectoryBuffer(S, A, 0.99, 0.95, cap)
+    nz = RunningNormalizers(S, A, 0.99)
+    out = dict(meta=np.array([S, A, cap], np.int64))
+    for t, n in enumerate((20, 25, 30)):
+        tr = dict(s=rng.standard_normal((n, S)).astype(np.float32) * 2 + 1, a=rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                  r=rng.standard_normal(n).astype(np.float32), sp=rng.standard_normal((n, S)).astype(np.float32),
+                  d=rng.random(n) < 0.1)
+        for k, v in tr.items():
+            out[f"traj{t}_{k}"] = v
+        buf.add(tr["s"], tr["a"], tr["r"], tr["sp"], tr["d"])
+        nz.update_rms(tr["s"], tr["a"], tr["r"], tr["sp"])
+        out[f"after{t}_size"] = np.array([buf.current_size, buf.traj_total, buf.steps_total], np.int64)
+    for k in ("s_all", "a_all", "r_all", "sp_all", "d_all", "idx_all"):
+        out["buf_" + k] = getattr(buf, k)
+    np.random.seed(7)
+    for k, v in zip(("s", "a", "sp", "r", "d"), buf.get_offmodel_info(batch_size=16)):
+        out["off_" + k] = v
+    for k, v in zip(("s", "a", "sp", "r"), buf.get_model_info(batch_size=8)):
+        out["mod_" + k] = v
+    out["states"] = buf.get_states(batch_size=4)
+    for nm_, r_ in zip(("s", "a", "r", "delta", "ret"), nz.get_rms()):
+        out[f"rms_{nm_}_mean"], out[f"rms_{nm_}_var"], out[f"rms_{nm_}_std"] = (np.asarray(r_.mean), np.asarray(r_.var),
+                                                                           np.asarray(r_.std))
+        out[f"rms_{nm_}_t"] = np.int64(r_.t_last)
+    x = rng.standard_normal((5, S)).astype(np.float32)
+    out["norm_x"], out["norm_y"] = x, nz.s_rms.normalize(x)
+    out["denorm_y"] = nz.delta_rms.denormalize(x)
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: buffer size {buf.current_size}, s_rms.std {nz.s_rms.std}")
+
+
 TRPO_CASES = dict(
     # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
     trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
@@ -422,10 +502,16 @@ CASES = dict(
 
 
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES)):
+    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES) + list(BC_CASES)
+                 + ["host_buffers_normalizers"]):
         if name in CASES:
             cfg, *rest = CASES[name]
             run_case(name, cfg, *rest)
+        elif name == "host_buffers_normalizers":
+            run_host_case()
+        elif name in BC_CASES:
+            cfg, *rest = BC_CASES[name]
+            run_bc_case(name, cfg, *rest)
         elif name in FIT_CASES:
             cfg, *rest = FIT_CASES[name]
             run_fit_case(name, cfg, *rest)

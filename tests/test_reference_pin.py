@@ -424,3 +424,131 @@ def test_cuda_reproduces_reference_model_fitting():
         assert e < 2e-3, (k, e)
     print(f"\n[fit_mse_relu] dtheta vs reference {worst:.2e}")
     pop.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BC._update (BC.py:298-363) - row f4 (behaviour cloning from expert observations)
+# ---------------------------------------------------------------------------------------------------------------------
+BC_CFG = NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2)
+
+
+def load_bc_case():
+    g = np.load(os.path.join(GOLD, "ref_bc2_relu.npz"))
+    S, A, E, seed, K = (int(x) for x in g["meta"])
+    st, replay, expert, hyper = make_problem(BC_CFG, 8, E, 50, seed=seed, perturb=0.05)
+    for k in ("actor", "m1", "m2"):
+        st[k] = [g[f"in_{k}_{i}"] for i in range(len(st[k]))]
+    st["adam_actor"] = dict(m=[g[f"in_adam_actor_m_{i}"] for i in range(len(st["actor"]))],
+                            v=[g[f"in_adam_actor_v_{i}"] for i in range(len(st["actor"]))], t=int(g["in_adam_actor_t"]))
+    for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
+        st[k] = g["in_" + k]
+    expert = {k: g["in_expert_" + k] for k in expert}
+    hyper["lr_pi"] = float(g["lr_pi"])
+
+    def batch(step):
+        I1, I2 = np.array_split(g[f"step{step}_perm"], 2)
+        return dict(sE=expert["sE"], spE=expert["spE"], I1=I1, I2=I2, u3=g[f"step{step}_u3"].astype(np.float32),
+                    u4=g[f"step{step}_u4"].astype(np.float32))
+    return g, st, replay, expert, hyper, batch, E, K
+
+
+def test_oracle_reproduces_reference_bc_updates():
+    from oracle.sac_eo_oracle import bc_update
+    g, st, replay, expert, hyper, batch, E, K = load_bc_case()
+    state = to_torch_state(st, torch.float32)
+    for step in range(K):
+        o = bc_update(BC_CFG, state, batch(step), hyper)
+        assert abs(float(o["mse"]) - float(g[f"step{step}_mse"])) < 2e-6 * float(o["mse"])
+        assert rel(flat(o["g_actor"]), g[f"step{step}_g_actor"]) < 5e-6
+        assert rel(flat(o["new"]["actor"]), g[f"step{step}_theta_actor"]) < 1e-6
+        state["actor"], state["adam_actor"] = o["new"]["actor"], o["new"]["adam_actor"]
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_bc_updates():
+    from sac_expert_b200.population import Population
+    from tests.helpers import spec_from_cfg
+    g, st, replay, expert, hyper, batch, E, K = load_bc_case()
+    B, A = 8, BC_CFG.A
+    pop = Population(spec_from_cfg(BC_CFG, 1, B, E, 50))
+    pop.load_agent(0, st, hyper)
+    pop.append_rows(0, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    pop.set_expert(0, expert["sE"], expert["spE"])
+    worst = 0.0
+    for step in range(K):
+        b = batch(step)
+        noise = np.zeros((1, 3 * B + E, A), np.float32)
+        noise[0, 2 * B:2 * B + E] = np.concatenate([b["u3"], b["u4"]])
+        pop.set_draws(np.zeros((1, B), np.int64), noise, np.concatenate([b["I1"], b["I2"]]).astype(np.int32)[None])
+        losses = pop.bc_update(1, use_device_rng=False).cpu().numpy()
+        torch.cuda.synchronize()
+        assert abs(losses[0, 3] - float(g[f"step{step}_mse"])) < 1e-5 * float(g[f"step{step}_mse"])
+        want = g[f"step{step}_g_actor"]
+        e = rel(pop.debug("g_actor").cpu().numpy().reshape(-1)[:want.size], want)
+        assert e < 2e-5, e
+        d0 = flat(st["actor"]).astype(np.float64)
+        e = rel(flat(pop.get_net(0, "actor")).astype(np.float64) - d0, g[f"step{step}_theta_actor"].astype(np.float64) - d0)
+        worst = max(worst, e)
+        assert e < 2e-3, e
+    print(f"\n[bc2_relu] dtheta vs reference {worst:.2e}")
+    pop.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's pure-NumPy host classes, run as they are (no emulation): rows a1 - a3
+# ---------------------------------------------------------------------------------------------------------------------
+def _replay_host_case(buf, nz, g):
+    for t in range(3):
+        tr = {k: g[f"traj{t}_{k}"] for k in ("s", "a", "r", "sp", "d")}
+        buf.add(tr["s"], tr["a"], tr["r"], tr["sp"], tr["d"])
+        if nz is not None:
+            nz.update_rms(tr["s"], tr["a"], tr["r"], tr["sp"])
+        assert [buf.current_size, buf.traj_total, buf.steps_total] == g[f"after{t}_size"].tolist()
+
+
+def test_mirror_buffer_and_normalizers_match_reference_bitwise():
+    """The mirror TrajectoryBuffer (pre-allocated sliding window) and RunningNormalizers against the reference's own
+    classes: identical bytes in every exposed array after appends that overflow buffer_size, identical statistics."""
+    from sac_expert_b200.sac_eo.common.buffers import TrajectoryBuffer
+    from sac_expert_b200.sac_eo.common.normalizer import RunningNormalizers
+    g = np.load(os.path.join(GOLD, "ref_host_buffers_normalizers.npz"))
+    S, A, cap = (int(x) for x in g["meta"])
+    buf, nz = TrajectoryBuffer(S, A, 0.99, 0.95, cap), RunningNormalizers(S, A, 0.99)
+    _replay_host_case(buf, nz, g)
+    for k in ("s_all", "a_all", "r_all", "sp_all", "d_all", "idx_all"):
+        got, want = np.asarray(getattr(buf, k)), g["buf_" + k]
+        assert got.dtype == want.dtype and got.shape == want.shape and got.tobytes() == want.tobytes(), k
+    np.random.seed(7)
+    idx = np.random.randint(buf.current_size, size=16)                    # buffers.py:135
+    assert buf.s_all[idx].tobytes() == g["off_s"].tobytes() and buf.d_all[idx].tobytes() == g["off_d"].tobytes()
+    for nm_, r_ in zip(("s", "a", "r", "delta", "ret"), nz.get_rms()):
+        assert int(r_.t_last) == int(g[f"rms_{nm_}_t"])
+        for stat in ("mean", "var", "std"):
+            got, want = np.asarray(getattr(r_, stat)), g[f"rms_{nm_}_{stat}"]
+            assert got.dtype == want.dtype, (nm_, stat, got.dtype, want.dtype)
+            assert np.array_equal(got, want), (nm_, stat)
+    assert np.array_equal(np.asarray(nz.s_rms.normalize(g["norm_x"])), g["norm_y"])
+    assert np.array_equal(np.asarray(nz.delta_rms.denormalize(g["norm_x"])), g["denorm_y"])
+
+
+@pytest.mark.gpu
+def test_device_replay_gather_matches_reference_bitwise():
+    """The device ring behind the mirror buffer: the reference's seeded get_offmodel_info / get_model_info draws after
+    the buffer overflowed, byte for byte."""
+    from sac_expert_b200.population import Population
+    from sac_expert_b200.sac_eo.common.buffers import TrajectoryBuffer
+    from tests.helpers import spec_from_cfg
+    g = np.load(os.path.join(GOLD, "ref_host_buffers_normalizers.npz"))
+    S, A, cap = (int(x) for x in g["meta"])
+    cfg = NetCfg(S=S, A=A, actor_hidden=(16, 16), critic_hidden=(16, 16), model_hidden=(16, 16), num_models=0)
+    pop = Population(spec_from_cfg(cfg, 2, 16, 0, cap))
+    buf = TrajectoryBuffer(S, A, 0.99, 0.95, cap)
+    buf.attach(pop, agent=1)
+    _replay_host_case(buf, None, g)
+    np.random.seed(7)
+    for k, v in zip(("s", "a", "sp", "r", "d"), buf.get_offmodel_info(batch_size=16)):
+        want = g["off_" + k]
+        assert v.dtype == want.dtype and v.tobytes() == want.tobytes(), k
+    for k, v in zip(("s", "a", "sp", "r"), buf.get_model_info(batch_size=8)):
+        assert np.asarray(v).tobytes() == g["mod_" + k].tobytes(), k
+    pop.close()
