@@ -864,7 +864,9 @@ class Adam:
                  legacy_one_minus_beta=False, **kw):
         assert not amsgrad
         self.legacy_one_minus_beta = legacy_one_minus_beta
-        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        # a float32 variable like Keras' (ppo.py:109-118 reads it with .numpy() and re-assigns it)
+        self.learning_rate = Variable(_np.float32(learning_rate), dtype=float32, name="learning_rate", trainable=False)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
         self.iterations = 0
         self.slots = {}
         self.last_grads = None
@@ -884,7 +886,7 @@ class Adam:
             if id(var) not in self.slots:
                 self.slots[id(var)] = (_torch.zeros_like(var._t), _torch.zeros_like(var._t))
             m, v = self.slots[id(var)]
-            lr = _torch.tensor(float(self.learning_rate), dtype=dt)
+            lr = self.learning_rate._t.detach().to(dt)
             b1 = _torch.tensor(self.beta_1, dtype=dt)
             b2 = _torch.tensor(self.beta_2, dtype=dt)
             one = _torch.tensor(1.0, dtype=dt)

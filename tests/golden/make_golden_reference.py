@@ -479,6 +479,62 @@ def run_host_case(name="host_buffers_normalizers"):
     print(f"{name}: buffer size {buf.current_size}, s_rms.std {nz.s_rms.std}")
 
 
+def run_ppo_case(name, cfg: NetCfg, N, seed, update_it, nminibatch, eps_ppo, max_grad_norm, lr):
+    """``PPO.update(rollout_data)`` (ppo.py:41-119, 121-238 with expert_reg = None): epochs x shuffled minibatches,
+    per-minibatch advantage normalisation, clipped surrogate, global-norm clip, Keras Adam on the actor."""
+    import torch
+    from sac_eo.actors import init_actor
+    from sac_eo.algs.model_free import ppo as ppo_mod
+    from sac_eo.common.normalizer import RunningNormalizers
+    from sac_eo.common.train_parser import create_train_parser
+    from sac_eo.common.train_utils import gather_inputs
+    from oracle.sac_eo_oracle import gaussian_forward, to_torch_state
+    st, replay, expert, hyper = make_problem(cfg, 8, 4, max(N, 300), seed=seed, perturb=0.2)
+    inputs = gather_inputs(create_train_parser().parse_args(["--alg_type", "mbrl", "--mf_algo", "ppo"]))
+    ak, uk = inputs["actor_kwargs"], inputs["mf_update_kwargs"]
+    ak.update(actor_layers=list(cfg.actor_hidden), actor_activations=list(cfg.actor_acts), actor_weights=None,
+              actor_per_state_std=cfg.per_state_std, actor_squash=False, actor_std_mult=cfg.std_mult)
+    uk.update(actor_lr=lr, actor_update_it=update_it, actor_nminibatch=nminibatch, eps_ppo=eps_ppo,
+              max_grad_norm=max_grad_norm, adaptlr=False, ent_reg=False, ent_targ=-cfg.A, adv_center=True, adv_scale=True)
+    actor = init_actor(_Env(cfg.S, cfg.A), **ak)
+    actor.set_weights([np.asarray(w) for w in st["actor"]])
+    nz = RunningNormalizers(cfg.S, cfg.A, 0.99)
+    nz.s_rms.mean, nz.s_rms.std = st["s_mean"].copy(), st["s_std"].copy()
+    actor.set_rms(nz)
+    algo = ppo_mod.PPO(actor, uk)
+    rng = np.random.default_rng(seed + 500)
+    s_all = replay["s"][:N]
+    th64 = to_torch_state(st, torch.float64)
+    with torch.no_grad():
+        mean, ls = gaussian_forward(cfg, th64["actor"], torch.as_tensor(s_all, dtype=torch.float64), th64)
+    a_all = (mean + torch.exp(ls) * torch.from_numpy(rng.standard_normal((N, cfg.A)))).numpy().astype(np.float32)
+    adv_all = (rng.standard_normal(N) * 1.5 + 0.3).astype(np.float32)
+    out = dict(meta=np.array([cfg.S, cfg.A, N, seed, update_it, nminibatch, int(cfg.per_state_std)], np.int64),
+               hyper=np.array([eps_ppo, max_grad_norm, lr, cfg.std_mult], np.float64), s_all=s_all, a_all=a_all, adv_all=adv_all)
+    for i, w in enumerate(st["actor"]):
+        out[f"in_actor_{i}"] = np.asarray(w, np.float32)
+    out["in_s_mean"], out["in_s_std"] = st["s_mean"], st["s_std"]
+    np.random.seed(5000 + seed)
+    with _Recorder() as rec:
+        log = algo.update((s_all, a_all, adv_all, None, None, None))
+    assert [k for k, _ in rec.calls] == ["shuffle"] * update_it
+    out["shuffles"] = np.stack([v for _, v in rec.calls]).astype(np.int64)
+    for k in ("ent", "tv", "kl", "outside_clip", "actor_grad_norm_pre", "actor_grad_norm"):
+        out["log_" + k] = np.float64(np.asarray(log[k]))
+    out["theta_new"] = flat(actor.get_weights())
+    ms, vs = zip(*(algo.actor_optimizer.get_slot_arrays(v) for v in actor.trainable))
+    out["adam_m"], out["adam_v"] = flat(ms), flat(vs)
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: " + " ".join(f"{k} {float(out['log_' + k]):.4g}" for k in ("tv", "kl", "outside_clip", "actor_grad_norm_pre",
+                                                                          "actor_grad_norm")))
+
+
+PPO_CASES = dict(
+    # name: (cfg, N, seed, update_it, nminibatch, eps_ppo, max_grad_norm, lr)
+    ppo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(8, 8), per_state_std=True,
+                         actor_acts=("tanh", "tanh"), std_mult=0.7, num_models=0), 100, 51, 2, 4, 0.2, 0.5, 3e-3),
+)
+
 TRPO_CASES = dict(
     # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
     trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
@@ -502,11 +558,14 @@ CASES = dict(
 
 
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES) + list(BC_CASES)
+    for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES) + list(BC_CASES) + list(PPO_CASES)
                  + ["host_buffers_normalizers"]):
         if name in CASES:
             cfg, *rest = CASES[name]
             run_case(name, cfg, *rest)
+        elif name in PPO_CASES:
+            cfg, *rest = PPO_CASES[name]
+            run_ppo_case(name, cfg, *rest)
         elif name == "host_buffers_normalizers":
             run_host_case()
         elif name in BC_CASES:

@@ -552,3 +552,61 @@ def test_device_replay_gather_matches_reference_bitwise():
     for k, v in zip(("s", "a", "sp", "r"), buf.get_model_info(batch_size=8)):
         assert np.asarray(v).tobytes() == g["mod_" + k].tobytes(), k
     pop.close()
+
+
+def test_keras_adam_one_minus_beta_rounding_variants_are_bounded():
+    """oracle/tfemu implements the TF >= 2.11 Keras formula (Python-double ``1 - beta`` rounded to fp32); the fused
+    ApplyAdam kernel of TF <= 2.10 forms it in fp32.  The two differ by 1.3e-5 relative in v and < 5e-5 in 20 accumulated steps -
+    far inside every Δθ tolerance used against the reference vectors, so the pin does not hinge on the TF version."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_tfemu_tensorflow", os.path.join(os.path.dirname(GOLD), "..", "oracle", "tfemu", "tensorflow", "__init__.py"))
+    tf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tf)
+    rng = np.random.default_rng(0)
+    w0 = rng.standard_normal(4096).astype(np.float32)
+    out = {}
+    for legacy in (False, True):
+        v = tf.Variable(w0.copy(), dtype=tf.float32)
+        opt = tf.keras.optimizers.Adam(learning_rate=3e-4, legacy_one_minus_beta=legacy)
+        r = np.random.default_rng(1)
+        for _ in range(20):
+            opt.apply_gradients([(tf.constant(r.standard_normal(4096).astype(np.float32)), v)])
+        out[legacy] = (v.numpy() - w0, opt.get_slot_arrays(v)[1])
+    assert 5e-6 < rel(out[True][1], out[False][1]) < 2e-5          # v: (1 - 0.999) rounding
+    assert rel(out[True][0], out[False][0]) < 5e-5                 # accumulated step (incl. the fp32 rounding of theta itself)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PPO.update (ppo.py:41-119, 121-238 with expert_reg = None) - row f4
+# ---------------------------------------------------------------------------------------------------------------------
+def test_oracle_reproduces_reference_ppo_update():
+    from oracle import sac_eo_oracle as O
+    g = np.load(os.path.join(GOLD, "ref_ppo_psd_tanh.npz"))
+    S, A, N, seed, update_it, nminibatch, psd = (int(x) for x in g["meta"])
+    eps_ppo, mgn, lr, std_mult = (float(x) for x in g["hyper"])
+    cfg = NetCfg(S=S, A=A, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(8, 8), per_state_std=bool(psd),
+                 actor_acts=("tanh", "tanh"), std_mult=std_mult, num_models=0)
+    st, _, _, _ = make_problem(cfg, 8, 4, max(N, 300), seed=seed, perturb=0.2)
+    st["actor"] = [g[f"in_actor_{i}"] for i in range(len(st["actor"]))]
+    st["s_mean"], st["s_std"] = g["in_s_mean"], g["in_s_std"]
+
+    class Replay:                                  # np.random.shuffle, replayed: the permutations the reference drew
+        def __init__(self):
+            self.k = 0
+
+        def shuffle(self, idx):
+            idx[:] = g["shuffles"][self.k]
+            self.k += 1
+    th = O.to_torch_state(st, torch.float32)
+    adam = {"m": [torch.zeros_like(t) for t in th["actor"]], "v": [torch.zeros_like(t) for t in th["actor"]], "t": 0}
+    new, log = O.ppo_update(cfg, th["actor"], adam, g["s_all"], g["a_all"], g["adv_all"], th, actor_lr=lr,
+                            actor_update_it=update_it, actor_nminibatch=nminibatch, eps_ppo=eps_ppo, max_grad_norm=mgn,
+                            alpha=0.0, ent_targ=-A, np_rng=Replay())
+    d0 = flat(st["actor"]).astype(np.float64)
+    assert rel(O.flat(new).numpy().astype(np.float64) - d0, g["theta_new"].astype(np.float64) - d0) < 1e-3
+    assert rel(flat(adam["m"]), g["adam_m"]) < 1e-4 and rel(flat(adam["v"]), g["adam_v"]) < 1e-4
+    assert adam["t"] == update_it * nminibatch
+    assert float(g["log_actor_grad_norm_pre"]) > mgn and abs(float(g["log_actor_grad_norm"]) - mgn) < 1e-6   # clip active
+    for k in ("ent", "tv", "kl", "outside_clip", "actor_grad_norm_pre", "actor_grad_norm"):
+        assert abs(log[k] - float(g["log_" + k])) <= 2e-3 * max(abs(float(g["log_" + k])), 1e-3), (k, log[k], float(g["log_" + k]))
