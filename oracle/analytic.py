@@ -1,6 +1,6 @@
 """Hand-derived forward/backward of one SAC-EO update in NumPy.  TEST INFRASTRUCTURE ONLY.
 
-Same contract as ``oracle/sac_eo_oracle.py`` (see its header: parity unpinned, checker only).
+Same contract as ``oracle/sac_eo_oracle.py`` (see its header for the parity status; checker only).
 This twin uses NO autograd: every gradient is the explicit chain the CUDA kernels implement
 (SURVEY.md App. A "analytic backward"), phase by phase and GEMM by GEMM, so that the kernel
 sequence can be validated on the CPU against ``sac_eo_update`` (autograd) before any GPU time

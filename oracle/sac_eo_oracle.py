@@ -5,18 +5,25 @@ This file is the *checker*, never the product: only ``tests/``,
 legs may import it.  The product path (``sac_expert_b200``) must never import it and
 fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference (noc-lab/sac-expert) is TensorFlow-2-eager Python and
-ships no tests, golden vectors or known-answer fixtures for this path; TensorFlow and gym
-are not installable in the build container (no wheels, no network), so the reference's
-own classes cannot be executed here.  This oracle is therefore a *restatement* of the
-reference algorithm in PyTorch-CPU (eager, autograd standing in for ``tf.GradientTape``)
-that follows the reference's operation order line by line, citing each source location.
-It is pinned only by its own cross-checks (tests/test_oracle.py): fp32 vs fp64 twin,
-autograd vs hand-derived analytic backward (``analytic_update``), Fisher-vector product
-in double-backprop form vs J^T M J form, and one unit test per reference quirk.
-Exception: the GaussianActor entropy / logstd parameterisation and the TRPO line-search control
-flow (``backtrack``) ARE checked against outputs of the reference itself - the TRPO log it
-recorded in sac_eo/logs/TEMPLOG_0 (tests/golden/templog0_trpo_log.json).
+PARITY STATUS: PINNED TO THE REFERENCE'S PYTHON, NOT TO TENSORFLOW'S KERNELS.  The reference (noc-lab/sac-expert) is
+TensorFlow-2-eager Python and ships no tests, golden vectors or known-answer fixtures for this path; TensorFlow and gym
+are not installable in the build container (no wheels, no network).  This oracle is a *restatement* of the reference
+algorithm in PyTorch-CPU (eager, autograd standing in for ``tf.GradientTape``) that follows the reference's operation
+order line by line, citing each source location.  Since round 2 it is pinned against outputs of the reference's OWN,
+UNMODIFIED code: ``oracle/tfemu`` executes the ~55 TensorFlow / gym symbols the reference imports on torch-CPU, the
+reference's classes are imported from /root/reference and run over it (``tests/golden/make_golden_reference.py``), and
+``tests/test_reference_pin.py`` holds this oracle (and the CUDA path) to the resulting vectors ``tests/golden/ref_*.npz``:
+SAC_exp._update / SAC._update (3 consecutive updates, 1 / 2 / 0 models, both std parameterisations), BC._update,
+TRPO.update (gradient, expert blend, Fisher-vector product, fp32 CG, line search), PPO.update, _update_models +
+the adaptive expert weight, and the pure-NumPy TrajectoryBuffer / RunningNormalizers (bit-exact, no emulation involved).
+What stays a restatement is the semantics of the TensorFlow PRIMITIVES themselves (Keras Adam's formula, reduce_min /
+clip_by_value / maximum tie gradients, NumPy -> tensor dtype conversion, Dense) - listed with their TF sources in
+``oracle/tfemu/tensorflow/__init__.py``; a real-TensorFlow cross-check hook exists (``oracle/tf_reference.py``) but has
+never met a TensorFlow install.  Also checked against reference outputs: the GaussianActor entropy / logstd
+parameterisation and the TRPO line-search control flow against the TRPO log the reference recorded in
+sac_eo/logs/TEMPLOG_0 (tests/golden/templog0_trpo_log.json).  Own cross-checks (tests/test_oracle.py): fp32 vs fp64
+twin, autograd vs hand-derived analytic backward (``analytic_update``), Fisher-vector product in double-backprop form vs
+J^T M J form, one unit test per reference quirk.
 
 All citations are relative to /root/reference/ (read-only, absent on the GPU box).
 

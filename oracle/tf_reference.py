@@ -8,7 +8,8 @@ under ``baseline/_ref`` or ``/root/reference``); only when ALL are present this 
   (2) fills ``env_data`` / ``expert_data`` with the oracle problem's rows and weights,
   (3) runs ``SAC_exp._update`` once with a seeded global NumPy RNG and compares the updated parameters with
       ``oracle.sac_eo_update`` fed with the draws that the same RNG state produces (consumption order of SURVEY.md
-      App. A) - this is what would turn "parity unpinned" into "pinned",
+      App. A) - this would extend the pin of tests/test_reference_pin.py (reference code over oracle/tfemu) to
+      TensorFlow's own kernels,
   (4) times the reference's ``_update`` for the CPU arm (``cpu_baseline.kind = "reference (TF eager)"``).
 It has never been executed (no TensorFlow anywhere in this project's environments); every failure is reported to the
 caller as a reason string, never raised."""

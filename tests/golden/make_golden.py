@@ -6,7 +6,7 @@ It reads the two weight-bearing pickles the reference ships (the only data artef
 tests or golden vectors) and stores (a) the real trained Pendulum actor + running-normaliser statistics of
 /root/reference/sac_eo/logs/TEMPLOG_0 as inputs, and (b) outputs of the fp64 CPU oracle on those inputs.
 The reference itself (TensorFlow eager) cannot be executed here, so (b) pins the ORACLE, not the reference:
-parity stays "unpinned" in the sense of DESIGN.md.  /root/reference does not exist on the GPU box, hence
+the pins against the reference's own code are make_golden_reference.py's.  /root/reference does not exist on the GPU box, hence
 the fixtures are committed.
 """
 import os

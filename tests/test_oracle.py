@@ -1,5 +1,5 @@
-"""CPU tests pinning the ORACLE (it is the checker for the CUDA path; the reference ships no tests and
-cannot run here - parity unpinned, see oracle/sac_eo_oracle.py header): fp32 vs fp64 twin, autograd vs the
+"""CPU tests of the ORACLE's internal consistency (it is the checker for the CUDA path; the pins against the reference's
+own code are in tests/test_reference_pin.py, see oracle/sac_eo_oracle.py header): fp32 vs fp64 twin, autograd vs the
 hand-derived backward, both Fisher-vector forms, the committed golden fixtures, and one test per reference
 quirk (SURVEY.md §8a closing list)."""
 import math

@@ -10,5 +10,5 @@ timeout 240 ncu --profile-from-start off --set full --clock-control none -f -o /
   && ncu -i /tmp/${T}_step.ncu-rep --page raw --csv > gpurun_out/${T}_step_raw.csv 2>/dev/null \
   && python tools/traffic_from_ncu.py gpurun_out/${T}_step_raw.csv 256 profiles/r2_step_traffic.json && cp profiles/r2_step_traffic.json gpurun_out/${T}_step_traffic.json
 timeout 300 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py --steps 2 --warmup 3 > gpurun_out/${T}_ncu_bench.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1
 tail -4 gpurun_out/${T}_pin_tests.log; tail -3 gpurun_out/${T}_gpu_tests.log; tail -2 gpurun_out/${T}_smoke.log; cut -c1-300 gpurun_out/${T}_bench.json
