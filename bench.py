@@ -429,7 +429,7 @@ def run_b200(a):
         tr = json.load(open(tj))          # ncu dram__bytes_{read,write}.sum summed over the launches of one step
         if tr.get("source_hash") == source_hash():
             traffic = (tr["dram_read_bytes_per_step"] + tr["dram_write_bytes_per_step"]) / tr["agents"] * n_local
-            traffic_note = ("DRAM bytes per step from profiles/r2_step_traffic.json (ncu --set full, every launch of one step), "
+            traffic_note = ("DRAM bytes per step from profiles/r2_step_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of every launch of one step; capture command in the file's note), "
                             "taken with exactly these kernel sources (source hash %s)" % tr["source_hash"])
         else:
             traffic_note = ("profiles/r2_step_traffic.json was taken with other kernel sources (hash %s, now %s): not reported"
