@@ -75,7 +75,7 @@ class _Recorder:
         return False
 
 
-def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int, alg_type=None):
+def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int, alg_type=None, gaussian_logstd=None, setup_kw=None):
     from sac_eo.actors import init_actor
     from sac_eo.algs import init_alg
     from sac_eo.common.train_parser import create_train_parser
@@ -90,8 +90,9 @@ def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int, alg_type
               actor_per_state_std=cfg.per_state_std, actor_squash=True, actor_std_mult=cfg.std_mult)
     ck.update(critic_layers=list(cfg.critic_hidden), critic_activations=list(cfg.critic_acts), critic_weights=None)
     mk.update(model_layers=list(cfg.model_hidden), model_activations=list(cfg.model_acts), model_weights=None,
-              reward_weights=None, num_models=max(cfg.num_models, 1), gaussian_model=False)
+              reward_weights=None, num_models=max(cfg.num_models, 1), gaussian_model=gaussian_logstd is not None)
     msk.update(separate_reward_nn=cfg.separate_reward_nn, delta_clip_pred=cfg.delta_clip_pred or None)
+    msk.update(setup_kw or {})
     al.update(init_rms_stats=None, alg_seed=0, gamma=hyper["gamma"], soft_tau=hyper["tau"], q_crit_lr=hyper["lr_q"],
               mbpo_actor_lr=hyper["lr_pi"], mbpo_alpha_lr=hyper["lr_alpha"], sac_batch_size=B,
               target_update_int=target_update_int, only_model_normalizer=True, epsilon=hyper["eps"],
@@ -109,8 +110,9 @@ def build(cfg: NetCfg, st, replay, expert, hyper, B, target_update_int, alg_type
         net.set_weights([np.asarray(w) for w in st[key]])
     for net, key in zip(q_targets, ("t1", "t2")):
         net.set_weights([np.asarray(w) for w in st[key]])
-    for net, key in zip(models, ("m1", "m2")):
-        net.set_weights([np.asarray(w) for w in st[key]])
+    for k_, (net, key) in enumerate(zip(models, ("m1", "m2"))):
+        extra = [] if gaussian_logstd is None else [np.asarray(gaussian_logstd[k_], np.float32).reshape(1, -1)]
+        net.set_weights([np.asarray(w) for w in st[key]] + extra)
     alg.alpha.assign(float(st["alpha"]))
     import torch
     for opt, variables, key in ((alg.q_critic1_optimizer, q_critics[0].trainable, "adam_q1"),
@@ -343,13 +345,14 @@ def run_trpo_case(name, cfg: NetCfg, N, E, seed, eps, delta, cg_it, kl_maxfactor
           f"improve {float(out['log_improve']):.4g} |eta_v| {np.linalg.norm(out['eta_v_flat']):.4g}")
 
 
-def run_fit_case(name, cfg: NetCfg, n_rows, E, seed, epochs, mbs, max_grad_norm, lr):
+def run_fit_case(name, cfg: NetCfg, n_rows, E, seed, epochs, mbs, max_grad_norm, lr, gaussian=False, setup_kw=None):
     """``SAC_exp._update_models`` (SAC_expert.py:478-621: per-model shuffled minibatches, ``_apply_model_grads`` =
     summed losses, global-norm clip, ONE shared Keras Adam; then the MSE-on-expert bookkeeping) followed by
     ``_expert_preprocess`` with ``scale_epsilon_by_true_MSE`` (:375-404)."""
     st, replay, expert, hyper = make_problem(cfg, 8, E, n_rows, seed=seed, perturb=0.05)
-    alg, _ = build(cfg, st, replay, expert, hyper, 8, 1)
     rng = np.random.default_rng(seed + 900)
+    logstd = (0.4 * rng.standard_normal((2, cfg.S)) - 0.3).astype(np.float32) if gaussian else None
+    alg, _ = build(cfg, st, replay, expert, hyper, 8, 1, gaussian_logstd=logstd, setup_kw=setup_kw)
     expert["rE"] = rng.standard_normal(E).astype(np.float32)
     alg.model_data.add(replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
     alg.expert_data.add(expert["sE"], expert["aE"], expert["rE"], expert["spE"], np.zeros(E))
@@ -360,6 +363,11 @@ def run_fit_case(name, cfg: NetCfg, n_rows, E, seed, epochs, mbs, max_grad_norm,
     alg.model_optimizer = tf.keras.optimizers.Adam(learning_rate=lr)
     out = dict(meta=np.array([cfg.S, cfg.A, n_rows, E, seed, epochs, mbs], np.int64),
                hyper=np.array([max_grad_norm, lr], np.float64), in_expert_rE=expert["rE"])
+    if gaussian:
+        out["in_logstd"] = logstd
+        sk = dict(setup_kw or {})
+        out["setup"] = np.array([float(sk.get("reward_loss_coef", 1.0)), float(sk.get("delta_clip_loss") or 0.0),
+                                 float(bool(sk.get("scale_model_loss", False)))], np.float64)
     for k in ("actor", "m1", "m2"):
         for i, w in enumerate(st[k]):
             out[f"in_{k}_{i}"] = np.asarray(w, np.float32)
@@ -377,7 +385,9 @@ def run_fit_case(name, cfg: NetCfg, n_rows, E, seed, epochs, mbs, max_grad_norm,
     out["shuffles"] = np.stack([v for k, v in rec.calls if k == "shuffle"]).astype(np.int64)
     out["u_cf"] = rec.calls[-1][1]
     for k, mdl in zip(("m1", "m2"), alg.models):
-        out["theta_" + k] = flat(mdl.get_weights())
+        out["theta_" + k] = flat(mdl.get_weights()[:6])
+        if gaussian:
+            out["logstd_" + k] = np.asarray(mdl.get_weights()[6], np.float32).ravel()
     out["mse_expert"] = np.float64(alg.model_MSE_on_expert_data[-1])
     out["mse_counterfactual"] = np.float64(alg.model_MSE_on_expert_counterfactual_action[-1])
     # adaptive expert weight from the bookkeeping above (SAC_expert.py:381-404)
@@ -397,6 +407,10 @@ FIT_CASES = dict(
     # name: (cfg, rows, E, seed, epochs, minibatch, max_grad_norm, lr)
     fit_mse_relu=(NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2),
                   72, 8, 31, 2, 16, 0.05, 1e-3),
+    # GaussianModel.get_loss (continuous_models.py:101-131): trainable logstd in the joint optimiser, scale_model_loss
+    fit_gauss_tanh=(NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2,
+                           model_acts=("tanh", "relu")), 72, 8, 32, 2, 16, 0.5, 1e-3, True,
+                    dict(reward_loss_coef=0.5, delta_clip_loss=2.5, scale_model_loss=True)),
 )
 
 def run_bc_case(name, cfg: NetCfg, E, seed, K):

@@ -352,10 +352,16 @@ def test_cuda_reproduces_reference_trpo_update(name):
 FIT_CFG = NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2)
 
 
-def load_fit_case():
-    g = np.load(os.path.join(GOLD, "ref_fit_mse_relu.npz"))
+FIT_CFGS = dict(fit_mse_relu=FIT_CFG,
+                fit_gauss_tanh=NetCfg(S=5, A=2, actor_hidden=(16, 16), critic_hidden=(8, 8), model_hidden=(24, 24), num_models=2,
+                                      model_acts=("tanh", "relu")))
+
+
+def load_fit_case(name="fit_mse_relu"):
+    g = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    cfg = FIT_CFGS[name]
     S, A, n_rows, E, seed, epochs, mbs = (int(x) for x in g["meta"])
-    st, replay, expert, hyper = make_problem(FIT_CFG, 8, E, n_rows, seed=seed, perturb=0.05)
+    st, replay, expert, hyper = make_problem(cfg, 8, E, n_rows, seed=seed, perturb=0.05)
     for k in ("actor", "m1", "m2"):
         st[k] = [g[f"in_{k}_{i}"] for i in range(len(st[k]))]
     for k in ("s_mean", "s_std", "m_s_mean", "m_s_std", "m_a_mean", "m_a_std", "m_d_mean", "m_d_std"):
@@ -367,29 +373,40 @@ def load_fit_case():
         idx = g["shuffles"][2 * ep:2 * ep + 2]
         sec = np.array_split(idx, np.arange(0, n_rows, mbs)[1:], axis=1)
         batches += sec[:-1] if n_rows % mbs else sec
-    return g, st, replay, batches, dict(E=E, mgn=float(g["hyper"][0]), lr=float(g["hyper"][1]))
+    fit = dict(model_lr=float(g["hyper"][1]), model_max_grad_norm=float(g["hyper"][0]))
+    if "in_logstd" in g.files:
+        coef, dclip, scale = (float(x) for x in g["setup"])
+        fit.update(gaussian=True, reward_loss_coef=coef, delta_clip_loss=dclip, scale_model_loss=bool(scale))
+    return g, st, replay, batches, dict(E=E, mgn=float(g["hyper"][0]), lr=float(g["hyper"][1]), fit=fit, cfg=cfg)
 
 
-def test_oracle_reproduces_reference_model_fitting():
+@pytest.mark.parametrize("name", list(FIT_CFGS))
+def test_oracle_reproduces_reference_model_fitting(name):
     from oracle import sac_eo_oracle as O
-    g, st, replay, batches, m = load_fit_case()
+    g, st, replay, batches, m = load_fit_case(name)
+    cfg, fit = m["cfg"], m["fit"]
+    gauss = bool(fit.get("gaussian"))
     th = O.to_torch_state(st, torch.float32)
-    models = [th["m1"], th["m2"]]
+    models = [list(th["m1"]), list(th["m2"])]
+    if gauss:
+        models = [ml + [torch.as_tensor(g["in_logstd"][k])[None]] for k, ml in enumerate(models)]
     adam = dict(m=[[torch.zeros_like(w) for w in ml] for ml in models], v=[[torch.zeros_like(w) for w in ml] for ml in models], t=0)
-    fit = dict(model_lr=m["lr"], model_max_grad_norm=m["mgn"])
     clipped = 0
     for idx in batches:
         bs = [{k: torch.as_tensor(replay[k][idx[j]]) for k in ("s", "a", "sp", "r")} for j in range(2)]
-        o = O.apply_model_grads(FIT_CFG, models, adam, bs, th, fit)
+        o = O.apply_model_grads(cfg, models, adam, bs, th, fit)
         clipped += float(o["gnorm"]) > m["mgn"] * 2
         models, adam = o["models"], dict(m=o["m"], v=o["v"], t=o["t"])
     assert len(batches) == 8 and 0 < clipped                                  # the global-norm clip was active
     for k, ml in zip(("m1", "m2"), models):
         d0 = flat(st[k]).astype(np.float64)
-        assert rel(flat(ml).astype(np.float64) - d0, g["theta_" + k].astype(np.float64) - d0) < 2e-4, k
-    th["m1"], th["m2"] = models
-    mse_e = O.model_mse_on_expert(FIT_CFG, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"], use_expert_actions=True)
-    mse_c = O.model_mse_on_expert(FIT_CFG, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"],
+        assert rel(flat(ml[:6]).astype(np.float64) - d0, g["theta_" + k].astype(np.float64) - d0) < 2e-4, k
+        if gauss:
+            i = int(k[1]) - 1
+            assert rel(ml[6].numpy().ravel() - g["in_logstd"][i], g["logstd_" + k] - g["in_logstd"][i]) < 2e-4
+    th["m1"], th["m2"] = models[0][:6], models[1][:6]
+    mse_e = O.model_mse_on_expert(cfg, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"], use_expert_actions=True)
+    mse_c = O.model_mse_on_expert(cfg, th, g["in_expert_sE"], g["in_expert_aE"], g["in_expert_spE"],
                                   u=g["u_cf"].astype(np.float32))
     assert abs(float(mse_e) - float(g["mse_expert"])) < 1e-5 * float(g["mse_expert"])
     assert abs(float(mse_c) - float(g["mse_counterfactual"])) < 1e-5 * float(g["mse_counterfactual"])
@@ -401,28 +418,35 @@ def test_oracle_reproduces_reference_model_fitting():
 
 
 @pytest.mark.gpu
-def test_cuda_reproduces_reference_model_fitting():
+@pytest.mark.parametrize("name", list(FIT_CFGS))
+def test_cuda_reproduces_reference_model_fitting(name):
     """saceo_model_fit over the eight minibatches the reference's _update_models drew (per-model shuffles, global-norm
-    clip active, one joint Adam), then saceo_model_eval-free check of the final weights against the reference's."""
+    clip active, one joint Adam; MSE and Gaussian-NLL losses): final weights (and logstd) against the reference's."""
     from sac_expert_b200.population import Population
     from tests.helpers import spec_from_cfg
-    g, st, replay, batches, m = load_fit_case()
+    g, st, replay, batches, m = load_fit_case(name)
+    cfg, fit = m["cfg"], dict(m["fit"])
+    gauss = bool(fit.pop("gaussian", False))
     mbs = batches[0].shape[1]
-    pop = Population(spec_from_cfg(FIT_CFG, 1, 8, m["E"], len(replay["r"])))
-    pop.fit_bind(mbs, use_grad_clip=True)
-    _, _, _, hyper = make_problem(FIT_CFG, 8, m["E"], len(replay["r"]), seed=int(g["meta"][4]), perturb=0.05)
+    pop = Population(spec_from_cfg(cfg, 1, 8, m["E"], len(replay["r"])))
+    pop.fit_bind(mbs, use_grad_clip=True, gaussian=gauss, std_mult=1.0)
+    if gauss:
+        pop.t["model_logstd"].copy_(torch.as_tensor(g["in_logstd"])[None].to(pop.dev))
+    _, _, _, hyper = make_problem(cfg, 8, m["E"], len(replay["r"]), seed=int(g["meta"][4]), perturb=0.05)
     pop.load_agent(0, st, hyper)
     pop.append_rows(0, replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
-    pop.set_fit_hyper(0, model_lr=m["lr"], model_max_grad_norm=m["mgn"], r_mean=0.0, r_std=1.0)
+    pop.set_fit_hyper(0, r_mean=0.0, r_std=1.0, **fit)
     pop.model_fit(np.stack(batches)[:, None])                        # [steps, agent, model, minibatch]
     torch.cuda.synchronize()
     worst = 0.0
-    for k in ("m1", "m2"):
+    for i, k in enumerate(("m1", "m2")):
         d0 = flat(st[k]).astype(np.float64)
         e = rel(flat(pop.get_net(0, k)).astype(np.float64) - d0, g["theta_" + k].astype(np.float64) - d0)
+        if gauss:
+            e = max(e, rel(pop.t["model_logstd"][0, i].cpu().numpy() - g["in_logstd"][i], g["logstd_" + k] - g["in_logstd"][i]))
         worst = max(worst, e)
         assert e < 2e-3, (k, e)
-    print(f"\n[fit_mse_relu] dtheta vs reference {worst:.2e}")
+    print(f"\n[{name}] dtheta vs reference {worst:.2e}")
     pop.close()
 
 
