@@ -634,3 +634,67 @@ def test_oracle_reproduces_reference_ppo_update():
     assert float(g["log_actor_grad_norm_pre"]) > mgn and abs(float(g["log_actor_grad_norm"]) - mgn) < 1e-6   # clip active
     for k in ("ent", "tv", "kl", "outside_clip", "actor_grad_norm_pre", "actor_grad_norm"):
         assert abs(log[k] - float(g["log_" + k])) <= 2e-3 * max(abs(float(g["log_" + k])), 1e-3), (k, log[k], float(g["log_" + k]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the drop-in boundary itself: this repository's reference-named classes, driven like the reference's, same seeds
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu"])
+def test_mirror_classes_with_the_same_seeds_reproduce_the_reference(name):
+    """No injected draws here: the mirror ``init_actor / init_critics / init_world_models / init_alg`` objects are loaded
+    with the golden problem, the global NumPy RNG is seeded the way the generator seeded it for the reference's run
+    (``np.random.seed(1000 + seed)``, ``alg_seed = 0``), and ``alg._update(step[, expert_reg])`` is called K times - the
+    call a user of the reference makes.  Parameters after every update must equal what the reference's own classes
+    produced, which also proves that the two RNG streams are consumed identically."""
+    from sac_expert_b200 import lib as _lib
+    from sac_expert_b200.sac_eo.actors.init_actor import init_actor
+    from sac_expert_b200.sac_eo.algs.init_alg import init_alg
+    from sac_expert_b200.sac_eo.critics.init_critic import init_critics
+    from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
+    from sac_expert_b200.sac_eo.models.init_world_models import init_world_models
+    cfg, g, (st, replay, expert, hyper), m = load_case(name)
+    seed = int(g["meta"][5])
+    env = SyntheticEnv(cfg.S, cfg.A)
+    setup = dict(separate_reward_nn=False, reward_loss_coef=1.0, scale_model_loss=False, delta_clip_loss=None,
+                 reward_clip_loss=None, delta_clip_pred=cfg.delta_clip_pred or None, reward_clip_pred=None)
+    actor = init_actor(env, list(cfg.actor_hidden), list(cfg.actor_acts), 0.01, 1.0, "orthogonal", False, None,
+                       cfg.per_state_std, True, False)
+    critics, q_targets, q_critics = init_critics(env, list(cfg.critic_hidden), list(cfg.critic_acts), 1.0, None, 2, False,
+                                                 "orthogonal", False)
+    models = init_world_models(env, list(cfg.model_hidden), list(cfg.model_acts), 0.01, 1.0, None, list(cfg.model_hidden),
+                               list(cfg.model_acts), 0.01, None, max(m["nm"], 1), False, setup)
+    kw = dict(alg_type="sac_imit" if m["nm"] else "sac", sac_batch_size=m["B"], expert_buffer_size=m["E"], gamma=hyper["gamma"],
+              soft_tau=hyper["tau"], q_crit_lr=hyper["lr_q"], mbpo_actor_lr=hyper["lr_pi"], mbpo_alpha_lr=hyper["lr_alpha"],
+              alg_seed=0, epsilon=hyper["eps"], target_update_int=m["tui"], device_replay_capacity=m["N"],
+              env_buffer_size=m["N"], only_model_normalizer=True, gemm_mode=_lib.GEMM_FP32_SIMT)
+    alg = init_alg(0, env, env, env, actor, critics, q_targets, q_critics, models, kw, {}, None, None)
+    for nz, pre in ((alg.normalizer, ""), (alg.model_normalizer, "m_")):
+        nz.s_rms.mean, nz.s_rms.std = st[pre + "s_mean"].copy(), st[pre + "s_std"].copy()
+        nz.a_rms.mean, nz.a_rms.std = st[pre + "a_mean"].copy(), st[pre + "a_std"].copy()
+        for r_ in nz.get_rms():
+            r_.version += 1
+    alg.normalizer.ret_rms.std = np.float32(st["ret_std"])
+    alg.model_normalizer.delta_rms.mean, alg.model_normalizer.delta_rms.std = st["m_d_mean"].copy(), st["m_d_std"].copy()
+    alg._set_rms()
+    alg.pop.load_agent(0, st, hyper)                    # weights, Adam slots at t = 7, alpha; same normaliser record again
+    alg.env_data.add(replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    expert_reg = (expert["sE"], expert["aE"], expert["spE"], hyper["eps"], False)
+    np.random.seed(1000 + seed)
+    worst = 0.0
+    for step in range(m["K"]):
+        if m["nm"]:
+            alg._update(step, expert_reg)
+        else:
+            alg._update(step)
+        assert np.array_equal(alg.last_idx, g[f"step{step}_idx"])          # same minibatch as the reference drew
+        for k, net in (("actor", alg.actor), ("q1", alg.q_critics[0]), ("q2", alg.q_critics[1]),
+                       ("t1", alg.q_targets[0]), ("t2", alg.q_targets[1])):
+            got = flat(net.get_weights())
+            assert rel(got, g[f"step{step}_theta_{k}"]) < 2e-6, (k, step)
+            d0 = flat(st[k]).astype(np.float64)
+            e = rel(got.astype(np.float64) - d0, g[f"step{step}_theta_{k}"].astype(np.float64) - d0)
+            worst = max(worst, e)
+            assert e < 2e-3, (k, step, e)
+        assert abs(alg.alpha - float(g[f"step{step}_alpha"])) < 1e-6
+    print(f"\n[{name}] mirror classes, same seeds: worst dtheta vs reference {worst:.2e}")
