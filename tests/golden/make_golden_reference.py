@@ -549,6 +549,31 @@ PPO_CASES = dict(
                          actor_acts=("tanh", "tanh"), std_mult=0.7, num_models=0), 100, 51, 2, 4, 0.2, 0.5, 3e-3),
 )
 
+def run_disc_case(name="disc_saceo2"):
+    """``SAC_exp._calc_disc`` and the disagreement-scaled expert weight of ``_expert_preprocess`` (SAC_expert.py:405-460):
+    counterfactual actions ``tf_clip(actor.sample(sE))`` through BOTH models, row-wise L2 disagreement, max / median /
+    total, ``eps = 1 / (epsilon * max_disc + 1)``.  Same problem as the ``saceo2_relu`` case."""
+    import contextlib
+    cfg, B, E, N, seed, K, eps, tui, _, _ = CASES["saceo2_relu"]
+    st, replay, expert, hyper = make_problem(cfg, B, E, N, seed=seed, perturb=0.05)
+    hyper["eps"] = eps
+    alg, _ = build(cfg, st, replay, expert, hyper, B, tui)
+    alg.expert_data.add(expert["sE"], expert["aE"], np.zeros(E, np.float32), expert["spE"], np.zeros(E))
+    alg.scale_max_disc, alg.epsilon, alg.expert_batch_size = True, 2.0, None
+    out = dict(epsilon=np.float64(2.0))
+    np.random.seed(6000 + seed)
+    with _Recorder() as rec, contextlib.redirect_stdout(io.StringIO()):
+        reg = alg._expert_preprocess()
+        ratio, mx, med, tot = alg._calc_disc(expert["sE"], expert["aE"], expert["spE"])
+    assert [k for k, _ in rec.calls] == ["normal", "normal"]
+    out["u_pre"], out["u_disc"] = rec.calls[0][1], rec.calls[1][1]
+    out["epsilon_coef"] = np.float64(reg[3])
+    out["disc_ratio"], out["max_disc"], out["median_disc"], out["total_disc"] = (np.asarray(ratio), np.float64(mx),
+                                                                                 np.float64(med), np.float64(tot))
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
+    print(f"{name}: epsilon_coef {float(reg[3]):.6f} max {float(mx):.5f} median {float(med):.5f} total {float(tot):.5f}")
+
+
 TRPO_CASES = dict(
     # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
     trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
@@ -573,13 +598,15 @@ CASES = dict(
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES) + list(BC_CASES) + list(PPO_CASES)
-                 + ["host_buffers_normalizers"]):
+                 + ["host_buffers_normalizers", "disc_saceo2"]):
         if name in CASES:
             cfg, *rest = CASES[name]
             run_case(name, cfg, *rest)
         elif name in PPO_CASES:
             cfg, *rest = PPO_CASES[name]
             run_ppo_case(name, cfg, *rest)
+        elif name == "disc_saceo2":
+            run_disc_case()
         elif name == "host_buffers_normalizers":
             run_host_case()
         elif name in BC_CASES:

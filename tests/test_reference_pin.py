@@ -639,22 +639,14 @@ def test_oracle_reproduces_reference_ppo_update():
 # ---------------------------------------------------------------------------------------------------------------------
 # the drop-in boundary itself: this repository's reference-named classes, driven like the reference's, same seeds
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu"])
-def test_mirror_classes_with_the_same_seeds_reproduce_the_reference(name):
-    """No injected draws here: the mirror ``init_actor / init_critics / init_world_models / init_alg`` objects are loaded
-    with the golden problem, the global NumPy RNG is seeded the way the generator seeded it for the reference's run
-    (``np.random.seed(1000 + seed)``, ``alg_seed = 0``), and ``alg._update(step[, expert_reg])`` is called K times - the
-    call a user of the reference makes.  Parameters after every update must equal what the reference's own classes
-    produced, which also proves that the two RNG streams are consumed identically."""
+def _build_mirror(cfg, st, replay, expert, hyper, m):
+    """This repository's reference-named classes around a single-agent device population, loaded with a golden problem."""
     from sac_expert_b200 import lib as _lib
     from sac_expert_b200.sac_eo.actors.init_actor import init_actor
     from sac_expert_b200.sac_eo.algs.init_alg import init_alg
     from sac_expert_b200.sac_eo.critics.init_critic import init_critics
     from sac_expert_b200.sac_eo.envs.synthetic import SyntheticEnv
     from sac_expert_b200.sac_eo.models.init_world_models import init_world_models
-    cfg, g, (st, replay, expert, hyper), m = load_case(name)
-    seed = int(g["meta"][5])
     env = SyntheticEnv(cfg.S, cfg.A)
     setup = dict(separate_reward_nn=False, reward_loss_coef=1.0, scale_model_loss=False, delta_clip_loss=None,
                  reward_clip_loss=None, delta_clip_pred=cfg.delta_clip_pred or None, reward_clip_pred=None)
@@ -679,6 +671,20 @@ def test_mirror_classes_with_the_same_seeds_reproduce_the_reference(name):
     alg._set_rms()
     alg.pop.load_agent(0, st, hyper)                    # weights, Adam slots at t = 7, alpha; same normaliser record again
     alg.env_data.add(replay["s"], replay["a"], replay["r"], replay["sp"], replay["d"])
+    return alg
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu"])
+def test_mirror_classes_with_the_same_seeds_reproduce_the_reference(name):
+    """No injected draws here: the mirror ``init_actor / init_critics / init_world_models / init_alg`` objects are loaded
+    with the golden problem, the global NumPy RNG is seeded the way the generator seeded it for the reference's run
+    (``np.random.seed(1000 + seed)``, ``alg_seed = 0``), and ``alg._update(step[, expert_reg])`` is called K times - the
+    call a user of the reference makes.  Parameters after every update must equal what the reference's own classes
+    produced, which also proves that the two RNG streams are consumed identically."""
+    cfg, g, (st, replay, expert, hyper), m = load_case(name)
+    seed = int(g["meta"][5])
+    alg = _build_mirror(cfg, st, replay, expert, hyper, m)
     expert_reg = (expert["sE"], expert["aE"], expert["spE"], hyper["eps"], False)
     np.random.seed(1000 + seed)
     worst = 0.0
@@ -698,3 +704,45 @@ def test_mirror_classes_with_the_same_seeds_reproduce_the_reference(name):
             assert e < 2e-3, (k, step, e)
         assert abs(alg.alpha - float(g[f"step{step}_alpha"])) < 1e-6
     print(f"\n[{name}] mirror classes, same seeds: worst dtheta vs reference {worst:.2e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SAC_exp._calc_disc / disagreement-scaled expert weight (SAC_expert.py:405-460) - row a13
+# ---------------------------------------------------------------------------------------------------------------------
+def test_oracle_reproduces_reference_model_disagreement():
+    from oracle import sac_eo_oracle as O
+    cfg, _, (st, replay, expert, hyper), m = load_case("saceo2_relu")
+    g = np.load(os.path.join(GOLD, "ref_disc_saceo2.npz"))
+    th = O.to_torch_state(st, torch.float32)
+    sE = torch.as_tensor(expert["sE"])
+    with torch.no_grad():
+        for u, check_eps in ((g["u_pre"], True), (g["u_disc"], False)):
+            act, _ = O.head(cfg, th["actor"], sE, torch.as_tensor(u.astype(np.float32)), th)
+            act = torch.clamp(act, -1.0, 1.0)                                   # tf_clip to the action limits (:438)
+            disc = torch.linalg.norm(O.model_sample(cfg, th["m1"], sE, act, th) - O.model_sample(cfg, th["m2"], sE, act, th), dim=1).numpy()
+            if check_eps:
+                assert abs(1 / (float(g["epsilon"]) * float(disc.max()) + 1) - float(g["epsilon_coef"])) < 1e-6
+            else:
+                assert rel(disc / disc.sum(), g["disc_ratio"]) < 1e-5
+                assert abs(disc.max() - float(g["max_disc"])) < 1e-6 and abs(np.median(disc) - float(g["median_disc"])) < 1e-6
+                assert abs(disc.sum() - float(g["total_disc"])) < 1e-5
+
+
+@pytest.mark.gpu
+def test_mirror_expert_preprocess_disagreement_matches_reference():
+    """``alg._expert_preprocess()`` with ``scale_max_disc`` and ``alg._calc_disc`` of the reference-named classes (device
+    forwards of the actor and both models), seeded like the reference's run."""
+    cfg, _, (st, replay, expert, hyper), m = load_case("saceo2_relu")
+    g = np.load(os.path.join(GOLD, "ref_disc_saceo2.npz"))
+    alg = _build_mirror(cfg, st, replay, expert, hyper, m)
+    E = m["E"]
+    alg.expert_data.add(expert["sE"], expert["aE"], np.zeros(E, np.float32), expert["spE"], np.zeros(E))
+    alg.scale_max_disc, alg.epsilon, alg.expert_batch_size = True, float(g["epsilon"]), None
+    np.random.seed(6000 + 11)
+    reg = alg._expert_preprocess()
+    ratio, mx, med, tot = alg._calc_disc(expert["sE"], expert["aE"], expert["spE"])
+    assert abs(reg[3] - float(g["epsilon_coef"])) < 1e-5 and reg[4] is False
+    assert rel(ratio, g["disc_ratio"]) < 1e-4
+    for got, key in ((mx, "max_disc"), (med, "median_disc"), (tot, "total_disc")):
+        assert abs(got - float(g[key])) < 1e-4 * float(g[key]), key
+    print(f"\n[disc_saceo2] eps {reg[3]:.6f} vs {float(g['epsilon_coef']):.6f}, ratio {rel(ratio, g['disc_ratio']):.2e}")
