@@ -593,6 +593,9 @@ CASES = dict(
     sac_plain_relu=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(8, 8),
                            num_models=0), 32, 8, 300, 13, 3, 0.0, 2, True, 0),
     saceo2_hopper_256=(NetCfg(S=11, A=3), 256, 20, 2000, 14, 2, 1e-3, 1, False, 48),
+    # separate_reward_nn (base_world_model.py:34-41, 72-74): the dynamics net predicts the S delta columns only
+    saceo2_sepreward=(NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(32, 24), num_models=2,
+                             separate_reward_nn=True, model_acts=("elu", "tanh")), 32, 8, 300, 15, 2, 0.4, 1, True, 0),
 )
 
 

@@ -24,6 +24,8 @@ CFGS = dict(
                                per_state_std=False, num_models=1, delta_clip_pred=0.05),
     sac_plain_relu=NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(8, 8), num_models=0),
     saceo2_hopper_256=NetCfg(S=11, A=3),
+    saceo2_sepreward=NetCfg(S=5, A=2, actor_hidden=(32, 24), critic_hidden=(32, 24), model_hidden=(32, 24), num_models=2,
+                            separate_reward_nn=True, model_acts=("elu", "tanh")),
 )
 NETS = ("actor", "q1", "q2", "t1", "t2")
 
