@@ -489,8 +489,56 @@ def run_host_case(name="host_buffers_normalizers"):
     x = rng.standard_normal((5, S)).astype(np.float32)
     out["norm_x"], out["norm_y"] = x, nz.s_rms.normalize(x)
     out["denorm_y"] = nz.delta_rms.denormalize(x)
+    # ---- trajectory_sampler (samplers.py:3-77) on a deterministic stub environment / actor --------------------------------
+    from sac_eo.common.samplers import trajectory_sampler
+    for tag, (horizon, term_at, ev) in dict(trunc=(6, None, True), term=(9, 4, True), plain=(5, None, False)).items():
+        res = trajectory_sampler(StubEnv(S, term_at), StubActor(A), horizon, eval=ev)
+        for k, v in zip(("s", "a", "r", "sp", "d", "J"), res):
+            out[f"samp_{tag}_{k}"] = np.asarray(v)
+    # ---- the command line: every flag of the reference's parser with its default (train_parser.py) ---------------------
+    import json
+    from sac_eo.common.train_parser import create_train_parser, all_kwargs
+    args = vars(create_train_parser().parse_args([]))
+    json.dump(dict(defaults={k: (v if isinstance(v, (int, float, str, bool, list, type(None))) else repr(v)) for k, v in args.items()},
+                   groups={k: list(v) for k, v in all_kwargs.items()}),
+              open(os.path.join(OUT, "ref_train_parser.json"), "w"), indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **out)
-    print(f"{name}: buffer size {buf.current_size}, s_rms.std {nz.s_rms.std}")
+    print(f"{name}: buffer size {buf.current_size}, s_rms.std {nz.s_rms.std}, {len(args)} parser flags")
+
+
+class StubEnv:
+    """Deterministic linear environment for the sampler pin (shared with tests/test_reference_pin.py by construction)."""
+
+    def __init__(self, S, term_at=None):
+        self.S, self.term_at, self.t = S, term_at, 0
+
+    def reset(self, s_init=None):
+        self.t = 0
+        self.s = np.arange(self.S, dtype=np.float64) * 0.1 if s_init is None else np.asarray(s_init, np.float64)
+        return self.s
+
+    def step(self, a):
+        self.t += 1
+        self.s = 0.9 * self.s + 0.05 * float(np.sum(a)) + 0.01 * self.t
+        return self.s, float(np.sum(self.s)) * 0.5, (self.term_at is not None and self.t >= self.term_at), {}
+
+
+class StubActor:
+    class _T:
+        def __init__(self, v):
+            self.v = v
+
+        def numpy(self):
+            return self.v
+
+    def __init__(self, A):
+        self.A = A
+
+    def sample(self, s, deterministic=False):
+        return self._T(np.tanh(np.asarray(s, np.float64)[:self.A] * 3.0) * 1.5)
+
+    def clip(self, a):
+        return np.clip(a, -1.0, 1.0)
 
 
 def run_ppo_case(name, cfg: NetCfg, N, seed, update_it, nminibatch, eps_ppo, max_grad_norm, lr):

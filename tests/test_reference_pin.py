@@ -748,3 +748,73 @@ def test_mirror_expert_preprocess_disagreement_matches_reference():
     for got, key in ((mx, "max_disc"), (med, "median_disc"), (tot, "total_disc")):
         assert abs(got - float(g[key])) < 1e-4 * float(g[key]), key
     print(f"\n[disc_saceo2] eps {reg[3]:.6f} vs {float(g['epsilon_coef']):.6f}, ratio {rel(ratio, g['disc_ratio']):.2e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the callers either side of the path: trajectory_sampler and the command line (pure Python in the reference)
+# ---------------------------------------------------------------------------------------------------------------------
+class _StubEnv:
+    """Same deterministic environment as tests/golden/make_golden_reference.py::StubEnv."""
+
+    def __init__(self, S, term_at=None):
+        self.S, self.term_at, self.t = S, term_at, 0
+
+    def reset(self, s_init=None):
+        self.t = 0
+        self.s = np.arange(self.S, dtype=np.float64) * 0.1 if s_init is None else np.asarray(s_init, np.float64)
+        return self.s
+
+    def step(self, a):
+        self.t += 1
+        self.s = 0.9 * self.s + 0.05 * float(np.sum(a)) + 0.01 * self.t
+        return self.s, float(np.sum(self.s)) * 0.5, (self.term_at is not None and self.t >= self.term_at), {}
+
+
+class _StubActor:
+    class _T:
+        def __init__(self, v):
+            self.v = v
+
+        def numpy(self):
+            return self.v
+
+    def __init__(self, A):
+        self.A = A
+
+    def sample(self, s, deterministic=False):
+        return self._T(np.tanh(np.asarray(s, np.float64)[:self.A] * 3.0) * 1.5)
+
+    def clip(self, a):
+        return np.clip(a, -1.0, 1.0)
+
+
+def test_mirror_trajectory_sampler_matches_reference_bitwise():
+    """Time-limit truncation (last done forced False), early termination, eval return: the reference's own
+    trajectory_sampler on a stub environment vs the mirror's, byte for byte."""
+    from sac_expert_b200.sac_eo.common.samplers import trajectory_sampler
+    g = np.load(os.path.join(GOLD, "ref_host_buffers_normalizers.npz"))
+    S, A, _ = (int(x) for x in g["meta"])
+    for tag, (horizon, term_at, ev) in dict(trunc=(6, None, True), term=(9, 4, True), plain=(5, None, False)).items():
+        res = trajectory_sampler(_StubEnv(S, term_at), _StubActor(A), horizon, eval=ev)
+        assert len(res) == (6 if ev else 5)
+        for k, v in zip(("s", "a", "r", "sp", "d", "J"), res):
+            want = g[f"samp_{tag}_{k}"]
+            got = np.asarray(v)
+            assert got.dtype == want.dtype and got.shape == want.shape and got.tobytes() == want.tobytes(), (tag, k)
+    assert len(g["samp_term_r"]) == 4 and bool(g["samp_term_d"][-1]) and not bool(g["samp_trunc_d"][-1])
+
+
+def test_mirror_command_line_has_every_reference_flag_with_its_default():
+    """Every one of the reference parser's 135 flags exists in the mirror parser with the same default, and the kwargs
+    groups ``gather_inputs`` builds (train_parser.py: all_kwargs) hold the same keys - ``train.py``'s argument set."""
+    import json
+    from sac_expert_b200.sac_eo.common.train_parser import all_kwargs, create_train_parser
+    ref = json.load(open(os.path.join(GOLD, "ref_train_parser.json")))
+    mine = vars(create_train_parser().parse_args([]))
+    missing = sorted(set(ref["defaults"]) - set(mine))
+    assert not missing, missing
+    diff = {k: (mine[k], v) for k, v in ref["defaults"].items()
+            if (mine[k] if isinstance(mine[k], (int, float, str, bool, list, type(None))) else repr(mine[k])) != v}
+    assert not diff, diff
+    for grp, keys in ref["groups"].items():
+        assert grp in all_kwargs and set(keys) <= set(all_kwargs[grp]), grp
