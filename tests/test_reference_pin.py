@@ -228,9 +228,10 @@ def test_cuda_fp32_engine_reproduces_reference_updates(name):
 def test_cuda_tcgen05_engine_reproduces_reference_updates_hopper():
     """The benchmarked engine (tcgen05 fp16 hi/lo x3, fused kernels, CUDA graph) at the Hopper benchmark shape (2x256
     / 2x512, B = 256, E = 20), two consecutive updates vs the reference's own outputs through fixed random projections of
-    the gradients and of Δθ."""
+    the gradients and of Δθ.  Measured: gradients 1e-6 ... 1.4e-4 (q1: one ReLU unit on the other side of zero, DESIGN.md 4
+    "ReLU masks"), Δθ <= 8e-5; bounds 5e-4 / 5e-3 as for every ReLU case on this engine."""
     print("\n[saceo2_hopper_256] %s" % {k: float("%.2e" % v) for k, v in
-                                        _device_run("saceo2_hopper_256", "GEMM_TCGEN05_BF16X3", True, 2e-4, None, 5e-3).items()})
+                                        _device_run("saceo2_hopper_256", "GEMM_TCGEN05_BF16X3", True, 5e-4, None, 5e-3).items()})
 
 
 # ---------------------------------------------------------------------------------------------------------------------
