@@ -304,9 +304,10 @@ def _T(x, hint=None):
     return x if isinstance(x, Tensor) else Tensor(_raw(x, hint))
 
 
-def _f32(x):
-    """Argument of a float op: tensors as they are, NumPy / Python values as float32 unless they are float64 ARRAYS
-    (tf.square(np.float64 array) stays float64, like convert_to_tensor without a hint)."""
+def _arg(x):
+    """Argument of a unary op / reduction as a raw torch tensor (convert_to_tensor WITHOUT a dtype hint): tensors as they
+    are, Python scalars as float32, NumPy arrays and NumPy scalars in their own dtype (tf.square(np.float64 array) stays
+    float64), sequences that contain Tensors stacked in the first Tensor's dtype."""
     if isinstance(x, Tensor):
         return x._t
     a = _np.asarray(x) if not isinstance(x, (list, tuple)) or not any(isinstance(e, Tensor) for e in _flatten(x)) else None
@@ -366,7 +367,7 @@ class GradientTape:
 
 
 def stop_gradient(x):
-    return Tensor(_f32(x).detach())
+    return Tensor(_arg(x).detach())
 
 
 def function(fn=None, **kw):
@@ -381,7 +382,7 @@ def _axis(axis):
 
 
 def _reduce(fn, x, axis, keepdims):
-    t = _f32(x)
+    t = _arg(x)
     ax = _axis(axis)
     if ax is None:
         r = fn(t)
@@ -406,13 +407,13 @@ def reduce_max(x, axis=None, keepdims=False):
 
 
 def reduce_logsumexp(x, axis=None, keepdims=False):
-    t = _f32(x)
+    t = _arg(x)
     ax = _axis(axis)
     return Tensor(_torch.logsumexp(t, dim=tuple(range(t.dim())) if ax is None else ax, keepdim=keepdims))
 
 
 def reduce_euclidean_norm(x, axis=None, keepdims=False):
-    t = _f32(x)
+    t = _arg(x)
     return Tensor(_torch.sqrt(_torch.sum(t * t, dim=_axis(axis), keepdim=keepdims)) if axis is not None
                   else _torch.sqrt(_torch.sum(t * t)))
 
@@ -423,35 +424,35 @@ def norm(x, ord="euclidean", axis=None, keepdims=False):
 
 
 def square(x):
-    t = _f32(x); return Tensor(t * t)
+    t = _arg(x); return Tensor(t * t)
 
 
 def exp(x):
-    return Tensor(_torch.exp(_f32(x)))
+    return Tensor(_torch.exp(_arg(x)))
 
 
 def log(x):
-    return Tensor(_torch.log(_f32(x)))
+    return Tensor(_torch.log(_arg(x)))
 
 
 def sqrt(x):
-    return Tensor(_torch.sqrt(_f32(x)))
+    return Tensor(_torch.sqrt(_arg(x)))
 
 
 def abs(x):                                                   # noqa: A001
-    return Tensor(_torch.abs(_f32(x)))
+    return Tensor(_torch.abs(_arg(x)))
 
 
 def tanh(x):
-    return Tensor(_torch.tanh(_f32(x)))
+    return Tensor(_torch.tanh(_arg(x)))
 
 
 def atanh(x):
-    return Tensor(_torch.atanh(_f32(x)))
+    return Tensor(_torch.atanh(_arg(x)))
 
 
 def softplus(x):
-    return Tensor(_softplus(_f32(x)))
+    return Tensor(_softplus(_arg(x)))
 
 
 def _softplus(t):
@@ -488,7 +489,7 @@ def maximum(x, y):
     if isinstance(x, Tensor) or isinstance(y, Tensor):
         a, b = _pair(x, y)
     else:
-        a, b = _f32(x), _f32(y)
+        a, b = _arg(x), _arg(y)
         b = b.to(a.dtype)
     return Tensor(_MaxGrad.apply(a, b))
 
@@ -512,14 +513,14 @@ class _ClipGrad(_torch.autograd.Function):
 
 
 def clip_by_value(t, clip_value_min, clip_value_max):
-    x = _f32(t)
+    x = _arg(t)
     lo = _raw(clip_value_min, x.dtype).detach()
     hi = _raw(clip_value_max, x.dtype).detach()
     return Tensor(_ClipGrad.apply(x, lo, hi))
 
 
 def global_norm(t_list):
-    ts = [_f32(t) for t in t_list if t is not None]
+    ts = [_arg(t) for t in t_list if t is not None]
     return Tensor(_torch.sqrt(sum(_torch.sum(t * t) for t in ts)))
 
 
@@ -528,11 +529,11 @@ def clip_by_global_norm(t_list, clip_norm, use_norm=None):
     gn = global_norm(t_list) if use_norm is None else _T(use_norm)
     c = _raw(clip_norm, gn._t.dtype)
     scale = c * _torch.minimum(1.0 / gn._t, 1.0 / c)
-    return [None if t is None else Tensor(_f32(t) * scale) for t in t_list], gn
+    return [None if t is None else Tensor(_arg(t) * scale) for t in t_list], gn
 
 
 def squeeze(x, axis=None):
-    t = _f32(x)
+    t = _arg(x)
     if axis is None:
         return Tensor(t.squeeze())
     ax = _axis(axis)
@@ -544,18 +545,18 @@ def squeeze(x, axis=None):
 
 
 def expand_dims(x, axis):
-    return Tensor(_f32(x).unsqueeze(builtins.int(axis)))
+    return Tensor(_arg(x).unsqueeze(builtins.int(axis)))
 
 
 def reshape(x, shape):
-    return Tensor(_f32(x).reshape([builtins.int(s) for s in shape]))
+    return Tensor(_arg(x).reshape([builtins.int(s) for s in shape]))
 
 
 def _seq(values):
     vals = list(values)
     first = next((v for v in vals if isinstance(v, Tensor)), None)
     if first is None:
-        ts = [_f32(v) for v in vals]
+        ts = [_arg(v) for v in vals]
         return [t.to(ts[0].dtype) for t in ts]
     return [_raw(v, first._t.dtype) if not isinstance(v, Tensor) else v._t for v in vals]
 
@@ -572,7 +573,7 @@ def stack(values, axis=0):
 
 
 def split(value, num_or_size_splits, axis=0):
-    t = _f32(value)
+    t = _arg(value)
     if isinstance(num_or_size_splits, builtins.int):
         assert t.shape[axis] % num_or_size_splits == 0
         return [Tensor(p) for p in _torch.split(t, t.shape[axis] // num_or_size_splits, dim=axis)]
@@ -616,23 +617,23 @@ def zeros(shape, dtype=float32):
 
 
 def ones_like(x, dtype=None):
-    return Tensor(_torch.ones_like(_f32(x).detach(), dtype=_tdtype(dtype)))
+    return Tensor(_torch.ones_like(_arg(x).detach(), dtype=_tdtype(dtype)))
 
 
 def zeros_like(x, dtype=None):
-    return Tensor(_torch.zeros_like(_f32(x).detach(), dtype=_tdtype(dtype)))
+    return Tensor(_torch.zeros_like(_arg(x).detach(), dtype=_tdtype(dtype)))
 
 
 def shape(x):
-    return Tensor(_torch.tensor(list(_f32(x).shape), dtype=_torch.int32))
+    return Tensor(_torch.tensor(list(_arg(x).shape), dtype=_torch.int32))
 
 
 def size(x):
-    return Tensor(_torch.tensor(_f32(x).numel(), dtype=_torch.int32))
+    return Tensor(_torch.tensor(_arg(x).numel(), dtype=_torch.int32))
 
 
 def argmax(x, axis=None):
-    return Tensor(_torch.argmax(_f32(x), dim=0 if axis is None else builtins.int(axis)))
+    return Tensor(_torch.argmax(_arg(x), dim=0 if axis is None else builtins.int(axis)))
 
 
 def one_hot(indices, depth, dtype=float32):
@@ -656,15 +657,15 @@ def _module(name, **members):
 
 
 def _relu(x):
-    return Tensor(_torch.relu(_f32(x)))
+    return Tensor(_torch.relu(_arg(x)))
 
 
 def _elu(x):
-    return Tensor(_torch.nn.functional.elu(_f32(x)))
+    return Tensor(_torch.nn.functional.elu(_arg(x)))
 
 
 def _softmax_xent(labels, logits, axis=-1):
-    lg = _f32(logits)
+    lg = _arg(logits)
     return Tensor(-_torch.sum(_raw(labels, lg.dtype) * _torch.log_softmax(lg, dim=axis), dim=axis))
 
 
@@ -768,7 +769,7 @@ class Dense(_Layer):
         return [self.kernel, self.bias]
 
     def __call__(self, x):
-        y = Tensor(_f32(x) @ self.kernel._t + self.bias._t)
+        y = Tensor(_arg(x) @ self.kernel._t + self.bias._t)
         return self.activation(y) if self.activation is not None else y
 
 
@@ -788,7 +789,7 @@ class LayerNormalization(_Layer):
         return [self.gamma, self.beta]
 
     def __call__(self, x):
-        t = _f32(x)
+        t = _arg(x)
         mu = t.mean(-1, keepdim=True)
         var = ((t - mu) ** 2).mean(-1, keepdim=True)
         return Tensor((t - mu) * _torch.rsqrt(var + self.eps) * self.gamma._t + self.beta._t)
@@ -875,14 +876,14 @@ class Adam:
 
     def apply_gradients(self, grads_and_vars):
         gv = [(g, v) for g, v in grads_and_vars]
-        self.last_grads = [None if g is None else _np.array(_f32(g).detach().numpy()) for g, _ in gv]
+        self.last_grads = [None if g is None else _np.array(_arg(g).detach().numpy()) for g, _ in gv]
         self.iterations += 1
         t = self.iterations
         for g, var in gv:
             if g is None:
                 continue
             dt = var._t.dtype
-            g = _f32(g).detach().to(dt).reshape(var._t.shape)
+            g = _arg(g).detach().to(dt).reshape(var._t.shape)
             if id(var) not in self.slots:
                 self.slots[id(var)] = (_torch.zeros_like(var._t), _torch.zeros_like(var._t))
             m, v = self.slots[id(var)]
