@@ -622,6 +622,73 @@ def run_disc_case(name="disc_saceo2"):
     print(f"{name}: epsilon_coef {float(reg[3]):.6f} max {float(mx):.5f} median {float(med):.5f} total {float(tot):.5f}")
 
 
+def run_quirks(name="quirks"):
+    """Behaviours of the reference that DESIGN.md / the oracle docstrings cite, observed by running its code: which
+    call patterns raise.  Stored as exception type names (the emulation raises Python / torch errors where TensorFlow
+    would raise its own; only "raises or not" and the Python-level error names are meaningful)."""
+    import json
+    rec = {}
+
+    def attempt(key, fn):
+        try:
+            fn()
+            rec[key] = None
+        except Exception as e:                                  # noqa: BLE001 - the type is the datum
+            rec[key] = type(e).__name__
+
+    # TRPO.update without expert_reg: grad_final is only defined inside the expert branches (trpo.py:107-111, 154-158)
+    cfg, N, E, seed, eps, delta, cg_it, klf, damp = TRPO_CASES["trpo_psd_tanh"]
+    import torch
+    from sac_eo.actors import init_actor
+    from sac_eo.algs.model_free import trpo as trpo_mod
+    from sac_eo.common.normalizer import RunningNormalizers
+    from sac_eo.common.train_parser import create_train_parser
+    from sac_eo.common.train_utils import gather_inputs
+    from sac_eo.models import init_world_models
+    st, replay, expert, hyper = make_problem(cfg, 8, E, 300, seed=seed, perturb=0.2)
+    inputs = gather_inputs(create_train_parser().parse_args(["--alg_type", "mbrl"]))
+    ak, mk, msk, uk = (inputs[k] for k in ("actor_kwargs", "model_kwargs", "model_setup_kwargs", "mf_update_kwargs"))
+    ak.update(actor_layers=list(cfg.actor_hidden), actor_activations=list(cfg.actor_acts), actor_weights=None,
+              actor_per_state_std=True, actor_squash=False)
+    mk.update(model_layers=list(cfg.model_hidden), model_activations=list(cfg.model_acts), model_weights=None,
+              reward_weights=None, num_models=2, gaussian_model=False)
+    uk.update(ent_reg=False, ent_targ=-cfg.A)
+    env = _Env(cfg.S, cfg.A)
+    actor = init_actor(env, **ak)
+    models = init_world_models(env, **mk, model_setup_kwargs=msk)
+    nz = RunningNormalizers(cfg.S, cfg.A, 0.99)
+    actor.set_rms(nz)
+    for m_ in models:
+        m_.set_rms(nz)
+    algo = trpo_mod.TRPO(actor, uk)
+    s_all = replay["s"][:32]
+    a_all = np.random.default_rng(0).uniform(-1, 1, (32, cfg.A)).astype(np.float32)
+    adv = np.random.default_rng(1).standard_normal(32).astype(np.float32)
+    roll = (s_all, a_all, adv, None, None, None)
+
+    class _Rng:
+        def shuffle(self_, v):
+            np.random.default_rng(0).shuffle(v)
+    np.random.seed(0)
+    attempt("trpo_update_without_expert_reg", lambda: algo.update(roll))
+    attempt("trpo_update_one_model_branch",
+            lambda: algo.update(roll, (expert["sE"], expert["aE"], expert["spE"], 0.3, models[:1], False, _Rng())))
+    attempt("trpo_update_two_model_branch",
+            lambda: algo.update(roll, (expert["sE"], expert["aE"], expert["spE"], 0.3, models, False, _Rng())))
+    # SAC-EO two-model branch with an odd number of expert rows: the two halves differ in length (SAC_expert.py:329-332)
+    cfg2, B, E2, N2, seed2, K, eps2, tui, _, _ = CASES["saceo2_relu"]
+    st2, replay2, expert2, hyper2 = make_problem(cfg2, B, 7, N2, seed=seed2, perturb=0.05)
+    alg, reg = build(cfg2, st2, replay2, expert2, hyper2, B, tui)
+    attempt("saceo_update_odd_expert_rows_two_models", lambda: alg._update(0, reg))
+    st3, replay3, expert3, hyper3 = make_problem(cfg2, B, 8, N2, seed=seed2, perturb=0.05)
+    alg, reg = build(cfg2, st3, replay3, expert3, hyper3, B, tui)
+    alg.alpha.assign(-3.0)                                      # raw temperature may be negative; clamped AFTER its step (:348)
+    attempt("saceo_update_even_expert_rows_two_models", lambda: alg._update(0, reg))
+    rec["alpha_after_update_from_minus_3"] = float(alg.alpha.numpy())
+    json.dump(rec, open(os.path.join(OUT, "ref_quirks.json"), "w"), indent=1, sort_keys=True)
+    print(name, rec)
+
+
 TRPO_CASES = dict(
     # name: (cfg, N, E, seed, eps, delta, cg_it, kl_maxfactor, trust_damp)
     trpo_psd_tanh=(NetCfg(S=9, A=3, actor_hidden=(32, 24), critic_hidden=(8, 8), model_hidden=(24, 24), per_state_std=True,
@@ -649,13 +716,15 @@ CASES = dict(
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES) + list(TRPO_CASES) + list(FIT_CASES) + list(BC_CASES) + list(PPO_CASES)
-                 + ["host_buffers_normalizers", "disc_saceo2"]):
+                 + ["host_buffers_normalizers", "disc_saceo2", "quirks"]):
         if name in CASES:
             cfg, *rest = CASES[name]
             run_case(name, cfg, *rest)
         elif name in PPO_CASES:
             cfg, *rest = PPO_CASES[name]
             run_ppo_case(name, cfg, *rest)
+        elif name == "quirks":
+            run_quirks()
         elif name == "disc_saceo2":
             run_disc_case()
         elif name == "host_buffers_normalizers":

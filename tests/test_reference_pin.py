@@ -819,3 +819,24 @@ def test_mirror_command_line_has_every_reference_flag_with_its_default():
     assert not diff, diff
     for grp, keys in ref["groups"].items():
         assert grp in all_kwargs and set(keys) <= set(all_kwargs[grp]), grp
+
+
+def test_reference_quirks_observed_by_running_it():
+    """What DESIGN.md and the oracle docstrings say the reference does in its corner cases, as recorded from its own
+    code (tests/golden/ref_quirks.json), and the oracle's matching behaviour."""
+    import json
+    q = json.load(open(os.path.join(GOLD, "ref_quirks.json")))
+    assert q["trpo_update_without_expert_reg"] == "UnboundLocalError"       # grad_final exists only in the expert branches
+    assert q["trpo_update_one_model_branch"] == "TypeError"                # epsilon * None (MSE_alpha_grad), trpo.py:111
+    assert q["trpo_update_two_model_branch"] is None
+    assert q["saceo_update_odd_expert_rows_two_models"] is not None        # halves of different length cannot be added
+    assert q["saceo_update_even_expert_rows_two_models"] is None
+    assert q["alpha_after_update_from_minus_3"] == float(np.float32(1e-5))  # raw alpha clamped AFTER its Adam step (:348)
+    cfg, g, (st, replay, expert, hyper), m = load_case("saceo2_relu")
+    b = step_batch(g, 0, replay, expert, m)
+    state = to_torch_state(st, torch.float32)
+    state["alpha"] = torch.tensor(-3.0)
+    assert float(sac_eo_update(cfg, state, b, hyper)["new"]["alpha"]) == float(np.float32(1e-5))
+    b["I2"], b["u4"] = b["I2"][:-1], b["u4"][:-1]                           # 4 + 3 expert rows
+    with pytest.raises(RuntimeError):
+        sac_eo_update(cfg, to_torch_state(st, torch.float32), b, hyper)
