@@ -218,7 +218,7 @@ def _device_run(name, gemm_mode, use_graph, tol_g, tol_theta, tol_dtheta):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu"])
+@pytest.mark.parametrize("name", ["saceo2_relu", "saceo1_tanh_elu_sis", "sac_plain_relu", "saceo2_sepreward"])
 def test_cuda_fp32_engine_reproduces_reference_updates(name):
     """Three consecutive updates on the fp32 engine vs the reference's own outputs (gradients 2e-5, θ 1e-6, Δθ 2e-3)."""
     print("\n[%s] %s" % (name, {k: float("%.2e" % v) for k, v in _device_run(name, "GEMM_FP32_SIMT", False, 2e-5, 2e-6, 2e-3).items()}))
